@@ -1,0 +1,1003 @@
+// patch_match.cu — B200-native PatchMatch MVS sweep behind the C-ABI of include/b200_patch_match.h.
+//
+// Reference behaviour: src/colmap/mvs/patch_match_cuda.cu (PatchMatchCuda).  Design:
+//   * no physical Rotate() between sweeps (patch_match_cuda.cu:1859-1939): the four sweep
+//     directions are index maps over buffers that stay in the original orientation;
+//   * one CTA per image column (in the sweep's frame), WPC warps per CTA: warp 0 carries the
+//     sequential state of the column (PRNG, propagated plane, HMM forward messages), all warps share
+//     the photo-consistency work; each NCC is evaluated by an 8-lane group, the four groups of a warp
+//     being the four alternative plane hypotheses of SweepFromTopToBottom (:1117-1126);
+//   * bilateral weights are computed once per pixel (they only depend on the reference patch) instead
+//     of once per NCC evaluation, and each (hypothesis, source image) pair is evaluated once per pixel
+//     instead of once per Monte-Carlo sample (NCC is a pure function of the pair);
+//   * source images are stored as 2x2-footprint words so a bilinear tap is one 32-bit load;
+//   * XORWOW state is kept only for the border pixels the sweeps actually consume
+//     (the reference keeps and rotates a 48 B/pixel state map, :1811,1872-1878).
+#include <cuda_runtime.h>
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/b200_patch_match.h"
+#include "pm_device.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// parameter blocks
+// ------------------------------------------------------------------------------------------------
+struct PmSrcDesc {
+  int w, h, pitch, pad;
+  long long quad_off;   // in 32-bit words
+  long long depth_off;  // in floats
+};
+
+struct PmParams {
+  int W0, H0, N;
+  int radius, step, nside, ntaps, ntaps_pad, num_samples;
+  int geom, filter_min_num_consistent;
+  float depth_min, depth_max, spatial_norm, color_norm;
+  PmLikelihood L;
+  float geom_reg, geom_max_cost, filter_geom_max_cost, min_ncc_prob, cos_filter_tri;
+  const uint8_t* ref_raw;
+  uint8_t* ref_img;
+  float* ref_sum;
+  float* ref_sqsum;
+  float4* hyp;     // {depth, nx, ny, nz} per pixel, original orientation
+  float* cost;     // [pixel][N]
+  uint8_t* mask;   // [pixel][N]
+  const uint32_t* quads;
+  const float* src_depth;
+  const PmSrcDesc* src;
+  const float* poses;  // [4][N][43]
+  const float* init_depth;   // geom mode
+  const float* init_normal;  // geom mode, 3 planes
+  uint32_t* rng;       // [perimeter][6]
+  float K[4][4], invK[4][4];
+};
+
+struct PmSweepArgs {
+  int rot;
+  float perturbation, perturbation_pi, prev_w;
+  int last_filter;
+  float* sel_cur;
+  const float* sel_prev;
+};
+
+// ------------------------------------------------------------------------------------------------
+// frame maps: frame k = the reference's buffers after k Rotate() calls (cuda_rotate.h:57-75):
+//   (r_{k+1}, c_{k+1}) = (w_k - 1 - c_k, r_k)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pm_frame_to_orig(int W0, int H0, int rot, int r, int c, int* r0, int* c0) {
+  switch (rot) {
+    case 0: *r0 = r; *c0 = c; break;
+    case 1: *r0 = c; *c0 = W0 - 1 - r; break;
+    case 2: *r0 = H0 - 1 - r; *c0 = W0 - 1 - c; break;
+    default: *r0 = H0 - 1 - c; *c0 = r; break;
+  }
+}
+__device__ __forceinline__ size_t pm_pix0(int W0, int H0, int rot, int r, int c) {
+  int r0, c0;
+  pm_frame_to_orig(W0, H0, rot, r, c, &r0, &c0);
+  return (size_t)r0 * W0 + c0;
+}
+// RotateNormalMap applied k times / undone (patch_match_cuda.cu:849-861)
+__device__ __forceinline__ void pm_normal_to_frame(int rot, float& nx, float& ny) {
+  const float x = nx, y = ny;
+  switch (rot) {
+    case 0: break;
+    case 1: nx = y; ny = -x; break;
+    case 2: nx = -x; ny = -y; break;
+    default: nx = -y; ny = x; break;
+  }
+}
+__device__ __forceinline__ void pm_normal_to_orig(int rot, float& nx, float& ny) {
+  const float x = nx, y = ny;
+  switch (rot) {
+    case 0: break;
+    case 1: nx = -y; ny = x; break;
+    case 2: nx = -x; ny = -y; break;
+    default: nx = y; ny = -x; break;
+  }
+}
+// index of a border pixel in the compact PRNG state array
+__host__ __device__ __forceinline__ int pm_border_index(int W0, int H0, int r0, int c0) {
+  if (r0 == 0) return c0;
+  if (r0 == H0 - 1) return W0 + c0;
+  if (c0 == 0) return 2 * W0 + (r0 - 1);
+  return 2 * W0 + (H0 - 2) + (r0 - 1);
+}
+__device__ __forceinline__ float pm_ref_color(const PmParams& P, int rot, int fw, int fh, int r, int c) {
+  if (r < 0 || c < 0 || r >= fh || c >= fw) return 0.0f;
+  return (float)P.ref_img[pm_pix0(P.W0, P.H0, rot, r, c)] / 255.0f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one-off kernels
+// ------------------------------------------------------------------------------------------------
+// GpuMatRefImage::Filter / FilterKernel (gpu_mat_ref_image.cu:39-82)
+__global__ void pm_prefilter_kernel(const PmParams P) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = blockIdx.y * blockDim.y + threadIdx.y;
+  if (col >= P.W0 || row >= P.H0) return;
+  const int w = P.W0, h = P.H0, r = P.radius, s = P.step;
+  const float center = (float)P.ref_raw[(size_t)row * w + col] / 255.0f;
+  float cs = 0.0f, cq = 0.0f, ws = 0.0f;
+  for (int dr = -r; dr <= r; dr += s) {
+    for (int dc = -r; dc <= r; dc += s) {
+      const int rr = row + dr, cc = col + dc;
+      const float color = (rr < 0 || cc < 0 || rr >= h || cc >= w) ? 0.0f : (float)P.ref_raw[(size_t)rr * w + cc] / 255.0f;
+      const float bw = pm_bilateral_weight(P.spatial_norm, P.color_norm, dr, dc, center, color);
+      const float wc = bw * color;
+      cs += wc;
+      cq = fmaf(wc, color, cq);
+      ws += bw;
+    }
+  }
+  P.ref_sum[(size_t)row * w + col] = cs / ws;
+  P.ref_sqsum[(size_t)row * w + col] = cq / ws;
+  P.ref_img[(size_t)row * w + col] = (uint8_t)(255.0f * center);
+}
+
+// 2x2 footprint packing of one source image with a 2-pixel zero apron.
+__global__ void pm_pack_quads_kernel(const uint8_t* __restrict__ img, int w, int h, int pitch, uint32_t* __restrict__ out) {
+  const int X = blockIdx.x * blockDim.x + threadIdx.x;  // 0 .. w+3
+  const int Y = blockIdx.y * blockDim.y + threadIdx.y;  // 0 .. h+3
+  if (X >= w + 4 || Y >= h + 4) return;
+  const int x = X - 2, y = Y - 2;
+  auto T = [&](int xx, int yy) -> uint32_t {
+    return (xx < 0 || yy < 0 || xx >= w || yy >= h) ? 0u : (uint32_t)img[(size_t)yy * w + xx];
+  };
+  out[(size_t)Y * pitch + X] = T(x, y) | (T(x + 1, y) << 8) | (T(x, y + 1) << 16) | (T(x + 1, y + 1) << 24);
+}
+
+// GpuMatPRNG ctor + FillWithRandomNumbers + InitNormalMap (gpu_mat_prng.cu:36-48, gpu_mat.h:371-387,
+// patch_match_cuda.cu:835-846), or the geometric-mode copy (:1814-1852); prev_sel_prob = 0.5 (:1835).
+__global__ void pm_init_kernel(const PmParams P, float* sel_prev) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = blockIdx.y * blockDim.y + threadIdx.y;
+  if (col >= P.W0 || row >= P.H0) return;
+  const size_t p = (size_t)row * P.W0 + col;
+  const int gx = (P.W0 - 1) / 32 + 1;
+  const unsigned long long id =
+      (unsigned long long)((row / 16) * gx + (col / 32)) * 512ull + (unsigned long long)((row % 16) * 32 + (col % 32));
+  PmRng rs;
+  pm_rng_init(rs, id);
+  float4 hy;
+  if (P.geom) {
+    const size_t n = (size_t)P.W0 * P.H0;
+    hy = make_float4(P.init_depth[p], P.init_normal[p], P.init_normal[n + p], P.init_normal[2 * n + p]);
+  } else {
+    const float depth = fmaf(pm_rng_uniform(rs), P.depth_max - P.depth_min, P.depth_min);
+    float nv[3];
+    pm_random_normal(P.invK[0], (float)row, (float)col, rs, nv);
+    hy = make_float4(depth, nv[0], nv[1], nv[2]);
+  }
+  P.hyp[p] = hy;
+  if (row == 0 || col == 0 || row == P.H0 - 1 || col == P.W0 - 1) {
+    uint32_t* st = P.rng + 6 * (size_t)pm_border_index(P.W0, P.H0, row, col);
+    st[0] = rs.v0; st[1] = rs.v1; st[2] = rs.v2; st[3] = rs.v3; st[4] = rs.v4; st[5] = rs.d;
+  }
+  for (int i = 0; i < P.N; ++i) sel_prev[p * P.N + i] = 0.5f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCC of one (hypothesis, source image) pair by an 8-lane group
+// (PhotoConsistencyCostComputer::Compute, patch_match_cuda.cu:489-593)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float pm_ncc_group(const float4* __restrict__ patch, int ntaps, const float* __restrict__ pose,
+                                              const float iK[4], const uint32_t* __restrict__ quads, int pitch, int W,
+                                              int H, float rowf, float colf, float d, float n0, float n1, float n2,
+                                              float inv_wsum, float rsum, float rsq, int sub, unsigned gmask) {
+  float Hm[9];
+  pm_compose_homography(pose, iK, rowf, colf, d, n0, n1, n2, Hm);
+  float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll 4
+  for (int t = sub; t < ntaps; t += 8) {
+    const float4 tp = patch[t];
+    const float x = colf + tp.z;
+    const float y = rowf + tp.w;
+    const float zx = fmaf(Hm[0], x, fmaf(Hm[1], y, Hm[2]));
+    const float zy = fmaf(Hm[3], x, fmaf(Hm[4], y, Hm[5]));
+    const float zz = fmaf(Hm[6], x, fmaf(Hm[7], y, Hm[8]));
+    const float inv_z = 1.0f / zz;
+    const float color = pm_sample_quad(quads, pitch, W, H, inv_z * zx, inv_z * zy);
+    const float ws = tp.x * color;
+    s1 += ws;
+    s2 = fmaf(ws, color, s2);
+    s3 = fmaf(tp.y, color, s3);
+  }
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    s1 = s1 + __shfl_xor_sync(gmask, s1, o);
+    s2 = s2 + __shfl_xor_sync(gmask, s2, o);
+    s3 = s3 + __shfl_xor_sync(gmask, s3, o);
+  }
+  return pm_ncc_finalize(s1, s2, s3, inv_wsum, rsum, rsq);
+}
+
+// reference patch of one pixel: bilateral weights + weighted colours + 1/sum(w); executed by one warp.
+__device__ __forceinline__ void pm_build_patch(const PmParams& P, int rot, int fw, int fh, int row, int col, float4* patch,
+                                               int lane, float* inv_wsum_out) {
+  const float center = pm_ref_color(P, rot, fw, fh, row, col);
+  float partial = 0.0f;
+  for (int t = lane; t < P.ntaps; t += 32) {
+    const float4 tp = patch[t];
+    const int dc = (int)tp.z, dr = (int)tp.w;
+    const float c = pm_ref_color(P, rot, fw, fh, row + dr, col + dc);
+    const float bw = pm_bilateral_weight(P.spatial_norm, P.color_norm, dr, dc, center, c);
+    reinterpret_cast<float2*>(&patch[t])[0] = make_float2(bw, bw * c);
+    partial += bw;
+  }
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) partial = partial + __shfl_xor_sync(0xffffffffu, partial, o);
+  *inv_wsum_out = 1.0f / partial;
+}
+
+__device__ __forceinline__ void pm_fill_tap_offsets(const PmParams& P, float4* patch, int tid, int nthreads) {
+  for (int t = tid; t < P.ntaps_pad; t += nthreads) {
+    const int tr = t / P.nside, tc = t - tr * P.nside;
+    patch[t] = make_float4(0.0f, 0.0f, (float)(-P.radius + P.step * tc), (float)(-P.radius + P.step * tr));
+  }
+}
+
+// ComputeInitialCost (patch_match_cuda.cu:863-912), pixel-parallel: one warp per pixel.
+__global__ void __launch_bounds__(128) pm_initial_cost_kernel(const PmParams P) {
+  extern __shared__ float4 smem4[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = P.N;
+  float* poses = reinterpret_cast<float*>(smem4 + 4 * P.ntaps_pad);
+  float4* patch = smem4 + warp * P.ntaps_pad;
+  for (int i = threadIdx.x; i < N * PM_POSE_STRIDE; i += blockDim.x) poses[i] = P.poses[i];
+  pm_fill_tap_offsets(P, patch, lane, 32);
+  __syncthreads();
+  const size_t npix = (size_t)P.W0 * P.H0;
+  const int g = lane >> 3, sub = lane & 7;
+  const unsigned gmask = 0xffu << (8 * g);
+  for (size_t p = (size_t)blockIdx.x * 4 + warp; p < npix; p += (size_t)gridDim.x * 4) {
+    const int row = (int)(p / P.W0), col = (int)(p - (size_t)row * P.W0);
+    float inv_wsum;
+    pm_build_patch(P, 0, P.W0, P.H0, row, col, patch, lane, &inv_wsum);
+    __syncwarp();
+    const float4 hy = P.hyp[p];
+    const float rsum = P.ref_sum[p], rsq = P.ref_sqsum[p];
+    for (int base = 0; base < N; base += 4) {
+      const int img = base + g;
+      if (img < N) {
+        const PmSrcDesc sd = P.src[img];
+        const float c = pm_ncc_group(patch, P.ntaps, poses + img * PM_POSE_STRIDE, P.invK[0], P.quads + sd.quad_off,
+                                     sd.pitch, sd.w, sd.h, (float)row, (float)col, hy.x, hy.y, hy.z, hy.w, inv_wsum,
+                                     rsum, rsq, sub, gmask);
+        if (sub == 0) P.cost[p * N + img] = c;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SweepFromTopToBottom (patch_match_cuda.cu:933-1288): one CTA per column of the sweep frame.
+// ------------------------------------------------------------------------------------------------
+template <int WPC, bool GEOM>
+__global__ void __launch_bounds__(32 * WPC) pm_sweep_kernel(const PmParams P, const PmSweepArgs A) {
+  extern __shared__ float4 smem4[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = blockIdx.x;
+  const int rot = A.rot, N = P.N;
+  const int fw = (rot & 1) ? P.H0 : P.W0, fh = (rot & 1) ? P.W0 : P.H0;
+
+  float4* patch = smem4;
+  float* poses = reinterpret_cast<float*>(patch + P.ntaps_pad);
+  float* tab = poses + N * PM_POSE_STRIDE;  // [5][32] cost of hypothesis k for image i (k = 0: cached cost)
+  float* gtab = tab + 160;                  // [3][32] geometric cost at cur / prev / rand depth
+  float* hyp = gtab + 96;                   // [5][4]  depth, normal of the five hypotheses (:1117-1126)
+  float* fctl = hyp + 20;                   // inv_wsum, ref_sum, ref_sqsum
+  int* ctrl = reinterpret_cast<int*>(fctl + 4);  // needed, remaining, best
+  int* samples = ctrl + 4;                  // [num_samples]
+
+  for (int i = threadIdx.x; i < N * PM_POSE_STRIDE; i += blockDim.x) poses[i] = P.poses[(size_t)rot * N * PM_POSE_STRIDE + i];
+  pm_fill_tap_offsets(P, patch, threadIdx.x, blockDim.x);
+  const float iK[4] = {P.invK[rot][0], P.invK[rot][1], P.invK[rot][2], P.invK[rot][3]};
+  const float Kr[4] = {P.K[rot][0], P.K[rot][1], P.K[rot][2], P.K[rot][3]};
+  const float colf = (float)col;
+  const int g = lane >> 3, sub = lane & 7;
+  const unsigned gmask = 0xffu << (8 * g);
+  const bool img_lane = lane < N;
+  const unsigned nmask = (N >= 32) ? 0xffffffffu : ((1u << N) - 1u);
+  __syncthreads();
+
+  // ---- backward messages for the whole column (:976-989); lane = image
+  float fwd = 0.5f;
+  PmRng rs;
+  float prev_d = 0.0f, prev_n0 = 0.0f, prev_n1 = 0.0f, prev_n2 = 0.0f;
+  uint32_t* rng_slot = nullptr;
+  if (warp == 0) {
+    if (img_lane) {
+      float beta = 0.5f;
+      for (int row = fh - 1; row >= 0; --row) {
+        const size_t p = pm_pix0(P.W0, P.H0, rot, row, col);
+        beta = pm_backward_message(P.L, P.cost[p * N + lane], beta);
+        A.sel_cur[p * N + lane] = beta;
+      }
+    }
+    int r0, c0;
+    pm_frame_to_orig(P.W0, P.H0, rot, 0, col, &r0, &c0);
+    rng_slot = P.rng + 6 * (size_t)pm_border_index(P.W0, P.H0, r0, c0);
+    rs.v0 = rng_slot[0]; rs.v1 = rng_slot[1]; rs.v2 = rng_slot[2]; rs.v3 = rng_slot[3]; rs.v4 = rng_slot[4]; rs.d = rng_slot[5];
+    const float4 h0 = P.hyp[(size_t)r0 * P.W0 + c0];
+    prev_d = h0.x; prev_n0 = h0.y; prev_n1 = h0.z; prev_n2 = h0.w;
+    pm_normal_to_frame(rot, prev_n0, prev_n1);
+  }
+
+  for (int row = 0; row < fh; ++row) {
+    const size_t p = pm_pix0(P.W0, P.H0, rot, row, col);
+    const float rowf = (float)row;
+
+    // ---- reference patch (one warp), overlapped with phase A on warp 0 when WPC > 1
+    if (warp == WPC - 1) {
+      float inv_wsum;
+      pm_build_patch(P, rot, fw, fh, row, col, patch, lane, &inv_wsum);
+      if (lane == 0) { fctl[0] = inv_wsum; fctl[1] = P.ref_sum[p]; fctl[2] = P.ref_sqsum[p]; }
+    }
+
+    // ---- phase A (warp 0): hypotheses, sampling distribution, Monte-Carlo samples
+    float cost_i = 0.0f, beta_i = 0.0f, prevp_i = 0.0f, rx = 0.0f, ry = 0.0f;
+    if (warp == 0) {
+      prev_d = pm_propagate_depth(iK, prev_d, prev_n1, prev_n2, (float)(row - 1), rowf);
+      const float4 cur4 = P.hyp[p];
+      const float cur_d = cur4.x;
+      float cur_n0 = cur4.y, cur_n1 = cur4.z;
+      const float cur_n2 = cur4.w;
+      pm_normal_to_frame(rot, cur_n0, cur_n1);
+      float rand_d, rand_n[3];
+      {
+        const float dmin = (1.0f - A.perturbation) * cur_d;
+        const float dmax = (1.0f + A.perturbation) * cur_d;
+        rand_d = fmaf(pm_rng_uniform(rs), dmax - dmin, dmin);
+      }
+      pm_perturb_normal(iK, rowf, colf, A.perturbation_pi, cur_n0, cur_n1, cur_n2, rs, rand_n);
+      rx = fmaf(iK[0], colf, iK[1]);
+      ry = fmaf(iK[2], rowf, iK[3]);
+      float prob = 0.0f;
+      if (img_lane) {
+        const float* pose = poses + lane * PM_POSE_STRIDE;
+        cost_i = P.cost[p * N + lane];
+        beta_i = A.sel_cur[p * N + lane];
+        prevp_i = A.sel_prev[p * N + lane];
+        const float alpha = pm_forward_message(P.L, cost_i, fwd);
+        const float sp = pm_sel_prob(alpha, beta_i, prevp_i, A.prev_w);
+        float ct, ci;
+        pm_viewing_angles(pose, cur_d * rx, cur_d * ry, cur_d, cur_n0, cur_n1, cur_n2, &ct, &ci);
+        float Hm[9];
+        pm_compose_homography(pose, iK, rowf, colf, cur_d, cur_n0, cur_n1, cur_n2, Hm);
+        prob = sp * pm_tri_prob(P.L, ct) * pm_inc_prob(P.L, ci) * pm_res_prob(Hm, rowf, colf, P.radius);
+        tab[lane] = cost_i;
+      }
+      // TransformPDFToCDF (:683-696)
+      float sum = 0.0f;
+      for (int i = 0; i < N; ++i) sum += __shfl_sync(0xffffffffu, prob, i);
+      const float inv = 1.0f / sum;
+      float cum = 0.0f, cdf = 0.0f;
+      for (int i = 0; i < N; ++i) {
+        cum += __shfl_sync(0xffffffffu, prob, i) * inv;
+        if (lane == i) cdf = cum;
+      }
+      unsigned needed = 0u;
+      for (int s = 0; s < P.num_samples; ++s) {
+        const float u = pm_rng_uniform(rs) - FLT_EPSILON;
+        const unsigned m = __ballot_sync(0xffffffffu, img_lane && (cdf > u));
+        const int img = m ? (__ffs(m) - 1) : -1;
+        if (lane == 0) samples[s] = img;
+        if (img >= 0) needed |= 1u << img;
+      }
+      if (lane == 0) {
+        ctrl[0] = (int)needed;
+        hyp[0] = cur_d;  hyp[1] = cur_n0;  hyp[2] = cur_n1;  hyp[3] = cur_n2;
+        hyp[4] = prev_d; hyp[5] = prev_n0; hyp[6] = prev_n1; hyp[7] = prev_n2;
+        hyp[8] = rand_d; hyp[9] = rand_n[0]; hyp[10] = rand_n[1]; hyp[11] = rand_n[2];
+        hyp[12] = cur_d; hyp[13] = rand_n[0]; hyp[14] = rand_n[1]; hyp[15] = rand_n[2];
+        hyp[16] = rand_d; hyp[17] = cur_n0; hyp[18] = cur_n1; hyp[19] = cur_n2;
+      }
+      if (GEOM) {
+        if (img_lane && ((needed >> lane) & 1u)) {
+          const PmSrcDesc sd = P.src[lane];
+          const float* pose = poses + lane * PM_POSE_STRIDE;
+          const float* dm = P.src_depth + sd.depth_off;
+          gtab[lane] = pm_geom_cost(pose, Kr, iK, dm, sd.w, sd.h, rowf, colf, cur_d, P.geom_max_cost);
+          gtab[32 + lane] = pm_geom_cost(pose, Kr, iK, dm, sd.w, sd.h, rowf, colf, prev_d, P.geom_max_cost);
+          gtab[64 + lane] = pm_geom_cost(pose, Kr, iK, dm, sd.w, sd.h, rowf, colf, rand_d, P.geom_max_cost);
+        }
+      }
+    }
+    __syncthreads();  // #1: patch, hypotheses, samples visible
+
+    // ---- phase B (all warps): NCC of the four alternative hypotheses for every sampled image
+    const float inv_wsum = fctl[0], rsum = fctl[1], rsq = fctl[2];
+    {
+      const unsigned needed = (unsigned)ctrl[0];
+      const int h = g + 1;
+      const float hd = hyp[4 * h], hn0 = hyp[4 * h + 1], hn1 = hyp[4 * h + 2], hn2 = hyp[4 * h + 3];
+      int k = 0;
+      for (unsigned m = needed; m; m &= m - 1, ++k) {
+        if ((k % WPC) != warp) continue;
+        const int img = __ffs(m) - 1;
+        const PmSrcDesc sd = P.src[img];
+        const float c = pm_ncc_group(patch, P.ntaps, poses + img * PM_POSE_STRIDE, iK, P.quads + sd.quad_off, sd.pitch,
+                                     sd.w, sd.h, rowf, colf, hd, hn0, hn1, hn2, inv_wsum, rsum, rsq, sub, gmask);
+        if (sub == 0) tab[h * 32 + img] = c;
+      }
+    }
+    __syncthreads();  // #2: cost table complete
+
+    // ---- phase C (warp 0): accumulate sampled costs, pick the best hypothesis (:1128-1182)
+    int best = 0;
+    if (warp == 0) {
+      float c = 0.0f;
+      if (lane < 5) {
+        const int gi = (lane == 1) ? 1 : ((lane == 2 || lane == 4) ? 2 : 0);
+        for (int s = 0; s < P.num_samples; ++s) {
+          const int img = samples[s];
+          if (img < 0) continue;
+          c += tab[lane * 32 + img];
+          if (GEOM) c = fmaf(P.geom_reg, gtab[gi * 32 + img], c);
+        }
+      }
+      float mn = __shfl_sync(0xffffffffu, c, 0);
+      for (int k = 1; k < 5; ++k) {
+        const float ck = __shfl_sync(0xffffffffu, c, k);
+        if (ck <= mn) { mn = ck; best = k; }
+      }
+      if (lane == 0) {
+        const unsigned needed = (unsigned)ctrl[0];
+        ctrl[1] = (best == 0) ? 0 : (int)(~needed & nmask);
+        ctrl[2] = best;
+      }
+    }
+    __syncthreads();  // #3: best / remaining visible
+
+    // ---- phase D (all warps): cost of the winning hypothesis for the images that were not sampled
+    {
+      const unsigned remaining = (unsigned)ctrl[1];
+      if (remaining) {
+        const int b = ctrl[2];
+        const float hd = hyp[4 * b], hn0 = hyp[4 * b + 1], hn1 = hyp[4 * b + 2], hn2 = hyp[4 * b + 3];
+        const int item = warp * 4 + g;
+        int k = 0;
+        for (unsigned m = remaining; m; m &= m - 1, ++k) {
+          if ((k % (4 * WPC)) != item) continue;
+          const int img = __ffs(m) - 1;
+          const PmSrcDesc sd = P.src[img];
+          const float c = pm_ncc_group(patch, P.ntaps, poses + img * PM_POSE_STRIDE, iK, P.quads + sd.quad_off,
+                                       sd.pitch, sd.w, sd.h, rowf, colf, hd, hn0, hn1, hn2, inv_wsum, rsum, rsq, sub,
+                                       gmask);
+          if (sub == 0) tab[b * 32 + img] = c;
+        }
+      }
+    }
+    __syncthreads();  // #4
+
+    // ---- phase E (warp 0): new messages / selection probabilities, filter, carry state (:1184-1283)
+    if (warp == 0) {
+      const float best_d = hyp[4 * best];
+      const float bn0 = hyp[4 * best + 1], bn1 = hyp[4 * best + 2], bn2 = hyp[4 * best + 3];
+      float sp = 0.0f;
+      if (img_lane) {
+        float c = cost_i;
+        if (best != 0) {
+          c = tab[best * 32 + lane];
+          P.cost[p * N + lane] = c;
+        }
+        const float alpha = pm_forward_message(P.L, c, fwd);
+        sp = pm_sel_prob(alpha, beta_i, prevp_i, A.prev_w);
+        A.sel_cur[p * N + lane] = sp;
+        fwd = alpha;
+      }
+      bool zero = false;
+      if (A.last_filter) {
+        bool ok = false;
+        if (img_lane) {
+          const float* pose = poses + lane * PM_POSE_STRIDE;
+          float ct, ci;
+          pm_viewing_angles(pose, best_d * rx, best_d * ry, best_d, bn0, bn1, bn2, &ct, &ci);
+          if (!(ct > P.cos_filter_tri || ci <= 0.0f)) {
+            ok = sp >= P.min_ncc_prob;
+            if (GEOM && ok) {
+              const PmSrcDesc sd = P.src[lane];
+              ok = pm_geom_cost(pose, Kr, iK, P.src_depth + sd.depth_off, sd.w, sd.h, rowf, colf, best_d,
+                                P.geom_max_cost) <= P.filter_geom_max_cost;
+            }
+          }
+        }
+        const int cnt = __popc(__ballot_sync(0xffffffffu, ok));
+        zero = cnt < P.filter_min_num_consistent;
+        if (img_lane) P.mask[p * N + lane] = (ok && !zero) ? 1 : 0;
+      }
+      if (lane == 0) {
+        float o0 = bn0, o1 = bn1;
+        pm_normal_to_orig(rot, o0, o1);
+        if (zero) {
+          // the reference stores +0 in the sweep frame and then rotates (:1268-1271)
+          float z0 = 0.0f, z1 = 0.0f;
+          pm_normal_to_orig(rot, z0, z1);
+          P.hyp[p] = make_float4(0.0f, z0, z1, 0.0f);
+        } else {
+          P.hyp[p] = make_float4(best_d, o0, o1, bn2);
+        }
+      }
+      prev_d = best_d; prev_n0 = bn0; prev_n1 = bn1; prev_n2 = bn2;
+    }
+  }
+  if (warp == 0 && lane == 0) {
+    rng_slot[0] = rs.v0; rng_slot[1] = rs.v1; rng_slot[2] = rs.v2; rng_slot[3] = rs.v3; rng_slot[4] = rs.v4; rng_slot[5] = rs.d;
+  }
+}
+
+// outputs in mvs::Mat<float> layout (slice-major)
+__global__ void pm_export_kernel(const PmParams P, const float* sel, float* depth, float* normal, float* sel_out,
+                                 uint8_t* mask_out) {
+  const size_t n = (size_t)P.W0 * P.H0;
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const float4 h = P.hyp[p];
+  if (depth) depth[p] = h.x;
+  if (normal) { normal[p] = h.y; normal[n + p] = h.z; normal[2 * n + p] = h.w; }
+  if (sel_out) for (int i = 0; i < P.N; ++i) sel_out[(size_t)i * n + p] = sel[p * P.N + i];
+  if (mask_out) for (int i = 0; i < P.N; ++i) mask_out[(size_t)i * n + p] = P.mask ? P.mask[p * P.N + i] : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_pm_error;
+static int pm_fail(int code, const std::string& msg) { g_pm_error = msg; return code; }
+#define PM_CUDA(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return pm_fail(-100, std::string(#call) + ": " + cudaGetErrorString(e__));                  \
+  } while (0)
+
+struct b200pm_context {
+  b200pm_options opt;
+  PmParams P;
+  int device = 0;
+  int wpc = 2;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<void*> allocs;
+  float* sel[2] = {nullptr, nullptr};
+  int final_sel = 0;
+  bool dirty = false, ran = false;
+  float last_ms = 0.0f, last_sweep_ms = 0.0f;
+  int last_launches = 0;
+  std::vector<int> src_image_idxs;
+  size_t smem_sweep = 0, smem_init = 0;
+};
+
+template <typename T>
+static cudaError_t pm_alloc(b200pm_context* c, T** p, size_t count) {
+  cudaError_t e = cudaMalloc((void**)p, sizeof(T) * (count ? count : 1));
+  if (e == cudaSuccess) c->allocs.push_back((void*)*p);
+  return e;
+}
+
+// image.cc:97-150 composed in double and rounded once (ComputeRelativePose, ComputeProjectionCenter,
+// ComposeProjectionMatrix, ComposeInverseProjectionMatrix)
+static void pm_compose_pose_row(const double refR[9], const double refT[3], const float K[9], const float R2f[9],
+                                const float T2f[3], float out[PM_POSE_STRIDE]) {
+  double R2[9], T2[3], R[9], T[3], C[3], Pm[12], iP[12];
+  for (int i = 0; i < 9; ++i) R2[i] = R2f[i];
+  for (int i = 0; i < 3; ++i) T2[i] = T2f[i];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+      R[3 * r + c] = R2[3 * r] * refR[3 * c] + R2[3 * r + 1] * refR[3 * c + 1] + R2[3 * r + 2] * refR[3 * c + 2];
+  for (int r = 0; r < 3; ++r) T[r] = T2[r] - (R[3 * r] * refT[0] + R[3 * r + 1] * refT[1] + R[3 * r + 2] * refT[2]);
+  for (int c = 0; c < 3; ++c) C[c] = -(R[c] * T[0] + R[3 + c] * T[1] + R[6 + c] * T[2]);
+  const double fx = K[0], cx = K[2], fy = K[4], cy = K[5];
+  for (int c = 0; c < 3; ++c) {
+    Pm[c] = fx * R[c] + cx * R[6 + c];
+    Pm[4 + c] = fy * R[3 + c] + cy * R[6 + c];
+    Pm[8 + c] = R[6 + c];
+  }
+  Pm[3] = fx * T[0] + cx * T[2];
+  Pm[7] = fy * T[1] + cy * T[2];
+  Pm[11] = T[2];
+  for (int r = 0; r < 3; ++r) {
+    iP[4 * r + 0] = R[r] / fx;
+    iP[4 * r + 1] = R[3 + r] / fy;
+    iP[4 * r + 2] = R[6 + r] - R[r] * cx / fx - R[3 + r] * cy / fy;
+    iP[4 * r + 3] = C[r];
+  }
+  out[0] = K[0]; out[1] = K[2]; out[2] = K[4]; out[3] = K[5];
+  for (int i = 0; i < 9; ++i) out[4 + i] = (float)R[i];
+  for (int i = 0; i < 3; ++i) out[13 + i] = (float)T[i];
+  for (int i = 0; i < 3; ++i) out[16 + i] = (float)C[i];
+  for (int i = 0; i < 12; ++i) out[19 + i] = (float)Pm[i];
+  for (int i = 0; i < 12; ++i) out[31 + i] = (float)iP[i];
+}
+
+// PatchMatchCuda::InitTransforms (patch_match_cuda.cu:1694-1808)
+static void pm_init_transforms(const b200pm_problem* p, float K4[4][4], float iK4[4][4], std::vector<float>& poses) {
+  const float fx = p->ref_K[0], cx = p->ref_K[2], fy = p->ref_K[4], cy = p->ref_K[5];
+  const float Wm1 = (float)(p->ref_width - 1), Hm1 = (float)(p->ref_height - 1);
+  const float Kt[4][4] = {{fx, cx, fy, cy}, {fy, cy, fx, Wm1 - cx}, {fx, Wm1 - cx, fy, Hm1 - cy}, {fy, Hm1 - cy, fx, cx}};
+  for (int k = 0; k < 4; ++k) {
+    for (int i = 0; i < 4; ++i) K4[k][i] = Kt[k][i];
+    iK4[k][0] = 1.0f / Kt[k][0];
+    iK4[k][1] = -Kt[k][1] / Kt[k][0];
+    iK4[k][2] = 1.0f / Kt[k][2];
+    iK4[k][3] = -Kt[k][3] / Kt[k][2];
+  }
+  const int N = p->num_src;
+  poses.resize((size_t)4 * N * PM_POSE_STRIDE);
+  double R[9], T[3];
+  for (int i = 0; i < 9; ++i) R[i] = p->ref_R[i];
+  for (int i = 0; i < 3; ++i) T[i] = p->ref_T[i];
+  for (int k = 0; k < 4; ++k) {
+    for (int i = 0; i < N; ++i)
+      pm_compose_pose_row(R, T, p->src_K + 9 * i, p->src_R + 9 * i, p->src_T + 3 * i,
+                          poses.data() + ((size_t)k * N + i) * PM_POSE_STRIDE);
+    double nR[9], nT[3];
+    for (int c = 0; c < 3; ++c) { nR[c] = R[3 + c]; nR[3 + c] = -R[c]; nR[6 + c] = R[6 + c]; }
+    nT[0] = T[1]; nT[1] = -T[0]; nT[2] = T[2];
+    memcpy(R, nR, sizeof(R)); memcpy(T, nT, sizeof(T));
+  }
+}
+
+extern "C" {
+
+void b200pm_options_init(b200pm_options* o) {
+  o->depth_min = -1.0; o->depth_max = -1.0; o->sigma_spatial = -1.0; o->sigma_color = 0.2f;
+  o->ncc_sigma = 0.6f; o->min_triangulation_angle = 1.0f; o->incident_angle_sigma = 0.9f;
+  o->geom_consistency_regularizer = 0.3f; o->geom_consistency_max_cost = 3.0f; o->filter_min_ncc = 0.1f;
+  o->filter_min_triangulation_angle = 3.0f; o->filter_geom_consistency_max_cost = 1.0f;
+  o->window_radius = 5; o->window_step = 1; o->num_samples = 15; o->num_iterations = 5;
+  o->filter_min_num_consistent = 2; o->geom_consistency = 1; o->filter = 1; o->gpu_index = -1;
+}
+
+const char* b200pm_last_error(void) { return g_pm_error.c_str(); }
+
+int b200pm_check(const b200pm_options* o, const b200pm_problem* p) {
+  if (!o || !p) return pm_fail(-1, "null options/problem");
+  // PatchMatchOptions::Check (patch_match_options.cc:72-99)
+  if (!(o->depth_min >= 0.0 && o->depth_min <= o->depth_max)) return pm_fail(-2, "depth range must be resolved: 0 <= depth_min <= depth_max");
+  if (o->window_radius <= 0 || o->window_radius > 20) return pm_fail(-2, "window_radius must be in 1..20");
+  if (o->window_step <= 0 || o->window_step > 2) return pm_fail(-2, "window_step must be 1 or 2");
+  if (!(o->sigma_color > 0.0)) return pm_fail(-2, "sigma_color must be > 0");
+  if (o->num_samples <= 0 || o->num_samples > 1024) return pm_fail(-2, "num_samples must be in 1..1024");
+  if (!(o->ncc_sigma > 0.0)) return pm_fail(-2, "ncc_sigma must be > 0");
+  if (!(o->min_triangulation_angle >= 0.0 && o->min_triangulation_angle < 180.0)) return pm_fail(-2, "min_triangulation_angle out of range");
+  if (!(o->incident_angle_sigma > 0.0)) return pm_fail(-2, "incident_angle_sigma must be > 0");
+  if (o->num_iterations <= 0) return pm_fail(-2, "num_iterations must be > 0");
+  if (!(o->geom_consistency_regularizer >= 0.0) || !(o->geom_consistency_max_cost >= 0.0)) return pm_fail(-2, "geom_consistency_* must be >= 0");
+  if (!(o->filter_min_ncc >= -1.0 && o->filter_min_ncc <= 1.0)) return pm_fail(-2, "filter_min_ncc out of range");
+  if (!(o->filter_min_triangulation_angle >= 0.0 && o->filter_min_triangulation_angle <= 180.0)) return pm_fail(-2, "filter_min_triangulation_angle out of range");
+  if (o->filter_min_num_consistent < 0) return pm_fail(-2, "filter_min_num_consistent must be >= 0");
+  if (!(o->filter_geom_consistency_max_cost >= 0.0)) return pm_fail(-2, "filter_geom_consistency_max_cost must be >= 0");
+  // PatchMatch::Check (patch_match.cc:67-126)
+  if (p->ref_width <= 0 || p->ref_height <= 0 || !p->ref_gray) return pm_fail(-3, "reference image missing");
+  if (p->num_src < 1) return pm_fail(-3, "at least one source image is required");
+  if (p->num_src > PM_MAX_SRC) return pm_fail(-3, "more than 32 source images are not supported");
+  if (!p->src_width || !p->src_height || !p->src_gray || !p->src_K || !p->src_R || !p->src_T) return pm_fail(-3, "source image arrays missing");
+  auto checkK = [](const float* K) { return K[1] == 0.0f && K[3] == 0.0f && K[6] == 0.0f && K[7] == 0.0f && K[8] == 1.0f; };
+  if (!checkK(p->ref_K)) return pm_fail(-3, "reference K must have zero skew and K[8] == 1");
+  for (int i = 0; i < p->num_src; ++i) {
+    if (p->src_width[i] <= 0 || p->src_height[i] <= 0 || !p->src_gray[i]) return pm_fail(-3, "source bitmap missing");
+    if (!checkK(p->src_K + 9 * i)) return pm_fail(-3, "source K must have zero skew and K[8] == 1");
+    if (p->src_image_idxs)
+      for (int j = 0; j < i; ++j)
+        if (p->src_image_idxs[i] == p->src_image_idxs[j]) return pm_fail(-3, "duplicate source image index");
+  }
+  if (o->geom_consistency) {
+    if (!p->src_depth || !p->ref_depth_init || !p->ref_normal_init) return pm_fail(-3, "geom_consistency requires depth and normal maps");
+    for (int i = 0; i < p->num_src; ++i)
+      if (!p->src_depth[i]) return pm_fail(-3, "geom_consistency requires every source depth map");
+  }
+  return 0;
+}
+
+int b200pm_create(const b200pm_options* o, const b200pm_problem* p, b200pm_handle* out) {
+  if (!out) return pm_fail(-1, "null handle pointer");
+  *out = nullptr;
+  const int rc = b200pm_check(o, p);
+  if (rc != 0) return rc;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return pm_fail(-101, "no CUDA device: colmap_b200 has no CPU fallback");
+  b200pm_context* c = new b200pm_context();
+  c->opt = *o;
+  if (o->gpu_index >= 0) {
+    if (o->gpu_index >= ndev) { delete c; return pm_fail(-101, "gpu_index out of range"); }
+    c->device = o->gpu_index;
+  } else {
+    cudaGetDevice(&c->device);
+  }
+  PM_CUDA(cudaSetDevice(c->device));
+  PM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 4; ++i) PM_CUDA(cudaEventCreate(&c->ev[i]));
+  if (const char* e = getenv("B200PM_WPC")) c->wpc = atoi(e);
+  if (c->wpc != 1 && c->wpc != 2 && c->wpc != 4) c->wpc = 2;
+
+  PmParams& P = c->P;
+  memset(&P, 0, sizeof(P));
+  P.W0 = p->ref_width; P.H0 = p->ref_height; P.N = p->num_src;
+  P.radius = o->window_radius; P.step = o->window_step;
+  P.nside = (2 * P.radius) / P.step + 1;
+  P.ntaps = P.nside * P.nside;
+  P.ntaps_pad = (P.ntaps + 7) & ~7;
+  P.num_samples = o->num_samples;
+  P.geom = o->geom_consistency ? 1 : 0;
+  P.filter_min_num_consistent = o->filter_min_num_consistent;
+  P.depth_min = (float)o->depth_min; P.depth_max = (float)o->depth_max;
+  const float sigma_spatial = (float)(o->sigma_spatial <= 0 ? (double)o->window_radius : o->sigma_spatial);
+  const float sigma_color = (float)o->sigma_color, ncc_sigma = (float)o->ncc_sigma;
+  const float inc_sigma = (float)o->incident_angle_sigma;
+  P.spatial_norm = 1.0f / (2.0f * sigma_spatial * sigma_spatial);
+  P.color_norm = 1.0f / (2.0f * sigma_color * sigma_color);
+  P.L.cos_min_tri = cosf((float)(o->min_triangulation_angle * 0.0174532925199432));
+  P.L.inv_inc_sigma_sq = -0.5f / (inc_sigma * inc_sigma);
+  P.L.inv_ncc_sigma_sq = -0.5f / (ncc_sigma * ncc_sigma);
+  P.L.ncc_norm = 2.0f / (sqrtf(2.0f * (float)M_PI) * ncc_sigma * erff(2.0f / (ncc_sigma * 1.414213562f)));
+  P.geom_reg = (float)o->geom_consistency_regularizer;
+  P.geom_max_cost = (float)o->geom_consistency_max_cost;
+  P.filter_geom_max_cost = (float)o->filter_geom_consistency_max_cost;
+  P.min_ncc_prob = pm_ncc_prob(P.L, 1.0f - (float)o->filter_min_ncc);
+  P.cos_filter_tri = cosf((float)(o->filter_min_triangulation_angle * 0.0174532925199432));
+
+  const size_t n = (size_t)P.W0 * P.H0;
+  const int N = P.N;
+  c->src_image_idxs.resize(N);
+  for (int i = 0; i < N; ++i) c->src_image_idxs[i] = p->src_image_idxs ? p->src_image_idxs[i] : i;
+
+  std::vector<float> poses;
+  pm_init_transforms(p, P.K, P.invK, poses);
+
+  uint8_t* d_ref_raw; float* d_poses; PmSrcDesc* d_src; uint32_t* d_quads; float* d_src_depth = nullptr;
+  float *d_init_depth = nullptr, *d_init_normal = nullptr;
+  PM_CUDA(pm_alloc(c, &d_ref_raw, n));
+  PM_CUDA(pm_alloc(c, &P.ref_img, n));
+  PM_CUDA(pm_alloc(c, &P.ref_sum, n));
+  PM_CUDA(pm_alloc(c, &P.ref_sqsum, n));
+  PM_CUDA(pm_alloc(c, &P.hyp, n));
+  PM_CUDA(pm_alloc(c, &P.cost, n * N));
+  PM_CUDA(pm_alloc(c, &c->sel[0], n * N));
+  PM_CUDA(pm_alloc(c, &c->sel[1], n * N));
+  if (o->filter) PM_CUDA(pm_alloc(c, &P.mask, n * N));
+  PM_CUDA(pm_alloc(c, &d_poses, poses.size()));
+  PM_CUDA(pm_alloc(c, &d_src, (size_t)N));
+  PM_CUDA(pm_alloc(c, &P.rng, (size_t)6 * (2 * (size_t)P.W0 + 2 * (size_t)P.H0)));
+  std::vector<PmSrcDesc> descs(N);
+  size_t quad_words = 0, depth_floats = 0, raw_bytes = 0;
+  for (int i = 0; i < N; ++i) {
+    descs[i].w = p->src_width[i]; descs[i].h = p->src_height[i];
+    descs[i].pitch = (p->src_width[i] + 4 + 7) & ~7;
+    descs[i].pad = 0;
+    descs[i].quad_off = (long long)quad_words;
+    descs[i].depth_off = (long long)depth_floats;
+    quad_words += (size_t)descs[i].pitch * (descs[i].h + 4);
+    depth_floats += (size_t)descs[i].w * descs[i].h;
+    raw_bytes = std::max(raw_bytes, (size_t)descs[i].w * descs[i].h);
+  }
+  PM_CUDA(pm_alloc(c, &d_quads, quad_words));
+  uint8_t* d_raw;
+  PM_CUDA(pm_alloc(c, &d_raw, raw_bytes));
+  if (P.geom) {
+    PM_CUDA(pm_alloc(c, &d_src_depth, depth_floats));
+    PM_CUDA(pm_alloc(c, &d_init_depth, n));
+    PM_CUDA(pm_alloc(c, &d_init_normal, 3 * n));
+  }
+  P.ref_raw = d_ref_raw; P.poses = d_poses; P.src = d_src; P.quads = d_quads; P.src_depth = d_src_depth;
+  P.init_depth = d_init_depth; P.init_normal = d_init_normal;
+
+  cudaStream_t s = c->stream;
+  PM_CUDA(cudaMemcpyAsync(d_ref_raw, p->ref_gray, n, cudaMemcpyHostToDevice, s));
+  PM_CUDA(cudaMemcpyAsync(d_poses, poses.data(), poses.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+  PM_CUDA(cudaMemcpyAsync(d_src, descs.data(), sizeof(PmSrcDesc) * N, cudaMemcpyHostToDevice, s));
+  for (int i = 0; i < N; ++i) {
+    const size_t bytes = (size_t)descs[i].w * descs[i].h;
+    PM_CUDA(cudaMemcpyAsync(d_raw, p->src_gray[i], bytes, cudaMemcpyHostToDevice, s));
+    dim3 blk(32, 8), grd((descs[i].w + 4 + 31) / 32, (descs[i].h + 4 + 7) / 8);
+    pm_pack_quads_kernel<<<grd, blk, 0, s>>>(d_raw, descs[i].w, descs[i].h, descs[i].pitch, d_quads + descs[i].quad_off);
+    if (P.geom)
+      PM_CUDA(cudaMemcpyAsync(d_src_depth + descs[i].depth_off, p->src_depth[i], bytes * sizeof(float), cudaMemcpyHostToDevice, s));
+  }
+  if (P.geom) {
+    PM_CUDA(cudaMemcpyAsync(d_init_depth, p->ref_depth_init, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    PM_CUDA(cudaMemcpyAsync(d_init_normal, p->ref_normal_init, 3 * n * sizeof(float), cudaMemcpyHostToDevice, s));
+  }
+  {
+    dim3 blk(32, 8), grd((P.W0 + 31) / 32, (P.H0 + 7) / 8);
+    pm_prefilter_kernel<<<grd, blk, 0, s>>>(P);
+    pm_init_kernel<<<grd, blk, 0, s>>>(P, c->sel[1]);
+  }
+  c->smem_sweep = sizeof(float4) * P.ntaps_pad + sizeof(float) * ((size_t)N * PM_POSE_STRIDE + 160 + 96 + 20 + 4) +
+                  sizeof(int) * (4 + (size_t)P.num_samples);
+  c->smem_init = sizeof(float4) * 4 * P.ntaps_pad + sizeof(float) * (size_t)N * PM_POSE_STRIDE;
+  PM_CUDA(cudaStreamSynchronize(s));
+  PM_CUDA(cudaGetLastError());
+  *out = c;
+  return 0;
+}
+
+}  // extern "C"
+
+template <int WPC>
+static void pm_launch_sweep(b200pm_context* c, const PmSweepArgs& A, int fw) {
+  if (c->P.geom)
+    pm_sweep_kernel<WPC, true><<<fw, 32 * WPC, c->smem_sweep, c->stream>>>(c->P, A);
+  else
+    pm_sweep_kernel<WPC, false><<<fw, 32 * WPC, c->smem_sweep, c->stream>>>(c->P, A);
+}
+
+extern "C" {
+
+// PatchMatchCuda::RunWithWindowSizeAndStep (patch_match_cuda.cu:1393-1546)
+int b200pm_run(b200pm_handle c) {
+  if (!c) return pm_fail(-1, "null handle");
+  PM_CUDA(cudaSetDevice(c->device));
+  const PmParams& P = c->P;
+  cudaStream_t s = c->stream;
+  if (c->smem_sweep > 48 * 1024) {
+    PM_CUDA(cudaFuncSetAttribute(pm_sweep_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_sweep));
+    PM_CUDA(cudaFuncSetAttribute(pm_sweep_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_sweep));
+    PM_CUDA(cudaFuncSetAttribute(pm_sweep_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_sweep));
+    PM_CUDA(cudaFuncSetAttribute(pm_sweep_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_sweep));
+    PM_CUDA(cudaFuncSetAttribute(pm_sweep_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_sweep));
+    PM_CUDA(cudaFuncSetAttribute(pm_sweep_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_sweep));
+  }
+  if (c->smem_init > 48 * 1024)
+    PM_CUDA(cudaFuncSetAttribute(pm_initial_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_init));
+  int launches = 0;
+  PM_CUDA(cudaEventRecord(c->ev[0], s));
+  if (c->dirty) {  // a previous run consumed the initial state: rebuild it (same as the constructor)
+    dim3 blk(32, 8), grd((P.W0 + 31) / 32, (P.H0 + 7) / 8);
+    pm_init_kernel<<<grd, blk, 0, s>>>(P, c->sel[1]);
+    ++launches;
+  }
+  c->dirty = true;
+  {
+    const size_t n = (size_t)P.W0 * P.H0;
+    const int grid = (int)std::min<size_t>((n + 3) / 4, (size_t)148 * 64);
+    pm_initial_cost_kernel<<<grid, 128, c->smem_init, s>>>(P);
+    ++launches;
+  }
+  PM_CUDA(cudaEventRecord(c->ev[1], s));
+  const int iters = c->opt.num_iterations;
+  const float total_steps = (float)(iters * 4);
+  int t = 0;
+  const int max_sweeps = getenv("B200PM_MAX_SWEEPS") ? atoi(getenv("B200PM_MAX_SWEEPS")) : -1;
+  for (int iter = 0; iter < iters; ++iter) {
+    for (int sweep = 0; sweep < 4; ++sweep, ++t) {
+      if (max_sweeps >= 0 && t >= max_sweeps) break;
+      PmSweepArgs A;
+      A.rot = sweep;
+      A.perturbation = 1.0f / powf(2.0f, (float)iter + (float)sweep / 4.0f);
+      A.perturbation_pi = (float)((double)A.perturbation * M_PI);
+      A.prev_w = (float)(iter * 4 + sweep) / total_steps;
+      A.last_filter = (iter == iters - 1 && sweep == 3 && c->opt.filter) ? 1 : 0;
+      A.sel_cur = c->sel[t & 1];
+      A.sel_prev = c->sel[(t + 1) & 1];
+      const int fw = (sweep & 1) ? P.H0 : P.W0;
+      if (c->wpc == 1) pm_launch_sweep<1>(c, A, fw);
+      else if (c->wpc == 2) pm_launch_sweep<2>(c, A, fw);
+      else pm_launch_sweep<4>(c, A, fw);
+      ++launches;
+      c->final_sel = t & 1;
+    }
+  }
+  PM_CUDA(cudaEventRecord(c->ev[2], s));
+  PM_CUDA(cudaStreamSynchronize(s));
+  PM_CUDA(cudaGetLastError());
+  PM_CUDA(cudaEventElapsedTime(&c->last_ms, c->ev[0], c->ev[2]));
+  PM_CUDA(cudaEventElapsedTime(&c->last_sweep_ms, c->ev[1], c->ev[2]));
+  c->last_launches = launches;
+  c->ran = true;
+  return 0;
+}
+
+float b200pm_last_run_ms(b200pm_handle c) { return c ? c->last_ms : -1.0f; }
+float b200pm_last_sweep_ms(b200pm_handle c) { return c ? c->last_sweep_ms : -1.0f; }
+int b200pm_last_num_launches(b200pm_handle c) { return c ? c->last_launches : -1; }
+
+static int pm_export(b200pm_handle c, float* depth, float* normal, float* sel, uint8_t* mask) {
+  if (!c) return pm_fail(-1, "null handle");
+  PM_CUDA(cudaSetDevice(c->device));
+  const PmParams& P = c->P;
+  const size_t n = (size_t)P.W0 * P.H0;
+  float *d_depth = nullptr, *d_normal = nullptr, *d_sel = nullptr;
+  uint8_t* d_mask = nullptr;
+  if (depth) PM_CUDA(cudaMalloc(&d_depth, n * sizeof(float)));
+  if (normal) PM_CUDA(cudaMalloc(&d_normal, 3 * n * sizeof(float)));
+  if (sel) PM_CUDA(cudaMalloc(&d_sel, n * P.N * sizeof(float)));
+  if (mask) PM_CUDA(cudaMalloc(&d_mask, n * P.N));
+  pm_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(P, c->sel[c->ran ? c->final_sel : 1], d_depth, d_normal, d_sel, d_mask);
+  if (depth) PM_CUDA(cudaMemcpyAsync(depth, d_depth, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (normal) PM_CUDA(cudaMemcpyAsync(normal, d_normal, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (sel) PM_CUDA(cudaMemcpyAsync(sel, d_sel, n * P.N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (mask) PM_CUDA(cudaMemcpyAsync(mask, d_mask, n * P.N, cudaMemcpyDeviceToHost, c->stream));
+  PM_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d_depth); cudaFree(d_normal); cudaFree(d_sel); cudaFree(d_mask);
+  PM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int b200pm_get_depth(b200pm_handle c, float* depth) { return pm_export(c, depth, nullptr, nullptr, nullptr); }
+int b200pm_get_normal(b200pm_handle c, float* normal) { return pm_export(c, nullptr, normal, nullptr, nullptr); }
+int b200pm_get_sel_prob(b200pm_handle c, float* sel) { return pm_export(c, nullptr, nullptr, sel, nullptr); }
+int b200pm_get_consistency_mask(b200pm_handle c, uint8_t* mask) { return pm_export(c, nullptr, nullptr, nullptr, mask); }
+
+// PatchMatchCuda::GetConsistentImageIdxs (patch_match_cuda.cu:1367-1391)
+int b200pm_get_consistency(b200pm_handle c, int** data, size_t* count) {
+  if (!c || !data || !count) return pm_fail(-1, "null argument");
+  const PmParams& P = c->P;
+  const size_t n = (size_t)P.W0 * P.H0;
+  std::vector<uint8_t> mask(n * P.N);
+  const int rc = pm_export(c, nullptr, nullptr, nullptr, mask.data());
+  if (rc != 0) return rc;
+  std::vector<int> list;
+  std::vector<int> px;
+  for (int r = 0; r < P.H0; ++r)
+    for (int col = 0; col < P.W0; ++col) {
+      px.clear();
+      const size_t p = (size_t)r * P.W0 + col;
+      for (int d = 0; d < P.N; ++d)
+        if (mask[(size_t)d * n + p]) px.push_back(c->src_image_idxs[d]);
+      if (!px.empty()) {
+        list.push_back(col); list.push_back(r); list.push_back((int)px.size());
+        list.insert(list.end(), px.begin(), px.end());
+      }
+    }
+  *count = list.size();
+  *data = (int*)malloc(sizeof(int) * (list.size() ? list.size() : 1));
+  memcpy(*data, list.data(), sizeof(int) * list.size());
+  return 0;
+}
+
+void b200pm_free(void* p) { free(p); }
+
+void b200pm_destroy(b200pm_handle c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  for (void* p : c->allocs) cudaFree(p);
+  for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+// debug: cost map in slice-major layout (N*H*W)
+int b200pm_debug_get_cost(b200pm_handle c, float* cost) {
+  if (!c) return pm_fail(-1, "null handle");
+  const PmParams& P = c->P;
+  const size_t n = (size_t)P.W0 * P.H0;
+  std::vector<float> tmp(n * P.N);
+  PM_CUDA(cudaMemcpy(tmp.data(), P.cost, sizeof(float) * n * P.N, cudaMemcpyDeviceToHost));
+  for (size_t p = 0; p < n; ++p)
+    for (int i = 0; i < P.N; ++i) cost[(size_t)i * n + p] = tmp[p * P.N + i];
+  return 0;
+}
+
+// ---- host-side hooks for the CPU test tier (bit-level comparison with the oracle; no GPU needed) ----
+float b200pm_test_expf(float x) { return pm_expf(x); }
+void b200pm_test_sincosf(float a, float* s, float* c) { pm_sincosf(a, s, c); }
+void b200pm_test_rng_stream(unsigned long long seed, int count, float* out) {
+  PmRng r; pm_rng_init(r, seed);
+  for (int i = 0; i < count; ++i) out[i] = pm_rng_uniform(r);
+}
+int b200pm_test_poses(const b200pm_problem* p, int k, float* poses_out, float* K_out, float* invK_out) {
+  float K4[4][4], iK4[4][4];
+  std::vector<float> poses;
+  pm_init_transforms(p, K4, iK4, poses);
+  memcpy(poses_out, poses.data() + (size_t)k * p->num_src * PM_POSE_STRIDE, sizeof(float) * p->num_src * PM_POSE_STRIDE);
+  memcpy(K_out, K4[k], 16); memcpy(invK_out, iK4[k], 16);
+  return 0;
+}
+void b200pm_test_homography(const float* pose, const float* iK, float row, float col, float depth, const float* n, float* H) {
+  pm_compose_homography(pose, iK, row, col, depth, n[0], n[1], n[2], H);
+}
+int b200pm_test_border_index(int W0, int H0, int r0, int c0) { return pm_border_index(W0, H0, r0, c0); }
+
+}  // extern "C"

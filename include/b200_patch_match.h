@@ -1,0 +1,123 @@
+/*
+ * b200_patch_match.h — C-ABI of the B200-native PatchMatch MVS sweep.
+ *
+ * This is the drop-in boundary for COLMAP's `mvs::PatchMatchCuda`
+ * (reference: src/colmap/mvs/patch_match_cuda.h:49-59, the only caller being
+ * src/colmap/mvs/patch_match.cc:128-154).  Every entry point below replaces
+ * one member of that class; INTEGRATION.md shows the ~60-line C++ adapter a
+ * COLMAP maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only, no exceptions cross the ABI,
+ * 0 == success, negative == error (text via b200pm_last_error()).  A handle
+ * is owned by one host thread at a time (same contract as the reference: one
+ * PatchMatchCuda instance per host thread per GPU).
+ */
+#ifndef B200_PATCH_MATCH_H_
+#define B200_PATCH_MATCH_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Mirrors mvs::PatchMatchOptions (src/colmap/mvs/patch_match_options.h:37-126);
+ * same names, same defaults (b200pm_options_init).  Only the fields that reach
+ * PatchMatchCuda are present; cache_size / num_threads / max_image_size /
+ * allow_missing_files / write_consistency_graph belong to the controller. */
+typedef struct b200pm_options {
+  double depth_min;                        /* must be >= 0 here: the controller resolves -1 (patch_match.cc:423-432) */
+  double depth_max;
+  double sigma_spatial;                    /* <= 0 -> window_radius (patch_match.cc:436-438) */
+  double sigma_color;                      /* 0.2 */
+  double ncc_sigma;                        /* 0.6 */
+  double min_triangulation_angle;          /* degrees, 1.0 */
+  double incident_angle_sigma;             /* 0.9 */
+  double geom_consistency_regularizer;     /* 0.3 */
+  double geom_consistency_max_cost;        /* 3.0 */
+  double filter_min_ncc;                   /* 0.1 */
+  double filter_min_triangulation_angle;   /* degrees, 3.0 */
+  double filter_geom_consistency_max_cost; /* 1.0 */
+  int window_radius;                       /* 5 */
+  int window_step;                         /* 1 (1 or 2) */
+  int num_samples;                         /* 15 */
+  int num_iterations;                      /* 5 */
+  int filter_min_num_consistent;           /* 2 */
+  int geom_consistency;                    /* bool, default 1 */
+  int filter;                              /* bool, default 1 */
+  int gpu_index;                           /* CUDA device ordinal; -1 = current device */
+} b200pm_options;
+
+/* Mirrors mvs::PatchMatch::Problem + the mvs::Image fields PatchMatchCuda reads
+ * (patch_match.h:57-75, image.h:39-104): 8-bit grey bitmaps, float K (3x3
+ * row-major, zero skew, K[8]==1), R (3x3 row-major), T (3).  All pointers are
+ * host memory and only need to stay valid for the duration of b200pm_create. */
+typedef struct b200pm_problem {
+  int ref_width, ref_height;
+  const uint8_t* ref_gray;        /* ref_height * ref_width, row-major */
+  float ref_K[9], ref_R[9], ref_T[3];
+  int num_src;                    /* 1..32 */
+  const int* src_width;           /* [num_src] */
+  const int* src_height;          /* [num_src] */
+  const uint8_t* const* src_gray; /* [num_src] row-major bitmaps */
+  const float* src_K;             /* [num_src*9] */
+  const float* src_R;             /* [num_src*9] */
+  const float* src_T;             /* [num_src*3] */
+  /* geom_consistency only (PatchMatchCuda::InitSourceImages / InitWorkspaceMemory,
+   * patch_match_cuda.cu:1657-1691,1814-1852): photometric depth maps of the
+   * source images (src_height*src_width each) and the photometric depth /
+   * normal map of the reference image (normal: 3 slices of H*W). */
+  const float* const* src_depth;  /* [num_src] or NULL */
+  const float* ref_depth_init;    /* H*W or NULL */
+  const float* ref_normal_init;   /* 3*H*W slice-major or NULL */
+  const int* src_image_idxs;      /* [num_src] global image ids reported by get_consistency; NULL -> 0..num_src-1 */
+} b200pm_problem;
+
+typedef struct b200pm_context* b200pm_handle;
+
+/* Defaults of PatchMatchOptions (patch_match_options.h:37-126). */
+void b200pm_options_init(b200pm_options* o);
+
+/* PatchMatch::Check (patch_match.cc:67-126) + PatchMatchOptions::Check
+ * (patch_match_options.cc:72-99).  Returns 0 or a negative code. */
+int b200pm_check(const b200pm_options* o, const b200pm_problem* p);
+
+/* PatchMatchCuda::PatchMatchCuda (patch_match_cuda.cu:1290-1302): selects the
+ * device, uploads images/poses, prefilters the reference image, initialises
+ * depth / normal / PRNG state.  Host -> device copies happen here. */
+int b200pm_create(const b200pm_options* o, const b200pm_problem* p, b200pm_handle* out);
+
+/* PatchMatchCuda::Run (patch_match_cuda.cu:1304-1352,1393-1546): initial cost +
+ * num_iterations x 4 sweeps.  Asynchronous work is complete on return. */
+int b200pm_run(b200pm_handle h);
+
+/* Device time of the last b200pm_run in milliseconds (CUDA events), the
+ * analogue of the reference's "Total" CudaTimer (patch_match_cuda.cu:1398,1545). */
+float b200pm_last_run_ms(b200pm_handle h);
+/* Device time spent in the sweep kernels only during the last run, and their launch count. */
+float b200pm_last_sweep_ms(b200pm_handle h);
+int b200pm_last_num_launches(b200pm_handle h);
+
+/* PatchMatchCuda::GetDepthMap / GetNormalMap / GetSelProbMap
+ * (patch_match_cuda.cu:1354-1365).  Layouts match mvs::Mat<float>: slice-major,
+ * then row-major: depth H*W, normal 3*H*W, sel_prob num_src*H*W. */
+int b200pm_get_depth(b200pm_handle h, float* depth);
+int b200pm_get_normal(b200pm_handle h, float* normal);
+int b200pm_get_sel_prob(b200pm_handle h, float* sel_prob);
+
+/* PatchMatchCuda::GetConsistentImageIdxs (patch_match_cuda.cu:1367-1391): flat
+ * int list [col,row,n,idx_1..idx_n]... ; *data is malloc'ed, release with
+ * b200pm_free.  Only valid when options.filter was set. */
+int b200pm_get_consistency(b200pm_handle h, int** data, size_t* count);
+/* Raw mask num_src*H*W (slice-major) behind the list above. */
+int b200pm_get_consistency_mask(b200pm_handle h, uint8_t* mask);
+void b200pm_free(void* p);
+
+void b200pm_destroy(b200pm_handle h);
+const char* b200pm_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_PATCH_MATCH_H_ */

@@ -1,0 +1,128 @@
+"""GPU parity tier for the PatchMatch path: the CUDA kernels, called through the C-ABI, against the
+CPU oracle on the same inputs.  Bar: bit-exact depth / normal / selection-probability / consistency
+outputs (the oracle's fp32 contract is the spec the kernels implement)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_pm
+from colmap_b200.patch_match import PatchMatch, PatchMatchOptions, consistency_list_from_mask
+from colmap_b200.synthetic import make_patch_match_scene
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _run_cuda(o, problem, wpc=None):
+    if wpc is not None:
+        os.environ["B200PM_WPC"] = str(wpc)
+    os.environ.pop("B200PM_MAX_SWEEPS", None)
+    pm = PatchMatch(o, problem)
+    pm.Run()
+    out = dict(depth=pm.GetDepthMap(), normal=pm.GetNormalMap(), sel_prob=pm.GetSelProbMap())
+    if o.filter:
+        out["mask"] = pm.GetConsistencyMask()
+        out["list"] = pm.GetConsistentImageIdxs()
+    pm.close()
+    os.environ.pop("B200PM_WPC", None)
+    return out
+
+
+def _assert_bit_exact(got, ref, keys=("depth", "normal", "sel_prob")):
+    for k in keys:
+        eq = _bits(got[k]) == _bits(ref[k])
+        assert eq.all(), f"{k}: {(~eq).sum()} of {eq.size} values differ"
+
+
+@pytest.mark.parametrize("wpc", [1, 2, 4])
+def test_photometric_bit_exact_vs_oracle(wpc):
+    sc = make_patch_match_scene(96, 72, 4, seed=0)
+    o = PatchMatchOptions(depth_min=sc["depth_min"], depth_max=sc["depth_max"], geom_consistency=False,
+                          num_iterations=2)
+    got = _run_cuda(o, sc["problem"], wpc)
+    ref = oracle_pm.run(o, sc["problem"])
+    _assert_bit_exact(got, ref)
+    assert np.array_equal(got["mask"], ref["mask"])
+    assert np.array_equal(got["list"], consistency_list_from_mask(ref["mask"], sc["problem"].src_image_idxs))
+
+
+@pytest.mark.parametrize("w,h,n,radius,step,samples", [
+    (70, 50, 3, 3, 1, 7),      # ragged sizes, small window
+    (64, 80, 8, 5, 2, 15),     # window_step 2, portrait, 8 sources
+    (33, 17, 1, 2, 1, 4),      # single source image: filter_min_num_consistent=2 zeroes everything
+    (50, 40, 5, 7, 1, 20),     # big window
+])
+def test_option_grid_bit_exact(w, h, n, radius, step, samples):
+    sc = make_patch_match_scene(w, h, n, seed=11)
+    o = PatchMatchOptions(depth_min=sc["depth_min"], depth_max=sc["depth_max"], geom_consistency=False,
+                          num_iterations=1, window_radius=radius, window_step=step, num_samples=samples)
+    got = _run_cuda(o, sc["problem"])
+    ref = oracle_pm.run(o, sc["problem"])
+    _assert_bit_exact(got, ref)
+    assert np.array_equal(got["mask"], ref["mask"])
+
+
+def test_no_filter_and_mixed_source_sizes():
+    sc = make_patch_match_scene(80, 60, 3, seed=2)
+    # crop one source image (different size than the reference; principal point unchanged)
+    img = sc["images"][2]
+    img.bitmap = np.ascontiguousarray(img.bitmap[:50, :70])
+    o = PatchMatchOptions(depth_min=sc["depth_min"], depth_max=sc["depth_max"], geom_consistency=False,
+                          num_iterations=1, filter=False)
+    got = _run_cuda(o, sc["problem"])
+    ref = oracle_pm.run(o, sc["problem"])
+    _assert_bit_exact(got, ref)
+    assert (got["depth"] > 0).all()
+
+
+def test_geometric_consistency_bit_exact():
+    sc = make_patch_match_scene(80, 60, 4, seed=4, with_gt_maps=True)
+    prob = sc["problem"]
+    # photometric maps stand in: ground truth + noise for the sources, for the reference
+    rng = np.random.default_rng(0)
+    prob.depth_maps = [(d * (1 + 0.002 * rng.standard_normal(d.shape))).astype(np.float32) for d in sc["depth_maps"]]
+    prob.depth_maps[2][10:20, 10:30] = 0.0          # holes -> max cost
+    prob.normal_maps = [n.copy() for n in sc["normal_maps"]]
+    o = PatchMatchOptions(depth_min=sc["depth_min"], depth_max=sc["depth_max"], geom_consistency=True,
+                          num_iterations=1)
+    got = _run_cuda(o, prob)
+    ref = oracle_pm.run(o, prob)
+    _assert_bit_exact(got, ref)
+    assert np.array_equal(got["mask"], ref["mask"])
+
+
+def test_rerun_on_resident_inputs_is_reproducible():
+    sc = make_patch_match_scene(64, 48, 3, seed=9)
+    o = PatchMatchOptions(depth_min=sc["depth_min"], depth_max=sc["depth_max"], geom_consistency=False,
+                          num_iterations=1)
+    pm = PatchMatch(o, sc["problem"])
+    pm.Run()
+    a = pm.GetDepthMap()
+    pm.RunOnly()
+    b = pm.GetDepthMap()
+    pm.close()
+    assert np.array_equal(_bits(a), _bits(b))
+
+
+def test_full_hd_properties():
+    """BASELINE config C2 size (1 ref + 8 src, 1920x1080, window 11) with fewer iterations: properties
+    that do not need the oracle."""
+    sc = make_patch_match_scene(1920, 1080, 8, seed=0)
+    o = PatchMatchOptions(depth_min=sc["depth_min"], depth_max=sc["depth_max"], geom_consistency=False,
+                          num_iterations=2)
+    got = _run_cuda(o, sc["problem"])
+    d = got["depth"]
+    valid = d > 0
+    assert valid.mean() > 0.85
+    assert (d[valid] >= 0.5 * sc["depth_min"]).all() and (d[valid] <= 2 * sc["depth_max"]).all()
+    rel = np.abs(d - sc["depth_gt"])[valid] / sc["depth_gt"][valid]
+    assert np.median(rel) < 5e-3
+    nn = np.linalg.norm(got["normal"][:, valid], axis=0)
+    assert np.allclose(nn, 1, atol=1e-4)
+    assert (got["normal"][:, ~valid] == 0).all() and (got["mask"][:, ~valid] == 0).all()
+    assert (got["mask"][:, valid].sum(axis=0) >= 2).all()
+    assert np.isfinite(got["sel_prob"]).all() and (got["sel_prob"] >= 0).all() and (got["sel_prob"] <= 1).all()
