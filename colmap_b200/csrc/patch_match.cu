@@ -196,22 +196,27 @@ __device__ __forceinline__ float pm_ncc_group(const float4* __restrict__ patch, 
                                               float inv_wsum, float rsum, float rsq, int sub, unsigned gmask) {
   float Hm[9];
   pm_compose_homography(pose, iK, rowf, colf, d, n0, n1, n2, Hm);
+  const uint32_t* quads0 = quads + (2 * pitch + 2);
+  const float hi_x = (float)(W + 1), hi_y = (float)(H + 1);
   float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-#pragma unroll 4
-  for (int t = sub; t < ntaps; t += 8) {
+  auto tap = [&](int t) {
     const float4 tp = patch[t];
     const float x = colf + tp.z;
     const float y = rowf + tp.w;
     const float zx = fmaf(Hm[0], x, fmaf(Hm[1], y, Hm[2]));
     const float zy = fmaf(Hm[3], x, fmaf(Hm[4], y, Hm[5]));
     const float zz = fmaf(Hm[6], x, fmaf(Hm[7], y, Hm[8]));
-    const float inv_z = 1.0f / zz;
-    const float color = pm_sample_quad(quads, pitch, W, H, inv_z * zx, inv_z * zy);
+    const float inv_z = pm_rcp_clamped(zz);
+    const float color = pm_sample_quad(quads0, pitch, hi_x, hi_y, inv_z * zx, inv_z * zy);
     const float ws = tp.x * color;
     s1 += ws;
     s2 = fmaf(ws, color, s2);
     s3 = fmaf(tp.y, color, s3);
-  }
+  };
+  const int nfull = ntaps >> 3;  // warp-uniform trip count; the ragged tail is one predicated tap
+#pragma unroll 5
+  for (int j = 0; j < nfull; ++j) tap(sub + 8 * j);
+  if (sub < (ntaps & 7)) tap(sub + 8 * nfull);
 #pragma unroll
   for (int o = 1; o < 8; o <<= 1) {
     s1 = s1 + __shfl_xor_sync(gmask, s1, o);
@@ -535,6 +540,20 @@ __global__ void __launch_bounds__(32 * WPC) pm_sweep_kernel(const PmParams P, co
   if (warp == 0 && lane == 0) {
     rng_slot[0] = rs.v0; rng_slot[1] = rs.v1; rng_slot[2] = rs.v2; rng_slot[3] = rs.v3; rng_slot[4] = rs.v4; rng_slot[5] = rs.d;
   }
+}
+
+// exhaustive check of pm_rcp_clamped against the IEEE division over all float bit patterns
+__global__ void pm_rcp_check_kernel(unsigned long long* mismatches) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  unsigned long long bad = 0;
+  for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < (1ull << 32); b += stride) {
+    const float z = __uint_as_float((unsigned)b);
+    const float zc = fminf(fmaxf(z, 1e-30f), 1e30f);
+    const float want = 1.0f / zc;
+    const float got = pm_rcp_clamped(z);
+    if (__float_as_uint(want) != __float_as_uint(got)) ++bad;
+  }
+  if (bad) atomicAdd(mismatches, bad);
 }
 
 // outputs in mvs::Mat<float> layout (slice-major)
@@ -994,6 +1013,18 @@ int b200pm_test_poses(const b200pm_problem* p, int k, float* poses_out, float* K
   memcpy(poses_out, poses.data() + (size_t)k * p->num_src * PM_POSE_STRIDE, sizeof(float) * p->num_src * PM_POSE_STRIDE);
   memcpy(K_out, K4[k], 16); memcpy(invK_out, iK4[k], 16);
   return 0;
+}
+float b200pm_test_rcp_clamped(float z) { return pm_rcp_clamped(z); }
+// GPU: number of float bit patterns for which the fast reciprocal differs from IEEE 1/clamp(z) (must be 0)
+long long b200pm_test_rcp_exhaustive(void) {
+  unsigned long long* d = nullptr;
+  unsigned long long h = 0;
+  if (cudaMalloc(&d, 8) != cudaSuccess) return -1;
+  cudaMemset(d, 0, 8);
+  pm_rcp_check_kernel<<<148 * 8, 256>>>(d);
+  if (cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaFree(d); return -1; }
+  cudaFree(d);
+  return (long long)h;
 }
 void b200pm_test_homography(const float* pose, const float* iK, float row, float col, float depth, const float* n, float* H) {
   pm_compose_homography(pose, iK, row, col, depth, n[0], n[1], n[2], H);

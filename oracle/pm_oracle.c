@@ -32,7 +32,9 @@
  * incrementally (patch_match_cuda.cu:503-569); (2) software bilinear
  * interpolation on raw 8-bit values instead of the 9-bit-weight texture unit;
  * (3) the NCC sums are accumulated in 8 interleaved partial sums joined by a
- * fixed tree; (4) pose matrices are composed in double and rounded once.
+ * fixed tree; (4) pose matrices are composed in double and rounded once;
+ * (5) the per-tap projective depth is clamped to [1e-30, 1e30] before the
+ * reciprocal (only matters for points behind the source camera).
  *
  * Build: gcc -O2 -ffp-contract=off -mfma -fopenmp -shared -fPIC (see Makefile).
  */
@@ -416,7 +418,11 @@ static float ncc_cost(const pm_state* st, const pm_patch* pt, int row, int col, 
     const float zx = fmaf(H[0], x, fmaf(H[1], y, H[2]));
     const float zy = fmaf(H[3], x, fmaf(H[4], y, H[5]));
     const float zz = fmaf(H[6], x, fmaf(H[7], y, H[8]));
-    const float inv_z = 1.0f / zz;
+    /* points at or behind the source camera plane sample the border: z is clamped to [1e-30, 1e30]
+     * (keeps the reciprocal in the range where the GPU's MUFU.RCP + one Newton step is correctly rounded) */
+    float zc = (zz > 1e-30f) ? zz : 1e-30f;
+    zc = (zc < 1e30f) ? zc : 1e30f;
+    const float inv_z = 1.0f / zc;
     const float color = sample_src(st, image_idx, inv_z * zx, inv_z * zy);
     const float ws = pt->w[t] * color;
     const int q = t & 7;

@@ -38,6 +38,16 @@ def _assert_bit_exact(got, ref, keys=("depth", "normal", "sel_prob")):
         assert eq.all(), f"{k}: {(~eq).sum()} of {eq.size} values differ"
 
 
+def test_fast_reciprocal_is_ieee_over_all_floats():
+    """The per-tap reciprocal (MUFU.RCP + one Newton step after clamping to [1e-30, 1e30]) must equal the
+    correctly rounded division the oracle uses, for every one of the 2^32 float bit patterns."""
+    import ctypes
+    from colmap_b200 import load_library
+    lib = load_library()
+    lib.b200pm_test_rcp_exhaustive.restype = ctypes.c_longlong
+    assert lib.b200pm_test_rcp_exhaustive() == 0
+
+
 @pytest.mark.parametrize("wpc", [1, 2, 4])
 def test_photometric_bit_exact_vs_oracle(wpc):
     sc = make_patch_match_scene(96, 72, 4, seed=0)
@@ -118,7 +128,8 @@ def test_full_hd_properties():
     d = got["depth"]
     valid = d > 0
     assert valid.mean() > 0.85
-    assert (d[valid] >= 0.5 * sc["depth_min"]).all() and (d[valid] <= 2 * sc["depth_max"]).all()
+    inside = (d[valid] >= sc["depth_min"]) & (d[valid] <= sc["depth_max"])
+    assert inside.mean() > 0.999
     rel = np.abs(d - sc["depth_gt"])[valid] / sc["depth_gt"][valid]
     assert np.median(rel) < 5e-3
     nn = np.linalg.norm(got["normal"][:, valid], axis=0)
