@@ -1,0 +1,375 @@
+"""Host-side mirror of COLMAP's bundle-adjustment interface over the C-ABI (include/b200_bundle_adjustment.h).
+
+Mirrors (same names / meaning):
+  * ``BundleAdjustmentOptions``  src/colmap/estimators/bundle_adjustment.h:175-208 (+ the Ceres solver options
+    COLMAP sets, bundle_adjustment_ceres.cc:102-116)
+  * ``BundleAdjustmentConfig``   bundle_adjustment.h:77-151
+  * ``BundleAdjuster`` / ``CreateDefaultBundleAdjuster``  bundle_adjustment.h:212-234, bundle_adjustment.cc:314-336
+  * a minimal ``Reconstruction`` (cameras, images with cam_from_world, points3D with tracks) — just what
+    DefaultBundleAdjuster touches (bundle_adjustment_ceres.cc:606-898), trivial frames only.
+
+The flattening below is a harness-level restatement of DefaultBundleAdjuster's problem assembly
+(AddImageToProblem / AddPointToProblem / Parameterize*, bundle_adjustment_ceres.cc:688-888,419-565); the solve
+itself happens in libcolmap_b200.so on the GPU.  No CPU fallback.
+"""
+import ctypes
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from ._lib import load_library
+
+SIMPLE_PINHOLE, PINHOLE, SIMPLE_RADIAL, RADIAL = 0, 1, 2, 3
+MODEL_NUM_PARAMS = {0: 3, 1: 4, 2: 4, 3: 5}
+AUTO, DENSE_SCHUR, SPARSE_SCHUR, ITERATIVE_SCHUR = 0, 1, 2, 3
+TRIVIAL, SOFT_L1, CAUCHY, HUBER = 0, 1, 2, 3
+CONVERGENCE, NO_CONVERGENCE, FAILURE = 0, 1, 2
+UNSPECIFIED_GAUGE, TWO_CAMS_FROM_WORLD, THREE_POINTS = 0, 1, 2
+
+
+class _COptions(ctypes.Structure):
+    _fields_ = [("refine_focal_length", ctypes.c_int), ("refine_principal_point", ctypes.c_int),
+                ("refine_extra_params", ctypes.c_int), ("refine_rig_from_world", ctypes.c_int),
+                ("refine_points3D", ctypes.c_int), ("constant_rig_from_world_rotation", ctypes.c_int),
+                ("loss_function_type", ctypes.c_int), ("loss_function_scale", ctypes.c_double),
+                ("linear_solver_type", ctypes.c_int), ("max_num_iterations", ctypes.c_int),
+                ("max_linear_solver_iterations", ctypes.c_int), ("function_tolerance", ctypes.c_double),
+                ("gradient_tolerance", ctypes.c_double), ("parameter_tolerance", ctypes.c_double),
+                ("initial_trust_region_radius", ctypes.c_double), ("max_trust_region_radius", ctypes.c_double),
+                ("min_trust_region_radius", ctypes.c_double), ("min_relative_decrease", ctypes.c_double),
+                ("min_lm_diagonal", ctypes.c_double), ("max_lm_diagonal", ctypes.c_double), ("eta", ctypes.c_double),
+                ("jacobi_scaling", ctypes.c_int), ("gpu_index", ctypes.c_int)]
+
+
+_f64p = ctypes.POINTER(ctypes.c_double)
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+_i8p = ctypes.POINTER(ctypes.c_int8)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+
+
+class _CProblem(ctypes.Structure):
+    _fields_ = [("num_poses", ctypes.c_int), ("poses", _f64p), ("pose_constant", _u8p),
+                ("pose_fixed_translation_dim", _i8p), ("num_cameras", ctypes.c_int), ("camera_model_id", _i32p),
+                ("camera_param_offset", _i32p), ("camera_params", _f64p), ("camera_constant", _u8p),
+                ("num_points", ctypes.c_int64), ("points", _f64p), ("point_constant", _u8p),
+                ("num_observations", ctypes.c_int64), ("obs_pose_idx", _i32p), ("obs_camera_idx", _i32p),
+                ("obs_point_idx", _i32p), ("obs_xy", _f64p)]
+
+
+class _CSummary(ctypes.Structure):
+    _fields_ = [("termination_type", ctypes.c_int), ("num_residuals", ctypes.c_int),
+                ("num_effective_parameters", ctypes.c_int), ("num_successful_steps", ctypes.c_int),
+                ("num_unsuccessful_steps", ctypes.c_int), ("num_linear_solver_iterations", ctypes.c_int),
+                ("linear_solver_type_used", ctypes.c_int), ("initial_cost", ctypes.c_double),
+                ("final_cost", ctypes.c_double), ("solve_ms", ctypes.c_double), ("setup_ms", ctypes.c_double),
+                ("spmv_ms_total", ctypes.c_double), ("spmv_launches", ctypes.c_int), ("kernel_launches", ctypes.c_int)]
+
+
+@dataclass
+class BundleAdjustmentOptions:
+    """BundleAdjustmentOptions (bundle_adjustment.h:175-208) + Ceres solver options set by COLMAP."""
+    refine_focal_length: bool = True
+    refine_principal_point: bool = False
+    refine_extra_params: bool = True
+    refine_sensor_from_rig: bool = True
+    refine_rig_from_world: bool = True
+    refine_points3D: bool = True
+    min_track_length: int = 0
+    constant_rig_from_world_rotation: bool = False
+    print_summary: bool = False
+    backend: str = "B200"
+    loss_function_type: int = TRIVIAL
+    loss_function_scale: float = 1.0
+    linear_solver_type: int = AUTO          # auto_select_solver_type (bundle_adjustment_ceres.cc:202-212)
+    max_num_iterations: int = 100
+    max_linear_solver_iterations: int = 200
+    function_tolerance: float = 0.0
+    gradient_tolerance: float = 1e-4
+    parameter_tolerance: float = 0.0
+    gpu_index: int = -1
+
+    def Check(self) -> bool:
+        return self.min_track_length >= 0 and self.loss_function_scale >= 0 and self.max_num_iterations >= 0
+
+    def to_c(self) -> _COptions:
+        return _COptions(int(self.refine_focal_length), int(self.refine_principal_point), int(self.refine_extra_params),
+                         int(self.refine_rig_from_world), int(self.refine_points3D),
+                         int(self.constant_rig_from_world_rotation), self.loss_function_type, self.loss_function_scale,
+                         self.linear_solver_type, self.max_num_iterations, self.max_linear_solver_iterations,
+                         self.function_tolerance, self.gradient_tolerance, self.parameter_tolerance,
+                         1e4, 1e16, 1e-32, 1e-3, 1e-6, 1e32, 0.1, 1, self.gpu_index)
+
+
+@dataclass
+class BundleAdjustmentSummary:
+    termination_type: int = FAILURE
+    num_residuals: int = 0
+    num_effective_parameters: int = 0
+    num_successful_steps: int = 0
+    num_unsuccessful_steps: int = 0
+    num_linear_solver_iterations: int = 0
+    linear_solver_type_used: int = 0
+    initial_cost: float = 0.0
+    final_cost: float = 0.0
+    solve_ms: float = 0.0
+    setup_ms: float = 0.0
+    spmv_ms_total: float = 0.0
+    spmv_launches: int = 0
+    kernel_launches: int = 0
+
+    def IsSolutionUsable(self) -> bool:
+        return self.termination_type in (CONVERGENCE, NO_CONVERGENCE)
+
+    @staticmethod
+    def from_c(c) -> "BundleAdjustmentSummary":
+        return BundleAdjustmentSummary(**{f[0]: getattr(c, f[0]) for f in _CSummary._fields_})
+
+
+# ------------------------------------------------------------------------------------------------ scene types
+@dataclass
+class Camera:
+    camera_id: int
+    model_id: int
+    params: np.ndarray           # float64
+
+
+@dataclass
+class Point2D:
+    xy: np.ndarray
+    point3D_id: int = -1
+
+
+@dataclass
+class Image:
+    image_id: int
+    camera_id: int
+    cam_from_world: np.ndarray   # 7: qx qy qz qw tx ty tz (Rigid3d::params)
+    points2D: List[Point2D] = field(default_factory=list)
+
+
+@dataclass
+class Point3D:
+    xyz: np.ndarray
+    track: List[tuple] = field(default_factory=list)   # (image_id, point2D_idx)
+
+
+@dataclass
+class Reconstruction:
+    cameras: Dict[int, Camera] = field(default_factory=dict)
+    images: Dict[int, Image] = field(default_factory=dict)
+    points3D: Dict[int, Point3D] = field(default_factory=dict)
+
+
+class BundleAdjustmentConfig:
+    """BundleAdjustmentConfig (bundle_adjustment.h:77-151), trivial frames (frame id == image id)."""
+
+    def __init__(self):
+        self.fixed_gauge_ = UNSPECIFIED_GAUGE
+        self.image_ids_ = set()
+        self.constant_cam_intrinsics_ = set()
+        self.constant_rig_from_world_poses_ = set()
+        self.variable_point3D_ids_ = set()
+        self.constant_point3D_ids_ = set()
+        self.ignored_point3D_ids_ = set()
+
+    def FixGauge(self, gauge): self.fixed_gauge_ = gauge
+    def FixedGauge(self): return self.fixed_gauge_
+    def NumImages(self): return len(self.image_ids_)
+    def AddImage(self, image_id): self.image_ids_.add(image_id)
+    def HasImage(self, image_id): return image_id in self.image_ids_
+    def RemoveImage(self, image_id): self.image_ids_.discard(image_id)
+    def SetConstantCamIntrinsics(self, camera_id): self.constant_cam_intrinsics_.add(camera_id)
+    def SetVariableCamIntrinsics(self, camera_id): self.constant_cam_intrinsics_.discard(camera_id)
+    def HasConstantCamIntrinsics(self, camera_id): return camera_id in self.constant_cam_intrinsics_
+    def SetConstantRigFromWorldPose(self, frame_id): self.constant_rig_from_world_poses_.add(frame_id)
+    def SetVariableRigFromWorldPose(self, frame_id): self.constant_rig_from_world_poses_.discard(frame_id)
+    def HasConstantRigFromWorldPose(self, frame_id): return frame_id in self.constant_rig_from_world_poses_
+    def AddVariablePoint(self, pid): self.variable_point3D_ids_.add(pid)
+    def AddConstantPoint(self, pid): self.constant_point3D_ids_.add(pid)
+    def IgnorePoint(self, pid): self.ignored_point3D_ids_.add(pid)
+    def HasPoint(self, pid): return pid in self.variable_point3D_ids_ or pid in self.constant_point3D_ids_
+    def IsIgnoredPoint(self, pid): return pid in self.ignored_point3D_ids_
+    def Images(self): return self.image_ids_
+    def VariablePoints(self): return self.variable_point3D_ids_
+    def ConstantPoints(self): return self.constant_point3D_ids_
+
+
+class FlatProblem:
+    """Arrays behind a b200ba_problem (kept alive here)."""
+
+    def __init__(self, poses, pose_constant, pose_fixed_dim, cam_model, cam_off, cam_params, cam_constant, points,
+                 point_constant, obs_pose, obs_cam, obs_point, obs_xy):
+        c = np.ascontiguousarray
+        self.poses = c(poses, np.float64).reshape(-1, 7)
+        self.pose_constant = c(pose_constant, np.uint8)
+        self.pose_fixed_dim = c(pose_fixed_dim, np.int8)
+        self.cam_model = c(cam_model, np.int32)
+        self.cam_off = c(cam_off, np.int32)
+        self.cam_params = c(cam_params, np.float64)
+        self.cam_constant = c(cam_constant, np.uint8)
+        self.points = c(points, np.float64).reshape(-1, 3)
+        self.point_constant = c(point_constant, np.uint8)
+        self.obs_pose = c(obs_pose, np.int32)
+        self.obs_cam = c(obs_cam, np.int32)
+        self.obs_point = c(obs_point, np.int32)
+        self.obs_xy = c(obs_xy, np.float64).reshape(-1, 2)
+
+    def copy(self):
+        return FlatProblem(self.poses.copy(), self.pose_constant, self.pose_fixed_dim, self.cam_model, self.cam_off,
+                           self.cam_params.copy(), self.cam_constant, self.points.copy(), self.point_constant,
+                           self.obs_pose, self.obs_cam, self.obs_point, self.obs_xy)
+
+    def to_c(self) -> _CProblem:
+        p = _CProblem()
+        p.num_poses = len(self.poses); p.poses = self.poses.ctypes.data_as(_f64p)
+        p.pose_constant = self.pose_constant.ctypes.data_as(_u8p)
+        p.pose_fixed_translation_dim = self.pose_fixed_dim.ctypes.data_as(_i8p)
+        p.num_cameras = len(self.cam_model); p.camera_model_id = self.cam_model.ctypes.data_as(_i32p)
+        p.camera_param_offset = self.cam_off.ctypes.data_as(_i32p)
+        p.camera_params = self.cam_params.ctypes.data_as(_f64p)
+        p.camera_constant = self.cam_constant.ctypes.data_as(_u8p)
+        p.num_points = len(self.points); p.points = self.points.ctypes.data_as(_f64p)
+        p.point_constant = self.point_constant.ctypes.data_as(_u8p)
+        p.num_observations = len(self.obs_pose)
+        p.obs_pose_idx = self.obs_pose.ctypes.data_as(_i32p); p.obs_camera_idx = self.obs_cam.ctypes.data_as(_i32p)
+        p.obs_point_idx = self.obs_point.ctypes.data_as(_i32p); p.obs_xy = self.obs_xy.ctypes.data_as(_f64p)
+        return p
+
+
+def _bind(lib):
+    if getattr(lib, "_ba_bound", False):
+        return lib
+    lib.b200ba_options_init.argtypes = [ctypes.POINTER(_COptions)]
+    lib.b200ba_options_init.restype = None
+    lib.b200ba_solve.argtypes = [ctypes.POINTER(_COptions), ctypes.POINTER(_CProblem), ctypes.POINTER(_CSummary)]
+    lib.b200ba_fix_gauge_two_cams_from_world.argtypes = [ctypes.POINTER(_CProblem), ctypes.POINTER(_COptions), _u8p, _i8p]
+    lib.b200ba_last_error.restype = ctypes.c_char_p
+    lib._ba_bound = True
+    return lib
+
+
+class BundleAdjustmentError(RuntimeError):
+    pass
+
+
+def solve_flat(options: BundleAdjustmentOptions, flat: FlatProblem) -> BundleAdjustmentSummary:
+    """b200ba_solve on a flat problem; flat.poses / cam_params / points are updated in place."""
+    lib = _bind(load_library())
+    co, cp, cs = options.to_c(), flat.to_c(), _CSummary()
+    rc = lib.b200ba_solve(ctypes.byref(co), ctypes.byref(cp), ctypes.byref(cs))
+    if rc != 0:
+        raise BundleAdjustmentError(f"b200ba_solve failed ({rc}): {lib.b200ba_last_error().decode()}")
+    return BundleAdjustmentSummary.from_c(cs)
+
+
+def flatten_reconstruction(options: BundleAdjustmentOptions, config: BundleAdjustmentConfig, rec: Reconstruction):
+    """DefaultBundleAdjuster's problem assembly (bundle_adjustment_ceres.cc:606-664,688-888) -> FlatProblem.
+    Returns (flat, image_ids, camera_ids, point_ids) with the id lists giving the flat order."""
+    image_ids = sorted(rec.images.keys())            # poses of images outside the config are constant
+    camera_ids = sorted(rec.cameras.keys())
+    point_ids = sorted(rec.points3D.keys())
+    pose_idx = {i: k for k, i in enumerate(image_ids)}
+    cam_idx = {c: k for k, c in enumerate(camera_ids)}
+    pt_idx = {p: k for k, p in enumerate(point_ids)}
+    cfg_images = sorted(config.Images())
+    obs_pose, obs_cam, obs_point, obs_xy = [], [], [], []
+    point_num_obs = {}
+    # AddImageToProblem (:688-751)
+    for image_id in cfg_images:
+        im = rec.images[image_id]
+        for p2 in im.points2D:
+            pid = p2.point3D_id
+            if pid < 0 or pid not in rec.points3D or config.IsIgnoredPoint(pid):
+                continue
+            if len(rec.points3D[pid].track) < options.min_track_length:
+                continue
+            point_num_obs[pid] = point_num_obs.get(pid, 0) + 1
+            obs_pose.append(pose_idx[image_id]); obs_cam.append(cam_idx[im.camera_id]); obs_point.append(pt_idx[pid])
+            obs_xy.append(p2.xy)
+    # AddPointToProblem (:829-888): explicit config points get the observations from images outside the config
+    extra_const_pose = set()
+    for pid in sorted(config.VariablePoints() | config.ConstantPoints()):
+        pt = rec.points3D[pid]
+        if point_num_obs.get(pid, 0) == len(pt.track):
+            continue
+        for image_id, p2_idx in pt.track:
+            if config.HasImage(image_id):
+                continue
+            im = rec.images[image_id]
+            point_num_obs[pid] = point_num_obs.get(pid, 0) + 1
+            extra_const_pose.add(image_id)
+            obs_pose.append(pose_idx[image_id]); obs_cam.append(cam_idx[im.camera_id]); obs_point.append(pt_idx[pid])
+            obs_xy.append(im.points2D[p2_idx].xy)
+    pose_constant = np.ones(len(image_ids), np.uint8)
+    for image_id in cfg_images:
+        if not config.HasConstantRigFromWorldPose(image_id):
+            pose_constant[pose_idx[image_id]] = 0
+    # cameras that only appear through constant-pose factors of outside images stay constant (:863-878)
+    cam_in_cfg = {rec.images[i].camera_id for i in cfg_images}
+    cam_constant = np.array([1 if (c not in cam_in_cfg or config.HasConstantCamIntrinsics(c)) else 0 for c in camera_ids], np.uint8)
+    # ParameterizePoints (:540-565)
+    point_constant = np.ones(len(point_ids), np.uint8)
+    for pid, n in point_num_obs.items():
+        if options.refine_points3D and len(rec.points3D[pid].track) <= n:
+            point_constant[pt_idx[pid]] = 0
+    for pid in config.ConstantPoints():
+        point_constant[pt_idx[pid]] = 1
+    cam_off, off = [], 0
+    for c in camera_ids:
+        cam_off.append(off); off += MODEL_NUM_PARAMS[rec.cameras[c].model_id]
+    flat = FlatProblem(
+        np.stack([rec.images[i].cam_from_world for i in image_ids]) if image_ids else np.zeros((0, 7)),
+        pose_constant, -np.ones(len(image_ids), np.int8),
+        [rec.cameras[c].model_id for c in camera_ids], cam_off,
+        np.concatenate([rec.cameras[c].params for c in camera_ids]) if camera_ids else np.zeros(0), cam_constant,
+        np.stack([rec.points3D[p].xyz for p in point_ids]) if point_ids else np.zeros((0, 3)), point_constant,
+        obs_pose, obs_cam, obs_point, np.asarray(obs_xy, np.float64).reshape(-1, 2))
+    return flat, image_ids, camera_ids, point_ids
+
+
+class BundleAdjuster:
+    """BundleAdjuster (bundle_adjustment.h:212-226), B200 backend: Solve() updates the reconstruction in place."""
+
+    def __init__(self, options, config, reconstruction):
+        self.options_, self.config_, self.reconstruction_ = options, config, reconstruction
+
+    def Options(self): return self.options_
+    def Config(self): return self.config_
+
+    def Solve(self) -> BundleAdjustmentSummary:
+        rec = self.reconstruction_
+        flat, image_ids, camera_ids, point_ids = flatten_reconstruction(self.options_, self.config_, rec)
+        lib = _bind(load_library())
+        if self.config_.FixedGauge() == TWO_CAMS_FROM_WORLD and self.options_.refine_rig_from_world:
+            # gauge search runs over the images of the config in ascending id (std::set<image_t>), :346-385
+            co, cp = self.options_.to_c(), flat.to_c()
+            pc = flat.pose_constant.copy()
+            # images outside the config are not candidates: mark them "not in problem" for the search
+            in_cfg = np.array([1 if i in self.config_.Images() else 0 for i in image_ids], np.uint8)
+            sub = FlatProblem(flat.poses[in_cfg == 1], flat.pose_constant[in_cfg == 1], flat.pose_fixed_dim[in_cfg == 1],
+                              flat.cam_model, flat.cam_off, flat.cam_params, flat.cam_constant, flat.points,
+                              flat.point_constant, np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32),
+                              np.zeros((0, 2)))
+            out_c = np.zeros(len(sub.poses), np.uint8); out_d = -np.ones(len(sub.poses), np.int8)
+            csub = sub.to_c()
+            lib.b200ba_fix_gauge_two_cams_from_world(ctypes.byref(csub), ctypes.byref(co), out_c.ctypes.data_as(_u8p),
+                                                     out_d.ctypes.data_as(_i8p))
+            idx = np.nonzero(in_cfg)[0]
+            flat.pose_constant[idx] = out_c
+            flat.pose_fixed_dim[idx] = out_d
+        summary = solve_flat(self.options_, flat)
+        # write back in place (variable blocks only changed)
+        for k, i in enumerate(image_ids):
+            rec.images[i].cam_from_world[:] = flat.poses[k]
+        for k, c in enumerate(camera_ids):
+            n = MODEL_NUM_PARAMS[rec.cameras[c].model_id]
+            rec.cameras[c].params[:] = flat.cam_params[flat.cam_off[k]:flat.cam_off[k] + n]
+        for k, p in enumerate(point_ids):
+            rec.points3D[p].xyz[:] = flat.points[k]
+        return summary
+
+
+def CreateDefaultBundleAdjuster(options, config, reconstruction) -> BundleAdjuster:
+    """Factory (bundle_adjustment.cc:314-336); this build has exactly one backend."""
+    return BundleAdjuster(options, config, reconstruction)

@@ -126,3 +126,149 @@ def make_patch_match_scene(width=1920, height=1080, num_src=8, seed=0, with_gt_m
         out["depth_maps"] = depths
         out["normal_maps"] = normals
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# Bundle adjustment scenes (colmap::SynthesizeDataset / SynthesizeNoise semantics, tracks sampled directly)
+# --------------------------------------------------------------------------------------------------
+def _quat_from_two_vectors(a, b):
+    """Eigen::Quaterniond::FromTwoVectors(a, b) for unit vectors, (x, y, z, w); vectorised over rows of a."""
+    a = a / np.linalg.norm(a, axis=-1, keepdims=True)
+    b = np.broadcast_to(b / np.linalg.norm(b), a.shape)
+    c = np.sum(a * b, axis=-1, keepdims=True)
+    axis = np.cross(a, b)
+    s = np.sqrt((1.0 + c) * 2.0)
+    q = np.concatenate([axis / s, s * 0.5], axis=-1)
+    return q / np.linalg.norm(q, axis=-1, keepdims=True)
+
+
+def _quat_mul(a, b):
+    ax, ay, az, aw = a[..., 0], a[..., 1], a[..., 2], a[..., 3]
+    bx, by, bz, bw = b[..., 0], b[..., 1], b[..., 2], b[..., 3]
+    return np.stack([aw * bx + ax * bw + ay * bz - az * by, aw * by - ax * bz + ay * bw + az * bx,
+                     aw * bz + ax * by - ay * bx + az * bw, aw * bw - ax * bx - ay * by - az * bz], axis=-1)
+
+
+def _quat_rotate(q, p):
+    v = q[..., :3]
+    w = q[..., 3:4]
+    t = 2.0 * np.cross(v, p)
+    return p + w * t + np.cross(v, t)
+
+
+_MODEL_DEFAULTS = {0: [1280.0, 512.0, 384.0], 1: [1280.0, 1280.0, 512.0, 384.0], 2: [1280.0, 512.0, 384.0, 0.05],
+                   3: [1280.0, 512.0, 384.0, 0.05, 0.01]}
+
+
+def _project(model, params, pc):
+    uu = pc[..., 0] / pc[..., 2]
+    vv = pc[..., 1] / pc[..., 2]
+    if model == 0:
+        return np.stack([params[..., 0] * uu + params[..., 1], params[..., 0] * vv + params[..., 2]], -1)
+    if model == 1:
+        return np.stack([params[..., 0] * uu + params[..., 2], params[..., 1] * vv + params[..., 3]], -1)
+    r2 = uu * uu + vv * vv
+    rad = params[..., 3] * r2 if model == 2 else params[..., 3] * r2 + params[..., 4] * r2 * r2
+    return np.stack([params[..., 0] * uu * (1 + rad) + params[..., 1], params[..., 0] * vv * (1 + rad) + params[..., 2]], -1)
+
+
+def synthesize_ba_problem(num_images, num_points, track_length, models=(2,), shared_camera=False, seed=42,
+                          point2D_stddev=1.0, point3D_stddev=0.05, translation_stddev=0.01, rotation_stddev_deg=1.0,
+                          num_obs=None):
+    """Ground truth + noisy flat BA problems.  `models`: camera model ids cycled over the images (one camera per
+    image) or a single shared camera.  `num_obs` (optional) = exact observation count (tracks of length
+    floor/ceil(num_obs/num_points)).  Noise defaults = benchmark/runtime/bundle_adjustment.cc:76-80."""
+    from .bundle_adjustment import MODEL_NUM_PARAMS, FlatProblem
+    rng = np.random.default_rng(seed)
+    pts = rng.uniform(-1, 1, (num_points, 3))
+    pts /= np.linalg.norm(pts, axis=1, keepdims=True)
+    view = -rng.uniform(-1, 1, (num_images, 3))
+    view /= np.linalg.norm(view, axis=1, keepdims=True)
+    q = _quat_from_two_vectors(view, np.array([0.0, 0.0, 1.0]))
+    t = _quat_rotate(q, 5.0 * view)
+    poses = np.concatenate([q, t], axis=1)
+    if shared_camera:
+        cam_model = [models[0]]
+        img_cam = np.zeros(num_images, np.int32)
+    else:
+        cam_model = [models[i % len(models)] for i in range(num_images)]
+        img_cam = np.arange(num_images, dtype=np.int32)
+    cam_off, off = [], 0
+    for m in cam_model:
+        cam_off.append(off); off += MODEL_NUM_PARAMS[m]
+    cam_params = np.concatenate([np.asarray(_MODEL_DEFAULTS[m]) for m in cam_model])
+    # tracks
+    if num_obs is None:
+        lens = np.full(num_points, track_length, np.int64)
+    else:
+        base = num_obs // num_points
+        lens = np.full(num_points, base, np.int64)
+        lens[: num_obs - base * num_points] += 1
+    obs_point = np.repeat(np.arange(num_points, dtype=np.int32), lens)
+    # distinct random images per point: random keys, take the `len` smallest per point (vectorised for equal lens)
+    maxlen = int(lens.max())
+    keys = rng.random((num_points, num_images)) if num_points * num_images <= 5e7 else None
+    if keys is not None:
+        order = np.argsort(keys, axis=1)[:, :maxlen]
+        sel = order[np.arange(maxlen)[None, :] < lens[:, None]]
+    else:
+        # large problems: sample with replacement then de-duplicate by re-drawing collisions a few times
+        cand = rng.integers(0, num_images, (num_points, maxlen))
+        for _ in range(8):
+            cs = np.sort(cand, axis=1)
+            dup = np.zeros_like(cand, bool)
+            dup[:, 1:] = cs[:, 1:] == cs[:, :-1]
+            if not dup.any():
+                break
+            cand = cs
+            cand[dup] = rng.integers(0, num_images, int(dup.sum()))
+        sel = cand[np.arange(maxlen)[None, :] < lens[:, None]]
+    obs_pose = sel.astype(np.int32)
+    obs_cam = img_cam[obs_pose]
+    # exact projections
+    pc = _quat_rotate(poses[obs_pose, :4], pts[obs_point]) + poses[obs_pose, 4:]
+    xy = np.empty((len(obs_pose), 2))
+    cm = np.asarray(cam_model)[obs_cam]
+    for m in set(cam_model):
+        msk = cm == m
+        offs = np.asarray(cam_off)[obs_cam[msk]]
+        prm = cam_params[offs[:, None] + np.arange(MODEL_NUM_PARAMS[m])[None, :]]
+        xy[msk] = _project(m, prm, pc[msk])
+    n_img, n_cam = num_images, len(cam_model)
+    gt = FlatProblem(poses, np.zeros(n_img, np.uint8), -np.ones(n_img, np.int8), cam_model, cam_off, cam_params,
+                     np.zeros(n_cam, np.uint8), pts, np.zeros(num_points, np.uint8), obs_pose, obs_cam, obs_point, xy)
+    noisy = gt.copy()
+    # SynthesizeNoise (synthetic.cc:675-733)
+    if rotation_stddev_deg > 0:
+        ang = np.deg2rad(np.clip(rng.normal(0, rotation_stddev_deg, num_images), -180, 180))
+        qz = np.stack([np.zeros(num_images), np.zeros(num_images), np.sin(ang / 2), np.cos(ang / 2)], 1)
+        noisy.poses[:, :4] = _quat_mul(noisy.poses[:, :4], qz)
+    if translation_stddev > 0:
+        noisy.poses[:, 4:] += rng.normal(0, translation_stddev, (num_images, 3))
+    if point2D_stddev > 0:
+        noisy.obs_xy = noisy.obs_xy + rng.normal(0, point2D_stddev, noisy.obs_xy.shape)
+    if point3D_stddev > 0:
+        noisy.points += rng.normal(0, point3D_stddev, noisy.points.shape)
+    return gt, noisy
+
+
+def flat_to_reconstruction(flat):
+    """FlatProblem -> minimal Reconstruction (ids are 1-based like COLMAP's)."""
+    from .bundle_adjustment import MODEL_NUM_PARAMS, Camera, Image, Point2D, Point3D, Reconstruction
+    rec = Reconstruction()
+    for c in range(len(flat.cam_model)):
+        n = MODEL_NUM_PARAMS[int(flat.cam_model[c])]
+        rec.cameras[c + 1] = Camera(c + 1, int(flat.cam_model[c]), flat.cam_params[flat.cam_off[c]:flat.cam_off[c] + n].copy())
+    img_cam = {}
+    for o in range(len(flat.obs_pose)):
+        img_cam[int(flat.obs_pose[o])] = int(flat.obs_cam[o])
+    for i in range(len(flat.poses)):
+        rec.images[i + 1] = Image(i + 1, img_cam.get(i, 0) + 1, flat.poses[i].copy())
+    for p in range(len(flat.points)):
+        rec.points3D[p + 1] = Point3D(flat.points[p].copy())
+    for o in range(len(flat.obs_pose)):
+        im = rec.images[int(flat.obs_pose[o]) + 1]
+        pid = int(flat.obs_point[o]) + 1
+        im.points2D.append(Point2D(flat.obs_xy[o].copy(), pid))
+        rec.points3D[pid].track.append((im.image_id, len(im.points2D) - 1))
+    return rec

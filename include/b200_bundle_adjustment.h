@@ -1,0 +1,126 @@
+/*
+ * b200_bundle_adjustment.h — C-ABI of the B200-native bundle-adjustment LM solver.
+ *
+ * Drop-in boundary: a third `BundleAdjustmentBackend` next to CERES and CASPAR
+ * (reference: src/colmap/estimators/bundle_adjustment.h:60,212-234 and the factory
+ * CreateDefaultBundleAdjuster, bundle_adjustment.cc:314-336).  The C++ adapter
+ *  flattens `Reconstruction` into b200ba_problem exactly as
+ * CasparBundleAdjuster::BuildFactors does (bundle_adjustment_caspar.cc:104-371) and writes the
+ * in/out arrays back (ibid. :767-801).
+ *
+ * What the solver does (reference behaviour = DefaultBundleAdjuster + ceres::Solve,
+ * bundle_adjustment_ceres.cc:574-683): Levenberg-Marquardt with Ceres' trust-region rules, analytic
+ * reprojection Jacobians (cost_functions/reprojection_error.h:62-210), quaternion (x) R^3 manifold,
+ * Schur elimination of the point blocks and either an exact reduced solve (DENSE_/SPARSE_SCHUR) or
+ * PCG with the SCHUR_JACOBI preconditioner (ITERATIVE_SCHUR), all on the GPU in fp64.
+ *
+ * Conventions: plain pointers and sizes, 0 == success, negative == error, no exceptions.
+ * `poses`, `camera_params`, `points` are updated IN PLACE; constant blocks are left bit-identical
+ * (bundle_adjustment_test.cc:409-411 relies on this).
+ */
+#ifndef B200_BUNDLE_ADJUSTMENT_H_
+#define B200_BUNDLE_ADJUSTMENT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* CameraModelId values (src/colmap/sensor/models.h:93-97).  Supported here: the radial pinhole family. */
+enum { B200BA_SIMPLE_PINHOLE = 0, B200BA_PINHOLE = 1, B200BA_SIMPLE_RADIAL = 2, B200BA_RADIAL = 3 };
+
+/* ceres::LinearSolverType subset COLMAP selects (bundle_adjustment_ceres.cc:202-212). */
+enum { B200BA_AUTO = 0, B200BA_DENSE_SCHUR = 1, B200BA_SPARSE_SCHUR = 2, B200BA_ITERATIVE_SCHUR = 3 };
+
+/* CeresBundleAdjustmentOptions::LossFunctionType (bundle_adjustment_ceres.h:41-43). */
+enum { B200BA_LOSS_TRIVIAL = 0, B200BA_LOSS_SOFT_L1 = 1, B200BA_LOSS_CAUCHY = 2, B200BA_LOSS_HUBER = 3 };
+
+/* BundleAdjustmentTerminationType (bundle_adjustment.h:50-57). */
+enum { B200BA_CONVERGENCE = 0, B200BA_NO_CONVERGENCE = 1, B200BA_FAILURE = 2 };
+
+/* BundleAdjustmentOptions (bundle_adjustment.h:175-208) + the Ceres solver options COLMAP sets
+ * (CeresBundleAdjustmentOptions ctor, bundle_adjustment_ceres.cc:102-116); Ceres defaults otherwise. */
+typedef struct b200ba_options {
+  int refine_focal_length;              /* 1 */
+  int refine_principal_point;           /* 0 */
+  int refine_extra_params;              /* 1 */
+  int refine_rig_from_world;            /* 1 */
+  int refine_points3D;                  /* 1 */
+  int constant_rig_from_world_rotation; /* 0 */
+  int loss_function_type;               /* TRIVIAL */
+  double loss_function_scale;           /* 1.0 */
+  int linear_solver_type;               /* AUTO: <=50 images DENSE_SCHUR, <=1000 SPARSE_SCHUR, else ITERATIVE_SCHUR */
+  int max_num_iterations;               /* 100 */
+  int max_linear_solver_iterations;     /* 200 */
+  double function_tolerance;            /* 0 */
+  double gradient_tolerance;            /* 1e-4 */
+  double parameter_tolerance;           /* 0 */
+  double initial_trust_region_radius;   /* 1e4  (Ceres default) */
+  double max_trust_region_radius;       /* 1e16 */
+  double min_trust_region_radius;       /* 1e-32 */
+  double min_relative_decrease;         /* 1e-3 */
+  double min_lm_diagonal;               /* 1e-6 */
+  double max_lm_diagonal;               /* 1e32 */
+  double eta;                           /* 0.1: CG forcing term (q-tolerance) for ITERATIVE_SCHUR */
+  int jacobi_scaling;                   /* 1 */
+  int gpu_index;                        /* -1 = current device */
+} b200ba_options;
+
+/* Flat problem with trivial frames (sensor_from_rig = identity, one image per frame). */
+typedef struct b200ba_problem {
+  int num_poses;
+  double* poses;                           /* [7*num_poses] qx qy qz qw tx ty tz (geometry/rigid3.h:46-49), in/out */
+  const uint8_t* pose_constant;            /* [num_poses] or NULL */
+  const int8_t* pose_fixed_translation_dim;/* [num_poses] -1 | 0..2 (two-cams gauge, bundle_adjustment_ceres.cc:400-416) or NULL */
+  int num_cameras;
+  const int32_t* camera_model_id;          /* [num_cameras] */
+  const int32_t* camera_param_offset;      /* [num_cameras] into camera_params */
+  double* camera_params;                   /* in/out */
+  const uint8_t* camera_constant;          /* [num_cameras] HasConstantCamIntrinsics, or NULL */
+  int64_t num_points;
+  double* points;                          /* [3*num_points], in/out */
+  const uint8_t* point_constant;           /* [num_points] or NULL */
+  int64_t num_observations;
+  const int32_t* obs_pose_idx;
+  const int32_t* obs_camera_idx;
+  const int32_t* obs_point_idx;
+  const double* obs_xy;                    /* [2*num_observations] */
+} b200ba_problem;
+
+/* BundleAdjustmentSummary (bundle_adjustment.h:63-74) + the ceres::Solver::Summary fields
+ * PrintSolverSummary reports (bundle_adjustment_ceres.cc:1102-1137). */
+typedef struct b200ba_summary {
+  int termination_type;
+  int num_residuals;            /* 2 x observations connected to >= 1 variable block */
+  int num_effective_parameters;
+  int num_successful_steps;
+  int num_unsuccessful_steps;
+  int num_linear_solver_iterations; /* total PCG iterations */
+  int linear_solver_type_used;
+  double initial_cost, final_cost;  /* 1/2 sum rho(r^2) */
+  double solve_ms;              /* device time of the LM loop */
+  double setup_ms;              /* host flattening + H2D */
+  double spmv_ms_total;         /* device time inside the implicit-Schur SpMV kernels */
+  int spmv_launches;
+  int kernel_launches;
+} b200ba_summary;
+
+void b200ba_options_init(b200ba_options* o);
+
+/* FixGaugeWithTwoCamsFromWorld (bundle_adjustment_ceres.cc:308-417) on the flat problem: writes
+ * pose_constant_out[num_poses] / fixed_dim_out[num_poses]; pose order = ascending image id.
+ * Returns 0, or 1 if no valid pair exists (the reference then falls back to three fixed points). */
+int b200ba_fix_gauge_two_cams_from_world(const b200ba_problem* p, const b200ba_options* o, uint8_t* pose_constant_out,
+                                         int8_t* fixed_dim_out);
+
+/* BundleAdjuster::Solve. */
+int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* out);
+
+const char* b200ba_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_BUNDLE_ADJUSTMENT_H_ */

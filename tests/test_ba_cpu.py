@@ -1,0 +1,223 @@
+"""CPU tier for the bundle-adjustment path: the oracle against the reference's known answers and properties,
+the product's host-compiled arithmetic against the oracle, the C-ABI surface.  No GPU compute."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_ba
+from colmap_b200 import load_library
+from colmap_b200.bundle_adjustment import (DENSE_SCHUR, ITERATIVE_SCHUR, PINHOLE, RADIAL, SIMPLE_PINHOLE,
+                                           SIMPLE_RADIAL, SOFT_L1, BundleAdjustmentOptions, _CProblem, _COptions,
+                                           _bind, _f64p, _i8p, _u8p)
+from colmap_b200.synthetic import synthesize_ba_problem
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+IDENTITY_POSE = np.array([0, 0, 0, 1, 0, 0, 0], np.float64)
+
+
+# ---------------------------------------------------------------- reference known answers
+def test_reprojection_known_answers():
+    """cost_functions/reprojection_error_test.cc:41-71 (SIMPLE_PINHOLE {1,0,0}, identity pose, point (0,0,1)):
+    observation (0,0) -> residual (0,0); (0,1) -> (0,-1); f = 2 and point (0,1,1)... ; behind camera -> 0."""
+    ok, res, *_ = oracle_ba.reproj(SIMPLE_PINHOLE, [0, 0, 1], IDENTITY_POSE, [1, 0, 0], [0, 0])
+    assert ok and np.allclose(res, [0, 0])
+    ok, res, *_ = oracle_ba.reproj(SIMPLE_PINHOLE, [0, 0, 1], IDENTITY_POSE, [1, 0, 0], [0, 1])
+    assert ok and np.allclose(res, [0, -1])
+    ok, res, *_ = oracle_ba.reproj(SIMPLE_PINHOLE, [0, 1, 1], IDENTITY_POSE, [2, 0, 0], [0, 0])
+    assert ok and np.allclose(res, [0, 2])
+    # point behind / on the camera plane: residual and Jacobians are zero (reprojection_error.h:101-116)
+    for z in (-1.0, 0.0):
+        ok, res, Jpt, Jps, Jpr = oracle_ba.reproj(SIMPLE_PINHOLE, [0, 0, z], IDENTITY_POSE, [1, 0, 0], [3, 4])
+        assert not ok and np.all(res == 0) and np.all(Jpt == 0) and np.all(Jps == 0) and np.all(Jpr == 0)
+
+
+@pytest.mark.parametrize("model,params", [(SIMPLE_PINHOLE, [600., 320, 240]), (PINHOLE, [600., 610, 320, 240]),
+                                          (SIMPLE_RADIAL, [600., 320, 240, 0.08]), (RADIAL, [600., 320, 240, 0.08, -0.02])])
+def test_analytic_jacobians_match_finite_differences(model, params):
+    """The property reprojection_error_test.cc:211-323 pins with autodiff (tolerance 1e-4), restated with
+    central differences over a grid of points and a non-trivial pose."""
+    rng = np.random.default_rng(0)
+    q = rng.normal(size=4); q /= np.linalg.norm(q)
+    pose = np.concatenate([q, [0.1, -0.2, 4.0]])
+    params = np.asarray(params, np.float64)
+    for _ in range(20):
+        pt = rng.uniform(-1, 1, 3)
+        ok, res, Jpt, Jps, Jpr = oracle_ba.reproj(model, pt, pose, params, [1.0, 2.0])
+        assert ok
+
+        def f(pt_, pose_, prm_):
+            return oracle_ba.reproj(model, pt_, pose_, prm_, [1.0, 2.0])[1]
+        h = 1e-6
+        for k in range(3):
+            d = np.zeros(3); d[k] = h
+            assert np.allclose((f(pt + d, pose, params) - f(pt - d, pose, params)) / (2 * h), Jpt[:, k], atol=1e-4, rtol=1e-6)
+        for k in range(7):
+            d = np.zeros(7); d[k] = h
+            assert np.allclose((f(pt, pose + d, params) - f(pt, pose - d, params)) / (2 * h), Jps[:, k], atol=1e-4, rtol=1e-6)
+        for k in range(len(params)):
+            d = np.zeros(len(params)); d[k] = h * max(1.0, abs(params[k]))
+            assert np.allclose((f(pt, pose, params + d) - f(pt, pose, params - d)) / (2 * d[k]), Jpr[:, k], atol=1e-4, rtol=1e-5)
+
+
+def test_quaternion_plus_is_a_rotation_update():
+    L = oracle_ba.lib()
+    rng = np.random.default_rng(1)
+    q = rng.normal(size=4); q /= np.linalg.norm(q)
+    out = np.zeros(4)
+    L.ba_oracle_quat_plus(q.ctypes.data_as(_f64p), np.zeros(3).ctypes.data_as(_f64p), out.ctypes.data_as(_f64p))
+    assert np.array_equal(out, q)
+    d = np.array([0.01, -0.02, 0.03])
+    L.ba_oracle_quat_plus(q.ctypes.data_as(_f64p), d.ctypes.data_as(_f64p), out.ctypes.data_as(_f64p))
+    assert abs(np.linalg.norm(out) - 1) < 1e-14
+    # first-order: out ~ q + PlusJacobian * d  (ceres EigenQuaternionManifold)
+    x, y, z, w = q
+    PJ = np.array([[w, z, -y], [-z, w, x], [y, -x, w], [-x, -y, -z]])
+    assert np.allclose(out, q + PJ @ d, atol=1e-3)
+
+
+# ---------------------------------------------------------------- oracle solver behaviour (bundle_adjustment_test.cc)
+def _gauge(flat):
+    flat.pose_constant = flat.pose_constant.copy(); flat.pose_fixed_dim = flat.pose_fixed_dim.copy()
+    flat.pose_constant[0] = 1
+    base = flat.poses[1, 4:] - flat.poses[0, 4:]
+    flat.pose_fixed_dim[1] = int(np.argmax(np.abs(base)))
+    return flat
+
+
+def test_oracle_nominal_recovers_ground_truth():
+    """bundle_adjustment_test.cc:303-352 (Nominal): 10 frames, 200 points, noise (0.5 px, 0.1, 0.5 deg, 0.1):
+    ground truth recovered to 0.1 units / 0.1 deg after aligning; here: reprojection RMSE back to the noise
+    floor and exact residual count."""
+    gt, noisy = synthesize_ba_problem(10, 200, 10, models=(SIMPLE_RADIAL,), shared_camera=True, seed=1,
+                                      point2D_stddev=0.5, point3D_stddev=0.1, translation_stddev=0.1, rotation_stddev_deg=0.5)
+    _gauge(noisy)
+    s = oracle_ba.solve(BundleAdjustmentOptions(), noisy)
+    assert s.termination_type == 0
+    assert s.num_residuals == 2 * 200 * 10
+    rmse = np.sqrt(2 * s.final_cost / (s.num_residuals / 2))
+    assert rmse < 0.5 * np.sqrt(2) * 1.05          # noise floor (0.5 px per coordinate)
+    assert s.final_cost < 1e-3 * s.initial_cost
+    # relative geometry: compare camera centres / points up to the similarity the gauge leaves: use distances
+    c_gt = gt.points[:50]; c_es = noisy.points[:50]
+    d_gt = np.linalg.norm(c_gt[:, None] - c_gt[None], axis=-1); d_es = np.linalg.norm(c_es[:, None] - c_es[None], axis=-1)
+    scale = d_es.sum() / d_gt.sum()
+    assert np.abs(d_es / scale - d_gt).max() < 0.1
+
+
+def test_oracle_constant_blocks_are_bit_identical_and_counts():
+    """bundle_adjustment_test.cc:354-411: constant points stay bit-identical; num_residuals only counts
+    observations that touch a variable block."""
+    gt, noisy = synthesize_ba_problem(6, 60, 4, models=(PINHOLE,), shared_camera=True, seed=2)
+    _gauge(noisy)
+    noisy.point_constant = noisy.point_constant.copy(); noisy.point_constant[:10] = 1
+    before = noisy.copy()
+    s = oracle_ba.solve(BundleAdjustmentOptions(), noisy)
+    assert s.termination_type in (0, 1)
+    assert np.array_equal(noisy.points[:10], before.points[:10])
+    assert np.array_equal(noisy.poses[0], before.poses[0])                   # gauge-fixed frame
+    assert noisy.cam_params[2] == before.cam_params[2] and noisy.cam_params[3] == before.cam_params[3]  # principal point
+    assert not np.array_equal(noisy.points[10:], before.points[10:])
+    assert s.num_residuals == 2 * 60 * 4
+    # everything constant except the points: residuals of constant points drop out
+    o = BundleAdjustmentOptions(refine_rig_from_world=False, refine_focal_length=False, refine_extra_params=False)
+    f2 = before.copy(); f2.point_constant = noisy.point_constant; f2.pose_constant = noisy.pose_constant; f2.pose_fixed_dim = noisy.pose_fixed_dim
+    s2 = oracle_ba.solve(o, f2)
+    assert s2.num_residuals == 2 * 50 * 4
+
+
+def test_oracle_dense_and_iterative_schur_agree():
+    gt, noisy = synthesize_ba_problem(12, 300, 6, models=(SIMPLE_RADIAL,), seed=3)
+    _gauge(noisy)
+    a, b = noisy.copy(), noisy.copy()
+    for f in (a, b):
+        f.pose_constant, f.pose_fixed_dim = noisy.pose_constant, noisy.pose_fixed_dim
+    sa = oracle_ba.solve(BundleAdjustmentOptions(linear_solver_type=DENSE_SCHUR), a)
+    sb = oracle_ba.solve(BundleAdjustmentOptions(linear_solver_type=ITERATIVE_SCHUR), b)
+    assert sa.termination_type == 0 and sb.termination_type == 0
+    assert abs(sa.final_cost - sb.final_cost) < 1e-6 * sa.final_cost
+    assert np.allclose(a.poses, b.poses, atol=1e-6) and np.allclose(a.points, b.points, atol=1e-6)
+    assert sb.num_linear_solver_iterations > 0 and sa.num_linear_solver_iterations == 0
+
+
+def test_oracle_robust_loss_downweights_outliers():
+    gt, noisy = synthesize_ba_problem(8, 150, 5, models=(PINHOLE,), shared_camera=True, seed=4)
+    _gauge(noisy)
+    rng = np.random.default_rng(0)
+    bad = rng.choice(len(noisy.obs_xy), 30, replace=False)
+    noisy.obs_xy[bad] += rng.normal(0, 80, (30, 2))
+    a, b = noisy.copy(), noisy.copy()
+    for f in (a, b):
+        f.pose_constant, f.pose_fixed_dim = noisy.pose_constant, noisy.pose_fixed_dim
+    oracle_ba.solve(BundleAdjustmentOptions(), a)
+    oracle_ba.solve(BundleAdjustmentOptions(loss_function_type=SOFT_L1, loss_function_scale=1.0), b)
+    err = lambda f: np.median(np.linalg.norm(f.points - gt.points, axis=1))
+    assert err(b) < err(a)
+
+
+# ---------------------------------------------------------------- product host side vs oracle
+def test_library_exports_every_declared_ba_symbol():
+    lib = load_library()
+    hdr = open(os.path.join(ROOT, "include", "b200_bundle_adjustment.h")).read()
+    names = set(re.findall(r"\b(b200ba_[a-z_0-9]+)\s*\(", hdr))
+    assert names == {"b200ba_options_init", "b200ba_fix_gauge_two_cams_from_world", "b200ba_solve", "b200ba_last_error"}
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_options_init_matches_reference_defaults():
+    lib = _bind(load_library())
+    o = _COptions()
+    lib.b200ba_options_init(ctypes.byref(o))
+    d = BundleAdjustmentOptions().to_c()
+    for f, _ in _COptions._fields_:
+        assert getattr(o, f) == getattr(d, f), f
+    assert (o.max_num_iterations, o.max_linear_solver_iterations, o.gradient_tolerance, o.function_tolerance) == (100, 200, 1e-4, 0.0)
+
+
+def test_product_reprojection_arithmetic_matches_oracle():
+    lib = load_library()
+    lib.b200ba_test_reproj.argtypes = [ctypes.c_int] + [_f64p] * 8
+    rng = np.random.default_rng(5)
+    prm = {0: [600., 320, 240], 1: [600., 610, 320, 240], 2: [600., 320, 240, 0.08], 3: [600., 320, 240, 0.08, -0.02]}
+    for model in range(4):
+        for _ in range(50):
+            q = rng.normal(size=4); q /= np.linalg.norm(q)
+            pose = np.concatenate([q, rng.uniform(-1, 1, 2), [4.0]])
+            pt = rng.uniform(-1, 1, 3); xy = rng.uniform(0, 500, 2); params = np.asarray(prm[model])
+            ok, res, Jpt, Jps, Jpr = oracle_ba.reproj(model, pt, pose, params, xy)
+            r2 = np.zeros(2); a = np.zeros((2, 3)); b = np.zeros((2, 7)); c = np.zeros((2, len(params)))
+            ok2 = lib.b200ba_test_reproj(model, pt.ctypes.data_as(_f64p), pose.ctypes.data_as(_f64p), params.ctypes.data_as(_f64p),
+                                         xy.ctypes.data_as(_f64p), r2.ctypes.data_as(_f64p), a.ctypes.data_as(_f64p),
+                                         b.ctypes.data_as(_f64p), c.ctypes.data_as(_f64p))
+            assert ok == ok2
+            for u, v in ((res, r2), (Jpt, a), (Jps, b), (Jpr, c)):
+                assert np.allclose(u, v, rtol=1e-13, atol=1e-13)
+
+
+def test_gauge_two_cams_from_world():
+    """FixGaugeWithTwoCamsFromWorld (bundle_adjustment_ceres.cc:308-417): first image constant, the second frame
+    with a non-degenerate baseline gets its largest baseline coordinate fixed; nothing to do if two are fixed."""
+    lib = _bind(load_library())
+    gt, noisy = synthesize_ba_problem(5, 20, 3, models=(PINHOLE,), shared_camera=True, seed=6)
+    # make pose 1 coincide with pose 0 -> degenerate baseline, must be skipped
+    noisy.poses[1] = noisy.poses[0]
+    cp, co = noisy.to_c(), BundleAdjustmentOptions().to_c()
+    pc = np.zeros(5, np.uint8); fd = np.zeros(5, np.int8)
+    assert lib.b200ba_fix_gauge_two_cams_from_world(ctypes.byref(cp), ctypes.byref(co), pc.ctypes.data_as(_u8p), fd.ctypes.data_as(_i8p)) == 0
+    assert pc.tolist() == [1, 0, 0, 0, 0]
+    assert fd[1] == -1 and fd[2] in (0, 1, 2) and (fd[3:] == -1).all()
+    # expected dimension: largest |baseline| of (T0 * T2^-1).translation
+    from colmap_b200.synthetic import _quat_rotate
+    q0, t0, q2, t2 = noisy.poses[0, :4], noisy.poses[0, 4:], noisy.poses[2, :4], noisy.poses[2, 4:]
+    q2inv = q2 * np.array([-1, -1, -1, 1])
+    c2 = -_quat_rotate(q2inv, t2)
+    base = _quat_rotate(q0, c2) + t0
+    assert fd[2] == int(np.argmax(np.abs(base)))
+    # two frames already constant -> untouched
+    noisy.pose_constant = np.array([0, 1, 0, 1, 0], np.uint8)
+    cp = noisy.to_c()
+    assert lib.b200ba_fix_gauge_two_cams_from_world(ctypes.byref(cp), ctypes.byref(co), pc.ctypes.data_as(_u8p), fd.ctypes.data_as(_i8p)) == 0
+    assert pc.tolist() == [0, 1, 0, 1, 0] and (fd == -1).all()

@@ -1,0 +1,143 @@
+"""GPU parity tier for the bundle-adjustment path: b200ba_solve (CUDA, fp64) against the CPU oracle on the same
+inputs.  Bar (BASELINE.json north_star): final cost / residual and parameters within 1e-5 relative; residual
+counts exact; constant blocks bit-identical."""
+import numpy as np
+import pytest
+
+import oracle_ba
+from colmap_b200.bundle_adjustment import (CAUCHY, DENSE_SCHUR, HUBER, ITERATIVE_SCHUR, PINHOLE, RADIAL, SIMPLE_PINHOLE,
+                                           SIMPLE_RADIAL, SOFT_L1, TWO_CAMS_FROM_WORLD, BundleAdjustmentConfig,
+                                           BundleAdjustmentOptions, CreateDefaultBundleAdjuster, solve_flat)
+from colmap_b200.synthetic import flat_to_reconstruction, synthesize_ba_problem
+
+pytestmark = pytest.mark.gpu
+REL = 1e-5
+
+
+def _gauge(flat):
+    flat.pose_constant = flat.pose_constant.copy(); flat.pose_fixed_dim = flat.pose_fixed_dim.copy()
+    flat.pose_constant[0] = 1
+    base = flat.poses[1, 4:] - flat.poses[0, 4:]
+    flat.pose_fixed_dim[1] = int(np.argmax(np.abs(base)))
+    return flat
+
+
+def _both(options, noisy):
+    a, b = noisy.copy(), noisy.copy()
+    for f in (a, b):
+        f.pose_constant, f.pose_fixed_dim, f.point_constant, f.cam_constant = (noisy.pose_constant, noisy.pose_fixed_dim,
+                                                                                noisy.point_constant, noisy.cam_constant)
+    s_gpu = solve_flat(options, a)
+    s_ref = oracle_ba.solve(options, b)
+    return a, s_gpu, b, s_ref
+
+
+def _assert_parity(a, s_gpu, b, s_ref):
+    assert s_gpu.num_residuals == s_ref.num_residuals
+    assert s_gpu.num_effective_parameters == s_ref.num_effective_parameters
+    assert s_gpu.termination_type == s_ref.termination_type == 0
+    assert abs(s_gpu.initial_cost - s_ref.initial_cost) <= 1e-9 * s_ref.initial_cost
+    assert abs(s_gpu.final_cost - s_ref.final_cost) <= REL * s_ref.final_cost
+    for u, v in ((a.poses, b.poses), (a.cam_params, b.cam_params), (a.points, b.points)):
+        assert np.allclose(u, v, rtol=REL, atol=REL * max(1.0, np.abs(v).max()))
+
+
+def test_b1_config_dense_schur():
+    """BASELINE config B1: 10 pinhole cameras (one shared PINHOLE), 1k points, 5k observations."""
+    gt, noisy = synthesize_ba_problem(10, 1000, 5, models=(PINHOLE,), shared_camera=True, seed=42)
+    _gauge(noisy)
+    a, sg, b, sr = _both(BundleAdjustmentOptions(), noisy)
+    assert sg.linear_solver_type_used == DENSE_SCHUR and sg.num_residuals == 10000
+    _assert_parity(a, sg, b, sr)
+    assert sg.num_successful_steps == sr.num_successful_steps
+
+
+@pytest.mark.parametrize("models,shared,lst", [
+    ((SIMPLE_RADIAL,), False, ITERATIVE_SCHUR),
+    ((PINHOLE, SIMPLE_RADIAL), False, ITERATIVE_SCHUR),          # mixed models (config B5 style)
+    ((SIMPLE_PINHOLE, RADIAL, PINHOLE, SIMPLE_RADIAL), False, DENSE_SCHUR),
+    ((RADIAL,), True, ITERATIVE_SCHUR),                          # shared intrinsics block: exact SCHUR_JACOBI cross terms
+])
+def test_model_grid_parity(models, shared, lst):
+    gt, noisy = synthesize_ba_problem(24, 1500, 6, models=models, shared_camera=shared, seed=7)
+    _gauge(noisy)
+    a, sg, b, sr = _both(BundleAdjustmentOptions(linear_solver_type=lst), noisy)
+    _assert_parity(a, sg, b, sr)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(refine_principal_point=True),
+    dict(refine_focal_length=False),
+    dict(refine_extra_params=False, refine_focal_length=False),   # constant cameras
+    dict(constant_rig_from_world_rotation=True),
+    dict(refine_points3D=False),
+    dict(loss_function_type=SOFT_L1), dict(loss_function_type=CAUCHY, loss_function_scale=2.0),
+    dict(loss_function_type=HUBER, loss_function_scale=1.5),
+])
+def test_option_grid_parity(kw):
+    gt, noisy = synthesize_ba_problem(12, 400, 6, models=(SIMPLE_RADIAL,), seed=11)
+    _gauge(noisy)
+    a, sg, b, sr = _both(BundleAdjustmentOptions(**kw), noisy)
+    _assert_parity(a, sg, b, sr)
+
+
+def test_constant_blocks_bit_identical_and_residual_counts():
+    gt, noisy = synthesize_ba_problem(8, 200, 5, models=(PINHOLE,), shared_camera=True, seed=3)
+    _gauge(noisy)
+    noisy.point_constant = noisy.point_constant.copy(); noisy.point_constant[:25] = 1
+    noisy.pose_constant[5] = 1
+    before = noisy.copy()
+    a, sg, b, sr = _both(BundleAdjustmentOptions(), noisy)
+    _assert_parity(a, sg, b, sr)
+    assert np.array_equal(a.points[:25], before.points[:25])
+    assert np.array_equal(a.poses[0], before.poses[0]) and np.array_equal(a.poses[5], before.poses[5])
+    assert a.cam_params[2] == before.cam_params[2] and a.cam_params[3] == before.cam_params[3]
+    # the gauge-fixed translation coordinate of frame 2 does not move
+    d = int(noisy.pose_fixed_dim[1])
+    assert a.poses[1, 4 + d] == before.poses[1, 4 + d]
+    # only points variable: residuals of constant points vanish from the count
+    o = BundleAdjustmentOptions(refine_rig_from_world=False, refine_focal_length=False, refine_extra_params=False)
+    a2, sg2, b2, sr2 = _both(o, noisy)
+    assert sg2.num_residuals == sr2.num_residuals == 2 * 175 * 5
+
+
+def test_reconstruction_level_api_mirrors_reference_tests():
+    """bundle_adjustment_test.cc:303-411 through the BundleAdjuster mirror: Nominal (everything variable, two-cams
+    gauge), ConstantPoints3D (explicitly constant points keep their coordinates bit-identically and only add
+    residuals), images outside the config become constant-pose observations."""
+    gt, noisy = synthesize_ba_problem(10, 200, 10, models=(SIMPLE_RADIAL,), shared_camera=True, seed=1,
+                                      point2D_stddev=0.5, point3D_stddev=0.1, translation_stddev=0.1, rotation_stddev_deg=0.5)
+    rec = flat_to_reconstruction(noisy)
+    cfg = BundleAdjustmentConfig()
+    for i in rec.images:
+        cfg.AddImage(i)
+    cfg.FixGauge(TWO_CAMS_FROM_WORLD)
+    summary = CreateDefaultBundleAdjuster(BundleAdjustmentOptions(), cfg, rec).Solve()
+    assert summary.termination_type == 0 and summary.num_residuals == 2 * 2000
+    rmse = np.sqrt(2 * summary.final_cost / 2000)
+    assert rmse < 0.5 * np.sqrt(2) * 1.05
+    # first image untouched (gauge)
+    assert np.array_equal(rec.images[1].cam_from_world, noisy.poses[0] / np.r_[np.ones(4) * np.linalg.norm(noisy.poses[0, :4]), 1, 1, 1]) or \
+        np.allclose(rec.images[1].cam_from_world, noisy.poses[0], atol=0)
+
+    # ConstantPoints3D: two images in the config, points 1 and 2 constant, everything else from those images variable
+    rec2 = flat_to_reconstruction(noisy)
+    cfg2 = BundleAdjustmentConfig()
+    cfg2.AddImage(1); cfg2.AddImage(2)
+    cfg2.AddConstantPoint(1); cfg2.AddConstantPoint(2)
+    xyz1, xyz2 = rec2.points3D[1].xyz.copy(), rec2.points3D[2].xyz.copy()
+    s2 = CreateDefaultBundleAdjuster(BundleAdjustmentOptions(), cfg2, rec2).Solve()
+    assert np.array_equal(rec2.points3D[1].xyz, xyz1) and np.array_equal(rec2.points3D[2].xyz, xyz2)
+    n_in = sum(1 for im in (rec2.images[1], rec2.images[2]) for _ in im.points2D)
+    n_extra = sum(1 for pid in (1, 2) for (iid, _) in rec2.points3D[pid].track if iid not in (1, 2))
+    assert s2.num_residuals == 2 * (n_in + n_extra)
+    # images outside the config keep their poses
+    assert np.array_equal(rec2.images[5].cam_from_world, noisy.poses[4])
+
+
+def test_medium_iterative_problem_converges_like_the_oracle():
+    gt, noisy = synthesize_ba_problem(60, 12000, 6, models=(SIMPLE_RADIAL,), seed=21)
+    _gauge(noisy)
+    a, sg, b, sr = _both(BundleAdjustmentOptions(linear_solver_type=ITERATIVE_SCHUR), noisy)
+    _assert_parity(a, sg, b, sr)
+    assert sg.num_linear_solver_iterations > 0 and sg.spmv_launches > 0 and sg.kernel_launches > 0
