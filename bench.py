@@ -116,6 +116,78 @@ def _oracle_pm_sample(threads=None):
     return w * h / 1e6 / dt, dt, f"{w}x{h} scene, {C2['num_src']} src, window 11, 5 iterations (all sweeps), oracle port"
 
 
+B3 = dict(num_images=500, num_points=300000, num_obs=2000000)
+
+
+def _b3_problem():
+    import numpy as np
+    from colmap_b200.bundle_adjustment import SIMPLE_RADIAL
+    from colmap_b200.synthetic import synthesize_ba_problem
+    gt, noisy = synthesize_ba_problem(B3["num_images"], B3["num_points"], 7, models=(SIMPLE_RADIAL,), seed=42,
+                                      num_obs=B3["num_obs"])
+    noisy.pose_constant = noisy.pose_constant.copy(); noisy.pose_fixed_dim = noisy.pose_fixed_dim.copy()
+    noisy.pose_constant[0] = 1                                   # TWO_CAMS_FROM_WORLD gauge
+    noisy.pose_fixed_dim[1] = int(np.argmax(np.abs(noisy.poses[1, 4:] - noisy.poses[0, 4:])))
+    return noisy
+
+
+def _fresh(noisy):
+    f = noisy.copy()
+    f.pose_constant, f.pose_fixed_dim = noisy.pose_constant, noisy.pose_fixed_dim
+    return f
+
+
+def _oracle_ba_sample(noisy, max_iters=3):
+    """Bounded CPU sample: the same B3 problem, first `max_iters` LM iterations, oracle port, all host threads."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_ba
+    from colmap_b200.bundle_adjustment import ITERATIVE_SCHUR, BundleAdjustmentOptions
+    o = BundleAdjustmentOptions(linear_solver_type=ITERATIVE_SCHUR, max_num_iterations=max_iters)
+    t = time.time()
+    s = oracle_ba.solve(o, _fresh(noisy))
+    dt = time.time() - t
+    steps = s.num_successful_steps + s.num_unsuccessful_steps
+    return steps / dt, dt, f"B3 problem (500 cams, 300k pts, 2M obs), first {max_iters} LM iterations, ITERATIVE_SCHUR, oracle port"
+
+
+def bench_ba(steps, warmup, peak, peak_src, with_cpu):
+    """BA leg: LM iterations/s on config B3 (500 SIMPLE_RADIAL cameras, 300k points, 2M observations, Schur-PCG)."""
+    from colmap_b200.bundle_adjustment import ITERATIVE_SCHUR, BundleAdjustmentOptions, solve_flat
+    noisy = _b3_problem()
+    o = BundleAdjustmentOptions(linear_solver_type=ITERATIVE_SCHUR)
+    for _ in range(max(warmup, 1)):
+        solve_flat(o, _fresh(noisy))
+    lm, dev_ms, wall_ms, spmv_ms, spmv_n, launches = 0, 0.0, 0.0, 0.0, 0, 0
+    for _ in range(steps):
+        f = _fresh(noisy)
+        t = time.time()
+        s = solve_flat(o, f)                       # host arrays in, host arrays out (H2D/D2H inside)
+        wall_ms += (time.time() - t) * 1e3
+        lm += s.num_successful_steps + s.num_unsuccessful_steps
+        dev_ms += s.solve_ms; spmv_ms += s.spmv_ms_total; spmv_n += s.spmv_launches; launches += s.kernel_launches
+    nobs = B3["num_obs"]
+    spmv_launch_ms = spmv_ms / max(spmv_n, 1)
+    alg = 192 * nobs                                # SURVEY.md §8(d): 2*(8*dc+24+8) B per observation per PCG iteration, dc = 8
+    achieved = alg / (spmv_launch_ms * 1e-3) / 1e9
+    h2d = f.poses.nbytes + f.cam_params.nbytes + f.points.nbytes + f.obs_xy.nbytes + 3 * f.obs_pose.nbytes
+    d2h = f.poses.nbytes + f.cam_params.nbytes + f.points.nbytes
+    out = {"metric": "ba_lm_iterations_per_s", "value": lm / (dev_ms * 1e-3), "unit": "LM iterations/s", "dtype": "f64",
+           "ms_per_step": dev_ms / steps, "lm_iterations_per_solve": lm / steps,
+           "config": {"workload": "BA B3: 500 cameras (SIMPLE_RADIAL, own intrinsics), 300k points, 2M observations, "
+                                  "ITERATIVE_SCHUR + SCHUR_JACOBI, two-cams gauge, trivial loss"},
+           "e2e": {"value": lm / (wall_ms * 1e-3), "unit": "LM iterations/s", "h2d_bytes_per_step": int(h2d),
+                   "d2h_bytes_per_step": int(d2h), "ms_per_step": wall_ms / steps},
+           "final_cost": s.final_cost, "termination_type": s.termination_type, "gpu_launches": int(launches),
+           "roofline": {"bound": "hbm", "kernel": "ba_schur_spmv_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": _ncu_traffic("ba_schur_spmv_kernel"), "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": alg, "launch_ms": spmv_launch_ms}}
+    if with_cpu:
+        v, dt, sample = _oracle_ba_sample(noisy)
+        out["cpu_baseline"] = {"value": v, "unit": "LM iterations/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": sample, "seconds": dt}
+    return out
+
+
 def run_reference(args, rank, world):
     """Reference arm.  COLMAP has no CPU implementation of PatchMatch (patch_match.cc requires CUDA,
     exe/mvs.cc:260), and its CUDA sources cannot be built in this image (Eigen / glog / OpenImageIO absent,
@@ -139,6 +211,15 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": v, "unit": "Mpixels/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if not args.no_ba:
+        try:
+            v, dt, sample = _oracle_ba_sample(_b3_problem())
+            line["ba"] = {"impl": "reference", "metric": "ba_lm_iterations_per_s", "value": v, "unit": "LM iterations/s",
+                          "cpu_baseline": {"value": v, "unit": "LM iterations/s", "cores": cores, "kind": "port",
+                                           "sample": sample},
+                          "note": "Ceres is not installed in this image; the fp64 oracle port restates its algorithm"}
+        except Exception as e:
+            line["ba"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
 
 
@@ -269,6 +350,11 @@ def main():
             v, dt, sample = _oracle_pm_sample()
             line["cpu_baseline"] = {"value": v, "unit": "Mpixels/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": sample, "seconds": dt}
+        if not args.no_ba and world == 1:
+            try:
+                line["ba"] = bench_ba(args.steps, args.warmup, peak, peak_src, not args.no_cpu_baseline)
+            except Exception as e:  # the primary metric must still be reported
+                line["ba"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
     if distributed:
         dist.destroy_process_group()

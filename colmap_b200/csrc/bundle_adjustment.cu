@@ -166,7 +166,7 @@ BA_HD void ba_loss(int type, double a, double s, double rho[3]) {
 // ------------------------------------------------------------------------------------------------
 struct BaCtl {          // device-resident scalars of the LM / PCG loops
   double cost, new_cost, model, gmax;
-  double rho, last_rho, pq, Q0, Q1, norm_b;
+  double rho, last_rho, pq, Q0, Q1, norm_b, rnorm2;
   int it, done, iters_total, pad;
 };
 
@@ -636,12 +636,12 @@ __global__ void ba_pcg_dot_pq_kernel(const BaDev D) {
   const double t = ba_block_sum(v, sm);
   if (threadIdx.x == 0) atomicAdd(&D.ctl->pq, t);
 }
-// x += alpha p ; r -= alpha q ; Q1 = -x.(b + r)
+// x += alpha p ; r -= alpha q ; Q1 = -x.(b + r) ; |r|^2
 __global__ void ba_pcg_update_kernel(const BaDev D) {
   __shared__ double sm[8];
   if (D.ctl->done) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  double v = 0;
+  double v = 0, w = 0;
   const double pq = D.ctl->pq;
   if (pq > 0.0 && i < D.nc) {
     const double alpha = D.ctl->rho / pq;
@@ -649,19 +649,26 @@ __global__ void ba_pcg_update_kernel(const BaDev D) {
     const double r = D.rr[i] - alpha * D.q[i];
     D.x[i] = x; D.rr[i] = r;
     v = -x * (D.rhs[i] + r);
+    w = r * r;
   }
   const double t = ba_block_sum(v, sm);
-  if (threadIdx.x == 0) atomicAdd(&D.ctl->Q1, t);
+  const double t2 = ba_block_sum(w, sm);
+  if (threadIdx.x == 0) { atomicAdd(&D.ctl->Q1, t); atomicAdd(&D.ctl->rnorm2, t2); }
 }
-// scalar bookkeeping + termination (ceres ConjugateGradientsSolver, Q-tolerance)
-__global__ void ba_pcg_step_kernel(const BaDev D, double q_tolerance, int max_iters) {
+// scalar bookkeeping + termination.  Inexact mode: ceres ConjugateGradientsSolver's Q-tolerance (zeta < eta).
+// Exact mode (DENSE_/SPARSE_SCHUR requested): relative residual |r| <= r_tolerance |b|.
+__global__ void ba_pcg_step_kernel(const BaDev D, double q_tolerance, double r_tolerance, int max_iters) {
   BaCtl* c = D.ctl;
   if (c->done) return;
   if (!(c->pq > 0.0)) { c->done = 1; return; }
   c->it += 1; c->iters_total += 1;
-  const double zeta = c->it * (c->Q1 - c->Q0) / c->Q1;
-  if (zeta < q_tolerance || c->it >= max_iters) c->done = 1;
-  c->Q0 = c->Q1; c->Q1 = 0.0;
+  if (r_tolerance > 0.0) {
+    if (c->rnorm2 <= r_tolerance * r_tolerance * c->norm_b || c->it >= max_iters) c->done = 1;
+  } else {
+    const double zeta = c->it * (c->Q1 - c->Q0) / c->Q1;
+    if (zeta < q_tolerance || c->it >= max_iters) c->done = 1;
+  }
+  c->Q0 = c->Q1; c->Q1 = 0.0; c->rnorm2 = 0.0;
   c->last_rho = c->rho; c->rho = 0.0; c->pq = 0.0;
 }
 
@@ -1034,9 +1041,9 @@ int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum
   int iter = 0;
   sum->termination_type = B200BA_NO_CONVERGENCE;
   const bool exact = (lst != B200BA_ITERATIVE_SCHUR);
-  // exact reduced solves (DENSE_/SPARSE_SCHUR) are obtained by running the same PCG to machine precision
-  const double q_tol = exact ? 1e-16 : o->eta;
-  const int max_cg = exact ? std::max(4 * nc + 50, o->max_linear_solver_iterations) : o->max_linear_solver_iterations;
+  // exact reduced solves (DENSE_/SPARSE_SCHUR) are obtained by running the same PCG to a 1e-12 relative residual
+  const double q_tol = o->eta, r_tol = exact ? 1e-12 : -1.0;
+  const int max_cg = exact ? std::max(10 * nc + 100, o->max_linear_solver_iterations) : o->max_linear_solver_iterations;
   bool finished = false;
   while (!finished) {
     // normal equations from the current (scaled) Jacobian
@@ -1077,7 +1084,7 @@ int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum
             if (b == 0) BA_CUDA(cudaEventRecord(evs1, st));
             ba_pcg_dot_pq_kernel<<<gc_blocks, 256, 0, st>>>(D);
             ba_pcg_update_kernel<<<gc_blocks, 256, 0, st>>>(D);
-            ba_pcg_step_kernel<<<1, 1, 0, st>>>(D, q_tol, max_cg);
+            ba_pcg_step_kernel<<<1, 1, 0, st>>>(D, q_tol, r_tol, max_cg);
             launches += 6;
           }
           issued += batch;

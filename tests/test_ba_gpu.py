@@ -35,7 +35,7 @@ def _both(options, noisy):
 def _assert_parity(a, s_gpu, b, s_ref):
     assert s_gpu.num_residuals == s_ref.num_residuals
     assert s_gpu.num_effective_parameters == s_ref.num_effective_parameters
-    assert s_gpu.termination_type == s_ref.termination_type == 0
+    assert s_gpu.termination_type == s_ref.termination_type
     assert abs(s_gpu.initial_cost - s_ref.initial_cost) <= 1e-9 * s_ref.initial_cost
     assert abs(s_gpu.final_cost - s_ref.final_cost) <= REL * s_ref.final_cost
     for u, v in ((a.poses, b.poses), (a.cam_params, b.cam_params), (a.points, b.points)):
