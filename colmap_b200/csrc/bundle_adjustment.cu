@@ -165,7 +165,7 @@ BA_HD void ba_loss(int type, double a, double s, double rho[3]) {
 // device problem
 // ------------------------------------------------------------------------------------------------
 struct BaCtl {          // device-resident scalars of the LM / PCG loops
-  double cost, new_cost, model, gmax;
+  double cost, new_cost, model, gmax, cost_delta;
   double rho, last_rho, pq, Q0, Q1, norm_b, rnorm2;
   int it, done, iters_total, pad;
 };
@@ -190,6 +190,7 @@ struct BaDev {
   const int *vpt_s0, *vpt_s1;         // [nvpt] slot range
   // linearisation (scaled) SoA
   double *Jc, *Jp, *r;                // Jc [2*DC][nslots], Jp [6][nslots], r [2][nslots]
+  double* cost_slot;                  // [nslots] 1/2 rho(|r|^2) at the linearisation point
   double *scale_c, *scale_p;          // [nc], [3*nvpt]
   // normal equations
   double *Hpp, *Hpp_inv, *gp, *diag_p, *Dp2;      // [6*nvpt] sym, [6*nvpt] sym, [3*nvpt]...
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_linearize_kernel(const BaDev D, c
                                                                 double* cost_out) {
   __shared__ double sm[8];
   const long long s = (long long)blockIdx.x * BA_BLOCK + threadIdx.x;
-  double cost = 0.0;
+  double cost = 0.0, delta = 0.0;
   const int pi = D.s_pose[s];
   if (pi >= 0) {
     const int ci = D.s_cam[s], ti = D.s_pt[s];
@@ -241,6 +242,8 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_linearize_kernel(const BaDev D, c
     double rho[3];
     ba_loss(D.loss_type, D.loss_scale, sq, rho);
     cost = 0.5 * rho[0];
+    if (MODE) D.cost_slot[s] = cost;
+    else delta = cost - D.cost_slot[s];   // per-residual difference: accurate cost change near convergence
     if (MODE) {
       double Jc[2 * (6 + BA_MAXDK)];
       const int DC = D.DC;
@@ -299,9 +302,14 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_linearize_kernel(const BaDev D, c
     for (int k = 0; k < 2 * D.DC; ++k) D.Jc[(long long)k * D.nslots + s] = 0.0;
     for (int k = 0; k < 6; ++k) D.Jp[(long long)k * D.nslots + s] = 0.0;
     D.r[s] = 0.0; D.r[D.nslots + s] = 0.0;
+    D.cost_slot[s] = 0.0;
   }
   const double t = ba_block_sum(cost, sm);
   if (threadIdx.x == 0) atomicAdd(cost_out, t);
+  if (!MODE) {
+    const double t2 = ba_block_sum(delta, sm);
+    if (threadIdx.x == 0) atomicAdd(&D.ctl->cost_delta, t2);
+  }
 }
 
 // squared column norms of the unscaled Jacobian (iteration 0) -> scale_c / scale_p hold the sums
@@ -995,7 +1003,7 @@ int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum
   { int* t; BA_CUDA(pool.upload(&t, blk_start, st)); D.blk_start = t; }
   { int* t; BA_CUDA(pool.upload(&t, blk_pack, st)); D.blk_pack = t; }
   { int* t; BA_CUDA(pool.upload(&t, off2blk, st)); D.off2blk = t; }
-  BA_CUDA(pool.alloc(&D.Jc, (size_t)2 * D.DC * nslots)); BA_CUDA(pool.alloc(&D.Jp, (size_t)6 * nslots)); BA_CUDA(pool.alloc(&D.r, (size_t)2 * nslots));
+  BA_CUDA(pool.alloc(&D.Jc, (size_t)2 * D.DC * nslots)); BA_CUDA(pool.alloc(&D.Jp, (size_t)6 * nslots)); BA_CUDA(pool.alloc(&D.r, (size_t)2 * nslots)); BA_CUDA(pool.alloc(&D.cost_slot, (size_t)nslots));
   BA_CUDA(pool.alloc(&D.scale_c, (size_t)nc)); BA_CUDA(pool.alloc(&D.scale_p, (size_t)3 * nvpt));
   BA_CUDA(pool.alloc(&D.Hpp, (size_t)6 * nvpt)); BA_CUDA(pool.alloc(&D.Hpp_inv, (size_t)6 * nvpt)); BA_CUDA(pool.alloc(&D.gp, (size_t)3 * nvpt));
   BA_CUDA(pool.alloc(&D.diag_p, (size_t)3 * nvpt)); BA_CUDA(pool.alloc(&D.Dp2, (size_t)3 * nvpt)); BA_CUDA(pool.alloc(&D.dp, (size_t)3 * nvpt));
@@ -1045,6 +1053,8 @@ int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum
   const double q_tol = o->eta, r_tol = exact ? 1e-12 : -1.0;
   const int max_cg = exact ? std::max(10 * nc + 100, o->max_linear_solver_iterations) : o->max_linear_solver_iterations;
   bool finished = false;
+  const bool verbose = getenv("B200BA_VERBOSE") != nullptr;
+  double last_gmax = 0.0;
   while (!finished) {
     // normal equations from the current (scaled) Jacobian
     BA_CUDA(cudaMemsetAsync(D.gc, 0, sizeof(double) * (nc ? nc : 1), st));
@@ -1056,6 +1066,7 @@ int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum
     { const long long n = (long long)NP + NCAM + 3LL * nvpt; ba_gradmax_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(D); }
     launches += 4;
     BA_CUDA(read_ctl());
+    last_gmax = h.gmax;
     if (h.gmax <= o->gradient_tolerance) { sum->termination_type = B200BA_CONVERGENCE; break; }
     bool accepted = false;
     while (!accepted) {
@@ -1097,18 +1108,23 @@ int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum
       BA_DISPATCH_DC(ba_launch_backsub, D, st);
       { const long long n = (long long)NP + NCAM + NPT; ba_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(D); }
       BA_CUDA(zero_field(&D.ctl->new_cost));
+      BA_CUDA(zero_field(&D.ctl->cost_delta));
       ba_linearize_kernel<0><<<nblocks, BA_BLOCK, 0, st>>>(D, D.nposes_, D.ncams_, D.npts_, 0, &D.ctl->new_cost);
       launches += 3;
       BA_CUDA(read_ctl());
       int failed = 0;
       BA_CUDA(cudaMemcpy(&failed, d_fail, sizeof(int), cudaMemcpyDeviceToHost));
       const double model = h.model, new_cost = h.new_cost;
-      const double rho_q = (!failed && model > 0) ? (cost - new_cost) / model : 0.0;
+      // cost change summed residual by residual (same quantity as cost - new_cost, without the cancellation)
+      const double cost_change_acc = -h.cost_delta;
+      const double rho_q = (!failed && model > 0) ? cost_change_acc / model : 0.0;
+      if (verbose) fprintf(stderr, "[b200ba] it %d cost %.12g new %.12g model %.6g rho %.6g radius %.4g pcg_it %d (total %d) gmax %.4g failed %d\n",
+                           iter, cost, new_cost, model, rho_q, radius, h.it, h.iters_total, last_gmax, failed);
       if (!failed && model > 0 && rho_q > o->min_relative_decrease) {
         accepted = true;
         sum->num_successful_steps++;
         std::swap(D.poses, D.nposes_); std::swap(D.cams, D.ncams_); std::swap(D.pts, D.npts_);
-        const double cost_change = cost - new_cost;
+        const double cost_change = cost_change_acc;
         linearize_current(1);
         BA_CUDA(read_ctl());
         cost = h.cost;

@@ -191,6 +191,8 @@ typedef struct {
   int64_t nobs_var;   /* observations of variable points (first in obs) */
   /* linearisation */
   double *r, *Jc, *Jp; /* per effective obs: r[2], Jc[2*JC], Jp[6] (already loss-corrected, unscaled) */
+  double* cost_obs;    /* per effective obs: 1/2 rho at the linearisation point */
+  double cost_delta;   /* sum over obs of (candidate cost - linearisation cost), filled by linearize(want_jac=0) */
   double* scale_c;    /* [nc] jacobi scaling */
   double* scale_p;    /* [3*nvpt] */
 } ba_flat;
@@ -265,6 +267,7 @@ static int flatten(ba_flat* F) {
   }
   for (int64_t k = 0; k < F->nvpt; ++k) F->pt_start[k + 1] += F->pt_start[k];
   F->r = (double*)calloc(2 * (F->nobs + 1), sizeof(double));
+  F->cost_obs = (double*)calloc(F->nobs + 1, sizeof(double));
   F->Jc = (double*)calloc(2 * JC * (F->nobs + 1), sizeof(double));
   F->Jp = (double*)calloc(6 * (F->nobs + 1), sizeof(double));
   F->scale_c = (double*)malloc(sizeof(double) * (F->nc + 1));
@@ -277,8 +280,8 @@ static int flatten(ba_flat* F) {
 static double linearize(ba_flat* F, const double* poses, const double* cams, const double* pts, int want_jac) {
   const b200ba_problem* p = F->p;
   const b200ba_options* o = F->o;
-  double cost = 0.0;
-#pragma omp parallel for reduction(+ : cost) schedule(static)
+  double cost = 0.0, delta = 0.0;
+#pragma omp parallel for reduction(+ : cost, delta) schedule(static)
   for (int64_t j = 0; j < F->nobs; ++j) {
     const int64_t i = F->obs[j];
     const int pi = p->obs_pose_idx[i], ci = p->obs_camera_idx[i], ti = p->obs_point_idx[i];
@@ -289,6 +292,7 @@ static double linearize(ba_flat* F, const double* poses, const double* cams, con
     double rho[3];
     loss_eval(o->loss_function_type, o->loss_function_scale, s, rho);
     cost += 0.5 * rho[0];
+    if (want_jac) F->cost_obs[j] = 0.5 * rho[0]; else delta += 0.5 * rho[0] - F->cost_obs[j];
     double* Jc = F->Jc + 2 * JC * j;
     double* Jp = F->Jp + 6 * j;
     if (want_jac) {
@@ -341,6 +345,7 @@ static double linearize(ba_flat* F, const double* poses, const double* cams, con
     }
     if (want_jac) { F->r[2 * j] = rs * res[0]; F->r[2 * j + 1] = rs * res[1]; }
   }
+  F->cost_delta = delta;
   return cost;
 }
 
@@ -720,13 +725,14 @@ int ba_oracle_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* 
         apply_step(&F, poses, cams, pts, udc, udp, nposes, ncams, npts, ncamparams);
         free(udc); free(udp);
         new_cost = linearize(&F, nposes, ncams, npts, 0);
-        rho_q = (cost - new_cost) / model;
+        /* cost change summed residual by residual: same quantity as cost - new_cost without the cancellation */
+        rho_q = (-F.cost_delta) / model;
       }
       if (ok && model > 0 && rho_q > o->min_relative_decrease) {
         accepted = 1;
         sum->num_successful_steps++;
         memcpy(poses, nposes, sizeof(double) * 7 * p->num_poses); memcpy(cams, ncams, sizeof(double) * ncamparams); memcpy(pts, npts, sizeof(double) * 3 * p->num_points);
-        const double cost_change = cost - new_cost;
+        const double cost_change = -F.cost_delta;
         cost = linearize(&F, poses, cams, pts, 1);
         const double t = 2.0 * rho_q - 1.0;
         radius = radius / fmax(1.0 / 3.0, 1.0 - t * t * t);
@@ -750,6 +756,6 @@ done:
   free(poses); free(cams); free(pts); free(nposes); free(ncams); free(npts); free(gc); free(gp); free(dc); free(dp); free(rhs);
   free(L.Hpp_inv); free(L.Dc2); free(L.Dp2); free(diag_c); free(diag_p); free(blk_start); free(blk_pack);
   free(F.pose_off); free(F.pose_mask); free(F.cam_off); free(F.cam_nvar); free(F.cam_var); free(F.pt_var); free(F.obs); free(F.pt_start);
-  free(F.r); free(F.Jc); free(F.Jp); free(F.scale_c); free(F.scale_p);
+  free(F.cost_obs); free(F.r); free(F.Jc); free(F.Jp); free(F.scale_c); free(F.scale_p);
   return 0;
 }
