@@ -67,6 +67,12 @@ struct PmSweepArgs {
   int last_filter;
   float* sel_cur;
   const float* sel_prev;
+  // split pipeline scratch (per pixel, original-orientation pixel index)
+  float4* rand_hyp;        // random hypothesis of the pixel in the sweep frame {depth, n}
+  unsigned char* ntrials;  // PerturbNormal rounds consumed (each 3 draws)
+  float* prior3;           // [pixel][3][N] triangulation / incident / resolution priors of the current hypothesis
+  float* tab3;             // [pixel][3][N] NCC of hypotheses 2,3,4 for every source image
+  float* gtab2;            // [pixel][2][N] geometric cost at cur / rand depth (geom mode)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -542,6 +548,309 @@ __global__ void __launch_bounds__(32 * WPC) pm_sweep_kernel(const PmParams P, co
   }
 }
 
+
+// ================================================================================================
+// Split sweep (default): the same SweepFromTopToBottom semantics in three passes.
+//   R  pm_rand_kernel    column-serial, one thread per column: consumes the column's XORWOW stream to
+//                        produce every row's random hypothesis (the stream position of a row does not
+//                        depend on the sweep's results, only on the hypotheses of the previous sweep);
+//   P  pm_pixel_kernel   pixel-parallel, one warp per pixel: everything that does not depend on the row
+//                        above — the NCC of hypotheses 2..4 (rand/rand, cur/rand-normal, rand-depth/cur)
+//                        against every source image, the per-image priors, geometric costs;
+//   S  pm_serial_kernel  one CTA per column: propagation, HMM messages, Monte-Carlo sampling, the NCC
+//                        of the propagated hypothesis, argmin, filter.
+// ================================================================================================
+__global__ void pm_rand_kernel(const PmParams P, const PmSweepArgs A) {
+  const int rot = A.rot;
+  const int fw = (rot & 1) ? P.H0 : P.W0, fh = (rot & 1) ? P.W0 : P.H0;
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= fw) return;
+  const float iK[4] = {P.invK[rot][0], P.invK[rot][1], P.invK[rot][2], P.invK[rot][3]};
+  int r0, c0;
+  pm_frame_to_orig(P.W0, P.H0, rot, 0, col, &r0, &c0);
+  const uint32_t* slot = P.rng + 6 * (size_t)pm_border_index(P.W0, P.H0, r0, c0);
+  PmRng rs;
+  rs.v0 = slot[0]; rs.v1 = slot[1]; rs.v2 = slot[2]; rs.v3 = slot[3]; rs.v4 = slot[4]; rs.d = slot[5];
+  const float colf = (float)col;
+  size_t p = pm_pix0(P.W0, P.H0, rot, 0, col);
+  float4 cur4 = P.hyp[p];
+  for (int row = 0; row < fh; ++row) {
+    const size_t pn = (row + 1 < fh) ? pm_pix0(P.W0, P.H0, rot, row + 1, col) : p;
+    const float4 next4 = P.hyp[pn];  // prefetch the next row while this one is processed
+    float n0 = cur4.y, n1 = cur4.z;
+    pm_normal_to_frame(rot, n0, n1);
+    const float dmin = (1.0f - A.perturbation) * cur4.x;
+    const float dmax = (1.0f + A.perturbation) * cur4.x;
+    const float rand_d = fmaf(pm_rng_uniform(rs), dmax - dmin, dmin);
+    float rn[3];
+    const int rounds = pm_perturb_normal(iK, (float)row, colf, A.perturbation_pi, n0, n1, cur4.w, rs, rn);
+    A.rand_hyp[p] = make_float4(rand_d, rn[0], rn[1], rn[2]);
+    A.ntrials[p] = (unsigned char)rounds;
+    for (int s = 0; s < P.num_samples; ++s) pm_rng_next(rs);
+    p = pn; cur4 = next4;
+  }
+}
+
+template <bool GEOM>
+__global__ void __launch_bounds__(128) pm_pixel_kernel(const PmParams P, const PmSweepArgs A) {
+  extern __shared__ float4 smem4[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rot = A.rot, N = P.N;
+  const int fw = (rot & 1) ? P.H0 : P.W0, fh = (rot & 1) ? P.W0 : P.H0;
+  float* poses = reinterpret_cast<float*>(smem4 + 4 * P.ntaps_pad);
+  float4* patch = smem4 + warp * P.ntaps_pad;
+  for (int i = threadIdx.x; i < N * PM_POSE_STRIDE; i += blockDim.x) poses[i] = P.poses[(size_t)rot * N * PM_POSE_STRIDE + i];
+  pm_fill_tap_offsets(P, patch, lane, 32);
+  const float iK[4] = {P.invK[rot][0], P.invK[rot][1], P.invK[rot][2], P.invK[rot][3]};
+  const float Kr[4] = {P.K[rot][0], P.K[rot][1], P.K[rot][2], P.K[rot][3]};
+  __syncthreads();
+  const size_t npix = (size_t)P.W0 * P.H0;
+  const int g = lane >> 3, sub = lane & 7;
+  const unsigned gmask = 0xffu << (8 * g);
+  const int npairs = 3 * N;
+  for (size_t q = (size_t)blockIdx.x * 4 + warp; q < npix; q += (size_t)gridDim.x * 4) {
+    const int row = (int)(q / fw), col = (int)(q - (size_t)row * fw);  // sweep-frame pixel
+    const size_t p = pm_pix0(P.W0, P.H0, rot, row, col);
+    const float rowf = (float)row, colf = (float)col;
+    float inv_wsum;
+    pm_build_patch(P, rot, fw, fh, row, col, patch, lane, &inv_wsum);
+    __syncwarp();
+    const float4 cur4 = P.hyp[p];
+    float cn0 = cur4.y, cn1 = cur4.z;
+    pm_normal_to_frame(rot, cn0, cn1);
+    const float cur_d = cur4.x, cn2 = cur4.w;
+    const float4 r4 = A.rand_hyp[p];
+    const float rsum = P.ref_sum[p], rsq = P.ref_sqsum[p];
+    if (lane < N) {  // per-image priors of the current hypothesis (:1079-1103)
+      const float* pose = poses + lane * PM_POSE_STRIDE;
+      const float rx = fmaf(iK[0], colf, iK[1]), ry = fmaf(iK[2], rowf, iK[3]);
+      float ct, ci;
+      pm_viewing_angles(pose, cur_d * rx, cur_d * ry, cur_d, cn0, cn1, cn2, &ct, &ci);
+      float Hm[9];
+      pm_compose_homography(pose, iK, rowf, colf, cur_d, cn0, cn1, cn2, Hm);
+      // kept as three factors: the serial pass evaluates sel_prob * tri * inc * res left to right (:1103)
+      A.prior3[(p * 3 + 0) * N + lane] = pm_tri_prob(P.L, ct);
+      A.prior3[(p * 3 + 1) * N + lane] = pm_inc_prob(P.L, ci);
+      A.prior3[(p * 3 + 2) * N + lane] = pm_res_prob(Hm, rowf, colf, P.radius);
+      if (GEOM) {
+        const PmSrcDesc sd = P.src[lane];
+        const float* dm = P.src_depth + sd.depth_off;
+        A.gtab2[(p * 2 + 0) * N + lane] = pm_geom_cost(pose, Kr, iK, dm, sd.w, sd.h, rowf, colf, cur_d, P.geom_max_cost);
+        A.gtab2[(p * 2 + 1) * N + lane] = pm_geom_cost(pose, Kr, iK, dm, sd.w, sd.h, rowf, colf, r4.x, P.geom_max_cost);
+      }
+    }
+    for (int base = 0; base < npairs; base += 4) {
+      const int pair = base + g;
+      if (pair < npairs) {
+        const int hsel = pair / N, img = pair - hsel * N;  // hsel 0: rand/rand, 1: cur depth + rand normal, 2: rand depth + cur normal
+        const float hd = (hsel == 1) ? cur_d : r4.x;
+        const float hn0 = (hsel == 2) ? cn0 : r4.y, hn1 = (hsel == 2) ? cn1 : r4.z, hn2 = (hsel == 2) ? cn2 : r4.w;
+        const PmSrcDesc sd = P.src[img];
+        const float c = pm_ncc_group(patch, P.ntaps, poses + img * PM_POSE_STRIDE, iK, P.quads + sd.quad_off, sd.pitch,
+                                     sd.w, sd.h, rowf, colf, hd, hn0, hn1, hn2, inv_wsum, rsum, rsq, sub, gmask);
+        if (sub == 0) A.tab3[(p * 3 + hsel) * N + img] = c;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int WPC, bool GEOM>
+__global__ void __launch_bounds__(32 * WPC) pm_serial_kernel(const PmParams P, const PmSweepArgs A) {
+  extern __shared__ float4 smem4[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = blockIdx.x;
+  const int rot = A.rot, N = P.N;
+  const int fw = (rot & 1) ? P.H0 : P.W0, fh = (rot & 1) ? P.W0 : P.H0;
+  float4* patch = smem4;
+  float* poses = reinterpret_cast<float*>(patch + P.ntaps_pad);
+  float* tab1 = poses + N * PM_POSE_STRIDE;  // [32] NCC of the propagated hypothesis per image
+  float* hyp1 = tab1 + 32;                   // depth, normal of the propagated hypothesis
+  float* fctl = hyp1 + 4;                    // inv_wsum, ref_sum, ref_sqsum
+  for (int i = threadIdx.x; i < N * PM_POSE_STRIDE; i += blockDim.x) poses[i] = P.poses[(size_t)rot * N * PM_POSE_STRIDE + i];
+  pm_fill_tap_offsets(P, patch, threadIdx.x, blockDim.x);
+  const float iK[4] = {P.invK[rot][0], P.invK[rot][1], P.invK[rot][2], P.invK[rot][3]};
+  const float Kr[4] = {P.K[rot][0], P.K[rot][1], P.K[rot][2], P.K[rot][3]};
+  const float colf = (float)col;
+  const int g = lane >> 3, sub = lane & 7;
+  const unsigned gmask = 0xffu << (8 * g);
+  const bool img_lane = lane < N;
+  __syncthreads();
+
+  float fwd = 0.5f;
+  PmRng rs;
+  float prev_d = 0.0f, prev_n0 = 0.0f, prev_n1 = 0.0f, prev_n2 = 0.0f;
+  uint32_t* rng_slot = nullptr;
+  if (warp == 0) {
+    if (img_lane) {  // backward messages (:976-989)
+      float beta = 0.5f;
+      for (int row = fh - 1; row >= 0; --row) {
+        const size_t p = pm_pix0(P.W0, P.H0, rot, row, col);
+        beta = pm_backward_message(P.L, P.cost[p * N + lane], beta);
+        A.sel_cur[p * N + lane] = beta;
+      }
+    }
+    int r0, c0;
+    pm_frame_to_orig(P.W0, P.H0, rot, 0, col, &r0, &c0);
+    rng_slot = P.rng + 6 * (size_t)pm_border_index(P.W0, P.H0, r0, c0);
+    rs.v0 = rng_slot[0]; rs.v1 = rng_slot[1]; rs.v2 = rng_slot[2]; rs.v3 = rng_slot[3]; rs.v4 = rng_slot[4]; rs.d = rng_slot[5];
+    const float4 h0 = P.hyp[(size_t)r0 * P.W0 + c0];
+    prev_d = h0.x; prev_n0 = h0.y; prev_n1 = h0.z; prev_n2 = h0.w;
+    pm_normal_to_frame(rot, prev_n0, prev_n1);
+  }
+
+  for (int row = 0; row < fh; ++row) {
+    const size_t p = pm_pix0(P.W0, P.H0, rot, row, col);
+    const float rowf = (float)row;
+    if (warp == WPC - 1) {
+      float inv_wsum;
+      pm_build_patch(P, rot, fw, fh, row, col, patch, lane, &inv_wsum);
+      if (lane == 0) { fctl[0] = inv_wsum; fctl[1] = P.ref_sum[p]; fctl[2] = P.ref_sqsum[p]; }
+    }
+    // ---- phase A (warp 0): propagated hypothesis, sampling distribution, samples
+    float cost_i = 0.0f, beta_i = 0.0f, prevp_i = 0.0f, cdf = 0.0f;
+    float c2 = 0.0f, c3 = 0.0f, c4 = 0.0f, g_cur = 0.0f, g_rand = 0.0f;
+    float cur_d = 0.0f, cur_n0 = 0.0f, cur_n1 = 0.0f, cur_n2 = 0.0f;
+    float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (warp == 0) {
+      prev_d = pm_propagate_depth(iK, prev_d, prev_n1, prev_n2, (float)(row - 1), rowf);
+      const float4 cur4 = P.hyp[p];
+      cur_d = cur4.x; cur_n0 = cur4.y; cur_n1 = cur4.z; cur_n2 = cur4.w;
+      pm_normal_to_frame(rot, cur_n0, cur_n1);
+      r4 = A.rand_hyp[p];
+      // stream position: 1 depth draw + 3 per PerturbNormal round were consumed by pass R
+      const int skip = 1 + 3 * (int)A.ntrials[p];
+      for (int s = 0; s < skip; ++s) pm_rng_next(rs);
+      float prob = 0.0f;
+      if (img_lane) {
+        cost_i = P.cost[p * N + lane];
+        beta_i = A.sel_cur[p * N + lane];
+        prevp_i = A.sel_prev[p * N + lane];
+        const float alpha = pm_forward_message(P.L, cost_i, fwd);
+        const float sp = pm_sel_prob(alpha, beta_i, prevp_i, A.prev_w);
+        prob = sp * A.prior3[(p * 3 + 0) * N + lane] * A.prior3[(p * 3 + 1) * N + lane] * A.prior3[(p * 3 + 2) * N + lane];
+        c2 = A.tab3[(p * 3 + 0) * N + lane]; c3 = A.tab3[(p * 3 + 1) * N + lane]; c4 = A.tab3[(p * 3 + 2) * N + lane];
+        if (GEOM) { g_cur = A.gtab2[(p * 2 + 0) * N + lane]; g_rand = A.gtab2[(p * 2 + 1) * N + lane]; }
+      }
+      float sum = 0.0f;
+      for (int i = 0; i < N; ++i) sum += __shfl_sync(0xffffffffu, prob, i);
+      const float inv = 1.0f / sum;
+      float cum = 0.0f;
+      for (int i = 0; i < N; ++i) {
+        cum += __shfl_sync(0xffffffffu, prob, i) * inv;
+        if (lane == i) cdf = cum;
+      }
+      if (lane == 0) { hyp1[0] = prev_d; hyp1[1] = prev_n0; hyp1[2] = prev_n1; hyp1[3] = prev_n2; }
+    }
+    __syncthreads();  // #1: patch + propagated hypothesis visible
+
+    // ---- phase B (all warps): NCC of the propagated hypothesis against every source image
+    {
+      const float inv_wsum = fctl[0], rsum = fctl[1], rsq = fctl[2];
+      const float hd = hyp1[0], hn0 = hyp1[1], hn1 = hyp1[2], hn2 = hyp1[3];
+      for (int img = warp * 4 + g; img < N; img += 4 * WPC) {
+        const PmSrcDesc sd = P.src[img];
+        const float c = pm_ncc_group(patch, P.ntaps, poses + img * PM_POSE_STRIDE, iK, P.quads + sd.quad_off, sd.pitch,
+                                     sd.w, sd.h, rowf, colf, hd, hn0, hn1, hn2, inv_wsum, rsum, rsq, sub, gmask);
+        if (sub == 0) tab1[img] = c;
+      }
+    }
+    __syncthreads();  // #2: tab1 complete
+
+    // ---- phase C+E (warp 0): sampled costs, argmin, messages, filter, carry state
+    if (warp == 0) {
+      const float c1 = img_lane ? tab1[lane] : 0.0f;
+      float g_prev = 0.0f;
+      if (GEOM && img_lane) {
+        const PmSrcDesc sd = P.src[lane];
+        g_prev = pm_geom_cost(poses + lane * PM_POSE_STRIDE, Kr, iK, P.src_depth + sd.depth_off, sd.w, sd.h, rowf, colf,
+                              prev_d, P.geom_max_cost);
+      }
+      // Monte-Carlo accumulation in sample order (:1128-1173); every lane keeps the five sums
+      float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f, a4 = 0.0f;
+      for (int s = 0; s < P.num_samples; ++s) {
+        const float u = pm_rng_uniform(rs) - FLT_EPSILON;
+        const unsigned m = __ballot_sync(0xffffffffu, img_lane && (cdf > u));
+        if (!m) continue;
+        const int img = __ffs(m) - 1;
+        a0 += __shfl_sync(0xffffffffu, cost_i, img);
+        a1 += __shfl_sync(0xffffffffu, c1, img);
+        a2 += __shfl_sync(0xffffffffu, c2, img);
+        a3 += __shfl_sync(0xffffffffu, c3, img);
+        a4 += __shfl_sync(0xffffffffu, c4, img);
+        if (GEOM) {
+          const float gc = __shfl_sync(0xffffffffu, g_cur, img), gp = __shfl_sync(0xffffffffu, g_prev, img),
+                      gr = __shfl_sync(0xffffffffu, g_rand, img);
+          a0 = fmaf(P.geom_reg, gc, a0); a1 = fmaf(P.geom_reg, gp, a1); a2 = fmaf(P.geom_reg, gr, a2);
+          a3 = fmaf(P.geom_reg, gc, a3); a4 = fmaf(P.geom_reg, gr, a4);
+        }
+      }
+      int best = 0;
+      float mn = a0;
+      if (a1 <= mn) { mn = a1; best = 1; }
+      if (a2 <= mn) { mn = a2; best = 2; }
+      if (a3 <= mn) { mn = a3; best = 3; }
+      if (a4 <= mn) { mn = a4; best = 4; }
+      float best_d, bn0, bn1, bn2;
+      switch (best) {
+        case 0: best_d = cur_d; bn0 = cur_n0; bn1 = cur_n1; bn2 = cur_n2; break;
+        case 1: best_d = prev_d; bn0 = prev_n0; bn1 = prev_n1; bn2 = prev_n2; break;
+        case 2: best_d = r4.x; bn0 = r4.y; bn1 = r4.z; bn2 = r4.w; break;
+        case 3: best_d = cur_d; bn0 = r4.y; bn1 = r4.z; bn2 = r4.w; break;
+        default: best_d = r4.x; bn0 = cur_n0; bn1 = cur_n1; bn2 = cur_n2; break;
+      }
+      float sp = 0.0f;
+      if (img_lane) {
+        float c = cost_i;
+        if (best != 0) {
+          c = (best == 1) ? c1 : ((best == 2) ? c2 : ((best == 3) ? c3 : c4));
+          P.cost[p * N + lane] = c;
+        }
+        const float alpha = pm_forward_message(P.L, c, fwd);
+        sp = pm_sel_prob(alpha, beta_i, prevp_i, A.prev_w);
+        A.sel_cur[p * N + lane] = sp;
+        fwd = alpha;
+      }
+      bool zero = false;
+      if (A.last_filter) {
+        bool ok = false;
+        if (img_lane) {
+          const float* pose = poses + lane * PM_POSE_STRIDE;
+          const float rx = fmaf(iK[0], colf, iK[1]), ry = fmaf(iK[2], rowf, iK[3]);
+          float ct, ci;
+          pm_viewing_angles(pose, best_d * rx, best_d * ry, best_d, bn0, bn1, bn2, &ct, &ci);
+          if (!(ct > P.cos_filter_tri || ci <= 0.0f)) {
+            ok = sp >= P.min_ncc_prob;
+            if (GEOM && ok) {
+              const PmSrcDesc sd = P.src[lane];
+              ok = pm_geom_cost(pose, Kr, iK, P.src_depth + sd.depth_off, sd.w, sd.h, rowf, colf, best_d,
+                                P.geom_max_cost) <= P.filter_geom_max_cost;
+            }
+          }
+        }
+        const int cnt = __popc(__ballot_sync(0xffffffffu, ok));
+        zero = cnt < P.filter_min_num_consistent;
+        if (img_lane) P.mask[p * N + lane] = (ok && !zero) ? 1 : 0;
+      }
+      if (lane == 0) {
+        float o0 = bn0, o1 = bn1;
+        pm_normal_to_orig(rot, o0, o1);
+        if (zero) {
+          float z0 = 0.0f, z1 = 0.0f;
+          pm_normal_to_orig(rot, z0, z1);
+          P.hyp[p] = make_float4(0.0f, z0, z1, 0.0f);
+        } else {
+          P.hyp[p] = make_float4(best_d, o0, o1, bn2);
+        }
+      }
+      prev_d = best_d; prev_n0 = bn0; prev_n1 = bn1; prev_n2 = bn2;
+    }
+  }
+  if (warp == 0 && lane == 0) {
+    rng_slot[0] = rs.v0; rng_slot[1] = rs.v1; rng_slot[2] = rs.v2; rng_slot[3] = rs.v3; rng_slot[4] = rs.v4; rng_slot[5] = rs.d;
+  }
+}
+
 // exhaustive check of pm_rcp_clamped against the IEEE division over all float bit patterns
 __global__ void pm_rcp_check_kernel(unsigned long long* mismatches) {
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
@@ -595,7 +904,9 @@ struct b200pm_context {
   float last_ms = 0.0f, last_sweep_ms = 0.0f;
   int last_launches = 0;
   std::vector<int> src_image_idxs;
-  size_t smem_sweep = 0, smem_init = 0;
+  size_t smem_sweep = 0, smem_init = 0, smem_serial = 0;
+  bool fused = false;
+  float4* rand_hyp = nullptr; unsigned char* ntrials = nullptr; float* prior3 = nullptr; float* tab3 = nullptr; float* gtab2 = nullptr;
 };
 
 template <typename T>
@@ -836,6 +1147,15 @@ int b200pm_create(const b200pm_options* o, const b200pm_problem* p, b200pm_handl
   c->smem_sweep = sizeof(float4) * P.ntaps_pad + sizeof(float) * ((size_t)N * PM_POSE_STRIDE + 160 + 96 + 20 + 4) +
                   sizeof(int) * (4 + (size_t)P.num_samples);
   c->smem_init = sizeof(float4) * 4 * P.ntaps_pad + sizeof(float) * (size_t)N * PM_POSE_STRIDE;
+  c->smem_serial = sizeof(float4) * P.ntaps_pad + sizeof(float) * ((size_t)N * PM_POSE_STRIDE + 32 + 4 + 4);
+  c->fused = getenv("B200PM_FUSED") != nullptr && atoi(getenv("B200PM_FUSED")) != 0;
+  if (!c->fused) {
+    PM_CUDA(pm_alloc(c, &c->rand_hyp, n));
+    PM_CUDA(pm_alloc(c, &c->ntrials, n));
+    PM_CUDA(pm_alloc(c, &c->prior3, 3 * n * N));
+    PM_CUDA(pm_alloc(c, &c->tab3, 3 * n * N));
+    if (P.geom) PM_CUDA(pm_alloc(c, &c->gtab2, 2 * n * N));
+  }
   PM_CUDA(cudaStreamSynchronize(s));
   PM_CUDA(cudaGetLastError());
   *out = c;
@@ -850,6 +1170,13 @@ static void pm_launch_sweep(b200pm_context* c, const PmSweepArgs& A, int fw) {
     pm_sweep_kernel<WPC, true><<<fw, 32 * WPC, c->smem_sweep, c->stream>>>(c->P, A);
   else
     pm_sweep_kernel<WPC, false><<<fw, 32 * WPC, c->smem_sweep, c->stream>>>(c->P, A);
+}
+template <int WPC>
+static void pm_launch_serial(b200pm_context* c, const PmSweepArgs& A, int fw) {
+  if (c->P.geom)
+    pm_serial_kernel<WPC, true><<<fw, 32 * WPC, c->smem_serial, c->stream>>>(c->P, A);
+  else
+    pm_serial_kernel<WPC, false><<<fw, 32 * WPC, c->smem_serial, c->stream>>>(c->P, A);
 }
 
 extern "C" {
@@ -868,8 +1195,11 @@ int b200pm_run(b200pm_handle c) {
     PM_CUDA(cudaFuncSetAttribute(pm_sweep_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_sweep));
     PM_CUDA(cudaFuncSetAttribute(pm_sweep_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_sweep));
   }
-  if (c->smem_init > 48 * 1024)
+  if (c->smem_init > 48 * 1024) {
     PM_CUDA(cudaFuncSetAttribute(pm_initial_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_init));
+    PM_CUDA(cudaFuncSetAttribute(pm_pixel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_init));
+    PM_CUDA(cudaFuncSetAttribute(pm_pixel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_init));
+  }
   int launches = 0;
   PM_CUDA(cudaEventRecord(c->ev[0], s));
   if (c->dirty) {  // a previous run consumed the initial state: rebuild it (same as the constructor)
@@ -893,6 +1223,7 @@ int b200pm_run(b200pm_handle c) {
     for (int sweep = 0; sweep < 4; ++sweep, ++t) {
       if (max_sweeps >= 0 && t >= max_sweeps) break;
       PmSweepArgs A;
+      memset(&A, 0, sizeof(A));
       A.rot = sweep;
       A.perturbation = 1.0f / powf(2.0f, (float)iter + (float)sweep / 4.0f);
       A.perturbation_pi = (float)((double)A.perturbation * M_PI);
@@ -901,10 +1232,23 @@ int b200pm_run(b200pm_handle c) {
       A.sel_cur = c->sel[t & 1];
       A.sel_prev = c->sel[(t + 1) & 1];
       const int fw = (sweep & 1) ? P.H0 : P.W0;
-      if (c->wpc == 1) pm_launch_sweep<1>(c, A, fw);
-      else if (c->wpc == 2) pm_launch_sweep<2>(c, A, fw);
-      else pm_launch_sweep<4>(c, A, fw);
-      ++launches;
+      if (c->fused) {
+        if (c->wpc == 1) pm_launch_sweep<1>(c, A, fw);
+        else if (c->wpc == 2) pm_launch_sweep<2>(c, A, fw);
+        else pm_launch_sweep<4>(c, A, fw);
+        ++launches;
+      } else {
+        A.rand_hyp = c->rand_hyp; A.ntrials = c->ntrials; A.prior3 = c->prior3; A.tab3 = c->tab3; A.gtab2 = c->gtab2;
+        pm_rand_kernel<<<(fw + 63) / 64, 64, 0, s>>>(P, A);
+        const size_t npx = (size_t)P.W0 * P.H0;
+        const int pgrid = (int)std::min<size_t>((npx + 3) / 4, (size_t)148 * 32);
+        if (P.geom) pm_pixel_kernel<true><<<pgrid, 128, c->smem_init, s>>>(P, A);
+        else pm_pixel_kernel<false><<<pgrid, 128, c->smem_init, s>>>(P, A);
+        if (c->wpc == 1) pm_launch_serial<1>(c, A, fw);
+        else if (c->wpc == 2) pm_launch_serial<2>(c, A, fw);
+        else pm_launch_serial<4>(c, A, fw);
+        launches += 3;
+      }
       c->final_sel = t & 1;
     }
   }

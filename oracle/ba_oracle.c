@@ -728,6 +728,7 @@ int ba_oracle_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* 
         /* cost change summed residual by residual: same quantity as cost - new_cost without the cancellation */
         rho_q = (-F.cost_delta) / model;
       }
+      if (getenv("BA_ORACLE_VERBOSE")) fprintf(stderr, "[oracle] it %d cost %.12g new %.12g model %.6g rho %.6g radius %.4g pcg_total %d\n", iter, cost, new_cost, model, rho_q, radius, sum->num_linear_solver_iterations);
       if (ok && model > 0 && rho_q > o->min_relative_decrease) {
         accepted = 1;
         sum->num_successful_steps++;

@@ -17,10 +17,11 @@ def _bits(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
 
 
-def _run_cuda(o, problem, wpc=None):
+def _run_cuda(o, problem, wpc=None, fused=False):
     if wpc is not None:
         os.environ["B200PM_WPC"] = str(wpc)
     os.environ.pop("B200PM_MAX_SWEEPS", None)
+    os.environ["B200PM_FUSED"] = "1" if fused else "0"
     pm = PatchMatch(o, problem)
     pm.Run()
     out = dict(depth=pm.GetDepthMap(), normal=pm.GetNormalMap(), sel_prob=pm.GetSelProbMap())
@@ -29,6 +30,7 @@ def _run_cuda(o, problem, wpc=None):
         out["list"] = pm.GetConsistentImageIdxs()
     pm.close()
     os.environ.pop("B200PM_WPC", None)
+    os.environ.pop("B200PM_FUSED", None)
     return out
 
 
@@ -48,12 +50,14 @@ def test_fast_reciprocal_is_ieee_over_all_floats():
     assert lib.b200pm_test_rcp_exhaustive() == 0
 
 
-@pytest.mark.parametrize("wpc", [1, 2, 4])
-def test_photometric_bit_exact_vs_oracle(wpc):
+@pytest.mark.parametrize("wpc,fused", [(1, False), (2, False), (4, False), (1, True), (2, True), (4, True)])
+def test_photometric_bit_exact_vs_oracle(wpc, fused):
+    """Both schedules (split rand/pixel/serial passes = default, and the single fused sweep kernel) for every
+    warps-per-column setting must reproduce the oracle bit for bit."""
     sc = make_patch_match_scene(96, 72, 4, seed=0)
     o = PatchMatchOptions(depth_min=sc["depth_min"], depth_max=sc["depth_max"], geom_consistency=False,
                           num_iterations=2)
-    got = _run_cuda(o, sc["problem"], wpc)
+    got = _run_cuda(o, sc["problem"], wpc, fused)
     ref = oracle_pm.run(o, sc["problem"])
     _assert_bit_exact(got, ref)
     assert np.array_equal(got["mask"], ref["mask"])
@@ -99,10 +103,11 @@ def test_geometric_consistency_bit_exact():
     prob.normal_maps = [n.copy() for n in sc["normal_maps"]]
     o = PatchMatchOptions(depth_min=sc["depth_min"], depth_max=sc["depth_max"], geom_consistency=True,
                           num_iterations=1)
-    got = _run_cuda(o, prob)
     ref = oracle_pm.run(o, prob)
-    _assert_bit_exact(got, ref)
-    assert np.array_equal(got["mask"], ref["mask"])
+    for fused in (False, True):
+        got = _run_cuda(o, prob, fused=fused)
+        _assert_bit_exact(got, ref)
+        assert np.array_equal(got["mask"], ref["mask"])
 
 
 def test_rerun_on_resident_inputs_is_reproducible():
