@@ -30,6 +30,7 @@
 
 #define BA_MAXDK 5
 #define BA_BLOCK 256
+#define BA_CHUNK 1024
 #define BA_HD __host__ __device__ __forceinline__
 
 // ------------------------------------------------------------------------------------------------
@@ -189,7 +190,15 @@ struct BaDev {
   const int *blk_pt0, *blk_npt;       // [nblocks] first variable point index / count
   const int *vpt_s0, *vpt_s1;         // [nvpt] slot range
   // linearisation (scaled) SoA
-  double *Jc, *Jp, *r;                // Jc [2*DC][nslots], Jp [6][nslots], r [2][nslots]
+  float *Jc, *Jp;                     // Jc [2*DC][nslots], Jp [6][nslots]: scaled Jacobians, fp32 storage (the PCG operator)
+  float* JcC;                         // [2*DC][nobs_c] the camera-side Jacobian again, in camera-sorted order
+  double* r;                          // r [2][nslots]
+  const int* s2c;                     // [nslots] slot -> position in camera order (-1 padding)
+  const int* s_seg;                   // [nslots] head lane | last lane << 8 of the slot's track inside its warp (warp-packed region)
+  int nblocks_warp;                   // leading blocks whose tracks never cross a warp (tracks <= 32 observations)
+  double* u;                          // [2][nobs_c] per-observation 2-vector exchanged between the two SpMV passes
+  const int4* chunks;                 // {c0, c1, out offset, comp0 | ncomp << 8}: <= BA_CHUNK observations of one block
+  int nchunks; long long nobs_c;
   double* cost_slot;                  // [nslots] 1/2 rho(|r|^2) at the linearisation point
   double *scale_c, *scale_p;          // [nc], [3*nvpt]
   // normal equations
@@ -293,8 +302,9 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_linearize_kernel(const BaDev D, c
         if (co >= 0) for (int c = 0; c < nv; ++c) { const double sc = D.scale_c[co + c]; Jc[6 + c] *= sc; Jc[DC + 6 + c] *= sc; }
         if (lp >= 0) for (int c = 0; c < 3; ++c) { const double sc = D.scale_p[3 * (long long)lp + c]; Jpt[c] *= sc; Jpt[3 + c] *= sc; }
       }
-      for (int k = 0; k < 2 * DC; ++k) D.Jc[(long long)k * D.nslots + s] = Jc[k];
-      for (int k = 0; k < 6; ++k) D.Jp[(long long)k * D.nslots + s] = Jpt[k];
+      const long long cp = D.s2c[s];
+      for (int k = 0; k < 2 * DC; ++k) { const float v = (float)Jc[k]; D.Jc[(long long)k * D.nslots + s] = v; D.JcC[(long long)k * D.nobs_c + cp] = v; }
+      for (int k = 0; k < 6; ++k) D.Jp[(long long)k * D.nslots + s] = (float)Jpt[k];
       D.r[s] = rs * res[0];
       D.r[D.nslots + s] = rs * res[1];
     }
@@ -569,16 +579,78 @@ __global__ void ba_pcg_direction_kernel(const BaDev D) {
   D.q[i] = D.Dc2[i] * p;
 }
 
-// THE ROOFLINE KERNEL: q += (H_cc - H_cp (H_pp + D_p^2)^-1 H_pc) p, one pass over the stored Jacobians.
+// Warp-packed variant of pass 1 (tracks of <= 32 observations, i.e. almost all of them): the track never crosses
+// a warp, so the point-block elimination is a segmented shuffle reduction — no shared memory, no block barrier,
+// every lane stays busy.  Same arithmetic as ba_schur_spmv_kernel below.
+__device__ __forceinline__ double ba_shfl_down_f64(double v, int off) { return __shfl_down_sync(0xffffffffu, v, off); }
+__device__ __forceinline__ double ba_shfl_f64(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+template <int DC>
+__global__ void __launch_bounds__(BA_BLOCK) ba_schur_spmv_warp_kernel(const BaDev D, const double* __restrict__ pvec) {
+  if (D.ctl->done) return;
+  const long long s = (long long)blockIdx.x * BA_BLOCK + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int pi = D.s_pose[s];
+  double y0 = 0.0, y1 = 0.0;
+  float jp[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int lp = -1, head = lane, last = lane;
+  if (pi >= 0) {
+    const int ci = D.s_cam[s];
+    const int po = D.pose_off[pi], co = D.cam_off[ci], nv = D.cam_nvar[ci];
+    float J0[DC], J1[DC];
+#pragma unroll
+    for (int c = 0; c < DC; ++c) { J0[c] = D.Jc[(long long)c * D.nslots + s]; J1[c] = D.Jc[(long long)(DC + c) * D.nslots + s]; }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) jp[c] = D.Jp[(long long)c * D.nslots + s];
+    lp = D.s_lpt[s];
+    const int seg = D.s_seg[s];
+    head = seg & 0xff; last = seg >> 8;
+    if (po >= 0) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { const double v = pvec[po + c]; y0 += (double)J0[c] * v; y1 += (double)J1[c] * v; }
+    }
+    if (co >= 0) {
+#pragma unroll
+      for (int c = 0; c < DC - 6; ++c) if (c < nv) { const double v = pvec[co + c]; y0 += (double)J0[6 + c] * v; y1 += (double)J1[6 + c] * v; }
+    }
+  }
+  double z0 = (double)jp[0] * y0 + (double)jp[3] * y1, z1 = (double)jp[1] * y0 + (double)jp[4] * y1, z2 = (double)jp[2] * y0 + (double)jp[5] * y1;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const double t0 = ba_shfl_down_f64(z0, off), t1 = ba_shfl_down_f64(z1, off), t2 = ba_shfl_down_f64(z2, off);
+    if (lane + off <= last) { z0 += t0; z1 += t1; z2 += t2; }
+  }
+  double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+  if (lane == head && lp >= 0) {
+    const double* I = D.Hpp_inv + 6 * (long long)lp;
+    w0 = I[0] * z0 + I[1] * z1 + I[2] * z2;
+    w1 = I[1] * z0 + I[3] * z1 + I[4] * z2;
+    w2 = I[2] * z0 + I[4] * z1 + I[5] * z2;
+  }
+  w0 = ba_shfl_f64(w0, head); w1 = ba_shfl_f64(w1, head); w2 = ba_shfl_f64(w2, head);
+  if (pi >= 0) {
+    if (lp >= 0) {
+      y0 -= (double)jp[0] * w0 + (double)jp[1] * w1 + (double)jp[2] * w2;
+      y1 -= (double)jp[3] * w0 + (double)jp[4] * w1 + (double)jp[5] * w2;
+    }
+    const long long cp = D.s2c[s];
+    D.u[cp] = y0;
+    D.u[D.nobs_c + cp] = y1;
+  }
+}
+
+// THE ROOFLINE KERNEL, pass 1 of 2: u_o = J_c p - J_p (H_pp + D_p^2)^-1 sum_track J_p^T J_c p per observation.
 // One thread per observation slot; a block holds whole tracks, so the point-block elimination
-// (z_p = sum J_p^T y, w_p = Hinv z_p) is a shared-memory exchange; the camera-side scatter uses fp64 red.
+// (z_p = sum J_p^T y, w_p = Hinv z_p) is a shared-memory exchange.  u is written in camera-sorted order and
+// reduced per camera-side block by ba_cam_reduce_kernel (no atomics on the hot data, deterministic).
 template <int DC>
 __global__ void __launch_bounds__(BA_BLOCK) ba_schur_spmv_kernel(const BaDev D, const double* __restrict__ pvec,
                                                                  double* __restrict__ qvec) {
   __shared__ double sy[2][BA_BLOCK];
   __shared__ double sw[3][BA_BLOCK];
   if (D.ctl->done) return;
-  const long long s = (long long)blockIdx.x * BA_BLOCK + threadIdx.x;
+  const int blk = blockIdx.x + D.nblocks_warp;   // blocks after the warp-packed region
+  const long long s = (long long)blk * BA_BLOCK + threadIdx.x;
   const int pi = D.s_pose[s];
   int po = -1, co = -1, nv = 0;
   double J0[DC], J1[DC], y0 = 0.0, y1 = 0.0;
@@ -596,17 +668,17 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_schur_spmv_kernel(const BaDev D, 
       for (int c = 0; c < DC - 6; ++c) if (c < nv) { const double v = pvec[co + c]; y0 += J0[6 + c] * v; y1 += J1[6 + c] * v; }
     }
   }
-  const bool var_block = blockIdx.x < D.nblocks_var;
+  const bool var_block = blk < D.nblocks_var;
   if (var_block) {
     sy[0][threadIdx.x] = y0; sy[1][threadIdx.x] = y1;
     __syncthreads();
     // one thread per track of this block
-    if (threadIdx.x < D.blk_npt[blockIdx.x]) {
-      const int k = D.blk_pt0[blockIdx.x] + threadIdx.x;
+    if (threadIdx.x < D.blk_npt[blk]) {
+      const int k = D.blk_pt0[blk] + threadIdx.x;
       const int s0 = D.vpt_s0[k], s1 = D.vpt_s1[k];
       double z0 = 0, z1 = 0, z2 = 0;
       for (int t = s0; t < s1; ++t) {
-        const int l = t - blockIdx.x * BA_BLOCK;
+        const int l = t - blk * BA_BLOCK;
         const double a0 = sy[0][l], a1 = sy[1][l];
         z0 += D.Jp[t] * a0 + D.Jp[3 * D.nslots + t] * a1;
         z1 += D.Jp[D.nslots + t] * a0 + D.Jp[4 * D.nslots + t] * a1;
@@ -620,19 +692,44 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_schur_spmv_kernel(const BaDev D, 
     __syncthreads();
     const int lp = (pi >= 0) ? D.s_lpt[s] : -1;
     if (lp >= 0) {
-      const int lt = lp - D.blk_pt0[blockIdx.x];
+      const int lt = lp - D.blk_pt0[blk];
       const double w0 = sw[0][lt], w1 = sw[1][lt], w2 = sw[2][lt];
       y0 -= D.Jp[s] * w0 + D.Jp[D.nslots + s] * w1 + D.Jp[2 * D.nslots + s] * w2;
       y1 -= D.Jp[3 * D.nslots + s] * w0 + D.Jp[4 * D.nslots + s] * w1 + D.Jp[5 * D.nslots + s] * w2;
     }
   }
-  if (po >= 0) {
-#pragma unroll
-    for (int c = 0; c < 6; ++c) atomicAdd(&qvec[po + c], J0[c] * y0 + J1[c] * y1);
+  if (pi >= 0) {
+    const long long cp = D.s2c[s];
+    D.u[cp] = y0;
+    D.u[D.nobs_c + cp] = y1;
   }
-  if (co >= 0) {
+}
+
+// Second SpMV pass (also used for the reduced right-hand side): out[block] += sum over the block's observations
+// of Jc^T u, observations in camera-sorted order so every block (pose or intrinsics) owns contiguous ranges.
+// One CTA per chunk of <= BA_CHUNK observations; deterministic tree inside the chunk, one red.add per output.
+__global__ void __launch_bounds__(BA_BLOCK) ba_cam_reduce_kernel(const BaDev D, double* __restrict__ out, int respect_done) {
+  if (respect_done && D.ctl->done) return;
+  const int chunk = blockIdx.x * (BA_BLOCK / 32) + (threadIdx.x >> 5);   // one warp per chunk: shuffles only, no barrier
+  if (chunk >= D.nchunks) return;
+  const int lane = threadIdx.x & 31;
+  const int4 ch = D.chunks[chunk];
+  const int comp0 = ch.w & 0xff, ncomp = ch.w >> 8;
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll 4
+  for (int k = ch.x + lane; k < ch.y; k += 32) {
+    const double u0 = D.u[k], u1 = D.u[D.nobs_c + k];
 #pragma unroll
-    for (int c = 0; c < DC - 6; ++c) if (c < nv) atomicAdd(&qvec[co + c], J0[6 + c] * y0 + J1[6 + c] * y1);
+    for (int c = 0; c < 6; ++c)
+      if (c < ncomp) acc[c] += (double)D.JcC[(long long)(comp0 + c) * D.nobs_c + k] * u0 + (double)D.JcC[(long long)(D.DC + comp0 + c) * D.nobs_c + k] * u1;
+  }
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    if (c < ncomp) {
+      double t = acc[c];
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) atomicAdd(&out[ch.z + c], t);
+    }
   }
 }
 
@@ -782,7 +879,9 @@ struct BaPool {
 
 template <int DC>
 static void ba_launch_spmv(const BaDev& D, cudaStream_t s) {
-  ba_schur_spmv_kernel<DC><<<D.nblocks, BA_BLOCK, 0, s>>>(D, D.p, D.q);
+  if (D.nblocks_warp) ba_schur_spmv_warp_kernel<DC><<<D.nblocks_warp, BA_BLOCK, 0, s>>>(D, D.p);
+  if (D.nblocks > D.nblocks_warp) ba_schur_spmv_kernel<DC><<<D.nblocks - D.nblocks_warp, BA_BLOCK, 0, s>>>(D, D.p, D.q);
+  if (D.nchunks) ba_cam_reduce_kernel<<<(D.nchunks + BA_BLOCK / 32 - 1) / (BA_BLOCK / 32), BA_BLOCK, 0, s>>>(D, D.q, 1);
 }
 template <int DC>
 static void ba_launch_backsub(const BaDev& D, cudaStream_t s) {
@@ -941,33 +1040,90 @@ int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum
     s_pose.push_back(p->obs_pose_idx[obs]); s_cam.push_back(p->obs_camera_idx[obs]); s_pt.push_back(p->obs_point_idx[obs]);
     s_lpt.push_back(lpt); sx.push_back(p->obs_xy[2 * obs]); sy.push_back(p->obs_xy[2 * obs + 1]);
   };
-  for (long long i = 0; i < NPT; ++i) if (pt_var[i] >= 0) vpt_point[pt_var[i]] = (int)i;
+  // variable points are renumbered: tracks of <= 32 observations first (packed so that none crosses a warp),
+  // then the longer ones (packed so that none crosses a block)
+  std::vector<int> s_seg;
+  int nblocks_warp = 0;
   {
-    int used = 0;
-    blk_pt0.push_back(0); blk_npt.push_back(0);
-    for (int k = 0; k < nvpt; ++k) {
-      const int len = (int)(vcount[k + 1] - vcount[k]);
-      if (used + len > BA_BLOCK) {
-        for (; used < BA_BLOCK; ++used) push_slot(-1, -1);
-        used = 0; blk_pt0.push_back(k); blk_npt.push_back(0);
-      }
-      vpt_s0[k] = (int)s_pose.size();
-      for (long long j = vcount[k]; j < vcount[k + 1]; ++j) push_slot(vobs[j], k);
-      vpt_s1[k] = (int)s_pose.size();
-      used += len; blk_npt.back()++;
+    std::vector<int> order_pts; order_pts.reserve(nvpt);
+    std::vector<long long> olen(nvpt), ostart(nvpt);
+    for (int k = 0; k < nvpt; ++k) { olen[k] = vcount[k + 1] - vcount[k]; ostart[k] = vcount[k]; }
+    for (int k = 0; k < nvpt; ++k) if (olen[k] <= 32) order_pts.push_back(k);
+    const int nshort = (int)order_pts.size();
+    for (int k = 0; k < nvpt; ++k) if (olen[k] > 32) order_pts.push_back(k);
+    // renumber: new variable index = position in order_pts
+    std::vector<int> newidx(nvpt);
+    for (int n = 0; n < nvpt; ++n) newidx[order_pts[n]] = n;
+    for (long long i = 0; i < NPT; ++i) if (pt_var[i] >= 0) pt_var[i] = newidx[pt_var[i]];
+    for (long long i = 0; i < NPT; ++i) if (pt_var[i] >= 0) vpt_point[pt_var[i]] = (int)i;
+    auto pad_to = [&](size_t mult) { while (s_pose.size() % mult) { push_slot(-1, -1); s_seg.push_back(0); } };
+    int cur_blk = -1;
+    auto note_block = [&](int k) {
+      const int b = (int)(s_pose.size() / BA_BLOCK);
+      while ((int)blk_pt0.size() <= b) { blk_pt0.push_back(k); blk_npt.push_back(0); }
+      blk_npt[b]++; cur_blk = b;
+    };
+    for (int n = 0; n < nshort; ++n) {
+      const int k = order_pts[n], len = (int)olen[k];
+      const int used = (int)(s_pose.size() % 32);
+      if (used + len > 32) pad_to(32);
+      note_block(n);
+      vpt_s0[n] = (int)s_pose.size();
+      const int head = (int)(s_pose.size() % 32), last = head + len - 1;
+      for (long long j = ostart[k]; j < ostart[k] + len; ++j) { push_slot(vobs[j], n); s_seg.push_back(head | (last << 8)); }
+      vpt_s1[n] = (int)s_pose.size();
     }
-    for (; used < BA_BLOCK && used > 0; ++used) push_slot(-1, -1);
-    if (nvpt == 0) { blk_pt0.clear(); blk_npt.clear(); }
+    pad_to(BA_BLOCK);
+    nblocks_warp = (int)(s_pose.size() / BA_BLOCK);
+    for (int n = nshort; n < nvpt; ++n) {
+      const int k = order_pts[n], len = (int)olen[k];
+      const int used = (int)(s_pose.size() % BA_BLOCK);
+      if (used + len > BA_BLOCK) pad_to(BA_BLOCK);
+      note_block(n);
+      vpt_s0[n] = (int)s_pose.size();
+      for (long long j = ostart[k]; j < ostart[k] + len; ++j) { push_slot(vobs[j], n); s_seg.push_back(0); }
+      vpt_s1[n] = (int)s_pose.size();
+    }
+    pad_to(BA_BLOCK);
+    (void)cur_blk;
   }
   const int nblocks_var = (int)(s_pose.size() / BA_BLOCK);
-  for (long long i : const_obs) push_slot(i, -1);
-  while (s_pose.size() % BA_BLOCK) push_slot(-1, -1);
+  for (long long i : const_obs) { push_slot(i, -1); s_seg.push_back(0); }
+  while (s_pose.size() % BA_BLOCK) { push_slot(-1, -1); s_seg.push_back(0); }
   const long long nslots = (long long)s_pose.size();
   const int nblocks = (int)(nslots / BA_BLOCK);
   blk_pt0.resize(nblocks, nvpt); blk_npt.resize(nblocks, 0);
   if (nslots >= (1LL << 31)) return ba_fail(-3, "problem too large for 32-bit slot indices");
   std::vector<double> s_xy(2 * nslots);
   for (long long s = 0; s < nslots; ++s) { s_xy[s] = sx[s]; s_xy[nslots + s] = sy[s]; }
+  // camera order: observations sorted by (camera, pose) so that every camera-side block owns contiguous ranges
+  std::vector<int> c2s;
+  c2s.reserve((size_t)nobs_eff);
+  for (long long s = 0; s < nslots; ++s) if (s_pose[s] >= 0) c2s.push_back((int)s);
+  std::stable_sort(c2s.begin(), c2s.end(), [&](int a, int b) {
+    if (s_cam[a] != s_cam[b]) return s_cam[a] < s_cam[b];
+    return s_pose[a] < s_pose[b];
+  });
+  const long long nobs_c = (long long)c2s.size();
+  std::vector<int> s2c(nslots, -1);
+  for (long long k = 0; k < nobs_c; ++k) s2c[c2s[k]] = (int)k;
+  std::vector<int4> chunks;
+  for (long long k = 0; k < nobs_c;) {  // pose runs
+    long long e = k;
+    const int pose = s_pose[c2s[k]];
+    while (e < nobs_c && s_pose[c2s[e]] == pose && s_cam[c2s[e]] == s_cam[c2s[k]]) ++e;
+    if (pose_off[pose] >= 0)
+      for (long long c0 = k; c0 < e; c0 += BA_CHUNK) chunks.push_back(make_int4((int)c0, (int)std::min<long long>(c0 + BA_CHUNK, e), pose_off[pose], 0 | (6 << 8)));
+    k = e;
+  }
+  for (long long k = 0; k < nobs_c;) {  // camera runs
+    long long e = k;
+    const int cam = s_cam[c2s[k]];
+    while (e < nobs_c && s_cam[c2s[e]] == cam) ++e;
+    if (cam_off[cam] >= 0)
+      for (long long c0 = k; c0 < e; c0 += BA_CHUNK) chunks.push_back(make_int4((int)c0, (int)std::min<long long>(c0 + BA_CHUNK, e), cam_off[cam], 6 | (cam_nvar[cam] << 8)));
+    k = e;
+  }
 
   // ---------------------------------------------------------------- device setup
   cudaStream_t st = nullptr;
@@ -1003,7 +1159,13 @@ int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum
   { int* t; BA_CUDA(pool.upload(&t, blk_start, st)); D.blk_start = t; }
   { int* t; BA_CUDA(pool.upload(&t, blk_pack, st)); D.blk_pack = t; }
   { int* t; BA_CUDA(pool.upload(&t, off2blk, st)); D.off2blk = t; }
-  BA_CUDA(pool.alloc(&D.Jc, (size_t)2 * D.DC * nslots)); BA_CUDA(pool.alloc(&D.Jp, (size_t)6 * nslots)); BA_CUDA(pool.alloc(&D.r, (size_t)2 * nslots)); BA_CUDA(pool.alloc(&D.cost_slot, (size_t)nslots));
+  BA_CUDA(pool.alloc(&D.Jc, (size_t)2 * D.DC * nslots)); BA_CUDA(pool.alloc(&D.Jp, (size_t)6 * nslots));
+  BA_CUDA(pool.alloc(&D.JcC, (size_t)2 * D.DC * nobs_c)); BA_CUDA(pool.alloc(&D.u, (size_t)2 * nobs_c));
+  { int* t; BA_CUDA(pool.upload(&t, s2c, st)); D.s2c = t; }
+  { int* t; BA_CUDA(pool.upload(&t, s_seg, st)); D.s_seg = t; }
+  D.nblocks_warp = nblocks_warp;
+  { int4* t; BA_CUDA(pool.upload(&t, chunks, st)); D.chunks = t; }
+  D.nchunks = (int)chunks.size(); D.nobs_c = nobs_c; BA_CUDA(pool.alloc(&D.r, (size_t)2 * nslots)); BA_CUDA(pool.alloc(&D.cost_slot, (size_t)nslots));
   BA_CUDA(pool.alloc(&D.scale_c, (size_t)nc)); BA_CUDA(pool.alloc(&D.scale_p, (size_t)3 * nvpt));
   BA_CUDA(pool.alloc(&D.Hpp, (size_t)6 * nvpt)); BA_CUDA(pool.alloc(&D.Hpp_inv, (size_t)6 * nvpt)); BA_CUDA(pool.alloc(&D.gp, (size_t)3 * nvpt));
   BA_CUDA(pool.alloc(&D.diag_p, (size_t)3 * nvpt)); BA_CUDA(pool.alloc(&D.Dp2, (size_t)3 * nvpt)); BA_CUDA(pool.alloc(&D.dp, (size_t)3 * nvpt));
@@ -1040,8 +1202,8 @@ int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum
   ba_colnorm_kernel<<<nblocks, BA_BLOCK, 0, st>>>(D);
   if (nc) ba_make_scale_kernel<<<gc_blocks, 256, 0, st>>>(D.scale_c, nc, o->jacobi_scaling);
   if (nvpt) ba_make_scale_kernel<<<(3 * nvpt + 255) / 256, 256, 0, st>>>(D.scale_p, 3LL * nvpt, o->jacobi_scaling);
-  ba_apply_scale_kernel<<<nblocks, BA_BLOCK, 0, st>>>(D);
-  launches += 4;
+  launches += 3;
+  linearize_current(1);  // store the scaled Jacobian (fp32) in both orders
   BA_CUDA(read_ctl());
   double cost = h.cost;
   sum->initial_cost = cost;

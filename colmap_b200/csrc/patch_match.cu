@@ -592,7 +592,7 @@ __global__ void pm_rand_kernel(const PmParams P, const PmSweepArgs A) {
 }
 
 template <bool GEOM>
-__global__ void __launch_bounds__(128) pm_pixel_kernel(const PmParams P, const PmSweepArgs A) {
+__global__ void __launch_bounds__(128, 8) pm_pixel_kernel(const PmParams P, const PmSweepArgs A) {
   extern __shared__ float4 smem4[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rot = A.rot, N = P.N;
@@ -699,6 +699,28 @@ __global__ void __launch_bounds__(32 * WPC) pm_serial_kernel(const PmParams P, c
     pm_normal_to_frame(rot, prev_n0, prev_n1);
   }
 
+  // software pipeline: the per-row inputs do not depend on the sweep state, so warp 0 fetches row + 1 while
+  // row is being processed (takes two L2 round trips off the per-row critical path)
+  float4 nx_cur4 = make_float4(0.f, 0.f, 0.f, 0.f), nx_r4 = nx_cur4;
+  int nx_skip = 0;
+  float nx_cost = 0.f, nx_beta = 0.f, nx_prevp = 0.f, nx_t = 0.f, nx_i = 0.f, nx_r = 0.f, nx_c2 = 0.f, nx_c3 = 0.f, nx_c4 = 0.f,
+        nx_gc = 0.f, nx_gr = 0.f;
+  auto fetch_row = [&](int row) {
+    const size_t p = pm_pix0(P.W0, P.H0, rot, row, col);
+    nx_cur4 = P.hyp[p];
+    nx_r4 = A.rand_hyp[p];
+    nx_skip = 1 + 3 * (int)A.ntrials[p];
+    if (img_lane) {
+      nx_cost = P.cost[p * N + lane];
+      nx_beta = A.sel_cur[p * N + lane];
+      nx_prevp = A.sel_prev[p * N + lane];
+      nx_t = A.prior3[(p * 3 + 0) * N + lane]; nx_i = A.prior3[(p * 3 + 1) * N + lane]; nx_r = A.prior3[(p * 3 + 2) * N + lane];
+      nx_c2 = A.tab3[(p * 3 + 0) * N + lane]; nx_c3 = A.tab3[(p * 3 + 1) * N + lane]; nx_c4 = A.tab3[(p * 3 + 2) * N + lane];
+      if (GEOM) { nx_gc = A.gtab2[(p * 2 + 0) * N + lane]; nx_gr = A.gtab2[(p * 2 + 1) * N + lane]; }
+    }
+  };
+  if (warp == 0) fetch_row(0);
+
   for (int row = 0; row < fh; ++row) {
     const size_t p = pm_pix0(P.W0, P.H0, rot, row, col);
     const float rowf = (float)row;
@@ -714,23 +736,21 @@ __global__ void __launch_bounds__(32 * WPC) pm_serial_kernel(const PmParams P, c
     float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (warp == 0) {
       prev_d = pm_propagate_depth(iK, prev_d, prev_n1, prev_n2, (float)(row - 1), rowf);
-      const float4 cur4 = P.hyp[p];
+      const float4 cur4 = nx_cur4;
       cur_d = cur4.x; cur_n0 = cur4.y; cur_n1 = cur4.z; cur_n2 = cur4.w;
       pm_normal_to_frame(rot, cur_n0, cur_n1);
-      r4 = A.rand_hyp[p];
+      r4 = nx_r4;
       // stream position: 1 depth draw + 3 per PerturbNormal round were consumed by pass R
-      const int skip = 1 + 3 * (int)A.ntrials[p];
+      const int skip = nx_skip;
       for (int s = 0; s < skip; ++s) pm_rng_next(rs);
       float prob = 0.0f;
       if (img_lane) {
-        cost_i = P.cost[p * N + lane];
-        beta_i = A.sel_cur[p * N + lane];
-        prevp_i = A.sel_prev[p * N + lane];
+        cost_i = nx_cost; beta_i = nx_beta; prevp_i = nx_prevp;
         const float alpha = pm_forward_message(P.L, cost_i, fwd);
         const float sp = pm_sel_prob(alpha, beta_i, prevp_i, A.prev_w);
-        prob = sp * A.prior3[(p * 3 + 0) * N + lane] * A.prior3[(p * 3 + 1) * N + lane] * A.prior3[(p * 3 + 2) * N + lane];
-        c2 = A.tab3[(p * 3 + 0) * N + lane]; c3 = A.tab3[(p * 3 + 1) * N + lane]; c4 = A.tab3[(p * 3 + 2) * N + lane];
-        if (GEOM) { g_cur = A.gtab2[(p * 2 + 0) * N + lane]; g_rand = A.gtab2[(p * 2 + 1) * N + lane]; }
+        prob = sp * nx_t * nx_i * nx_r;
+        c2 = nx_c2; c3 = nx_c3; c4 = nx_c4;
+        if (GEOM) { g_cur = nx_gc; g_rand = nx_gr; }
       }
       float sum = 0.0f;
       for (int i = 0; i < N; ++i) sum += __shfl_sync(0xffffffffu, prob, i);
@@ -743,6 +763,7 @@ __global__ void __launch_bounds__(32 * WPC) pm_serial_kernel(const PmParams P, c
       if (lane == 0) { hyp1[0] = prev_d; hyp1[1] = prev_n0; hyp1[2] = prev_n1; hyp1[3] = prev_n2; }
     }
     __syncthreads();  // #1: patch + propagated hypothesis visible
+    if (warp == 0 && row + 1 < fh) fetch_row(row + 1);
 
     // ---- phase B (all warps): NCC of the propagated hypothesis against every source image
     {
