@@ -30,8 +30,13 @@
 
 #define BA_MAXDK 5
 #define BA_BLOCK 256
-#define BA_CHUNK 1024
+#define BA_CHUNK 512
 #define BA_HD __host__ __device__ __forceinline__
+// Jacobian storage: tiles of 32 observations, component-major inside a tile ("AoSoA"): a warp reads a whole tile
+// as 2*DC (or 6) consecutive 128-byte lines, which keeps each warp on one DRAM page instead of 2*DC streams.
+#define BA_JC(k, s) ((((long long)(s) >> 5) * (2 * D.DC) + (k)) * 32 + ((s) & 31))
+#define BA_JP(k, s) ((((long long)(s) >> 5) * 6 + (k)) * 32 + ((s) & 31))
+#define BA_U(k, s) ((((long long)(s) >> 5) * 2 + (k)) * 32 + ((s) & 31))
 
 // ------------------------------------------------------------------------------------------------
 // camera models + reprojection (host/device so the CPU test tier can check them without a GPU)
@@ -303,14 +308,14 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_linearize_kernel(const BaDev D, c
         if (lp >= 0) for (int c = 0; c < 3; ++c) { const double sc = D.scale_p[3 * (long long)lp + c]; Jpt[c] *= sc; Jpt[3 + c] *= sc; }
       }
       const long long cp = D.s2c[s];
-      for (int k = 0; k < 2 * DC; ++k) { const float v = (float)Jc[k]; D.Jc[(long long)k * D.nslots + s] = v; D.JcC[(long long)k * D.nobs_c + cp] = v; }
-      for (int k = 0; k < 6; ++k) D.Jp[(long long)k * D.nslots + s] = (float)Jpt[k];
+      for (int k = 0; k < 2 * DC; ++k) { const float v = (float)Jc[k]; D.Jc[BA_JC(k, s)] = v; D.JcC[BA_JC(k, cp)] = v; }
+      for (int k = 0; k < 6; ++k) D.Jp[BA_JP(k, s)] = (float)Jpt[k];
       D.r[s] = rs * res[0];
       D.r[D.nslots + s] = rs * res[1];
     }
   } else if (MODE) {
-    for (int k = 0; k < 2 * D.DC; ++k) D.Jc[(long long)k * D.nslots + s] = 0.0;
-    for (int k = 0; k < 6; ++k) D.Jp[(long long)k * D.nslots + s] = 0.0;
+    for (int k = 0; k < 2 * D.DC; ++k) D.Jc[BA_JC(k, s)] = 0.0;
+    for (int k = 0; k < 6; ++k) D.Jp[BA_JP(k, s)] = 0.0;
     D.r[s] = 0.0; D.r[D.nslots + s] = 0.0;
     D.cost_slot[s] = 0.0;
   }
@@ -329,9 +334,9 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_colnorm_kernel(const BaDev D) {
   if (pi < 0) return;
   const int ci = D.s_cam[s], DC = D.DC;
   const int po = D.pose_off[pi], co = D.cam_off[ci], nv = D.cam_nvar[ci], lp = D.s_lpt[s];
-  if (po >= 0) for (int c = 0; c < 6; ++c) { const double a = D.Jc[(long long)c * D.nslots + s], b = D.Jc[(long long)(DC + c) * D.nslots + s]; atomicAdd(&D.scale_c[po + c], a * a + b * b); }
-  if (co >= 0) for (int c = 0; c < nv; ++c) { const double a = D.Jc[(long long)(6 + c) * D.nslots + s], b = D.Jc[(long long)(DC + 6 + c) * D.nslots + s]; atomicAdd(&D.scale_c[co + c], a * a + b * b); }
-  if (lp >= 0) for (int c = 0; c < 3; ++c) { const double a = D.Jp[(long long)c * D.nslots + s], b = D.Jp[(long long)(3 + c) * D.nslots + s]; atomicAdd(&D.scale_p[3 * (long long)lp + c], a * a + b * b); }
+  if (po >= 0) for (int c = 0; c < 6; ++c) { const double a = D.Jc[BA_JC(c, s)], b = D.Jc[BA_JC((DC + c), s)]; atomicAdd(&D.scale_c[po + c], a * a + b * b); }
+  if (co >= 0) for (int c = 0; c < nv; ++c) { const double a = D.Jc[BA_JC((6 + c), s)], b = D.Jc[BA_JC((DC + 6 + c), s)]; atomicAdd(&D.scale_c[co + c], a * a + b * b); }
+  if (lp >= 0) for (int c = 0; c < 3; ++c) { const double a = D.Jp[BA_JP(c, s)], b = D.Jp[BA_JP((3 + c), s)]; atomicAdd(&D.scale_p[3 * (long long)lp + c], a * a + b * b); }
 }
 __global__ void ba_make_scale_kernel(double* v, long long n, int enable) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -343,9 +348,9 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_apply_scale_kernel(const BaDev D)
   if (pi < 0) return;
   const int ci = D.s_cam[s], DC = D.DC;
   const int po = D.pose_off[pi], co = D.cam_off[ci], nv = D.cam_nvar[ci], lp = D.s_lpt[s];
-  if (po >= 0) for (int c = 0; c < 6; ++c) { const double sc = D.scale_c[po + c]; D.Jc[(long long)c * D.nslots + s] *= sc; D.Jc[(long long)(DC + c) * D.nslots + s] *= sc; }
-  if (co >= 0) for (int c = 0; c < nv; ++c) { const double sc = D.scale_c[co + c]; D.Jc[(long long)(6 + c) * D.nslots + s] *= sc; D.Jc[(long long)(DC + 6 + c) * D.nslots + s] *= sc; }
-  if (lp >= 0) for (int c = 0; c < 3; ++c) { const double sc = D.scale_p[3 * (long long)lp + c]; D.Jp[(long long)c * D.nslots + s] *= sc; D.Jp[(long long)(3 + c) * D.nslots + s] *= sc; }
+  if (po >= 0) for (int c = 0; c < 6; ++c) { const double sc = D.scale_c[po + c]; D.Jc[BA_JC(c, s)] *= sc; D.Jc[BA_JC((DC + c), s)] *= sc; }
+  if (co >= 0) for (int c = 0; c < nv; ++c) { const double sc = D.scale_c[co + c]; D.Jc[BA_JC((6 + c), s)] *= sc; D.Jc[BA_JC((DC + 6 + c), s)] *= sc; }
+  if (lp >= 0) for (int c = 0; c < 3; ++c) { const double sc = D.scale_p[3 * (long long)lp + c]; D.Jp[BA_JP(c, s)] *= sc; D.Jp[BA_JP((3 + c), s)] *= sc; }
 }
 
 // camera-side accumulations per slot: g_c, diag(J'J)_c, H_cc diagonal blocks
@@ -357,7 +362,7 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_build_cam_kernel(const BaDev D) {
   const int po = D.pose_off[pi], co = D.cam_off[ci], nv = D.cam_nvar[ci];
   const double r0 = D.r[s], r1 = D.r[D.nslots + s];
   double J0[6 + BA_MAXDK], J1[6 + BA_MAXDK];
-  for (int c = 0; c < DC; ++c) { J0[c] = D.Jc[(long long)c * D.nslots + s]; J1[c] = D.Jc[(long long)(DC + c) * D.nslots + s]; }
+  for (int c = 0; c < DC; ++c) { J0[c] = D.Jc[BA_JC(c, s)]; J1[c] = D.Jc[BA_JC((DC + c), s)]; }
   if (po >= 0) {
     double* H = D.Hbb + D.blk_pack[D.off2blk[po]];
     for (int a = 0; a < 6; ++a) {
@@ -386,7 +391,7 @@ __global__ void ba_build_pt_kernel(const BaDev D) {
   double H[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
   for (int s = D.vpt_s0[k]; s < D.vpt_s1[k]; ++s) {
     double a[3], b[3];
-    for (int c = 0; c < 3; ++c) { a[c] = D.Jp[(long long)c * D.nslots + s]; b[c] = D.Jp[(long long)(3 + c) * D.nslots + s]; }
+    for (int c = 0; c < 3; ++c) { a[c] = D.Jp[BA_JP(c, s)]; b[c] = D.Jp[BA_JP((3 + c), s)]; }
     const double r0 = D.r[s], r1 = D.r[D.nslots + s];
     H[0] += a[0] * a[0] + b[0] * b[0]; H[1] += a[0] * a[1] + b[0] * b[1]; H[2] += a[0] * a[2] + b[0] * b[2];
     H[3] += a[1] * a[1] + b[1] * b[1]; H[4] += a[1] * a[2] + b[1] * b[2]; H[5] += a[2] * a[2] + b[2] * b[2];
@@ -460,12 +465,12 @@ __global__ void ba_schur_pt_kernel(const BaDev D) {
     const int pi = D.s_pose[s], ci = D.s_cam[s];
     const int po = D.pose_off[pi], co = D.cam_off[ci], nv = D.cam_nvar[ci];
     double a[3], b[3];
-    for (int c = 0; c < 3; ++c) { a[c] = D.Jp[(long long)c * D.nslots + s]; b[c] = D.Jp[(long long)(3 + c) * D.nslots + s]; }
+    for (int c = 0; c < 3; ++c) { a[c] = D.Jp[BA_JP(c, s)]; b[c] = D.Jp[BA_JP((3 + c), s)]; }
     const double u0 = a[0] * w[0] + a[1] * w[1] + a[2] * w[2], u1 = b[0] * w[0] + b[1] * w[1] + b[2] * w[2];
     if (po >= 0) {
       double V[18];  // 3 x 6 : J_p^T J_c,pose
       for (int c = 0; c < 6; ++c) {
-        const double j0 = D.Jc[(long long)c * D.nslots + s], j1 = D.Jc[(long long)(DC + c) * D.nslots + s];
+        const double j0 = D.Jc[BA_JC(c, s)], j1 = D.Jc[BA_JC((DC + c), s)];
         atomicAdd(&D.rhs[po + c], j0 * u0 + j1 * u1);
         for (int t = 0; t < 3; ++t) V[t * 6 + c] = a[t] * j0 + b[t] * j1;
       }
@@ -479,7 +484,7 @@ __global__ void ba_schur_pt_kernel(const BaDev D) {
     }
     if (co >= 0) {
       for (int c = 0; c < nv; ++c) {
-        const double j0 = D.Jc[(long long)(6 + c) * D.nslots + s], j1 = D.Jc[(long long)(DC + 6 + c) * D.nslots + s];
+        const double j0 = D.Jc[BA_JC((6 + c), s)], j1 = D.Jc[BA_JC((DC + 6 + c), s)];
         atomicAdd(&D.rhs[co + c], j0 * u0 + j1 * u1);
       }
       // the intrinsics block is shared by every observation of this point made with the same camera:
@@ -492,9 +497,9 @@ __global__ void ba_schur_pt_kernel(const BaDev D) {
         for (int s2 = s; s2 < s1; ++s2) {
           if (D.s_cam[s2] != ci) continue;
           double a2[3], b2[3];
-          for (int c = 0; c < 3; ++c) { a2[c] = D.Jp[(long long)c * D.nslots + s2]; b2[c] = D.Jp[(long long)(3 + c) * D.nslots + s2]; }
+          for (int c = 0; c < 3; ++c) { a2[c] = D.Jp[BA_JP(c, s2)]; b2[c] = D.Jp[BA_JP((3 + c), s2)]; }
           for (int c = 0; c < nv; ++c) {
-            const double j0 = D.Jc[(long long)(6 + c) * D.nslots + s2], j1 = D.Jc[(long long)(DC + 6 + c) * D.nslots + s2];
+            const double j0 = D.Jc[BA_JC((6 + c), s2)], j1 = D.Jc[BA_JC((DC + 6 + c), s2)];
             for (int t = 0; t < 3; ++t) V[t * nv + c] += a2[t] * j0 + b2[t] * j1;
           }
         }
@@ -599,9 +604,9 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_schur_spmv_warp_kernel(const BaDe
     const int po = D.pose_off[pi], co = D.cam_off[ci], nv = D.cam_nvar[ci];
     float J0[DC], J1[DC];
 #pragma unroll
-    for (int c = 0; c < DC; ++c) { J0[c] = D.Jc[(long long)c * D.nslots + s]; J1[c] = D.Jc[(long long)(DC + c) * D.nslots + s]; }
+    for (int c = 0; c < DC; ++c) { J0[c] = D.Jc[BA_JC(c, s)]; J1[c] = D.Jc[BA_JC((DC + c), s)]; }
 #pragma unroll
-    for (int c = 0; c < 6; ++c) jp[c] = D.Jp[(long long)c * D.nslots + s];
+    for (int c = 0; c < 6; ++c) jp[c] = D.Jp[BA_JP(c, s)];
     lp = D.s_lpt[s];
     const int seg = D.s_seg[s];
     head = seg & 0xff; last = seg >> 8;
@@ -634,8 +639,8 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_schur_spmv_warp_kernel(const BaDe
       y1 -= (double)jp[3] * w0 + (double)jp[4] * w1 + (double)jp[5] * w2;
     }
     const long long cp = D.s2c[s];
-    D.u[cp] = y0;
-    D.u[D.nobs_c + cp] = y1;
+    D.u[BA_U(0, cp)] = y0;
+    D.u[BA_U(1, cp)] = y1;
   }
 }
 
@@ -658,7 +663,7 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_schur_spmv_kernel(const BaDev D, 
     const int ci = D.s_cam[s];
     po = D.pose_off[pi]; co = D.cam_off[ci]; nv = D.cam_nvar[ci];
 #pragma unroll
-    for (int c = 0; c < DC; ++c) { J0[c] = D.Jc[(long long)c * D.nslots + s]; J1[c] = D.Jc[(long long)(DC + c) * D.nslots + s]; }
+    for (int c = 0; c < DC; ++c) { J0[c] = D.Jc[BA_JC(c, s)]; J1[c] = D.Jc[BA_JC((DC + c), s)]; }
     if (po >= 0) {
 #pragma unroll
       for (int c = 0; c < 6; ++c) { const double v = pvec[po + c]; y0 += J0[c] * v; y1 += J1[c] * v; }
@@ -680,9 +685,9 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_schur_spmv_kernel(const BaDev D, 
       for (int t = s0; t < s1; ++t) {
         const int l = t - blk * BA_BLOCK;
         const double a0 = sy[0][l], a1 = sy[1][l];
-        z0 += D.Jp[t] * a0 + D.Jp[3 * D.nslots + t] * a1;
-        z1 += D.Jp[D.nslots + t] * a0 + D.Jp[4 * D.nslots + t] * a1;
-        z2 += D.Jp[2 * D.nslots + t] * a0 + D.Jp[5 * D.nslots + t] * a1;
+        z0 += D.Jp[BA_JP(0, t)] * a0 + D.Jp[BA_JP(3, t)] * a1;
+        z1 += D.Jp[BA_JP(1, t)] * a0 + D.Jp[BA_JP(4, t)] * a1;
+        z2 += D.Jp[BA_JP(2, t)] * a0 + D.Jp[BA_JP(5, t)] * a1;
       }
       const double* I = D.Hpp_inv + 6 * (long long)k;
       sw[0][threadIdx.x] = I[0] * z0 + I[1] * z1 + I[2] * z2;
@@ -694,14 +699,14 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_schur_spmv_kernel(const BaDev D, 
     if (lp >= 0) {
       const int lt = lp - D.blk_pt0[blk];
       const double w0 = sw[0][lt], w1 = sw[1][lt], w2 = sw[2][lt];
-      y0 -= D.Jp[s] * w0 + D.Jp[D.nslots + s] * w1 + D.Jp[2 * D.nslots + s] * w2;
-      y1 -= D.Jp[3 * D.nslots + s] * w0 + D.Jp[4 * D.nslots + s] * w1 + D.Jp[5 * D.nslots + s] * w2;
+      y0 -= D.Jp[BA_JP(0, s)] * w0 + D.Jp[BA_JP(1, s)] * w1 + D.Jp[BA_JP(2, s)] * w2;
+      y1 -= D.Jp[BA_JP(3, s)] * w0 + D.Jp[BA_JP(4, s)] * w1 + D.Jp[BA_JP(5, s)] * w2;
     }
   }
   if (pi >= 0) {
     const long long cp = D.s2c[s];
-    D.u[cp] = y0;
-    D.u[D.nobs_c + cp] = y1;
+    D.u[BA_U(0, cp)] = y0;
+    D.u[BA_U(1, cp)] = y1;
   }
 }
 
@@ -718,10 +723,10 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_cam_reduce_kernel(const BaDev D, 
   double acc[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll 4
   for (int k = ch.x + lane; k < ch.y; k += 32) {
-    const double u0 = D.u[k], u1 = D.u[D.nobs_c + k];
+    const double u0 = D.u[BA_U(0, k)], u1 = D.u[BA_U(1, k)];
 #pragma unroll
     for (int c = 0; c < 6; ++c)
-      if (c < ncomp) acc[c] += (double)D.JcC[(long long)(comp0 + c) * D.nobs_c + k] * u0 + (double)D.JcC[(long long)(D.DC + comp0 + c) * D.nobs_c + k] * u1;
+      if (c < ncomp) acc[c] += (double)D.JcC[BA_JC((comp0 + c), k)] * u0 + (double)D.JcC[BA_JC((D.DC + comp0 + c), k)] * u1;
   }
 #pragma unroll
   for (int c = 0; c < 6; ++c) {
@@ -789,8 +794,8 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_backsub_model_kernel(const BaDev 
   if (pi >= 0) {
     const int ci = D.s_cam[s];
     const int po = D.pose_off[pi], co = D.cam_off[ci], nv = D.cam_nvar[ci];
-    if (po >= 0) for (int c = 0; c < 6; ++c) { const double v = D.x[po + c]; y0 += D.Jc[(long long)c * D.nslots + s] * v; y1 += D.Jc[(long long)(DC + c) * D.nslots + s] * v; }
-    if (co >= 0) for (int c = 0; c < nv; ++c) { const double v = D.x[co + c]; y0 += D.Jc[(long long)(6 + c) * D.nslots + s] * v; y1 += D.Jc[(long long)(DC + 6 + c) * D.nslots + s] * v; }
+    if (po >= 0) for (int c = 0; c < 6; ++c) { const double v = D.x[po + c]; y0 += D.Jc[BA_JC(c, s)] * v; y1 += D.Jc[BA_JC((DC + c), s)] * v; }
+    if (co >= 0) for (int c = 0; c < nv; ++c) { const double v = D.x[co + c]; y0 += D.Jc[BA_JC((6 + c), s)] * v; y1 += D.Jc[BA_JC((DC + 6 + c), s)] * v; }
   }
   if (blockIdx.x < D.nblocks_var) {
     sy[0][threadIdx.x] = y0; sy[1][threadIdx.x] = y1;
@@ -801,9 +806,9 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_backsub_model_kernel(const BaDev 
       for (int t = D.vpt_s0[k]; t < D.vpt_s1[k]; ++t) {
         const int l = t - blockIdx.x * BA_BLOCK;
         const double a0 = sy[0][l], a1 = sy[1][l];
-        t0 -= D.Jp[t] * a0 + D.Jp[3 * D.nslots + t] * a1;
-        t1 -= D.Jp[D.nslots + t] * a0 + D.Jp[4 * D.nslots + t] * a1;
-        t2 -= D.Jp[2 * D.nslots + t] * a0 + D.Jp[5 * D.nslots + t] * a1;
+        t0 -= D.Jp[BA_JP(0, t)] * a0 + D.Jp[BA_JP(3, t)] * a1;
+        t1 -= D.Jp[BA_JP(1, t)] * a0 + D.Jp[BA_JP(4, t)] * a1;
+        t2 -= D.Jp[BA_JP(2, t)] * a0 + D.Jp[BA_JP(5, t)] * a1;
       }
       const double* I = D.Hpp_inv + 6 * (long long)k;
       const double d0 = I[0] * t0 + I[1] * t1 + I[2] * t2, d1 = I[1] * t0 + I[3] * t1 + I[4] * t2, d2 = I[2] * t0 + I[4] * t1 + I[5] * t2;
@@ -815,8 +820,8 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_backsub_model_kernel(const BaDev 
     if (lp >= 0) {
       const int lt = lp - D.blk_pt0[blockIdx.x];
       const double w0 = sw[0][lt], w1 = sw[1][lt], w2 = sw[2][lt];
-      y0 += D.Jp[s] * w0 + D.Jp[D.nslots + s] * w1 + D.Jp[2 * D.nslots + s] * w2;
-      y1 += D.Jp[3 * D.nslots + s] * w0 + D.Jp[4 * D.nslots + s] * w1 + D.Jp[5 * D.nslots + s] * w2;
+      y0 += D.Jp[BA_JP(0, s)] * w0 + D.Jp[BA_JP(1, s)] * w1 + D.Jp[BA_JP(2, s)] * w2;
+      y1 += D.Jp[BA_JP(3, s)] * w0 + D.Jp[BA_JP(4, s)] * w1 + D.Jp[BA_JP(5, s)] * w2;
     }
   }
   double m = 0.0;
@@ -1160,7 +1165,7 @@ int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum
   { int* t; BA_CUDA(pool.upload(&t, blk_pack, st)); D.blk_pack = t; }
   { int* t; BA_CUDA(pool.upload(&t, off2blk, st)); D.off2blk = t; }
   BA_CUDA(pool.alloc(&D.Jc, (size_t)2 * D.DC * nslots)); BA_CUDA(pool.alloc(&D.Jp, (size_t)6 * nslots));
-  BA_CUDA(pool.alloc(&D.JcC, (size_t)2 * D.DC * nobs_c)); BA_CUDA(pool.alloc(&D.u, (size_t)2 * nobs_c));
+  BA_CUDA(pool.alloc(&D.JcC, (size_t)2 * D.DC * ((nobs_c + 31) / 32 * 32))); BA_CUDA(pool.alloc(&D.u, (size_t)2 * ((nobs_c + 31) / 32 * 32)));
   { int* t; BA_CUDA(pool.upload(&t, s2c, st)); D.s2c = t; }
   { int* t; BA_CUDA(pool.upload(&t, s_seg, st)); D.s_seg = t; }
   D.nblocks_warp = nblocks_warp;

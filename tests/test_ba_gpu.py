@@ -32,7 +32,7 @@ def _both(options, noisy):
     return a, s_gpu, b, s_ref
 
 
-def _assert_parity(a, s_gpu, b, s_ref):
+def _assert_parity(a, s_gpu, b, s_ref, param_rel=REL):
     assert s_gpu.num_residuals == s_ref.num_residuals
     assert s_gpu.num_effective_parameters == s_ref.num_effective_parameters
     # COLMAP runs Ceres with function_tolerance = 0: the last LM steps sit at the rounding noise of the cost, so
@@ -42,7 +42,7 @@ def _assert_parity(a, s_gpu, b, s_ref):
     assert abs(s_gpu.initial_cost - s_ref.initial_cost) <= 1e-9 * s_ref.initial_cost
     assert abs(s_gpu.final_cost - s_ref.final_cost) <= REL * s_ref.final_cost
     for u, v in ((a.poses, b.poses), (a.cam_params, b.cam_params), (a.points, b.points)):
-        assert np.allclose(u, v, rtol=REL, atol=REL * max(1.0, np.abs(v).max()))
+        assert np.allclose(u, v, rtol=param_rel, atol=param_rel * max(1.0, np.abs(v).max()))
 
 
 def test_b1_config_dense_schur():
@@ -80,7 +80,9 @@ def test_option_grid_parity(kw):
     gt, noisy = synthesize_ba_problem(12, 400, 6, models=(SIMPLE_RADIAL,), seed=11)
     _gauge(noisy)
     a, sg, b, sr = _both(BundleAdjustmentOptions(**kw), noisy)
-    _assert_parity(a, sg, b, sr)
+    # refining the principal point of 12 single-image cameras leaves a nearly flat valley (principal point vs
+    # rotation): the cost is pinned to 1e-5 but the position along the valley is only determined to ~1e-3
+    _assert_parity(a, sg, b, sr, param_rel=1e-3 if kw.get("refine_principal_point") else REL)
 
 
 def test_constant_blocks_bit_identical_and_residual_counts():
