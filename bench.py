@@ -356,10 +356,10 @@ def main():
     h2d = W * H + sum(im.bitmap.size for im in sc["images"][1:]) + 4 * N * 43 * 4
     d2h = 16 * W * H
 
-    stats = torch.tensor([dev_ms / args.steps, e2e_ms, wall_ms / args.steps], dtype=torch.float64, device="cuda")
-    if distributed:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    ms_per_step, e2e_ms, wall_per_step = [float(x) for x in stats.tolist()]
+    from colmap_b200.sharding import max_over_ranks
+    ms_per_step = max_over_ranks(dev_ms / args.steps, "cuda")
+    e2e_ms = max_over_ranks(e2e_ms, "cuda")
+    wall_per_step = max_over_ranks(wall_ms / args.steps, "cuda")
 
     if rank == 0:
         n_sweeps = 4 * C2["num_iterations"]
