@@ -37,6 +37,7 @@
 #define BA_JC(k, s) ((((long long)(s) >> 5) * (2 * D.DC) + (k)) * 32 + ((s) & 31))
 #define BA_JP(k, s) ((((long long)(s) >> 5) * 6 + (k)) * 32 + ((s) & 31))
 #define BA_U(k, s) ((((long long)(s) >> 5) * 2 + (k)) * 32 + ((s) & 31))
+#define BA_T(k, s) ((((long long)(s) >> 5) * 21 + (k)) * 32 + ((s) & 31))
 
 // ------------------------------------------------------------------------------------------------
 // camera models + reprojection (host/device so the CPU test tier can check them without a GPU)
@@ -202,6 +203,8 @@ struct BaDev {
   const int* s_seg;                   // [nslots] head lane | last lane << 8 of the slot's track inside its warp (warp-packed region)
   int nblocks_warp;                   // leading blocks whose tracks never cross a warp (tracks <= 32 observations)
   double* u;                          // [2][nobs_c] per-observation 2-vector exchanged between the two SpMV passes
+  double* rC;                         // [2][nobs_c] residuals in camera order
+  double* T21;                        // [21][nobs_c] per-observation V^T Hinv V (pose block, symmetric) scratch
   const int4* chunks;                 // {c0, c1, out offset, comp0 | ncomp << 8}: <= BA_CHUNK observations of one block
   int nchunks; long long nobs_c;
   double* cost_slot;                  // [nslots] 1/2 rho(|r|^2) at the linearisation point
@@ -312,6 +315,8 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_linearize_kernel(const BaDev D, c
       for (int k = 0; k < 6; ++k) D.Jp[BA_JP(k, s)] = (float)Jpt[k];
       D.r[s] = rs * res[0];
       D.r[D.nslots + s] = rs * res[1];
+      D.rC[BA_U(0, cp)] = rs * res[0];
+      D.rC[BA_U(1, cp)] = rs * res[1];
     }
   } else if (MODE) {
     for (int k = 0; k < 2 * D.DC; ++k) D.Jc[BA_JC(k, s)] = 0.0;
@@ -428,6 +433,122 @@ __global__ void ba_gradmax_kernel(const BaDev D) {
   }
 }
 
+// camera-side accumulations without per-observation atomics: one warp per chunk of a block's observations in
+// camera order: g_c and the diagonal block of H_cc (both triangles), reduced with shuffles, one red.add per entry
+__global__ void __launch_bounds__(BA_BLOCK) ba_build_cam_sorted_kernel(const BaDev D) {
+  const int chunk = blockIdx.x * (BA_BLOCK / 32) + (threadIdx.x >> 5);
+  if (chunk >= D.nchunks) return;
+  const int lane = threadIdx.x & 31;
+  const int4 ch = D.chunks[chunk];
+  const int comp0 = ch.w & 0xff, n = ch.w >> 8;
+  double g[6] = {0, 0, 0, 0, 0, 0}, H[21];
+#pragma unroll
+  for (int i = 0; i < 21; ++i) H[i] = 0.0;
+  for (int k = ch.x + lane; k < ch.y; k += 32) {
+    const double r0 = D.rC[BA_U(0, k)], r1 = D.rC[BA_U(1, k)];
+    double a[6], b[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      a[c] = (c < n) ? (double)D.JcC[BA_JC(comp0 + c, k)] : 0.0;
+      b[c] = (c < n) ? (double)D.JcC[BA_JC(D.DC + comp0 + c, k)] : 0.0;
+      g[c] += a[c] * r0 + b[c] * r1;
+    }
+    int idx = 0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = r; c < 6; ++c) H[idx++] += a[r] * a[c] + b[r] * b[c];
+  }
+  double* Hb = D.Hbb + D.blk_pack[D.off2blk[ch.z]];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    double t = g[c];
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0 && c < n) atomicAdd(&D.gc[ch.z + c], t);
+  }
+  int idx = 0;
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = r; c < 6; ++c) {
+      double t = H[idx++];
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0 && r < n && c < n) { atomicAdd(&Hb[r * n + c], t); if (c != r) atomicAdd(&Hb[c * n + r], t); }
+    }
+}
+
+// per slot: u = J_p Hinv g_p (for the reduced right-hand side) and T = V^T Hinv V with V = J_p^T J_c,pose (the
+// point term of the pose's SCHUR_JACOBI block), both written in camera order for the chunk reductions
+__global__ void __launch_bounds__(BA_BLOCK) ba_schur_slot_kernel(const BaDev D) {
+  const long long s = (long long)blockIdx.x * BA_BLOCK + threadIdx.x;
+  const int pi = D.s_pose[s];
+  if (pi < 0) return;
+  const long long cp = D.s2c[s];
+  const int lp = D.s_lpt[s];
+  double u0 = 0.0, u1 = 0.0;
+  double T[21];
+#pragma unroll
+  for (int i = 0; i < 21; ++i) T[i] = 0.0;
+  if (lp >= 0) {
+    const double* I = D.Hpp_inv + 6 * (long long)lp;
+    const double Hi[9] = {I[0], I[1], I[2], I[1], I[3], I[4], I[2], I[4], I[5]};
+    const double g0 = D.gp[3 * (long long)lp], g1 = D.gp[3 * (long long)lp + 1], g2 = D.gp[3 * (long long)lp + 2];
+    const double w0 = Hi[0] * g0 + Hi[1] * g1 + Hi[2] * g2, w1 = Hi[3] * g0 + Hi[4] * g1 + Hi[5] * g2, w2 = Hi[6] * g0 + Hi[7] * g1 + Hi[8] * g2;
+    double a[3], b[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { a[c] = D.Jp[BA_JP(c, s)]; b[c] = D.Jp[BA_JP(3 + c, s)]; }
+    u0 = a[0] * w0 + a[1] * w1 + a[2] * w2;
+    u1 = b[0] * w0 + b[1] * w1 + b[2] * w2;
+    if (D.pose_off[pi] >= 0) {
+      double V[18], G[18];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const double j0 = D.Jc[BA_JC(c, s)], j1 = D.Jc[BA_JC(D.DC + c, s)];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) V[t * 6 + c] = a[t] * j0 + b[t] * j1;
+      }
+#pragma unroll
+      for (int c = 0; c < 6; ++c)
+#pragma unroll
+        for (int t = 0; t < 3; ++t) G[t * 6 + c] = Hi[3 * t] * V[c] + Hi[3 * t + 1] * V[6 + c] + Hi[3 * t + 2] * V[12 + c];
+      int idx = 0;
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = r; c < 6; ++c) T[idx++] = V[r] * G[c] + V[6 + r] * G[6 + c] + V[12 + r] * G[12 + c];
+    }
+  }
+  D.u[BA_U(0, cp)] = u0;
+  D.u[BA_U(1, cp)] = u1;
+#pragma unroll
+  for (int i = 0; i < 21; ++i) D.T21[BA_T(i, cp)] = T[i];
+}
+// Mbb(pose block) -= sum over the pose's observations of T
+__global__ void __launch_bounds__(BA_BLOCK) ba_pose_block_reduce_kernel(const BaDev D) {
+  const int chunk = blockIdx.x * (BA_BLOCK / 32) + (threadIdx.x >> 5);
+  if (chunk >= D.nchunks) return;
+  const int4 ch = D.chunks[chunk];
+  if ((ch.w & 0xff) != 0) return;  // pose chunks only
+  const int lane = threadIdx.x & 31;
+  double T[21];
+#pragma unroll
+  for (int i = 0; i < 21; ++i) T[i] = 0.0;
+  for (int k = ch.x + lane; k < ch.y; k += 32) {
+#pragma unroll
+    for (int i = 0; i < 21; ++i) T[i] += D.T21[BA_T(i, k)];
+  }
+  double* M = D.Mbb + D.blk_pack[D.off2blk[ch.z]];
+  int idx = 0;
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = r; c < 6; ++c) {
+      double t = T[idx++];
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) { atomicAdd(&M[r * 6 + c], -t); if (c != r) atomicAdd(&M[c * 6 + r], -t); }
+    }
+}
+
 // (H_pp + D_p^2)^-1 per point
 __global__ void ba_damp_pt_kernel(const BaDev D, double inv_radius, double dmin, double dmax, int* fail) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -452,65 +573,39 @@ __global__ void ba_damp_cam_kernel(const BaDev D, double inv_radius, double dmin
   const int b = D.off2blk[i], n = D.blk_start[b + 1] - D.blk_start[b], l = i - D.blk_start[b];
   for (int c = 0; c < n; ++c) D.Mbb[D.blk_pack[b] + l * n + c] = D.Hbb[D.blk_pack[b] + l * n + c] + (c == l ? d : 0.0);
 }
-// per point: reduced rhs += J_c^T J_p Hinv g_p ; SCHUR_JACOBI blocks -= V^T Hinv V (exact, incl. shared intrinsics)
+// per point: the point term of the INTRINSICS blocks of SCHUR_JACOBI, -= V^T Hinv V with V summed over every
+// observation of the track made with the same camera (exact cross terms for shared intrinsics).  The pose blocks
+// and the reduced right-hand side are handled by ba_schur_slot_kernel + the camera-order reductions.
 __global__ void ba_schur_pt_kernel(const BaDev D) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= D.nvpt) return;
   const double* I = D.Hpp_inv + 6 * (long long)k;
   const double Hi[9] = {I[0], I[1], I[2], I[1], I[3], I[4], I[2], I[4], I[5]};
-  const double g0 = D.gp[3 * (long long)k], g1 = D.gp[3 * (long long)k + 1], g2 = D.gp[3 * (long long)k + 2];
-  const double w[3] = {Hi[0] * g0 + Hi[1] * g1 + Hi[2] * g2, Hi[3] * g0 + Hi[4] * g1 + Hi[5] * g2, Hi[6] * g0 + Hi[7] * g1 + Hi[8] * g2};
-  const int DC = D.DC, s0 = D.vpt_s0[k], s1 = D.vpt_s1[k];
+  const int s0 = D.vpt_s0[k], s1 = D.vpt_s1[k];
   for (int s = s0; s < s1; ++s) {
-    const int pi = D.s_pose[s], ci = D.s_cam[s];
-    const int po = D.pose_off[pi], co = D.cam_off[ci], nv = D.cam_nvar[ci];
-    double a[3], b[3];
-    for (int c = 0; c < 3; ++c) { a[c] = D.Jp[BA_JP(c, s)]; b[c] = D.Jp[BA_JP((3 + c), s)]; }
-    const double u0 = a[0] * w[0] + a[1] * w[1] + a[2] * w[2], u1 = b[0] * w[0] + b[1] * w[1] + b[2] * w[2];
-    if (po >= 0) {
-      double V[18];  // 3 x 6 : J_p^T J_c,pose
-      for (int c = 0; c < 6; ++c) {
-        const double j0 = D.Jc[BA_JC(c, s)], j1 = D.Jc[BA_JC((DC + c), s)];
-        atomicAdd(&D.rhs[po + c], j0 * u0 + j1 * u1);
-        for (int t = 0; t < 3; ++t) V[t * 6 + c] = a[t] * j0 + b[t] * j1;
-      }
-      double* M = D.Mbb + D.blk_pack[D.off2blk[po]];
-      for (int r = 0; r < 6; ++r) {
-        const double t0 = V[r] * Hi[0] + V[6 + r] * Hi[3] + V[12 + r] * Hi[6];
-        const double t1 = V[r] * Hi[1] + V[6 + r] * Hi[4] + V[12 + r] * Hi[7];
-        const double t2 = V[r] * Hi[2] + V[6 + r] * Hi[5] + V[12 + r] * Hi[8];
-        for (int c = 0; c < 6; ++c) atomicAdd(&M[r * 6 + c], -(t0 * V[c] + t1 * V[6 + c] + t2 * V[12 + c]));
+    const int ci = D.s_cam[s];
+    const int co = D.cam_off[ci], nv = D.cam_nvar[ci];
+    if (co < 0) continue;
+    bool first = true;
+    for (int s2 = s0; s2 < s && first; ++s2) if (D.s_cam[s2] == ci) first = false;
+    if (!first) continue;
+    double V[15];
+    for (int t = 0; t < 3 * nv; ++t) V[t] = 0.0;
+    for (int s2 = s; s2 < s1; ++s2) {
+      if (D.s_cam[s2] != ci) continue;
+      double a2[3], b2[3];
+      for (int c = 0; c < 3; ++c) { a2[c] = D.Jp[BA_JP(c, s2)]; b2[c] = D.Jp[BA_JP(3 + c, s2)]; }
+      for (int c = 0; c < nv; ++c) {
+        const double j0 = D.Jc[BA_JC(6 + c, s2)], j1 = D.Jc[BA_JC(D.DC + 6 + c, s2)];
+        for (int t = 0; t < 3; ++t) V[t * nv + c] += a2[t] * j0 + b2[t] * j1;
       }
     }
-    if (co >= 0) {
-      for (int c = 0; c < nv; ++c) {
-        const double j0 = D.Jc[BA_JC((6 + c), s)], j1 = D.Jc[BA_JC((DC + 6 + c), s)];
-        atomicAdd(&D.rhs[co + c], j0 * u0 + j1 * u1);
-      }
-      // the intrinsics block is shared by every observation of this point made with the same camera:
-      // handle the block once, at its first occurrence inside the track
-      bool first = true;
-      for (int s2 = s0; s2 < s && first; ++s2) if (D.s_cam[s2] == ci) first = false;
-      if (first) {
-        double V[15];
-        for (int t = 0; t < 3 * nv; ++t) V[t] = 0.0;
-        for (int s2 = s; s2 < s1; ++s2) {
-          if (D.s_cam[s2] != ci) continue;
-          double a2[3], b2[3];
-          for (int c = 0; c < 3; ++c) { a2[c] = D.Jp[BA_JP(c, s2)]; b2[c] = D.Jp[BA_JP((3 + c), s2)]; }
-          for (int c = 0; c < nv; ++c) {
-            const double j0 = D.Jc[BA_JC((6 + c), s2)], j1 = D.Jc[BA_JC((DC + 6 + c), s2)];
-            for (int t = 0; t < 3; ++t) V[t * nv + c] += a2[t] * j0 + b2[t] * j1;
-          }
-        }
-        double* M = D.Mbb + D.blk_pack[D.off2blk[co]];
-        for (int r = 0; r < nv; ++r) {
-          const double t0 = V[r] * Hi[0] + V[nv + r] * Hi[3] + V[2 * nv + r] * Hi[6];
-          const double t1 = V[r] * Hi[1] + V[nv + r] * Hi[4] + V[2 * nv + r] * Hi[7];
-          const double t2 = V[r] * Hi[2] + V[nv + r] * Hi[5] + V[2 * nv + r] * Hi[8];
-          for (int c = 0; c < nv; ++c) atomicAdd(&M[r * nv + c], -(t0 * V[c] + t1 * V[nv + c] + t2 * V[2 * nv + c]));
-        }
-      }
+    double* M = D.Mbb + D.blk_pack[D.off2blk[co]];
+    for (int r = 0; r < nv; ++r) {
+      const double t0 = V[r] * Hi[0] + V[nv + r] * Hi[3] + V[2 * nv + r] * Hi[6];
+      const double t1 = V[r] * Hi[1] + V[nv + r] * Hi[4] + V[2 * nv + r] * Hi[7];
+      const double t2 = V[r] * Hi[2] + V[nv + r] * Hi[5] + V[2 * nv + r] * Hi[8];
+      for (int c = 0; c < nv; ++c) atomicAdd(&M[r * nv + c], -(t0 * V[c] + t1 * V[nv + c] + t2 * V[2 * nv + c]));
     }
   }
 }
@@ -1165,7 +1260,7 @@ int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum
   { int* t; BA_CUDA(pool.upload(&t, blk_pack, st)); D.blk_pack = t; }
   { int* t; BA_CUDA(pool.upload(&t, off2blk, st)); D.off2blk = t; }
   BA_CUDA(pool.alloc(&D.Jc, (size_t)2 * D.DC * nslots)); BA_CUDA(pool.alloc(&D.Jp, (size_t)6 * nslots));
-  BA_CUDA(pool.alloc(&D.JcC, (size_t)2 * D.DC * ((nobs_c + 31) / 32 * 32))); BA_CUDA(pool.alloc(&D.u, (size_t)2 * ((nobs_c + 31) / 32 * 32)));
+  BA_CUDA(pool.alloc(&D.JcC, (size_t)2 * D.DC * ((nobs_c + 31) / 32 * 32))); BA_CUDA(pool.alloc(&D.u, (size_t)2 * ((nobs_c + 31) / 32 * 32))); BA_CUDA(pool.alloc(&D.rC, (size_t)2 * ((nobs_c + 31) / 32 * 32))); BA_CUDA(pool.alloc(&D.T21, (size_t)21 * ((nobs_c + 31) / 32 * 32)));
   { int* t; BA_CUDA(pool.upload(&t, s2c, st)); D.s2c = t; }
   { int* t; BA_CUDA(pool.upload(&t, s_seg, st)); D.s_seg = t; }
   D.nblocks_warp = nblocks_warp;
@@ -1227,7 +1322,7 @@ int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum
     BA_CUDA(cudaMemsetAsync(D.gc, 0, sizeof(double) * (nc ? nc : 1), st));
     BA_CUDA(cudaMemsetAsync(D.Hbb, 0, sizeof(double) * (pack ? pack : 1), st));
     BA_CUDA(zero_field(&D.ctl->gmax));
-    ba_build_cam_kernel<<<nblocks, BA_BLOCK, 0, st>>>(D);
+    if (D.nchunks) ba_build_cam_sorted_kernel<<<(D.nchunks + 7) / 8, BA_BLOCK, 0, st>>>(D);
     if (nc) ba_diag_from_blocks_kernel<<<gc_blocks, 256, 0, st>>>(D);
     if (nvpt) ba_build_pt_kernel<<<gp_blocks, 256, 0, st>>>(D);
     { const long long n = (long long)NP + NCAM + 3LL * nvpt; ba_gradmax_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(D); }
@@ -1242,7 +1337,13 @@ int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum
       BA_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
       if (nvpt) ba_damp_pt_kernel<<<gp_blocks, 256, 0, st>>>(D, 1.0 / radius, o->min_lm_diagonal, o->max_lm_diagonal, d_fail);
       if (nc) ba_damp_cam_kernel<<<gc_blocks, 256, 0, st>>>(D, 1.0 / radius, o->min_lm_diagonal, o->max_lm_diagonal);
-      if (nvpt && nc) ba_schur_pt_kernel<<<gp_blocks, 256, 0, st>>>(D);
+      if (nvpt && nc) {
+        ba_schur_slot_kernel<<<nblocks, BA_BLOCK, 0, st>>>(D);
+        ba_cam_reduce_kernel<<<(D.nchunks + 7) / 8, BA_BLOCK, 0, st>>>(D, D.rhs, 0);
+        ba_pose_block_reduce_kernel<<<(D.nchunks + 7) / 8, BA_BLOCK, 0, st>>>(D);
+        if (dkmax > 0) ba_schur_pt_kernel<<<gp_blocks, 256, 0, st>>>(D);
+        launches += 3;
+      }
       if (nblk) ba_invert_blocks_kernel<<<(nblk + 127) / 128, 128, 0, st>>>(D);
       launches += 4;
       // PCG
