@@ -70,6 +70,7 @@ struct PmSweepArgs {
   // split pipeline scratch (per pixel, original-orientation pixel index)
   float4* rand_hyp;        // random hypothesis of the pixel in the sweep frame {depth, n}
   unsigned char* ntrials;  // PerturbNormal rounds consumed (each 3 draws)
+  float* usamp;            // [pixel][num_samples] Monte-Carlo uniforms (already minus FLT_EPSILON, :1129)
   float* prior3;           // [pixel][3][N] triangulation / incident / resolution priors of the current hypothesis
   float* tab3;             // [pixel][3][N] NCC of hypotheses 2,3,4 for every source image
   float* gtab2;            // [pixel][2][N] geometric cost at cur / rand depth (geom mode)
@@ -586,9 +587,11 @@ __global__ void pm_rand_kernel(const PmParams P, const PmSweepArgs A) {
     const int rounds = pm_perturb_normal(iK, (float)row, colf, A.perturbation_pi, n0, n1, cur4.w, rs, rn);
     A.rand_hyp[p] = make_float4(rand_d, rn[0], rn[1], rn[2]);
     A.ntrials[p] = (unsigned char)rounds;
-    for (int s = 0; s < P.num_samples; ++s) pm_rng_next(rs);
+    for (int s = 0; s < P.num_samples; ++s) A.usamp[p * P.num_samples + s] = pm_rng_uniform(rs) - FLT_EPSILON;
     p = pn; cur4 = next4;
   }
+  uint32_t* wslot = P.rng + 6 * (size_t)pm_border_index(P.W0, P.H0, r0, c0);
+  wslot[0] = rs.v0; wslot[1] = rs.v1; wslot[2] = rs.v2; wslot[3] = rs.v3; wslot[4] = rs.v4; wslot[5] = rs.d;
 }
 
 template <bool GEOM>
@@ -608,7 +611,15 @@ __global__ void __launch_bounds__(128, 8) pm_pixel_kernel(const PmParams P, cons
   const int g = lane >> 3, sub = lane & 7;
   const unsigned gmask = 0xffu << (8 * g);
   const int npairs = 3 * N;
-  for (size_t q = (size_t)blockIdx.x * 4 + warp; q < npix; q += (size_t)gridDim.x * 4) {
+  // Pixel order: the grid is 148 * R CTAs; CTAs b, b + 148, ... are co-resident on one SM (round-robin placement), so
+  // giving them the 4*R consecutive pixels of one tile makes their source-image footprints overlap in that SM's L1.
+  const int per_sm = (gridDim.x + 147) / 148;                 // CTAs per SM slot
+  const int sm_slot = blockIdx.x % 148, k_in_sm = blockIdx.x / 148;
+  const size_t tile = (size_t)per_sm * 4;                      // pixels processed per SM per iteration
+  for (size_t it = 0;; ++it) {
+    const size_t q = (it * 148 + sm_slot) * tile + (size_t)k_in_sm * 4 + warp;
+    if ((it * 148) * tile >= npix) break;
+    if (q >= npix) continue;
     const int row = (int)(q / fw), col = (int)(q - (size_t)row * fw);  // sweep-frame pixel
     const size_t p = pm_pix0(P.W0, P.H0, rot, row, col);
     const float rowf = (float)row, colf = (float)col;
@@ -678,9 +689,8 @@ __global__ void __launch_bounds__(32 * WPC) pm_serial_kernel(const PmParams P, c
   __syncthreads();
 
   float fwd = 0.5f;
-  PmRng rs;
   float prev_d = 0.0f, prev_n0 = 0.0f, prev_n1 = 0.0f, prev_n2 = 0.0f;
-  uint32_t* rng_slot = nullptr;
+  const int ns = P.num_samples;
   if (warp == 0) {
     if (img_lane) {  // backward messages (:976-989)
       float beta = 0.5f;
@@ -692,8 +702,6 @@ __global__ void __launch_bounds__(32 * WPC) pm_serial_kernel(const PmParams P, c
     }
     int r0, c0;
     pm_frame_to_orig(P.W0, P.H0, rot, 0, col, &r0, &c0);
-    rng_slot = P.rng + 6 * (size_t)pm_border_index(P.W0, P.H0, r0, c0);
-    rs.v0 = rng_slot[0]; rs.v1 = rng_slot[1]; rs.v2 = rng_slot[2]; rs.v3 = rng_slot[3]; rs.v4 = rng_slot[4]; rs.d = rng_slot[5];
     const float4 h0 = P.hyp[(size_t)r0 * P.W0 + c0];
     prev_d = h0.x; prev_n0 = h0.y; prev_n1 = h0.z; prev_n2 = h0.w;
     pm_normal_to_frame(rot, prev_n0, prev_n1);
@@ -702,14 +710,14 @@ __global__ void __launch_bounds__(32 * WPC) pm_serial_kernel(const PmParams P, c
   // software pipeline: the per-row inputs do not depend on the sweep state, so warp 0 fetches row + 1 while
   // row is being processed (takes two L2 round trips off the per-row critical path)
   float4 nx_cur4 = make_float4(0.f, 0.f, 0.f, 0.f), nx_r4 = nx_cur4;
-  int nx_skip = 0;
+  float nx_u = 2.0f;
   float nx_cost = 0.f, nx_beta = 0.f, nx_prevp = 0.f, nx_t = 0.f, nx_i = 0.f, nx_r = 0.f, nx_c2 = 0.f, nx_c3 = 0.f, nx_c4 = 0.f,
         nx_gc = 0.f, nx_gr = 0.f;
   auto fetch_row = [&](int row) {
     const size_t p = pm_pix0(P.W0, P.H0, rot, row, col);
     nx_cur4 = P.hyp[p];
     nx_r4 = A.rand_hyp[p];
-    nx_skip = 1 + 3 * (int)A.ntrials[p];
+    nx_u = (lane < ns) ? A.usamp[p * ns + lane] : 2.0f;   // first 32 Monte-Carlo uniforms, one per lane
     if (img_lane) {
       nx_cost = P.cost[p * N + lane];
       nx_beta = A.sel_cur[p * N + lane];
@@ -734,15 +742,14 @@ __global__ void __launch_bounds__(32 * WPC) pm_serial_kernel(const PmParams P, c
     float c2 = 0.0f, c3 = 0.0f, c4 = 0.0f, g_cur = 0.0f, g_rand = 0.0f;
     float cur_d = 0.0f, cur_n0 = 0.0f, cur_n1 = 0.0f, cur_n2 = 0.0f;
     float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float u_first = 2.0f;
     if (warp == 0) {
       prev_d = pm_propagate_depth(iK, prev_d, prev_n1, prev_n2, (float)(row - 1), rowf);
       const float4 cur4 = nx_cur4;
       cur_d = cur4.x; cur_n0 = cur4.y; cur_n1 = cur4.z; cur_n2 = cur4.w;
       pm_normal_to_frame(rot, cur_n0, cur_n1);
       r4 = nx_r4;
-      // stream position: 1 depth draw + 3 per PerturbNormal round were consumed by pass R
-      const int skip = nx_skip;
-      for (int s = 0; s < skip; ++s) pm_rng_next(rs);
+      u_first = nx_u;
       float prob = 0.0f;
       if (img_lane) {
         cost_i = nx_cost; beta_i = nx_beta; prevp_i = nx_prevp;
@@ -787,23 +794,33 @@ __global__ void __launch_bounds__(32 * WPC) pm_serial_kernel(const PmParams P, c
         g_prev = pm_geom_cost(poses + lane * PM_POSE_STRIDE, Kr, iK, P.src_depth + sd.depth_off, sd.w, sd.h, rowf, colf,
                               prev_d, P.geom_max_cost);
       }
-      // Monte-Carlo accumulation in sample order (:1128-1173); every lane keeps the five sums
+      // Monte-Carlo accumulation (:1128-1173).  The uniforms were drawn by pass R; lanes pick the sampled image of
+      // one sample each, then the five cost sums are accumulated in sample order (a skipped sample adds +0, exact).
       float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f, a4 = 0.0f;
-      for (int s = 0; s < P.num_samples; ++s) {
-        const float u = pm_rng_uniform(rs) - FLT_EPSILON;
-        const unsigned m = __ballot_sync(0xffffffffu, img_lane && (cdf > u));
-        if (!m) continue;
-        const int img = __ffs(m) - 1;
-        a0 += __shfl_sync(0xffffffffu, cost_i, img);
-        a1 += __shfl_sync(0xffffffffu, c1, img);
-        a2 += __shfl_sync(0xffffffffu, c2, img);
-        a3 += __shfl_sync(0xffffffffu, c3, img);
-        a4 += __shfl_sync(0xffffffffu, c4, img);
-        if (GEOM) {
-          const float gc = __shfl_sync(0xffffffffu, g_cur, img), gp = __shfl_sync(0xffffffffu, g_prev, img),
-                      gr = __shfl_sync(0xffffffffu, g_rand, img);
-          a0 = fmaf(P.geom_reg, gc, a0); a1 = fmaf(P.geom_reg, gp, a1); a2 = fmaf(P.geom_reg, gr, a2);
-          a3 = fmaf(P.geom_reg, gc, a3); a4 = fmaf(P.geom_reg, gr, a4);
+      for (int base = 0; base < ns; base += 32) {
+        const int sidx = base + lane;
+        const float u = (base == 0) ? u_first : ((sidx < ns) ? A.usamp[p * ns + sidx] : 2.0f);
+        int img = -1;
+        for (int i = 0; i < N; ++i) {
+          const float ci = __shfl_sync(0xffffffffu, cdf, i);
+          if (img < 0 && ci > u) img = i;
+        }
+        const int src = img < 0 ? 0 : img;
+        float v0 = __shfl_sync(0xffffffffu, cost_i, src), v1 = __shfl_sync(0xffffffffu, c1, src),
+              v2 = __shfl_sync(0xffffffffu, c2, src), v3 = __shfl_sync(0xffffffffu, c3, src),
+              v4 = __shfl_sync(0xffffffffu, c4, src);
+        float gcv = 0.0f, gpv = 0.0f, grv = 0.0f;
+        if (GEOM) { gcv = __shfl_sync(0xffffffffu, g_cur, src); gpv = __shfl_sync(0xffffffffu, g_prev, src); grv = __shfl_sync(0xffffffffu, g_rand, src); }
+        if (img < 0) { v0 = v1 = v2 = v3 = v4 = 0.0f; gcv = gpv = grv = 0.0f; }
+        const int cnt = min(32, ns - base);
+        for (int j = 0; j < cnt; ++j) {
+          a0 += __shfl_sync(0xffffffffu, v0, j); a1 += __shfl_sync(0xffffffffu, v1, j); a2 += __shfl_sync(0xffffffffu, v2, j);
+          a3 += __shfl_sync(0xffffffffu, v3, j); a4 += __shfl_sync(0xffffffffu, v4, j);
+          if (GEOM) {
+            const float gc = __shfl_sync(0xffffffffu, gcv, j), gp = __shfl_sync(0xffffffffu, gpv, j), gr = __shfl_sync(0xffffffffu, grv, j);
+            a0 = fmaf(P.geom_reg, gc, a0); a1 = fmaf(P.geom_reg, gp, a1); a2 = fmaf(P.geom_reg, gr, a2);
+            a3 = fmaf(P.geom_reg, gc, a3); a4 = fmaf(P.geom_reg, gr, a4);
+          }
         }
       }
       int best = 0;
@@ -867,9 +884,6 @@ __global__ void __launch_bounds__(32 * WPC) pm_serial_kernel(const PmParams P, c
       prev_d = best_d; prev_n0 = bn0; prev_n1 = bn1; prev_n2 = bn2;
     }
   }
-  if (warp == 0 && lane == 0) {
-    rng_slot[0] = rs.v0; rng_slot[1] = rs.v1; rng_slot[2] = rs.v2; rng_slot[3] = rs.v3; rng_slot[4] = rs.v4; rng_slot[5] = rs.d;
-  }
 }
 
 // exhaustive check of pm_rcp_clamped against the IEEE division over all float bit patterns
@@ -927,7 +941,7 @@ struct b200pm_context {
   std::vector<int> src_image_idxs;
   size_t smem_sweep = 0, smem_init = 0, smem_serial = 0;
   bool fused = false;
-  float4* rand_hyp = nullptr; unsigned char* ntrials = nullptr; float* prior3 = nullptr; float* tab3 = nullptr; float* gtab2 = nullptr;
+  float4* rand_hyp = nullptr; unsigned char* ntrials = nullptr; float* usamp = nullptr; float* prior3 = nullptr; float* tab3 = nullptr; float* gtab2 = nullptr;
 };
 
 template <typename T>
@@ -1173,6 +1187,7 @@ int b200pm_create(const b200pm_options* o, const b200pm_problem* p, b200pm_handl
   if (!c->fused) {
     PM_CUDA(pm_alloc(c, &c->rand_hyp, n));
     PM_CUDA(pm_alloc(c, &c->ntrials, n));
+    PM_CUDA(pm_alloc(c, &c->usamp, n * (size_t)o->num_samples));
     PM_CUDA(pm_alloc(c, &c->prior3, 3 * n * N));
     PM_CUDA(pm_alloc(c, &c->tab3, 3 * n * N));
     if (P.geom) PM_CUDA(pm_alloc(c, &c->gtab2, 2 * n * N));
@@ -1259,10 +1274,10 @@ int b200pm_run(b200pm_handle c) {
         else pm_launch_sweep<4>(c, A, fw);
         ++launches;
       } else {
-        A.rand_hyp = c->rand_hyp; A.ntrials = c->ntrials; A.prior3 = c->prior3; A.tab3 = c->tab3; A.gtab2 = c->gtab2;
+        A.rand_hyp = c->rand_hyp; A.ntrials = c->ntrials; A.usamp = c->usamp; A.prior3 = c->prior3; A.tab3 = c->tab3; A.gtab2 = c->gtab2;
         pm_rand_kernel<<<(fw + 63) / 64, 64, 0, s>>>(P, A);
         const size_t npx = (size_t)P.W0 * P.H0;
-        const int pgrid = (int)std::min<size_t>((npx + 3) / 4, (size_t)148 * 32);
+        const int pgrid = 148 * 8;  // 8 co-resident CTAs per SM (64 registers/thread): see the pixel order in the kernel
         if (P.geom) pm_pixel_kernel<true><<<pgrid, 128, c->smem_init, s>>>(P, A);
         else pm_pixel_kernel<false><<<pgrid, 128, c->smem_init, s>>>(P, A);
         if (c->wpc == 1) pm_launch_serial<1>(c, A, fw);
