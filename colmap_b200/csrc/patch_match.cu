@@ -611,15 +611,8 @@ __global__ void __launch_bounds__(128, 8) pm_pixel_kernel(const PmParams P, cons
   const int g = lane >> 3, sub = lane & 7;
   const unsigned gmask = 0xffu << (8 * g);
   const int npairs = 3 * N;
-  // Pixel order: the grid is 148 * R CTAs; CTAs b, b + 148, ... are co-resident on one SM (round-robin placement), so
-  // giving them the 4*R consecutive pixels of one tile makes their source-image footprints overlap in that SM's L1.
-  const int per_sm = (gridDim.x + 147) / 148;                 // CTAs per SM slot
-  const int sm_slot = blockIdx.x % 148, k_in_sm = blockIdx.x / 148;
-  const size_t tile = (size_t)per_sm * 4;                      // pixels processed per SM per iteration
-  for (size_t it = 0;; ++it) {
-    const size_t q = (it * 148 + sm_slot) * tile + (size_t)k_in_sm * 4 + warp;
-    if ((it * 148) * tile >= npix) break;
-    if (q >= npix) continue;
+  // (an SM-local tiling of the pixel order was measured: L1 hit rate 67% -> 55%, slower; plain grid stride kept)
+  for (size_t q = (size_t)blockIdx.x * 4 + warp; q < npix; q += (size_t)gridDim.x * 4) {
     const int row = (int)(q / fw), col = (int)(q - (size_t)row * fw);  // sweep-frame pixel
     const size_t p = pm_pix0(P.W0, P.H0, rot, row, col);
     const float rowf = (float)row, colf = (float)col;
@@ -1277,7 +1270,7 @@ int b200pm_run(b200pm_handle c) {
         A.rand_hyp = c->rand_hyp; A.ntrials = c->ntrials; A.usamp = c->usamp; A.prior3 = c->prior3; A.tab3 = c->tab3; A.gtab2 = c->gtab2;
         pm_rand_kernel<<<(fw + 63) / 64, 64, 0, s>>>(P, A);
         const size_t npx = (size_t)P.W0 * P.H0;
-        const int pgrid = 148 * 8;  // 8 co-resident CTAs per SM (64 registers/thread): see the pixel order in the kernel
+        const int pgrid = (int)std::min<size_t>((npx + 3) / 4, (size_t)148 * 32);
         if (P.geom) pm_pixel_kernel<true><<<pgrid, 128, c->smem_init, s>>>(P, A);
         else pm_pixel_kernel<false><<<pgrid, 128, c->smem_init, s>>>(P, A);
         if (c->wpc == 1) pm_launch_serial<1>(c, A, fw);
