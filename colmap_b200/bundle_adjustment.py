@@ -240,6 +240,12 @@ class FlatProblem:
 def _bind(lib):
     if getattr(lib, "_ba_bound", False):
         return lib
+    lib.b200ba_comm_unique_id.argtypes = [ctypes.c_void_p]
+    lib.b200ba_comm_init.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+    lib.b200ba_comm_destroy.argtypes = [ctypes.c_void_p]
+    lib.b200ba_comm_destroy.restype = None
+    lib.b200ba_solve_sharded.argtypes = [ctypes.POINTER(_COptions), ctypes.POINTER(_CProblem), ctypes.c_void_p,
+                                         ctypes.POINTER(_CSummary)]
     lib.b200ba_options_init.argtypes = [ctypes.POINTER(_COptions)]
     lib.b200ba_options_init.restype = None
     lib.b200ba_solve.argtypes = [ctypes.POINTER(_COptions), ctypes.POINTER(_CProblem), ctypes.POINTER(_CSummary)]
@@ -260,6 +266,64 @@ def solve_flat(options: BundleAdjustmentOptions, flat: FlatProblem) -> BundleAdj
     rc = lib.b200ba_solve(ctypes.byref(co), ctypes.byref(cp), ctypes.byref(cs))
     if rc != 0:
         raise BundleAdjustmentError(f"b200ba_solve failed ({rc}): {lib.b200ba_last_error().decode()}")
+    return BundleAdjustmentSummary.from_c(cs)
+
+
+# ------------------------------------------------------------------------------------------------ multi-GPU
+def shard_flat_problem(flat: FlatProblem, rank: int, world: int) -> "FlatProblem":
+    """Point sharding: contiguous point ranges balanced by observation count; a rank receives its
+    points and ALL their observations, poses and cameras are replicated.  Returns the local FlatProblem; its
+    `point_ids` attribute maps local points back to the global problem."""
+    npts = len(flat.points)
+    counts = np.bincount(flat.obs_point, minlength=npts).astype(np.int64)
+    csum = np.concatenate([[0], np.cumsum(counts)])
+    total = csum[-1]
+    bounds = [int(np.searchsorted(csum, total * r / world, side="left")) for r in range(world)] + [npts]
+    bounds[0] = 0
+    lo, hi = bounds[rank], bounds[rank + 1]
+    sel = (flat.obs_point >= lo) & (flat.obs_point < hi)
+    local = FlatProblem(flat.poses.copy(), flat.pose_constant, flat.pose_fixed_dim, flat.cam_model, flat.cam_off,
+                        flat.cam_params.copy(), flat.cam_constant, flat.points[lo:hi].copy(), flat.point_constant[lo:hi],
+                        flat.obs_pose[sel], flat.obs_cam[sel], flat.obs_point[sel] - lo, flat.obs_xy[sel])
+    local.point_ids = np.arange(lo, hi)
+    return local
+
+
+class BAComm:
+    """NCCL communicator of the sharded solve.  `id_bytes` comes from rank 0 (unique_id()) and is distributed by the
+    launcher (torch.distributed broadcast, a multiprocessing queue, ...).  Call on the rank's CUDA device."""
+
+    def __init__(self, id_bytes: bytes, rank: int, world: int):
+        self._lib = _bind(load_library())
+        self._h = ctypes.c_void_p()
+        buf = ctypes.create_string_buffer(id_bytes, 128)
+        rc = self._lib.b200ba_comm_init(buf, rank, world, ctypes.byref(self._h))
+        if rc != 0:
+            raise BundleAdjustmentError(f"b200ba_comm_init failed ({rc}): {self._lib.b200ba_last_error().decode()}")
+        self.rank, self.world = rank, world
+
+    @staticmethod
+    def unique_id() -> bytes:
+        lib = _bind(load_library())
+        buf = ctypes.create_string_buffer(128)
+        rc = lib.b200ba_comm_unique_id(buf)
+        if rc != 0:
+            raise BundleAdjustmentError(f"b200ba_comm_unique_id failed ({rc}): {lib.b200ba_last_error().decode()}")
+        return buf.raw
+
+    def close(self):
+        if self._h:
+            self._lib.b200ba_comm_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+
+def solve_flat_sharded(options: "BundleAdjustmentOptions", local: FlatProblem, comm: BAComm) -> "BundleAdjustmentSummary":
+    """b200ba_solve_sharded on this rank's shard; poses / cam_params come back identical on every rank."""
+    lib = _bind(load_library())
+    co, cp, cs = options.to_c(), local.to_c(), _CSummary()
+    rc = lib.b200ba_solve_sharded(ctypes.byref(co), ctypes.byref(cp), comm._h, ctypes.byref(cs))
+    if rc != 0:
+        raise BundleAdjustmentError(f"b200ba_solve_sharded failed ({rc}): {lib.b200ba_last_error().decode()}")
     return BundleAdjustmentSummary.from_c(cs)
 
 

@@ -997,6 +997,46 @@ static void ba_launch_backsub(const BaDev& D, cudaStream_t s) {
     default: FN<11>(D, s); break;                \
   }
 
+
+// ------------------------------------------------------------------------------------------------
+// NCCL binding (point-sharded multi-GPU solve).  libnccl is resolved at run time with dlopen so that the library
+// also loads where NCCL is absent; whichever libnccl.so.2 the process already holds (e.g. torch's) is reused.
+// ------------------------------------------------------------------------------------------------
+#include <dlfcn.h>
+#include <nccl.h>
+struct BaNccl {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+static BaNccl& ba_nccl() {
+  static BaNccl n;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h) {
+      n.GetUniqueId = (decltype(n.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+      n.CommInitRank = (decltype(n.CommInitRank))dlsym(h, "ncclCommInitRank");
+      n.AllReduce = (decltype(n.AllReduce))dlsym(h, "ncclAllReduce");
+      n.CommDestroy = (decltype(n.CommDestroy))dlsym(h, "ncclCommDestroy");
+      n.GetErrorString = (decltype(n.GetErrorString))dlsym(h, "ncclGetErrorString");
+      n.ok = n.GetUniqueId && n.CommInitRank && n.AllReduce && n.CommDestroy;
+    }
+  }
+  return n;
+}
+struct b200ba_comm {
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+};
+
+static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum, b200ba_comm* comm);
+
 extern "C" {
 
 const char* b200ba_last_error(void) { return g_ba_error.c_str(); }
@@ -1047,7 +1087,42 @@ int b200ba_fix_gauge_two_cams_from_world(const b200ba_problem* p, const b200ba_o
   return 0;
 }
 
-int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum) {
+int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum) { return ba_solve_impl(o, p, sum, nullptr); }
+
+// Point-sharded solve: every rank passes the SAME poses / cameras and its own shard of points with all their
+// observations.  Collectives: one all-reduce of the camera-side vector per PCG iteration, a handful
+// of small ones per LM iteration.  poses / camera_params come back identical on every rank.
+int b200ba_solve_sharded(const b200ba_options* o, b200ba_problem* p, b200ba_comm_t comm, b200ba_summary* sum) {
+  if (!comm) return ba_fail(-1, "null communicator");
+  return ba_solve_impl(o, p, sum, comm);
+}
+int b200ba_comm_unique_id(void* id128) {
+  if (!ba_nccl().ok) return ba_fail(-110, "libnccl not available");
+  ncclUniqueId id;
+  if (ba_nccl().GetUniqueId(&id) != ncclSuccess) return ba_fail(-110, "ncclGetUniqueId failed");
+  memcpy(id128, &id, sizeof(id));
+  return 0;
+}
+int b200ba_comm_init(const void* id128, int rank, int world, b200ba_comm_t* out) {
+  if (!ba_nccl().ok) return ba_fail(-110, "libnccl not available");
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  b200ba_comm* c = new b200ba_comm();
+  c->rank = rank; c->world = world;
+  const ncclResult_t r = ba_nccl().CommInitRank(&c->comm, world, id, rank);
+  if (r != ncclSuccess) { delete c; return ba_fail(-110, std::string("ncclCommInitRank: ") + (ba_nccl().GetErrorString ? ba_nccl().GetErrorString(r) : "error")); }
+  *out = c;
+  return 0;
+}
+void b200ba_comm_destroy(b200ba_comm_t c) {
+  if (!c) return;
+  if (c->comm) ba_nccl().CommDestroy(c->comm);
+  delete c;
+}
+
+}  // extern "C"
+
+static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum, b200ba_comm* comm) {
   if (!o || !p || !sum) return ba_fail(-1, "null argument");
   memset(sum, 0, sizeof(*sum));
   sum->termination_type = B200BA_FAILURE;
@@ -1068,6 +1143,27 @@ int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum
       return ba_fail(-2, "observation index out of range");
   std::vector<unsigned char> pose_used(NP, 0), cam_used(NCAM, 0), pt_used(NPT, 0);
   for (long long i = 0; i < NOBS; ++i) { pose_used[p->obs_pose_idx[i]] = 1; cam_used[p->obs_camera_idx[i]] = 1; pt_used[p->obs_point_idx[i]] = 1; }
+  const bool sharded = comm != nullptr && comm->world > 1;
+  cudaStream_t st = nullptr;
+  BA_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  // all-reduce of a device buffer over the ranks of a sharded solve (no-op otherwise)
+  auto allreduce = [&](void* buf, size_t count, ncclDataType_t dt, ncclRedOp_t op) -> cudaError_t {
+    if (!sharded || count == 0) return cudaSuccess;
+    const ncclResult_t r = ba_nccl().AllReduce(buf, buf, count, dt, op, comm->comm, st);
+    return r == ncclSuccess ? cudaSuccess : cudaErrorUnknown;
+  };
+  if (sharded) {  // a block is "used" if any rank observes it: keeps the camera-side layout identical on every rank
+    std::vector<int> flags(NP + NCAM);
+    for (int i = 0; i < NP; ++i) flags[i] = pose_used[i];
+    for (int c = 0; c < NCAM; ++c) flags[NP + c] = cam_used[c];
+    int* d_flags;
+    BA_CUDA(pool.upload(&d_flags, flags, st));
+    BA_CUDA(allreduce(d_flags, flags.size(), ncclInt32, ncclMax));
+    BA_CUDA(cudaMemcpyAsync(flags.data(), d_flags, sizeof(int) * flags.size(), cudaMemcpyDeviceToHost, st));
+    BA_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < NP; ++i) pose_used[i] = (unsigned char)flags[i];
+    for (int c = 0; c < NCAM; ++c) cam_used[c] = (unsigned char)flags[NP + c];
+  }
   std::vector<int> pose_off(NP, -1), cam_off(NCAM, -1), cam_nvar(NCAM, 0), cam_poff(NCAM), cam_model(NCAM), pt_var(NPT, -1);
   std::vector<unsigned char> pose_mask(NP, 0);
   std::vector<signed char> cam_var(5 * (size_t)NCAM, 0);
@@ -1117,12 +1213,23 @@ int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum
     if (pv >= 0) { vcount[pv + 1]++; nobs_eff++; }
     else if (pose_off[p->obs_pose_idx[i]] >= 0 || cam_off[p->obs_camera_idx[i]] >= 0) { const_obs.push_back(i); nobs_eff++; }
   }
-  sum->num_residuals = (int)(2 * nobs_eff);
+  long long g_nobs_eff = nobs_eff, g_pt_params = 3LL * nvpt;
+  if (sharded) {
+    std::vector<long long> cnt = {nobs_eff, 3LL * nvpt};
+    long long* d_cnt;
+    BA_CUDA(pool.upload(&d_cnt, cnt, st));
+    BA_CUDA(allreduce(d_cnt, 2, ncclInt64, ncclSum));
+    BA_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, 16, cudaMemcpyDeviceToHost, st));
+    BA_CUDA(cudaStreamSynchronize(st));
+    g_nobs_eff = cnt[0]; g_pt_params = cnt[1];
+  }
+  neff = neff - 3 * nvpt + (int)g_pt_params;
+  sum->num_residuals = (int)(2 * g_nobs_eff);
   sum->num_effective_parameters = neff;
   int lst = o->linear_solver_type;
   if (lst == B200BA_AUTO) lst = NP <= 50 ? B200BA_DENSE_SCHUR : (NP <= 1000 ? B200BA_SPARSE_SCHUR : B200BA_ITERATIVE_SCHUR);
   sum->linear_solver_type_used = lst;
-  if (nobs_eff == 0 || neff == 0) { sum->termination_type = B200BA_CONVERGENCE; return 0; }
+  if (g_nobs_eff == 0 || neff == 0) { sum->termination_type = B200BA_CONVERGENCE; cudaStreamDestroy(st); pool.release(); return 0; }
   for (int k = 0; k < nvpt; ++k) {
     if (vcount[k + 1] > BA_BLOCK) return ba_fail(-3, "a track longer than 256 observations is not supported yet");
     vcount[k + 1] += vcount[k];
@@ -1226,8 +1333,6 @@ int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum
   }
 
   // ---------------------------------------------------------------- device setup
-  cudaStream_t st = nullptr;
-  BA_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   BaDev D; memset(&D, 0, sizeof(D));
   D.nposes = NP; D.ncams = NCAM; D.npts = (int)NPT; D.nvpt = nvpt; D.nc = nc; D.DC = 6 + dkmax; D.nblocks = nblocks;
   D.nblocks_var = nblocks_var; D.nslots = nslots; D.loss_type = o->loss_function_type; D.loss_scale = o->loss_function_scale;
@@ -1291,6 +1396,7 @@ int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum
   auto linearize_current = [&](int apply_scale) {
     zero_field(&D.ctl->cost);
     ba_linearize_kernel<1><<<nblocks, BA_BLOCK, 0, st>>>(D, D.poses, D.cams, D.pts, apply_scale, &D.ctl->cost);
+    allreduce(&D.ctl->cost, 1, ncclDouble, ncclSum);
     ++launches;
   };
 
@@ -1300,6 +1406,7 @@ int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum
   BA_CUDA(cudaMemsetAsync(D.scale_c, 0, sizeof(double) * (nc ? nc : 1), st));
   BA_CUDA(cudaMemsetAsync(D.scale_p, 0, sizeof(double) * (nvpt ? 3 * (size_t)nvpt : 1), st));
   ba_colnorm_kernel<<<nblocks, BA_BLOCK, 0, st>>>(D);
+  BA_CUDA(allreduce(D.scale_c, nc, ncclDouble, ncclSum));
   if (nc) ba_make_scale_kernel<<<gc_blocks, 256, 0, st>>>(D.scale_c, nc, o->jacobi_scaling);
   if (nvpt) ba_make_scale_kernel<<<(3 * nvpt + 255) / 256, 256, 0, st>>>(D.scale_p, 3LL * nvpt, o->jacobi_scaling);
   launches += 3;
@@ -1323,10 +1430,13 @@ int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum
     BA_CUDA(cudaMemsetAsync(D.Hbb, 0, sizeof(double) * (pack ? pack : 1), st));
     BA_CUDA(zero_field(&D.ctl->gmax));
     if (D.nchunks) ba_build_cam_sorted_kernel<<<(D.nchunks + 7) / 8, BA_BLOCK, 0, st>>>(D);
+    BA_CUDA(allreduce(D.gc, nc, ncclDouble, ncclSum));
+    BA_CUDA(allreduce(D.Hbb, pack, ncclDouble, ncclSum));
     if (nc) ba_diag_from_blocks_kernel<<<gc_blocks, 256, 0, st>>>(D);
     if (nvpt) ba_build_pt_kernel<<<gp_blocks, 256, 0, st>>>(D);
     { const long long n = (long long)NP + NCAM + 3LL * nvpt; ba_gradmax_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(D); }
     launches += 4;
+    BA_CUDA(allreduce(&D.ctl->gmax, 1, ncclDouble, ncclMax));
     BA_CUDA(read_ctl());
     last_gmax = h.gmax;
     if (h.gmax <= o->gradient_tolerance) { sum->termination_type = B200BA_CONVERGENCE; break; }
@@ -1337,6 +1447,10 @@ int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum
       BA_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
       if (nvpt) ba_damp_pt_kernel<<<gp_blocks, 256, 0, st>>>(D, 1.0 / radius, o->min_lm_diagonal, o->max_lm_diagonal, d_fail);
       if (nc) ba_damp_cam_kernel<<<gc_blocks, 256, 0, st>>>(D, 1.0 / radius, o->min_lm_diagonal, o->max_lm_diagonal);
+      if (sharded && comm->rank != 0) {  // the replicated terms (-g_c, H_bb + D) are contributed by rank 0 only
+        BA_CUDA(cudaMemsetAsync(D.rhs, 0, sizeof(double) * (nc ? nc : 1), st));
+        BA_CUDA(cudaMemsetAsync(D.Mbb, 0, sizeof(double) * (pack ? pack : 1), st));
+      }
       if (nvpt && nc) {
         ba_schur_slot_kernel<<<nblocks, BA_BLOCK, 0, st>>>(D);
         ba_cam_reduce_kernel<<<(D.nchunks + 7) / 8, BA_BLOCK, 0, st>>>(D, D.rhs, 0);
@@ -1344,6 +1458,9 @@ int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum
         if (dkmax > 0) ba_schur_pt_kernel<<<gp_blocks, 256, 0, st>>>(D);
         launches += 3;
       }
+      BA_CUDA(allreduce(D.rhs, nc, ncclDouble, ncclSum));
+      BA_CUDA(allreduce(D.Mbb, pack, ncclDouble, ncclSum));
+      BA_CUDA(allreduce(d_fail, 1, ncclInt32, ncclMax));
       if (nblk) ba_invert_blocks_kernel<<<(nblk + 127) / 128, 128, 0, st>>>(D);
       launches += 4;
       // PCG
@@ -1358,9 +1475,11 @@ int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum
           for (int b = 0; b < batch; ++b) {
             ba_pcg_precond_kernel<<<gc_blocks, 256, 0, st>>>(D);
             ba_pcg_direction_kernel<<<gc_blocks, 256, 0, st>>>(D);
+            if (sharded && comm->rank != 0) BA_CUDA(cudaMemsetAsync(D.q, 0, sizeof(double) * nc, st));  // D_c^2 p from rank 0 only
             if (b == 0) BA_CUDA(cudaEventRecord(evs0, st));  // first SpMV of a batch always does real work
             BA_DISPATCH_DC(ba_launch_spmv, D, st);
             if (b == 0) BA_CUDA(cudaEventRecord(evs1, st));
+            BA_CUDA(allreduce(D.q, nc, ncclDouble, ncclSum));  // the one data-path collective of a PCG iteration
             ba_pcg_dot_pq_kernel<<<gc_blocks, 256, 0, st>>>(D);
             ba_pcg_update_kernel<<<gc_blocks, 256, 0, st>>>(D);
             ba_pcg_step_kernel<<<1, 1, 0, st>>>(D, q_tol, r_tol, max_cg);
@@ -1378,6 +1497,9 @@ int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum
       BA_CUDA(zero_field(&D.ctl->new_cost));
       BA_CUDA(zero_field(&D.ctl->cost_delta));
       ba_linearize_kernel<0><<<nblocks, BA_BLOCK, 0, st>>>(D, D.nposes_, D.ncams_, D.npts_, 0, &D.ctl->new_cost);
+      BA_CUDA(allreduce(&D.ctl->model, 1, ncclDouble, ncclSum));
+      BA_CUDA(allreduce(&D.ctl->new_cost, 1, ncclDouble, ncclSum));
+      BA_CUDA(allreduce(&D.ctl->cost_delta, 1, ncclDouble, ncclSum));
       launches += 3;
       BA_CUDA(read_ctl());
       int failed = 0;
@@ -1431,6 +1553,8 @@ int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum
   pool.release();
   return 0;
 }
+
+extern "C" {
 
 // ---- host-side hooks for the CPU test tier ----
 int b200ba_test_reproj(int model_id, const double* point, const double* pose, const double* params, const double* xy,

@@ -930,6 +930,8 @@ struct b200pm_context {
   int final_sel = 0;
   bool dirty = false, ran = false;
   float last_ms = 0.0f, last_sweep_ms = 0.0f;
+  float last_kernel_ms[3] = {0.0f, 0.0f, 0.0f};  // rand / pixel / serial(or fused) passes of the last run
+  std::vector<cudaEvent_t> sweep_ev;
   int last_launches = 0;
   std::vector<int> src_image_idxs;
   size_t smem_sweep = 0, smem_init = 0, smem_serial = 0;
@@ -1261,22 +1263,32 @@ int b200pm_run(b200pm_handle c) {
       A.sel_cur = c->sel[t & 1];
       A.sel_prev = c->sel[(t + 1) & 1];
       const int fw = (sweep & 1) ? P.H0 : P.W0;
+      auto mark = [&](int idx) {
+        const size_t id = (size_t)t * 4 + idx;
+        while (c->sweep_ev.size() <= id) { cudaEvent_t e; cudaEventCreate(&e); c->sweep_ev.push_back(e); }
+        cudaEventRecord(c->sweep_ev[id], s);
+      };
+      mark(0);
       if (c->fused) {
         if (c->wpc == 1) pm_launch_sweep<1>(c, A, fw);
         else if (c->wpc == 2) pm_launch_sweep<2>(c, A, fw);
         else pm_launch_sweep<4>(c, A, fw);
         ++launches;
+        mark(1); mark(2); mark(3);
       } else {
         A.rand_hyp = c->rand_hyp; A.ntrials = c->ntrials; A.usamp = c->usamp; A.prior3 = c->prior3; A.tab3 = c->tab3; A.gtab2 = c->gtab2;
         pm_rand_kernel<<<(fw + 63) / 64, 64, 0, s>>>(P, A);
+        mark(1);
         const size_t npx = (size_t)P.W0 * P.H0;
         const int pgrid = (int)std::min<size_t>((npx + 3) / 4, (size_t)148 * 32);
         if (P.geom) pm_pixel_kernel<true><<<pgrid, 128, c->smem_init, s>>>(P, A);
         else pm_pixel_kernel<false><<<pgrid, 128, c->smem_init, s>>>(P, A);
+        mark(2);
         if (c->wpc == 1) pm_launch_serial<1>(c, A, fw);
         else if (c->wpc == 2) pm_launch_serial<2>(c, A, fw);
         else pm_launch_serial<4>(c, A, fw);
         launches += 3;
+        mark(3);
       }
       c->final_sel = t & 1;
     }
@@ -1286,6 +1298,12 @@ int b200pm_run(b200pm_handle c) {
   PM_CUDA(cudaGetLastError());
   PM_CUDA(cudaEventElapsedTime(&c->last_ms, c->ev[0], c->ev[2]));
   PM_CUDA(cudaEventElapsedTime(&c->last_sweep_ms, c->ev[1], c->ev[2]));
+  c->last_kernel_ms[0] = c->last_kernel_ms[1] = c->last_kernel_ms[2] = 0.0f;
+  for (int i = 0; i < t; ++i)
+    for (int kk = 0; kk < 3; ++kk) {
+      float ms = 0.0f;
+      if (cudaEventElapsedTime(&ms, c->sweep_ev[(size_t)i * 4 + kk], c->sweep_ev[(size_t)i * 4 + kk + 1]) == cudaSuccess) c->last_kernel_ms[kk] += ms;
+    }
   c->last_launches = launches;
   c->ran = true;
   return 0;
@@ -1294,6 +1312,7 @@ int b200pm_run(b200pm_handle c) {
 float b200pm_last_run_ms(b200pm_handle c) { return c ? c->last_ms : -1.0f; }
 float b200pm_last_sweep_ms(b200pm_handle c) { return c ? c->last_sweep_ms : -1.0f; }
 int b200pm_last_num_launches(b200pm_handle c) { return c ? c->last_launches : -1; }
+float b200pm_last_pass_ms(b200pm_handle c, int which) { return (c && which >= 0 && which < 3) ? c->last_kernel_ms[which] : -1.0f; }
 
 static int pm_export(b200pm_handle c, float* depth, float* normal, float* sel, uint8_t* mask) {
   if (!c) return pm_fail(-1, "null handle");
@@ -1356,6 +1375,7 @@ void b200pm_destroy(b200pm_handle c) {
   cudaSetDevice(c->device);
   for (void* p : c->allocs) cudaFree(p);
   for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (cudaEvent_t e : c->sweep_ev) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }

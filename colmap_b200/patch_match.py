@@ -200,6 +200,8 @@ def _bind(lib):
     lib.b200pm_last_sweep_ms.argtypes = [H]
     lib.b200pm_last_sweep_ms.restype = ctypes.c_float
     lib.b200pm_last_num_launches.argtypes = [H]
+    lib.b200pm_last_pass_ms.argtypes = [H, ctypes.c_int]
+    lib.b200pm_last_pass_ms.restype = ctypes.c_float
     lib.b200pm_get_depth.argtypes = [H, _f32p]
     lib.b200pm_get_normal.argtypes = [H, _f32p]
     lib.b200pm_get_sel_prob.argtypes = [H, _f32p]
@@ -272,6 +274,9 @@ class PatchMatch:
 
     def last_sweep_ms(self):
         return float(self._lib.b200pm_last_sweep_ms(self._h))
+
+    def last_pass_ms(self, which):
+        return float(self._lib.b200pm_last_pass_ms(self._h, which))
 
     def last_num_launches(self):
         return int(self._lib.b200pm_last_num_launches(self._h))

@@ -118,6 +118,17 @@ int b200ba_fix_gauge_two_cams_from_world(const b200ba_problem* p, const b200ba_o
 /* BundleAdjuster::Solve. */
 int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* out);
 
+/* Multi-GPU (one process per GPU): points are sharded over the ranks, every rank passes the same poses / cameras and
+ * its own points with ALL their observations (so the point-block elimination stays local).  The communicator wraps
+ * NCCL: rank 0 creates a 128-byte id, the launcher broadcasts it (torch.distributed / MPI), every rank calls
+ * b200ba_comm_init on its CUDA device.  Collectives: one all-reduce of the camera-side vector per PCG iteration plus
+ * a few small ones per LM iteration.  poses / camera_params are returned identical on every rank. */
+typedef struct b200ba_comm* b200ba_comm_t;
+int b200ba_comm_unique_id(void* id128);
+int b200ba_comm_init(const void* id128, int rank, int world_size, b200ba_comm_t* out);
+void b200ba_comm_destroy(b200ba_comm_t comm);
+int b200ba_solve_sharded(const b200ba_options* o, b200ba_problem* local_shard, b200ba_comm_t comm, b200ba_summary* out);
+
 const char* b200ba_last_error(void);
 
 #ifdef __cplusplus

@@ -98,6 +98,9 @@ float b200pm_last_run_ms(b200pm_handle h);
 /* Device time spent in the sweep kernels only during the last run, and their launch count. */
 float b200pm_last_sweep_ms(b200pm_handle h);
 int b200pm_last_num_launches(b200pm_handle h);
+/* Device time summed over the sweeps of the last run for one pass of the split sweep: 0 = pm_rand_kernel (column-serial
+ * PRNG pass), 1 = pm_pixel_kernel (pixel-parallel NCC pass, the dominant kernel), 2 = pm_serial_kernel. */
+float b200pm_last_pass_ms(b200pm_handle h, int which);
 
 /* PatchMatchCuda::GetDepthMap / GetNormalMap / GetSelProbMap
  * (patch_match_cuda.cu:1354-1365).  Layouts match mvs::Mat<float>: slice-major,

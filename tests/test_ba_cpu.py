@@ -162,7 +162,8 @@ def test_library_exports_every_declared_ba_symbol():
     lib = load_library()
     hdr = open(os.path.join(ROOT, "include", "b200_bundle_adjustment.h")).read()
     names = set(re.findall(r"\b(b200ba_[a-z_0-9]+)\s*\(", hdr))
-    assert names == {"b200ba_options_init", "b200ba_fix_gauge_two_cams_from_world", "b200ba_solve", "b200ba_last_error"}
+    assert names == {"b200ba_options_init", "b200ba_fix_gauge_two_cams_from_world", "b200ba_solve", "b200ba_last_error",
+                     "b200ba_comm_unique_id", "b200ba_comm_init", "b200ba_comm_destroy", "b200ba_solve_sharded"}
     for n in names:
         assert hasattr(lib, n), n
 
@@ -221,3 +222,19 @@ def test_gauge_two_cams_from_world():
     cp = noisy.to_c()
     assert lib.b200ba_fix_gauge_two_cams_from_world(ctypes.byref(cp), ctypes.byref(co), pc.ctypes.data_as(_u8p), fd.ctypes.data_as(_i8p)) == 0
     assert pc.tolist() == [0, 1, 0, 1, 0] and (fd == -1).all()
+
+
+def test_point_sharding_covers_and_balances():
+    from colmap_b200.bundle_adjustment import shard_flat_problem
+    gt, noisy = synthesize_ba_problem(20, 3000, 6, models=(SIMPLE_RADIAL,), seed=8)
+    for world in (2, 3, 8):
+        shards = [shard_flat_problem(noisy, r, world) for r in range(world)]
+        ids = np.concatenate([s.point_ids for s in shards])
+        assert np.array_equal(ids, np.arange(3000))
+        nobs = [len(s.obs_pose) for s in shards]
+        assert sum(nobs) == len(noisy.obs_pose) and max(nobs) - min(nobs) <= 0.05 * len(noisy.obs_pose)
+        for s in shards:   # local indices are consistent and every observation of a local point is present
+            assert s.obs_point.min() >= 0 and s.obs_point.max() < len(s.points)
+            assert np.array_equal(s.points, noisy.points[s.point_ids])
+            assert len(s.obs_pose) == np.isin(noisy.obs_point, s.point_ids).sum()
+            assert np.array_equal(s.poses, noisy.poses)
