@@ -95,7 +95,8 @@ def _ncu_traffic(name):
     path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(path):
         with open(path) as f:
-            return json.load(f).get(name)
+            v = json.load(f).get(name)
+            return v.get("bytes") if isinstance(v, dict) else v
     return None
 
 

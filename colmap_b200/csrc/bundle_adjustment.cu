@@ -840,9 +840,11 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_cam_reduce_kernel(const BaDev D, 
 // thousands of observations long — the 6 + nv products are reduced with shuffles and lanes 0..5+nv issue one red.add each.
 template <int DC>
 __global__ void __launch_bounds__(BA_BLOCK) ba_cam_stream_kernel(const BaDev D, double* __restrict__ out, int respect_done) {
+  __shared__ double part[BA_BLOCK / 32][DC];
+  __shared__ int run0;
   if (respect_done && D.ctl->done) return;
   const long long k = (long long)blockIdx.x * BA_BLOCK + threadIdx.x;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int run = D.c_run[k];   // -1 on the padding of the last tile
   double v[DC];
 #pragma unroll
@@ -854,15 +856,35 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_cam_stream_kernel(const BaDev D, 
 #pragma unroll
     for (int c = 0; c < DC; ++c) v[c] = (double)D.JcC[BA_JC(c, k)] * u0 + (double)D.JcC[BA_JC(DC + c, k)] * u1;
   }
-  if (__all_sync(0xffffffffu, run == __shfl_sync(0xffffffffu, run, 0))) {
-    if (run < 0) return;
+  if (threadIdx.x == 0) run0 = run;
+  __syncthreads();
+  // the whole CTA (256 consecutive observations) inside one (camera, pose) run: one red.add per component per CTA
+  const bool cta_uniform = __syncthreads_and(run == run0) && run0 >= 0;
+  const bool warp_uniform = __all_sync(0xffffffffu, run == __shfl_sync(0xffffffffu, run, 0));
+  if (cta_uniform || warp_uniform) {
 #pragma unroll
     for (int c = 0; c < DC; ++c) {
       double t = v[c];
       for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
       v[c] = t;
     }
-    // lane c adds component c
+  }
+  if (cta_uniform) {
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < DC; ++c) part[warp][c] = v[c];
+    }
+    __syncthreads();
+    if (threadIdx.x < DC) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < BA_BLOCK / 32; ++w) t += part[w][threadIdx.x];
+      const int c = threadIdx.x;
+      if (c < 6) { if (rd.x >= 0) atomicAdd(&out[rd.x + c], t); }
+      else if (c < 6 + rd.z) { if (rd.y >= 0) atomicAdd(&out[rd.y + c - 6], t); }
+    }
+  } else if (warp_uniform) {
+    if (run < 0) return;
     double mine = 0.0;
 #pragma unroll
     for (int c = 0; c < DC; ++c) if (lane == c) mine = v[c];
