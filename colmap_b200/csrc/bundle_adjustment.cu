@@ -1385,12 +1385,20 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   for (long long s = 0; s < nslots; ++s) { s_xy[s] = sx[s]; s_xy[nslots + s] = sy[s]; }
   // camera order: observations sorted by (camera, pose) so that every camera-side block owns contiguous ranges
   std::vector<int> c2s;
-  c2s.reserve((size_t)nobs_eff);
-  for (long long s = 0; s < nslots; ++s) if (s_pose[s] >= 0) c2s.push_back((int)s);
-  std::stable_sort(c2s.begin(), c2s.end(), [&](int a, int b) {
-    if (s_cam[a] != s_cam[b]) return s_cam[a] < s_cam[b];
-    return s_pose[a] < s_pose[b];
-  });
+  {  // two stable counting sorts (by pose, then by camera) = lexicographic (camera, pose) order in O(n)
+    std::vector<int> tmp;
+    tmp.reserve((size_t)nobs_eff);
+    std::vector<long long> cnt((size_t)std::max(NP, NCAM) + 1, 0);
+    for (long long s2 = 0; s2 < nslots; ++s2) if (s_pose[s2] >= 0) cnt[s_pose[s2] + 1]++;
+    for (int i = 0; i < NP; ++i) cnt[i + 1] += cnt[i];
+    tmp.resize((size_t)cnt[NP]);
+    for (long long s2 = 0; s2 < nslots; ++s2) if (s_pose[s2] >= 0) tmp[cnt[s_pose[s2]]++] = (int)s2;
+    std::fill(cnt.begin(), cnt.end(), 0);
+    for (int v : tmp) cnt[s_cam[v] + 1]++;
+    for (int i = 0; i < NCAM; ++i) cnt[i + 1] += cnt[i];
+    c2s.resize(tmp.size());
+    for (int v : tmp) c2s[cnt[s_cam[v]]++] = v;
+  }
   const long long nobs_c = (long long)c2s.size();
   std::vector<int> s2c(nslots, -1);
   for (long long k = 0; k < nobs_c; ++k) s2c[c2s[k]] = (int)k;
