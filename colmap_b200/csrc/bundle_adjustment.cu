@@ -203,6 +203,8 @@ struct BaDev {
   const int4* s_pack;                 // [nslots] {pose offset, (cam offset + 1) | nv << 19 | head << 22 | last << 27, variable point, camera-order position}: one 16-byte load per slot in the SpMV
   const int* s_seg;                   // [nslots] head lane | last lane << 8 of the slot's track inside its warp (warp-packed region)
   int nblocks_warp;                   // leading blocks whose tracks never cross a warp (tracks <= 32 observations)
+  int nblocks_giant0, nblocks_giant1; // block range of the tracks longer than a block (> 256 observations): generic two-kernel path
+  double* zg;                         // [3*nvpt] scratch of the generic path (sum J_p^T y per point)
   float* u;                           // [2][nobs_c] per-observation 2-vector exchanged between the two SpMV passes (fp32 like the operator)
   double* rC;                         // [2][nobs_c] residuals in camera order
   double* T21;                        // [21][nobs_c] per-observation V^T Hinv V (pose block, symmetric) scratch
@@ -752,6 +754,7 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_schur_spmv_kernel(const BaDev D, 
   __shared__ double sw[3][BA_BLOCK];
   if (D.ctl->done) return;
   const int blk = blockIdx.x + D.nblocks_warp;   // blocks after the warp-packed region
+  if (blk >= D.nblocks_giant0 && blk < D.nblocks_giant1) return;   // tracks longer than a block: generic path
   const long long s = (long long)blk * BA_BLOCK + threadIdx.x;
   const int pi = D.s_pose[s];
   int po = -1, co = -1, nv = 0;
@@ -940,12 +943,63 @@ __global__ void ba_pcg_step_kernel(const BaDev D, double q_tolerance, double r_t
   c->last_rho = c->rho; c->rho = 0.0; c->pq = 0.0;
 }
 
+// Generic path for tracks longer than a block (> 256 observations; rare): the per-point sum goes through global
+// atomics.  MODE 0: SpMV (vec = p, writes u); MODE 1: back-substitution / model cost (vec = x, writes d_p, model).
+template <int MODE>
+__global__ void __launch_bounds__(BA_BLOCK) ba_giant_accumulate_kernel(const BaDev D, const double* __restrict__ vec) {
+  if (MODE == 0 && D.ctl->done) return;
+  const long long s = (long long)(blockIdx.x + D.nblocks_giant0) * BA_BLOCK + threadIdx.x;
+  const int pi = D.s_pose[s];
+  if (pi < 0) return;
+  const int ci = D.s_cam[s], DC = D.DC;
+  const int po = D.pose_off[pi], co = D.cam_off[ci], nv = D.cam_nvar[ci], lp = D.s_lpt[s];
+  double y0 = 0.0, y1 = 0.0;
+  if (po >= 0) for (int c = 0; c < 6; ++c) { const double v = vec[po + c]; y0 += D.Jc[BA_JC(c, s)] * v; y1 += D.Jc[BA_JC((DC + c), s)] * v; }
+  if (co >= 0) for (int c = 0; c < nv; ++c) { const double v = vec[co + c]; y0 += D.Jc[BA_JC((6 + c), s)] * v; y1 += D.Jc[BA_JC((DC + 6 + c), s)] * v; }
+  for (int c = 0; c < 3; ++c) atomicAdd(&D.zg[3 * (long long)lp + c], D.Jp[BA_JP(c, s)] * y0 + D.Jp[BA_JP(3 + c, s)] * y1);
+}
+template <int MODE>
+__global__ void __launch_bounds__(BA_BLOCK) ba_giant_finish_kernel(const BaDev D, const double* __restrict__ vec) {
+  __shared__ double sm[8];
+  if (MODE == 0 && D.ctl->done) return;
+  const long long s = (long long)(blockIdx.x + D.nblocks_giant0) * BA_BLOCK + threadIdx.x;
+  const int pi = D.s_pose[s];
+  double m = 0.0;
+  if (pi >= 0) {
+    const int ci = D.s_cam[s], DC = D.DC;
+    const int po = D.pose_off[pi], co = D.cam_off[ci], nv = D.cam_nvar[ci], lp = D.s_lpt[s];
+    double y0 = 0.0, y1 = 0.0;
+    if (po >= 0) for (int c = 0; c < 6; ++c) { const double v = vec[po + c]; y0 += D.Jc[BA_JC(c, s)] * v; y1 += D.Jc[BA_JC((DC + c), s)] * v; }
+    if (co >= 0) for (int c = 0; c < nv; ++c) { const double v = vec[co + c]; y0 += D.Jc[BA_JC((6 + c), s)] * v; y1 += D.Jc[BA_JC((DC + 6 + c), s)] * v; }
+    const double* I = D.Hpp_inv + 6 * (long long)lp;
+    double z0 = D.zg[3 * (long long)lp], z1 = D.zg[3 * (long long)lp + 1], z2 = D.zg[3 * (long long)lp + 2];
+    if (MODE == 1) { z0 = -D.gp[3 * (long long)lp] - z0; z1 = -D.gp[3 * (long long)lp + 1] - z1; z2 = -D.gp[3 * (long long)lp + 2] - z2; }
+    const double w0 = I[0] * z0 + I[1] * z1 + I[2] * z2, w1 = I[1] * z0 + I[3] * z1 + I[4] * z2, w2 = I[2] * z0 + I[4] * z1 + I[5] * z2;
+    const double j0 = D.Jp[BA_JP(0, s)] * w0 + D.Jp[BA_JP(1, s)] * w1 + D.Jp[BA_JP(2, s)] * w2;
+    const double j1 = D.Jp[BA_JP(3, s)] * w0 + D.Jp[BA_JP(4, s)] * w1 + D.Jp[BA_JP(5, s)] * w2;
+    if (MODE == 0) {
+      const long long cp = D.s2c[s];
+      D.u[BA_U(0, cp)] = (float)(y0 - j0);
+      D.u[BA_U(1, cp)] = (float)(y1 - j1);
+    } else {
+      if ((int)s == D.vpt_s0[lp]) { D.dp[3 * (long long)lp] = w0; D.dp[3 * (long long)lp + 1] = w1; D.dp[3 * (long long)lp + 2] = w2; }
+      y0 += j0; y1 += j1;
+      m = -(y0 * (D.r[s] + 0.5 * y0) + y1 * (D.r[D.nslots + s] + 0.5 * y1));
+    }
+  }
+  if (MODE == 1) {
+    const double t = ba_block_sum(m, sm);
+    if (threadIdx.x == 0) atomicAdd(&D.ctl->model, t);
+  }
+}
+
 // d_p = Hinv (-g_p - H_pc d_c); also the model cost change -(Jd)^T (r + Jd/2), one thread per slot block-wise
 template <int DC>
 __global__ void __launch_bounds__(BA_BLOCK) ba_backsub_model_kernel(const BaDev D) {
   __shared__ double sy[2][BA_BLOCK];
   __shared__ double sw[3][BA_BLOCK];
   __shared__ double sm[8];
+  if ((int)blockIdx.x >= D.nblocks_giant0 && (int)blockIdx.x < D.nblocks_giant1) return;
   const long long s = (long long)blockIdx.x * BA_BLOCK + threadIdx.x;
   const int pi = D.s_pose[s];
   double y0 = 0.0, y1 = 0.0;
@@ -1044,11 +1098,21 @@ template <int DC>
 static void ba_launch_spmv(const BaDev& D, cudaStream_t s) {
   if (D.nblocks_warp) ba_schur_spmv_warp_kernel<DC><<<D.nblocks_warp, BA_BLOCK, 0, s>>>(D, D.p);
   if (D.nblocks > D.nblocks_warp) ba_schur_spmv_kernel<DC><<<D.nblocks - D.nblocks_warp, BA_BLOCK, 0, s>>>(D, D.p, D.q);
+  if (D.nblocks_giant1 > D.nblocks_giant0) {
+    cudaMemsetAsync(D.zg, 0, sizeof(double) * 3 * (size_t)D.nvpt, s);
+    ba_giant_accumulate_kernel<0><<<D.nblocks_giant1 - D.nblocks_giant0, BA_BLOCK, 0, s>>>(D, D.p);
+    ba_giant_finish_kernel<0><<<D.nblocks_giant1 - D.nblocks_giant0, BA_BLOCK, 0, s>>>(D, D.p);
+  }
   if (D.nobs_c) ba_cam_stream_kernel<DC><<<(unsigned)((D.nobs_c + BA_BLOCK - 1) / BA_BLOCK), BA_BLOCK, 0, s>>>(D, D.q, 1);
 }
 template <int DC>
 static void ba_launch_backsub(const BaDev& D, cudaStream_t s) {
   ba_backsub_model_kernel<DC><<<D.nblocks, BA_BLOCK, 0, s>>>(D);
+  if (D.nblocks_giant1 > D.nblocks_giant0) {
+    cudaMemsetAsync(D.zg, 0, sizeof(double) * 3 * (size_t)D.nvpt, s);
+    ba_giant_accumulate_kernel<1><<<D.nblocks_giant1 - D.nblocks_giant0, BA_BLOCK, 0, s>>>(D, D.x);
+    ba_giant_finish_kernel<1><<<D.nblocks_giant1 - D.nblocks_giant0, BA_BLOCK, 0, s>>>(D, D.x);
+  }
 }
 #define BA_DISPATCH_DC(FN, D, s)                 \
   switch ((D).DC) {                              \
@@ -1294,7 +1358,6 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   sum->linear_solver_type_used = lst;
   if (g_nobs_eff == 0 || neff == 0) { sum->termination_type = B200BA_CONVERGENCE; cudaStreamDestroy(st); pool.release(); return 0; }
   for (int k = 0; k < nvpt; ++k) {
-    if (vcount[k + 1] > BA_BLOCK) return ba_fail(-3, "a track longer than 256 observations is not supported yet");
     vcount[k + 1] += vcount[k];
   }
   std::vector<long long> vobs(vcount[nvpt]);
@@ -1313,7 +1376,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   // variable points are renumbered: tracks of <= 32 observations first (packed so that none crosses a warp),
   // then the longer ones (packed so that none crosses a block)
   std::vector<int> s_seg;
-  int nblocks_warp = 0;
+  int nblocks_warp = 0, nblocks_giant0 = 0, nblocks_giant1 = 0;
   {
     std::vector<int> order_pts; order_pts.reserve(nvpt);
     std::vector<long long> olen(nvpt), ostart(nvpt);
@@ -1336,7 +1399,9 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
       }
     }
     const int nshort = (int)order_pts.size();
-    for (int k = 0; k < nvpt; ++k) if (olen[k] > 32) order_pts.push_back(k);
+    for (int k = 0; k < nvpt; ++k) if (olen[k] > 32 && olen[k] <= BA_BLOCK) order_pts.push_back(k);
+    const int nmid = (int)order_pts.size();
+    for (int k = 0; k < nvpt; ++k) if (olen[k] > BA_BLOCK) order_pts.push_back(k);
     // renumber: new variable index = position in order_pts
     std::vector<int> newidx(nvpt);
     for (int n = 0; n < nvpt; ++n) newidx[order_pts[n]] = n;
@@ -1361,7 +1426,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
     }
     pad_to(BA_BLOCK);
     nblocks_warp = (int)(s_pose.size() / BA_BLOCK);
-    for (int n = nshort; n < nvpt; ++n) {
+    for (int n = nshort; n < nmid; ++n) {
       const int k = order_pts[n], len = (int)olen[k];
       const int used = (int)(s_pose.size() % BA_BLOCK);
       if (used + len > BA_BLOCK) pad_to(BA_BLOCK);
@@ -1371,9 +1436,18 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
       vpt_s1[n] = (int)s_pose.size();
     }
     pad_to(BA_BLOCK);
+    nblocks_giant0 = (int)(s_pose.size() / BA_BLOCK);
+    for (int n = nmid; n < nvpt; ++n) {   // tracks longer than a block: laid out back to back, generic kernels
+      const int k = order_pts[n];
+      vpt_s0[n] = (int)s_pose.size();
+      for (long long j = ostart[k]; j < ostart[k] + olen[k]; ++j) { push_slot(vobs[j], n); s_seg.push_back(0); }
+      vpt_s1[n] = (int)s_pose.size();
+    }
+    pad_to(BA_BLOCK);
+    nblocks_giant1 = (int)(s_pose.size() / BA_BLOCK);
     (void)cur_blk;
   }
-  const int nblocks_var = (int)(s_pose.size() / BA_BLOCK);
+  const int nblocks_var = nblocks_giant0;   // blocks whose tracks are eliminated in shared memory / by shuffles
   for (long long i : const_obs) { push_slot(i, -1); s_seg.push_back(0); }
   while (s_pose.size() % BA_BLOCK) { push_slot(-1, -1); s_seg.push_back(0); }
   const long long nslots = (long long)s_pose.size();
@@ -1477,7 +1551,8 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   { int* t; BA_CUDA(pool.upload(&t, s2c, st)); D.s2c = t; }
   { int* t; BA_CUDA(pool.upload(&t, s_seg, st)); D.s_seg = t; }
   { int4* t; BA_CUDA(pool.upload(&t, s_pack, st)); D.s_pack = t; }
-  D.nblocks_warp = nblocks_warp;
+  D.nblocks_warp = nblocks_warp; D.nblocks_giant0 = nblocks_giant0; D.nblocks_giant1 = nblocks_giant1;
+  BA_CUDA(pool.alloc(&D.zg, (size_t)3 * nvpt));
   { int4* t; BA_CUDA(pool.upload(&t, chunks, st)); D.chunks = t; }
   { int* t; BA_CUDA(pool.upload(&t, c_run, st)); D.c_run = t; }
   { int4* t; BA_CUDA(pool.upload(&t, runs, st)); D.runs = t; }

@@ -174,7 +174,7 @@ def _project(model, params, pc):
 
 def synthesize_ba_problem(num_images, num_points, track_length, models=(2,), shared_camera=False, seed=42,
                           point2D_stddev=1.0, point3D_stddev=0.05, translation_stddev=0.01, rotation_stddev_deg=1.0,
-                          num_obs=None):
+                          num_obs=None, track_lengths=None):
     """Ground truth + noisy flat BA problems.  `models`: camera model ids cycled over the images (one camera per
     image) or a single shared camera.  `num_obs` (optional) = exact observation count (tracks of length
     floor/ceil(num_obs/num_points)).  Noise defaults = benchmark/runtime/bundle_adjustment.cc:76-80."""
@@ -198,7 +198,9 @@ def synthesize_ba_problem(num_images, num_points, track_length, models=(2,), sha
         cam_off.append(off); off += MODEL_NUM_PARAMS[m]
     cam_params = np.concatenate([np.asarray(_MODEL_DEFAULTS[m]) for m in cam_model])
     # tracks
-    if num_obs is None:
+    if track_lengths is not None:
+        lens = np.asarray(track_lengths, np.int64)
+    elif num_obs is None:
         lens = np.full(num_points, track_length, np.int64)
     else:
         base = num_obs // num_points

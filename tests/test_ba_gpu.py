@@ -147,3 +147,15 @@ def test_medium_iterative_problem_converges_like_the_oracle():
     # the cost agrees to 1e-5 (actually ~1e-10) while the weakest directions are only pinned to ~1e-4
     _assert_parity(a, sg, b, sr, param_rel=1e-4)
     assert sg.num_linear_solver_iterations > 0 and sg.spmv_launches > 0 and sg.kernel_launches > 0
+
+
+def test_long_tracks_use_the_generic_path():
+    """Tracks of every size class in one problem: <= 32 observations (warp-packed), 33..256 (block-packed) and > 256
+    (generic two-kernel path with global atomics) must all reproduce the oracle."""
+    lens = np.concatenate([np.full(600, 6), np.full(30, 40), np.full(12, 200), np.full(6, 300), np.full(3, 330)])
+    gt, noisy = synthesize_ba_problem(340, len(lens), 0, models=(SIMPLE_RADIAL,), shared_camera=True, seed=17,
+                                      track_lengths=lens)
+    _gauge(noisy)
+    a, sg, b, sr = _both(BundleAdjustmentOptions(linear_solver_type=ITERATIVE_SCHUR, max_num_iterations=15), noisy)
+    assert sg.num_residuals == 2 * int(lens.sum())
+    _assert_parity(a, sg, b, sr, param_rel=1e-4)

@@ -69,6 +69,9 @@ def test_photometric_bit_exact_vs_oracle(wpc, fused):
     (64, 80, 8, 5, 2, 15),     # window_step 2, portrait, 8 sources
     (33, 17, 1, 2, 1, 4),      # single source image: filter_min_num_consistent=2 zeroes everything
     (50, 40, 5, 7, 1, 20),     # big window
+    (36, 28, 2, 20, 2, 5),     # kMaxPatchMatchWindowRadius = 20 (41x41 window, step 2)
+    (30, 24, 2, 14, 1, 3),     # 29x29 window: 841 taps, > 48 KB of dynamic shared memory in the pixel pass
+    (40, 30, 3, 4, 1, 40),     # more than 32 Monte-Carlo samples
 ])
 def test_option_grid_bit_exact(w, h, n, radius, step, samples):
     sc = make_patch_match_scene(w, h, n, seed=11)
