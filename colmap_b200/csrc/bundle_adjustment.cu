@@ -1255,9 +1255,11 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   sum->termination_type = B200BA_FAILURE;
   BaPool pool;
   const auto t_setup0 = std::chrono::steady_clock::now();
+  const bool host_only = getenv("B200BA_HOST_ONLY") != nullptr;   // diagnostic: time the host flattening, then stop
+  auto tick = [&](const char* what) { if (host_only) fprintf(stderr, "[b200ba host] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_setup0).count()); };
   int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return ba_fail(-101, "no CUDA device: colmap_b200 has no CPU fallback");
-  if (o->gpu_index >= 0) {
+  if (!host_only && (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)) return ba_fail(-101, "no CUDA device: colmap_b200 has no CPU fallback");
+  if (!host_only && o->gpu_index >= 0) {
     if (o->gpu_index >= ndev) return ba_fail(-101, "gpu_index out of range");
     cudaSetDevice(o->gpu_index);
   }
@@ -1272,7 +1274,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   for (long long i = 0; i < NOBS; ++i) { pose_used[p->obs_pose_idx[i]] = 1; cam_used[p->obs_camera_idx[i]] = 1; pt_used[p->obs_point_idx[i]] = 1; }
   const bool sharded = comm != nullptr && comm->world > 1;
   cudaStream_t st = nullptr;
-  BA_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  if (!host_only) BA_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   // all-reduce of a device buffer over the ranks of a sharded solve (no-op otherwise)
   auto allreduce = [&](void* buf, size_t count, ncclDataType_t dt, ncclRedOp_t op) -> cudaError_t {
     if (!sharded || count == 0) return cudaSuccess;
@@ -1291,6 +1293,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
     for (int i = 0; i < NP; ++i) pose_used[i] = (unsigned char)flags[i];
     for (int c = 0; c < NCAM; ++c) cam_used[c] = (unsigned char)flags[NP + c];
   }
+  tick("validate + used flags");
   std::vector<int> pose_off(NP, -1), cam_off(NCAM, -1), cam_nvar(NCAM, 0), cam_poff(NCAM), cam_model(NCAM), pt_var(NPT, -1);
   std::vector<unsigned char> pose_mask(NP, 0);
   std::vector<signed char> cam_var(5 * (size_t)NCAM, 0);
@@ -1365,9 +1368,14 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
     std::vector<long long> cur(vcount.begin(), vcount.end() - 1);
     for (long long i = 0; i < NOBS; ++i) { const int pv = pt_var[p->obs_point_idx[i]]; if (pv >= 0) vobs[cur[pv]++] = i; }
   }
+  tick("group observations by point");
   // pack whole tracks into blocks of BA_BLOCK slots
   std::vector<int> s_pose, s_cam, s_pt, s_lpt, blk_pt0, blk_npt, vpt_s0(nvpt), vpt_s1(nvpt), vpt_point(nvpt);
   std::vector<double> sx, sy;
+  {
+    const size_t cap = (size_t)(nobs_eff + nobs_eff / 8 + 4 * BA_BLOCK);
+    s_pose.reserve(cap); s_cam.reserve(cap); s_pt.reserve(cap); s_lpt.reserve(cap); sx.reserve(cap); sy.reserve(cap);
+  }
   auto push_slot = [&](long long obs, int lpt) {
     if (obs < 0) { s_pose.push_back(-1); s_cam.push_back(-1); s_pt.push_back(-1); s_lpt.push_back(-1); sx.push_back(0); sy.push_back(0); return; }
     s_pose.push_back(p->obs_pose_idx[obs]); s_cam.push_back(p->obs_camera_idx[obs]); s_pt.push_back(p->obs_point_idx[obs]);
@@ -1376,6 +1384,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   // variable points are renumbered: tracks of <= 32 observations first (packed so that none crosses a warp),
   // then the longer ones (packed so that none crosses a block)
   std::vector<int> s_seg;
+  s_seg.reserve((size_t)(nobs_eff + nobs_eff / 8 + 4 * BA_BLOCK));
   int nblocks_warp = 0, nblocks_giant0 = 0, nblocks_giant1 = 0;
   {
     std::vector<int> order_pts; order_pts.reserve(nvpt);
@@ -1447,6 +1456,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
     nblocks_giant1 = (int)(s_pose.size() / BA_BLOCK);
     (void)cur_blk;
   }
+  tick("pack tracks into slots");
   const int nblocks_var = nblocks_giant0;   // blocks whose tracks are eliminated in shared memory / by shuffles
   for (long long i : const_obs) { push_slot(i, -1); s_seg.push_back(0); }
   while (s_pose.size() % BA_BLOCK) { push_slot(-1, -1); s_seg.push_back(0); }
@@ -1457,6 +1467,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   if (nc >= (1 << 19) - 1) return ba_fail(-3, "camera-side dimension above 2^19 is not supported");
   std::vector<double> s_xy(2 * nslots);
   for (long long s = 0; s < nslots; ++s) { s_xy[s] = sx[s]; s_xy[nslots + s] = sy[s]; }
+  tick("slot arrays");
   // camera order: observations sorted by (camera, pose) so that every camera-side block owns contiguous ranges
   std::vector<int> c2s;
   {  // two stable counting sorts (by pose, then by camera) = lexicographic (camera, pose) order in O(n)
@@ -1476,17 +1487,31 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   const long long nobs_c = (long long)c2s.size();
   std::vector<int> s2c(nslots, -1);
   for (long long k = 0; k < nobs_c; ++k) s2c[c2s[k]] = (int)k;
-  // runs of equal (camera, pose) in camera order
+  // runs of equal (camera, pose) in camera order; chunks (<= BA_CHUNK observations of one pose / one camera)
   const long long nobs_c_pad = (nobs_c + BA_BLOCK - 1) / BA_BLOCK * BA_BLOCK;
   std::vector<int> c_run(nobs_c_pad, -1);
-  std::vector<int4> runs;
-  for (long long k = 0; k < nobs_c;) {
-    long long e = k;
-    const int pose = s_pose[c2s[k]], cam = s_cam[c2s[k]];
-    while (e < nobs_c && s_pose[c2s[e]] == pose && s_cam[c2s[e]] == cam) ++e;
-    for (long long j = k; j < e; ++j) c_run[j] = (int)runs.size();
-    runs.push_back(make_int4(pose_off[pose], cam_off[cam], cam_nvar[cam], 0));
-    k = e;
+  std::vector<int4> runs, chunks;
+  {
+    std::vector<int> cpose((size_t)nobs_c), ccam((size_t)nobs_c);
+    for (long long k = 0; k < nobs_c; ++k) { const int sl = c2s[k]; cpose[k] = s_pose[sl]; ccam[k] = s_cam[sl]; }
+    auto add_chunks = [&](long long k0, long long k1, int out, int comp0, int ncomp) {
+      for (long long c0 = k0; c0 < k1; c0 += BA_CHUNK) chunks.push_back(make_int4((int)c0, (int)std::min<long long>(c0 + BA_CHUNK, k1), out, comp0 | (ncomp << 8)));
+    };
+    long long cam_start = 0;
+    for (long long k = 0; k < nobs_c;) {
+      long long e = k;
+      const int pose = cpose[k], cam = ccam[k];
+      while (e < nobs_c && cpose[e] == pose && ccam[e] == cam) ++e;
+      const int rid = (int)runs.size();
+      for (long long j = k; j < e; ++j) c_run[j] = rid;
+      runs.push_back(make_int4(pose_off[pose], cam_off[cam], cam_nvar[cam], 0));
+      if (pose_off[pose] >= 0) add_chunks(k, e, pose_off[pose], 0, 6);
+      if (e == nobs_c || ccam[e] != cam) {  // end of this camera's range
+        if (cam_off[cam] >= 0) add_chunks(cam_start, e, cam_off[cam], 6, cam_nvar[cam]);
+        cam_start = e;
+      }
+      k = e;
+    }
   }
   std::vector<int4> s_pack(nslots);
   for (long long sl = 0; sl < nslots; ++sl) {
@@ -1496,24 +1521,11 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
     const unsigned y = (unsigned)(co_ + 1) | ((unsigned)nv_ << 19) | (head_ << 22) | (last_ << 27);
     s_pack[sl] = make_int4(po_, (int)y, s_lpt[sl], s2c[sl]);
   }
-  std::vector<int4> chunks;
-  for (long long k = 0; k < nobs_c;) {  // pose runs
-    long long e = k;
-    const int pose = s_pose[c2s[k]];
-    while (e < nobs_c && s_pose[c2s[e]] == pose && s_cam[c2s[e]] == s_cam[c2s[k]]) ++e;
-    if (pose_off[pose] >= 0)
-      for (long long c0 = k; c0 < e; c0 += BA_CHUNK) chunks.push_back(make_int4((int)c0, (int)std::min<long long>(c0 + BA_CHUNK, e), pose_off[pose], 0 | (6 << 8)));
-    k = e;
+  tick("camera order, runs, chunks");
+  if (host_only) {
+    sum->setup_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_setup0).count();
+    return ba_fail(-102, "B200BA_HOST_ONLY: stopped after the host flattening");
   }
-  for (long long k = 0; k < nobs_c;) {  // camera runs
-    long long e = k;
-    const int cam = s_cam[c2s[k]];
-    while (e < nobs_c && s_cam[c2s[e]] == cam) ++e;
-    if (cam_off[cam] >= 0)
-      for (long long c0 = k; c0 < e; c0 += BA_CHUNK) chunks.push_back(make_int4((int)c0, (int)std::min<long long>(c0 + BA_CHUNK, e), cam_off[cam], 6 | (cam_nvar[cam] << 8)));
-    k = e;
-  }
-
   // ---------------------------------------------------------------- device setup
   BaDev D; memset(&D, 0, sizeof(D));
   D.nposes = NP; D.ncams = NCAM; D.npts = (int)NPT; D.nvpt = nvpt; D.nc = nc; D.DC = 6 + dkmax; D.nblocks = nblocks;
