@@ -204,15 +204,18 @@ __device__ __forceinline__ float pm_ncc_group(const float4* __restrict__ patch, 
   float Hm[9];
   pm_compose_homography(pose, iK, rowf, colf, d, n0, n1, n2, Hm);
   const uint32_t* quads0 = quads + (2 * pitch + 2);
+  asm("" : "+l"(quads0));  // keep the image base as one opaque 64-bit value: the tap address is a single IMAD.WIDE
   const float hi_x = (float)(W + 1), hi_y = (float)(H + 1);
   float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+  // H (x, y, 1) with (x, y) = (col + dx, row + dy): the pixel part is folded into the constant term once per NCC
+  const float cx = fmaf(Hm[0], colf, fmaf(Hm[1], rowf, Hm[2]));
+  const float cy = fmaf(Hm[3], colf, fmaf(Hm[4], rowf, Hm[5]));
+  const float cz = fmaf(Hm[6], colf, fmaf(Hm[7], rowf, Hm[8]));
   auto tap = [&](int t) {
-    const float4 tp = patch[t];
-    const float x = colf + tp.z;
-    const float y = rowf + tp.w;
-    const float zx = fmaf(Hm[0], x, fmaf(Hm[1], y, Hm[2]));
-    const float zy = fmaf(Hm[3], x, fmaf(Hm[4], y, Hm[5]));
-    const float zz = fmaf(Hm[6], x, fmaf(Hm[7], y, Hm[8]));
+    const float4 tp = patch[t];   // {w, w * ref, dx, dy}
+    const float zx = fmaf(Hm[0], tp.z, fmaf(Hm[1], tp.w, cx));
+    const float zy = fmaf(Hm[3], tp.z, fmaf(Hm[4], tp.w, cy));
+    const float zz = fmaf(Hm[6], tp.z, fmaf(Hm[7], tp.w, cz));
     const float inv_z = pm_rcp_clamped(zz);
     const float color = pm_sample_quad(quads0, pitch, hi_x, hi_y, inv_z * zx, inv_z * zy);
     const float ws = tp.x * color;

@@ -28,8 +28,8 @@
  * match this file bit for bit; the reference itself is built with
  * --use_fast_math and hardware texture filtering and therefore has no
  * bit-level definition).  Documented deviations from the reference, all at the
- * level of fp32 rounding: (1) homography applied per tap directly instead of
- * incrementally (patch_match_cuda.cu:503-569); (2) software bilinear
+ * level of fp32 rounding: (1) homography applied per tap directly (as
+ * H*(dx,dy,0) + H*(col,row,1)) instead of incrementally (patch_match_cuda.cu:503-569); (2) software bilinear
  * interpolation on raw 8-bit values instead of the 9-bit-weight texture unit;
  * (3) the NCC sums are accumulated in 8 interleaved partial sums joined by a
  * fixed tree; (4) pose matrices are composed in double and rounded once;
@@ -412,12 +412,16 @@ static float ncc_cost(const pm_state* st, const pm_patch* pt, int row, int col, 
   compose_homography(st, st->poses[st->rot] + PM_POSE_STRIDE * image_idx, row, col, depth, normal, H);
   const int r = st->radius, s = st->step, ns = st->nside;
   float s1[8] = {0}, s2[8] = {0}, s3[8] = {0};
+  /* H (col + dx, row + dy, 1): the pixel part is folded into the constant term once per evaluation */
+  const float cx = fmaf(H[0], (float)col, fmaf(H[1], (float)row, H[2]));
+  const float cy = fmaf(H[3], (float)col, fmaf(H[4], (float)row, H[5]));
+  const float cz = fmaf(H[6], (float)col, fmaf(H[7], (float)row, H[8]));
   for (int t = 0; t < st->ntaps; ++t) {
-    const float x = (float)(col - r + s * (t % ns));
-    const float y = (float)(row - r + s * (t / ns));
-    const float zx = fmaf(H[0], x, fmaf(H[1], y, H[2]));
-    const float zy = fmaf(H[3], x, fmaf(H[4], y, H[5]));
-    const float zz = fmaf(H[6], x, fmaf(H[7], y, H[8]));
+    const float dx = (float)(-r + s * (t % ns));
+    const float dy = (float)(-r + s * (t / ns));
+    const float zx = fmaf(H[0], dx, fmaf(H[1], dy, cx));
+    const float zy = fmaf(H[3], dx, fmaf(H[4], dy, cy));
+    const float zz = fmaf(H[6], dx, fmaf(H[7], dy, cz));
     /* points at or behind the source camera plane sample the border: z is clamped to [1e-30, 1e30]
      * (keeps the reciprocal in the range where the GPU's MUFU.RCP + one Newton step is correctly rounded) */
     float zc = (zz > 1e-30f) ? zz : 1e-30f;
