@@ -848,16 +848,21 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_cam_stream_kernel(const BaDev D, 
   if (respect_done && D.ctl->done) return;
   const long long k = (long long)blockIdx.x * BA_BLOCK + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // all loads are issued up front, independent of the run lookup (the padded tail of the arrays is allocated)
   const int run = D.c_run[k];   // -1 on the padding of the last tile
-  double v[DC];
+  float j0[DC], j1[DC];
 #pragma unroll
-  for (int c = 0; c < DC; ++c) v[c] = 0.0;
+  for (int c = 0; c < DC; ++c) { j0[c] = D.JcC[BA_JC(c, k)]; j1[c] = D.JcC[BA_JC(DC + c, k)]; }
+  const float uf0 = D.u[BA_U(0, k)], uf1 = D.u[BA_U(1, k)];
+  double v[DC];
   int4 rd = make_int4(-1, -1, 0, 0);
   if (run >= 0) {
     rd = D.runs[run];
-    const double u0 = D.u[BA_U(0, k)], u1 = D.u[BA_U(1, k)];
 #pragma unroll
-    for (int c = 0; c < DC; ++c) v[c] = (double)D.JcC[BA_JC(c, k)] * u0 + (double)D.JcC[BA_JC(DC + c, k)] * u1;
+    for (int c = 0; c < DC; ++c) v[c] = (double)j0[c] * (double)uf0 + (double)j1[c] * (double)uf1;
+  } else {
+#pragma unroll
+    for (int c = 0; c < DC; ++c) v[c] = 0.0;
   }
   if (threadIdx.x == 0) run0 = run;
   __syncthreads();
