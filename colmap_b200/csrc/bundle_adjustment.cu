@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "../../include/b200_bundle_adjustment.h"
+#include "device_cache.h"
 
 #define BA_MAXDK 5
 #define BA_BLOCK 256
@@ -678,8 +679,8 @@ __global__ void ba_pcg_direction_kernel(const BaDev D) {
   if (D.ctl->done) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= D.nc) return;
-  const double beta = (D.ctl->it == 0) ? 0.0 : D.ctl->rho / D.ctl->last_rho;
-  const double p = D.z[i] + beta * D.p[i];
+  // first iteration: p = z (never reads the uninitialised / recycled p buffer)
+  const double p = (D.ctl->it == 0) ? D.z[i] : D.z[i] + (D.ctl->rho / D.ctl->last_rho) * D.p[i];
   D.p[i] = p;
   D.q[i] = D.Dc2[i] * p;
 }
@@ -1085,10 +1086,11 @@ static int ba_fail(int code, const std::string& msg) { g_ba_error = msg; return 
   } while (0)
 
 struct BaPool {
-  std::vector<void*> ptrs;
+  std::vector<std::pair<void*, size_t>> ptrs;
   template <typename T> cudaError_t alloc(T** p, size_t n) {
-    cudaError_t e = cudaMalloc((void**)p, sizeof(T) * (n ? n : 1));
-    if (e == cudaSuccess) ptrs.push_back((void*)*p);
+    const size_t bytes = sizeof(T) * (n ? n : 1);
+    cudaError_t e = B200DeviceCache::get().alloc((void**)p, bytes);
+    if (e == cudaSuccess) ptrs.push_back({(void*)*p, bytes});
     return e;
   }
   template <typename T> cudaError_t upload(T** p, const std::vector<T>& v, cudaStream_t s) {
@@ -1096,7 +1098,7 @@ struct BaPool {
     if (e != cudaSuccess) return e;
     return cudaMemcpyAsync(*p, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, s);
   }
-  void release() { for (void* p : ptrs) cudaFree(p); ptrs.clear(); }
+  void release() { cudaDeviceSynchronize(); for (auto& a : ptrs) B200DeviceCache::get().free(a.first, a.second); ptrs.clear(); }
 };
 
 template <int DC>

@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "../../include/b200_patch_match.h"
+#include "device_cache.h"
 #include "pm_device.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -928,7 +929,7 @@ struct b200pm_context {
   int wpc = 2;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  std::vector<void*> allocs;
+  std::vector<std::pair<void*, size_t>> allocs;
   float* sel[2] = {nullptr, nullptr};
   int final_sel = 0;
   bool dirty = false, ran = false;
@@ -944,8 +945,9 @@ struct b200pm_context {
 
 template <typename T>
 static cudaError_t pm_alloc(b200pm_context* c, T** p, size_t count) {
-  cudaError_t e = cudaMalloc((void**)p, sizeof(T) * (count ? count : 1));
-  if (e == cudaSuccess) c->allocs.push_back((void*)*p);
+  const size_t bytes = sizeof(T) * (count ? count : 1);
+  cudaError_t e = B200DeviceCache::get().alloc((void**)p, bytes);
+  if (e == cudaSuccess) c->allocs.push_back({(void*)*p, bytes});
   return e;
 }
 
@@ -1324,17 +1326,18 @@ static int pm_export(b200pm_handle c, float* depth, float* normal, float* sel, u
   const size_t n = (size_t)P.W0 * P.H0;
   float *d_depth = nullptr, *d_normal = nullptr, *d_sel = nullptr;
   uint8_t* d_mask = nullptr;
-  if (depth) PM_CUDA(cudaMalloc(&d_depth, n * sizeof(float)));
-  if (normal) PM_CUDA(cudaMalloc(&d_normal, 3 * n * sizeof(float)));
-  if (sel) PM_CUDA(cudaMalloc(&d_sel, n * P.N * sizeof(float)));
-  if (mask) PM_CUDA(cudaMalloc(&d_mask, n * P.N));
+  B200DeviceCache& cache = B200DeviceCache::get();
+  if (depth) PM_CUDA(cache.alloc((void**)&d_depth, n * sizeof(float)));
+  if (normal) PM_CUDA(cache.alloc((void**)&d_normal, 3 * n * sizeof(float)));
+  if (sel) PM_CUDA(cache.alloc((void**)&d_sel, n * P.N * sizeof(float)));
+  if (mask) PM_CUDA(cache.alloc((void**)&d_mask, n * P.N));
   pm_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(P, c->sel[c->ran ? c->final_sel : 1], d_depth, d_normal, d_sel, d_mask);
   if (depth) PM_CUDA(cudaMemcpyAsync(depth, d_depth, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   if (normal) PM_CUDA(cudaMemcpyAsync(normal, d_normal, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   if (sel) PM_CUDA(cudaMemcpyAsync(sel, d_sel, n * P.N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   if (mask) PM_CUDA(cudaMemcpyAsync(mask, d_mask, n * P.N, cudaMemcpyDeviceToHost, c->stream));
   PM_CUDA(cudaStreamSynchronize(c->stream));
-  cudaFree(d_depth); cudaFree(d_normal); cudaFree(d_sel); cudaFree(d_mask);
+  cache.free(d_depth, n * sizeof(float)); cache.free(d_normal, 3 * n * sizeof(float)); cache.free(d_sel, n * P.N * sizeof(float)); cache.free(d_mask, n * P.N);
   PM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1373,10 +1376,14 @@ int b200pm_get_consistency(b200pm_handle c, int** data, size_t* count) {
 
 void b200pm_free(void* p) { free(p); }
 
+// Drops the device blocks kept for reuse by destroyed handles / finished solves (both paths share the cache).
+void b200_release_cached_memory(void) { B200DeviceCache::get().release(); }
+
 void b200pm_destroy(b200pm_handle c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  for (void* p : c->allocs) cudaFree(p);
+  cudaStreamSynchronize(c->stream);
+  for (auto& a : c->allocs) B200DeviceCache::get().free(a.first, a.second);
   for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (cudaEvent_t e : c->sweep_ev) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);

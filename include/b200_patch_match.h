@@ -118,6 +118,9 @@ int b200pm_get_consistency_mask(b200pm_handle h, uint8_t* mask);
 void b200pm_free(void* p);
 
 void b200pm_destroy(b200pm_handle h);
+/* Destroyed handles (and finished BA solves) keep their device blocks in a per-device cache for the next equally sized
+ * problem (a workspace run creates hundreds of them); this returns the cached blocks to the driver. */
+void b200_release_cached_memory(void);
 const char* b200pm_last_error(void);
 
 #ifdef __cplusplus
