@@ -38,7 +38,6 @@
 #define BA_JC(k, s) ((((long long)(s) >> 5) * (2 * D.DC) + (k)) * 32 + ((s) & 31))
 #define BA_JP(k, s) ((((long long)(s) >> 5) * 6 + (k)) * 32 + ((s) & 31))
 #define BA_U(k, s) ((((long long)(s) >> 5) * 2 + (k)) * 32 + ((s) & 31))
-#define BA_T(k, s) ((((long long)(s) >> 5) * 21 + (k)) * 32 + ((s) & 31))
 
 // ------------------------------------------------------------------------------------------------
 // camera models + reprojection (host/device so the CPU test tier can check them without a GPU)
@@ -52,7 +51,8 @@ BA_HD int ba_param_group(int id, int k) {  // 0 focal, 1 principal point, 2 extr
   }
 }
 
-// ImgFromCamWithJac (sensor/models_jacobian.h:139-398); depth guard models.h:281-285.
+// ImgFromCamWithJac (sensor/models_jacobian.h:139-398); depth guard models.h:281-285.  Jp = d(x,y)/d(params) as two
+// rows of stride 5 (fixed stride: the callers index it with compile-time constants).
 BA_HD bool ba_img_from_cam(int id, const double* q, double u, double v, double w, double* x, double* y, double* Jp,
                            double* Juvw) {
   if (!(w >= 2.220446049250313e-16)) return false;
@@ -62,11 +62,11 @@ BA_HD bool ba_img_from_cam(int id, const double* q, double u, double v, double w
     *x = f * uu + q[1]; *y = f * vv + q[2];
     const double fi = f * iw;
     Juvw[0] = fi; Juvw[1] = 0; Juvw[2] = -fi * uu; Juvw[3] = 0; Juvw[4] = fi; Juvw[5] = -fi * vv;
-    Jp[0] = uu; Jp[1] = 1; Jp[2] = 0; Jp[3] = vv; Jp[4] = 0; Jp[5] = 1;
+    Jp[0] = uu; Jp[1] = 1; Jp[2] = 0; Jp[5] = vv; Jp[6] = 0; Jp[7] = 1;
   } else if (id == 1) {
     *x = q[0] * uu + q[2]; *y = q[1] * vv + q[3];
     Juvw[0] = q[0] * iw; Juvw[1] = 0; Juvw[2] = -q[0] * iw * uu; Juvw[3] = 0; Juvw[4] = q[1] * iw; Juvw[5] = -q[1] * iw * vv;
-    Jp[0] = uu; Jp[1] = 0; Jp[2] = 1; Jp[3] = 0; Jp[4] = 0; Jp[5] = vv; Jp[6] = 0; Jp[7] = 1;
+    Jp[0] = uu; Jp[1] = 0; Jp[2] = 1; Jp[3] = 0; Jp[5] = 0; Jp[6] = vv; Jp[7] = 0; Jp[8] = 1;
   } else if (id == 2) {
     const double f = q[0], k = q[3];
     const double uu2 = uu * uu, vv2 = vv * vv, r2 = uu2 + vv2, kr2 = k * r2, alpha = 1.0 + kr2;
@@ -75,7 +75,7 @@ BA_HD bool ba_img_from_cam(int id, const double* q, double u, double v, double w
     const double two_k = 2.0 * k, fi = f * iw, beta = 1.0 + 3.0 * kr2, cross = two_k * uu * vv;
     Juvw[0] = fi * (alpha + two_k * uu2); Juvw[1] = fi * cross; Juvw[2] = -fi * uu * beta;
     Juvw[3] = fi * cross; Juvw[4] = fi * (alpha + two_k * vv2); Juvw[5] = -fi * vv * beta;
-    Jp[0] = xd; Jp[1] = 1; Jp[2] = 0; Jp[3] = f * uu * r2; Jp[4] = yd; Jp[5] = 0; Jp[6] = 1; Jp[7] = f * vv * r2;
+    Jp[0] = xd; Jp[1] = 1; Jp[2] = 0; Jp[3] = f * uu * r2; Jp[5] = yd; Jp[6] = 0; Jp[7] = 1; Jp[8] = f * vv * r2;
   } else {
     const double f = q[0], k1 = q[3], k2 = q[4];
     const double uu2 = uu * uu, vv2 = vv * vv, r2 = uu2 + vv2, r4 = r2 * r2, radial = k1 * r2 + k2 * r4;
@@ -125,8 +125,9 @@ BA_HD void ba_quat_plus(const double* q, const double* d, double* out) {
   out[3] = dw * w - dx * x - dy * y - dz * z;
 }
 // AnalyticalReprojErrorCostFunction::Evaluate (reprojection_error.h:69-135)
+// J_params: [2][P] when params_stride == 0, else two rows of `params_stride` (>= P) entries.
 BA_HD bool ba_reproj(int id, const double* point, const double* pose, const double* params, double ox, double oy,
-                     double* res, double* J_point, double* J_pose, double* J_params) {
+                     double* res, double* J_point, double* J_pose, double* J_params, int params_stride = 0) {
   double pc[3], Jq[12], Juvw[6];
   ba_quat_rotate_jac(pose, point, pc, J_pose ? Jq : nullptr);
   pc[0] += pose[4]; pc[1] += pose[5]; pc[2] += pose[6];
@@ -136,7 +137,13 @@ BA_HD bool ba_reproj(int id, const double* point, const double* pose, const doub
     res[0] = res[1] = 0;
     if (J_point) for (int i = 0; i < 6; ++i) J_point[i] = 0;
     if (J_pose) for (int i = 0; i < 14; ++i) J_pose[i] = 0;
-    if (J_params) for (int i = 0; i < 2 * P; ++i) J_params[i] = 0;
+    if (J_params) {
+      const int st = params_stride ? params_stride : P;
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) if (j < P) J_params[st * r + j] = 0;
+    }
     return false;
   }
   res[0] = x - ox; res[1] = y - oy;
@@ -151,7 +158,13 @@ BA_HD bool ba_reproj(int id, const double* point, const double* pose, const doub
       for (int c = 0; c < 3; ++c) J_pose[7 * r + 4 + c] = Juvw[3 * r + c];
     }
   }
-  if (J_params) for (int i = 0; i < 2 * P; ++i) J_params[i] = Jp[i];
+  if (J_params) {
+    const int st = params_stride ? params_stride : P;
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int j = 0; j < 5; ++j) if (j < P) J_params[st * r + j] = Jp[5 * r + j];
+  }
   return true;
 }
 // Ceres loss functions (SoftLOneLoss, CauchyLoss, HuberLoss): rho, rho', rho''
@@ -208,7 +221,11 @@ struct BaDev {
   double* zg;                         // [3*nvpt] scratch of the generic path (sum J_p^T y per point)
   float* u;                           // [2][nobs_c] per-observation 2-vector exchanged between the two SpMV passes (fp32 like the operator)
   double* rC;                         // [2][nobs_c] residuals in camera order
-  double* T21;                        // [21][nobs_c] per-observation V^T Hinv V (pose block, symmetric) scratch
+  float* JpC;                         // [6][nobs_c] point-side Jacobian in camera order
+  const double* xyC;                  // [2][nobs_c] observed image points in camera order
+  const int2* c_pack;                 // [nobs_c] {point index, variable point index or -1} in camera order
+  const int2* runs_pc;                // per run {pose index, camera index}
+  int intr_by_pt;                     // some track sees one variable-intrinsics camera twice: intrinsics blocks via ba_schur_pt_kernel
   const int* c_run;                   // [nobs_c padded] run id of the observation in camera order: one run = one (camera, pose) pair
   const int4* runs;                   // per run {pose offset or -1, camera offset or -1, #variable intrinsics, 0}
   const int4* chunks;                 // {c0, c1, out offset, comp0 | ncomp << 8}: <= BA_CHUNK observations of one block
@@ -220,6 +237,7 @@ struct BaDev {
   double *gc, *diag_c, *Dc2, *rhs;                // [nc]
   double *Hbb, *Mbb, *Minv;                       // packed camera-side blocks
   const int *blk_start, *blk_pack, *off2blk;      // [nblk+1], [nblk+1], [nc]
+  const int4* row_info;                           // [nc] {first row of the row's block, offset of the row in the packed blocks, block size, 0}
   int nblk;
   // PCG vectors
   double *x, *rr, *z, *p, *q, *dp;
@@ -240,12 +258,160 @@ __device__ __forceinline__ double ba_block_sum(double v, double* sm) {
   return t;  // valid in thread 0
 }
 
-// residual + Jacobians of one slot.  MODE 0: cost only (candidate parameters); 1: store J (scaled) and r.
-template <int MODE>
-__global__ void __launch_bounds__(BA_BLOCK) ba_linearize_kernel(const BaDev D, const double* __restrict__ poses,
-                                                                const double* __restrict__ cams,
-                                                                const double* __restrict__ pts, int apply_scale,
-                                                                double* cost_out) {
+// Residual, robustified + Jacobi-scaled Jacobian rows of ONE observation, in registers.  Shared by the slot-ordered and
+// the camera-ordered linearisation passes: both evaluate the same expression tree on the same inputs, so the two fp32
+// copies of the camera-side Jacobian hold identical values (the PCG operator stays symmetric) without any scattered
+// store.  Returns 1/2 rho(|r|^2).
+template <int DC>
+__device__ __forceinline__ double ba_obs_linearize(const BaDev& D, const double* __restrict__ poses,
+                                                   const double* __restrict__ cams, const double* __restrict__ pts,
+                                                   int pi, int ci, int ti, int lp, double ox, double oy, int apply_scale,
+                                                   double* Jc, double* Jpt, double* rr) {
+  const int id = D.cam_model[ci];
+  double pose[7], pt[3], prm[5];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) pose[k] = poses[7 * (long long)pi + k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) pt[k] = pts[3 * (long long)ti + k];
+  const int P = ba_model_num_params(id);
+  const int poff = D.cam_poff[ci];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) prm[k] = (k < P) ? cams[poff + k] : 0.0;
+  double res[2], Jps[14], Jpr[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) Jpr[k] = 0.0;
+  ba_reproj(id, pt, pose, prm, ox, oy, res, Jpt, Jps, Jpr, 5);
+  const double sq = res[0] * res[0] + res[1] * res[1];
+  double rho[3];
+  ba_loss(D.loss_type, D.loss_scale, sq, rho);
+#pragma unroll
+  for (int k = 0; k < 2 * DC; ++k) Jc[k] = 0.0;
+  const int po = D.pose_off[pi], co = D.cam_off[ci], nv = D.cam_nvar[ci];
+  if (po >= 0) {
+    const unsigned m = D.pose_mask[pi];
+    const double PJ[12] = {pose[3], pose[2], -pose[1], -pose[2], pose[3], pose[0], pose[1], -pose[0], pose[3], -pose[0], -pose[1], -pose[2]};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        double v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v += Jps[7 * r + k] * PJ[3 * k + c];
+        Jc[DC * r + c] = ((m >> c) & 1u) ? v : 0.0;
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) Jc[DC * r + 3 + c] = ((m >> (3 + c)) & 1u) ? Jps[7 * r + 4 + c] : 0.0;
+    }
+  }
+  if (co >= 0) {
+#pragma unroll
+    for (int k = 0; k < DC - 6; ++k) {
+      if (k < nv) {
+        const int var = D.cam_var[5 * ci + k];
+        // pick the entry with selects so that the array stays in registers
+        double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) if (j == var) { v0 = Jpr[j]; v1 = Jpr[5 + j]; }
+        Jc[6 + k] = v0; Jc[DC + 6 + k] = v1;
+      }
+    }
+  }
+  if (lp < 0) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) Jpt[k] = 0.0;
+  }
+  double rs = 1.0;
+  if (D.loss_type != B200BA_LOSS_TRIVIAL) {  // ceres Corrector
+    const double sqrt_rho1 = sqrt(rho[1]);
+    double alpha_sq_norm = 0.0;
+    rs = sqrt_rho1;
+    if (sq != 0.0 && rho[2] > 0.0) {
+      const double Dd = 1.0 + 2.0 * sq * rho[2] / rho[1];
+      const double alpha = 1.0 - sqrt(Dd);
+      rs = sqrt_rho1 / (1 - alpha);
+      alpha_sq_norm = alpha / sq;
+    }
+#pragma unroll
+    for (int c = 0; c < DC; ++c) {
+      const double rj = res[0] * Jc[c] + res[1] * Jc[DC + c];
+      Jc[c] = sqrt_rho1 * (Jc[c] - alpha_sq_norm * res[0] * rj);
+      Jc[DC + c] = sqrt_rho1 * (Jc[DC + c] - alpha_sq_norm * res[1] * rj);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const double rj = res[0] * Jpt[c] + res[1] * Jpt[3 + c];
+      Jpt[c] = sqrt_rho1 * (Jpt[c] - alpha_sq_norm * res[0] * rj);
+      Jpt[3 + c] = sqrt_rho1 * (Jpt[3 + c] - alpha_sq_norm * res[1] * rj);
+    }
+  }
+  if (apply_scale) {
+    if (po >= 0) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { const double sc = D.scale_c[po + c]; Jc[c] *= sc; Jc[DC + c] *= sc; }
+    }
+    if (co >= 0) {
+#pragma unroll
+      for (int c = 0; c < DC - 6; ++c) if (c < nv) { const double sc = D.scale_c[co + c]; Jc[6 + c] *= sc; Jc[DC + 6 + c] *= sc; }
+    }
+    if (lp >= 0) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { const double sc = D.scale_p[3 * (long long)lp + c]; Jpt[c] *= sc; Jpt[3 + c] *= sc; }
+    }
+  }
+  rr[0] = rs * res[0]; rr[1] = rs * res[1];
+  return 0.5 * rho[0];
+}
+
+// Linearisation, pass 1 (slot order = track order): scaled Jacobians Jc / Jp (fp32), residual, per-slot cost.
+template <int DC>
+__global__ void __launch_bounds__(BA_BLOCK) ba_linearize_slot_kernel(const BaDev D, int apply_scale, double* cost_out) {
+  __shared__ double sm[8];
+  const long long s = (long long)blockIdx.x * BA_BLOCK + threadIdx.x;
+  double cost = 0.0;
+  const int pi = D.s_pose[s];
+  double Jc[2 * DC], Jpt[6], rr[2] = {0.0, 0.0};
+  if (pi >= 0) {
+    cost = ba_obs_linearize<DC>(D, D.poses, D.cams, D.pts, pi, D.s_cam[s], D.s_pt[s], D.s_lpt[s], D.s_xy[s],
+                                D.s_xy[D.nslots + s], apply_scale, Jc, Jpt, rr);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 2 * DC; ++k) Jc[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) Jpt[k] = 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < 2 * DC; ++k) D.Jc[BA_JC(k, s)] = (float)Jc[k];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) D.Jp[BA_JP(k, s)] = (float)Jpt[k];
+  D.r[s] = rr[0];
+  D.r[D.nslots + s] = rr[1];
+  D.cost_slot[s] = cost;
+  const double t = ba_block_sum(cost, sm);
+  if (threadIdx.x == 0) atomicAdd(cost_out, t);
+}
+// Linearisation, pass 2 (camera order): the same rows again, written as JcC / JpC / rC for the passes that reduce per
+// camera-side block.  Recomputing (one 24-byte point gather per observation) replaces 2*DC + 2 scattered stores.
+template <int DC>
+__global__ void __launch_bounds__(BA_BLOCK) ba_linearize_cam_kernel(const BaDev D, int apply_scale) {
+  const long long k = (long long)blockIdx.x * BA_BLOCK + threadIdx.x;
+  const int run = D.c_run[k];
+  if (run < 0) return;
+  const int2 pc = D.runs_pc[run];
+  const int2 tl = D.c_pack[k];
+  double Jc[2 * DC], Jpt[6], rr[2];
+  ba_obs_linearize<DC>(D, D.poses, D.cams, D.pts, pc.x, pc.y, tl.x, tl.y, D.xyC[BA_U(0, k)], D.xyC[BA_U(1, k)], apply_scale,
+                       Jc, Jpt, rr);
+#pragma unroll
+  for (int c = 0; c < 2 * DC; ++c) D.JcC[BA_JC(c, k)] = (float)Jc[c];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) D.JpC[BA_JP(c, k)] = (float)Jpt[c];
+  D.rC[BA_U(0, k)] = rr[0];
+  D.rC[BA_U(1, k)] = rr[1];
+}
+// cost of the candidate parameters + per-residual cost change (accurate near convergence)
+__global__ void __launch_bounds__(BA_BLOCK) ba_cost_kernel(const BaDev D, const double* __restrict__ poses,
+                                                           const double* __restrict__ cams,
+                                                           const double* __restrict__ pts, double* cost_out) {
   __shared__ double sm[8];
   const long long s = (long long)blockIdx.x * BA_BLOCK + threadIdx.x;
   double cost = 0.0, delta = 0.0;
@@ -258,84 +424,17 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_linearize_kernel(const BaDev D, c
     for (int k = 0; k < 3; ++k) pt[k] = pts[3 * (long long)ti + k];
     const int P = ba_model_num_params(id);
     for (int k = 0; k < P; ++k) prm[k] = cams[D.cam_poff[ci] + k];
-    double res[2], Jpt[6], Jps[14], Jpr[10];
-    ba_reproj(id, pt, pose, prm, D.s_xy[s], D.s_xy[D.nslots + s], res, MODE ? Jpt : nullptr, MODE ? Jps : nullptr,
-              MODE ? Jpr : nullptr);
-    const double sq = res[0] * res[0] + res[1] * res[1];
+    double res[2];
+    ba_reproj(id, pt, pose, prm, D.s_xy[s], D.s_xy[D.nslots + s], res, nullptr, nullptr, nullptr);
     double rho[3];
-    ba_loss(D.loss_type, D.loss_scale, sq, rho);
+    ba_loss(D.loss_type, D.loss_scale, res[0] * res[0] + res[1] * res[1], rho);
     cost = 0.5 * rho[0];
-    if (MODE) D.cost_slot[s] = cost;
-    else delta = cost - D.cost_slot[s];   // per-residual difference: accurate cost change near convergence
-    if (MODE) {
-      double Jc[2 * (6 + BA_MAXDK)];
-      const int DC = D.DC;
-      for (int k = 0; k < 2 * DC; ++k) Jc[k] = 0.0;
-      const int po = D.pose_off[pi], co = D.cam_off[ci], nv = D.cam_nvar[ci];
-      if (po >= 0) {
-        const unsigned m = D.pose_mask[pi];
-        const double PJ[12] = {pose[3], pose[2], -pose[1], -pose[2], pose[3], pose[0], pose[1], -pose[0], pose[3], -pose[0], -pose[1], -pose[2]};
-        for (int r = 0; r < 2; ++r) {
-          for (int c = 0; c < 3; ++c) {
-            double v = 0;
-            for (int k = 0; k < 4; ++k) v += Jps[7 * r + k] * PJ[3 * k + c];
-            Jc[DC * r + c] = ((m >> c) & 1u) ? v : 0.0;
-          }
-          for (int c = 0; c < 3; ++c) Jc[DC * r + 3 + c] = ((m >> (3 + c)) & 1u) ? Jps[7 * r + 4 + c] : 0.0;
-        }
-      }
-      if (co >= 0)
-        for (int r = 0; r < 2; ++r)
-          for (int k = 0; k < nv; ++k) Jc[DC * r + 6 + k] = Jpr[P * r + D.cam_var[5 * ci + k]];
-      const int lp = D.s_lpt[s];
-      if (lp < 0) for (int k = 0; k < 6; ++k) Jpt[k] = 0.0;
-      double rs = 1.0;
-      if (D.loss_type != B200BA_LOSS_TRIVIAL) {  // ceres Corrector
-        const double sqrt_rho1 = sqrt(rho[1]);
-        double alpha_sq_norm = 0.0;
-        rs = sqrt_rho1;
-        if (sq != 0.0 && rho[2] > 0.0) {
-          const double Dd = 1.0 + 2.0 * sq * rho[2] / rho[1];
-          const double alpha = 1.0 - sqrt(Dd);
-          rs = sqrt_rho1 / (1 - alpha);
-          alpha_sq_norm = alpha / sq;
-        }
-        for (int c = 0; c < DC; ++c) {
-          const double rj = res[0] * Jc[c] + res[1] * Jc[DC + c];
-          Jc[c] = sqrt_rho1 * (Jc[c] - alpha_sq_norm * res[0] * rj);
-          Jc[DC + c] = sqrt_rho1 * (Jc[DC + c] - alpha_sq_norm * res[1] * rj);
-        }
-        for (int c = 0; c < 3; ++c) {
-          const double rj = res[0] * Jpt[c] + res[1] * Jpt[3 + c];
-          Jpt[c] = sqrt_rho1 * (Jpt[c] - alpha_sq_norm * res[0] * rj);
-          Jpt[3 + c] = sqrt_rho1 * (Jpt[3 + c] - alpha_sq_norm * res[1] * rj);
-        }
-      }
-      if (apply_scale) {
-        if (po >= 0) for (int c = 0; c < 6; ++c) { const double sc = D.scale_c[po + c]; Jc[c] *= sc; Jc[DC + c] *= sc; }
-        if (co >= 0) for (int c = 0; c < nv; ++c) { const double sc = D.scale_c[co + c]; Jc[6 + c] *= sc; Jc[DC + 6 + c] *= sc; }
-        if (lp >= 0) for (int c = 0; c < 3; ++c) { const double sc = D.scale_p[3 * (long long)lp + c]; Jpt[c] *= sc; Jpt[3 + c] *= sc; }
-      }
-      const long long cp = D.s2c[s];
-      for (int k = 0; k < 2 * DC; ++k) { const float v = (float)Jc[k]; D.Jc[BA_JC(k, s)] = v; D.JcC[BA_JC(k, cp)] = v; }
-      for (int k = 0; k < 6; ++k) D.Jp[BA_JP(k, s)] = (float)Jpt[k];
-      D.r[s] = rs * res[0];
-      D.r[D.nslots + s] = rs * res[1];
-      D.rC[BA_U(0, cp)] = rs * res[0];
-      D.rC[BA_U(1, cp)] = rs * res[1];
-    }
-  } else if (MODE) {
-    for (int k = 0; k < 2 * D.DC; ++k) D.Jc[BA_JC(k, s)] = 0.0;
-    for (int k = 0; k < 6; ++k) D.Jp[BA_JP(k, s)] = 0.0;
-    D.r[s] = 0.0; D.r[D.nslots + s] = 0.0;
-    D.cost_slot[s] = 0.0;
+    delta = cost - D.cost_slot[s];
   }
   const double t = ba_block_sum(cost, sm);
   if (threadIdx.x == 0) atomicAdd(cost_out, t);
-  if (!MODE) {
-    const double t2 = ba_block_sum(delta, sm);
-    if (threadIdx.x == 0) atomicAdd(&D.ctl->cost_delta, t2);
-  }
+  const double t2 = ba_block_sum(delta, sm);
+  if (threadIdx.x == 0) atomicAdd(&D.ctl->cost_delta, t2);
 }
 
 // squared column norms of the unscaled Jacobian (iteration 0) -> scale_c / scale_p hold the sums
@@ -352,42 +451,6 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_colnorm_kernel(const BaDev D) {
 __global__ void ba_make_scale_kernel(double* v, long long n, int enable) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[i] = enable ? 1.0 / (1.0 + sqrt(v[i])) : 1.0;
-}
-__global__ void __launch_bounds__(BA_BLOCK) ba_apply_scale_kernel(const BaDev D) {
-  const long long s = (long long)blockIdx.x * BA_BLOCK + threadIdx.x;
-  const int pi = D.s_pose[s];
-  if (pi < 0) return;
-  const int ci = D.s_cam[s], DC = D.DC;
-  const int po = D.pose_off[pi], co = D.cam_off[ci], nv = D.cam_nvar[ci], lp = D.s_lpt[s];
-  if (po >= 0) for (int c = 0; c < 6; ++c) { const double sc = D.scale_c[po + c]; D.Jc[BA_JC(c, s)] *= sc; D.Jc[BA_JC((DC + c), s)] *= sc; }
-  if (co >= 0) for (int c = 0; c < nv; ++c) { const double sc = D.scale_c[co + c]; D.Jc[BA_JC((6 + c), s)] *= sc; D.Jc[BA_JC((DC + 6 + c), s)] *= sc; }
-  if (lp >= 0) for (int c = 0; c < 3; ++c) { const double sc = D.scale_p[3 * (long long)lp + c]; D.Jp[BA_JP(c, s)] *= sc; D.Jp[BA_JP((3 + c), s)] *= sc; }
-}
-
-// camera-side accumulations per slot: g_c, diag(J'J)_c, H_cc diagonal blocks
-__global__ void __launch_bounds__(BA_BLOCK) ba_build_cam_kernel(const BaDev D) {
-  const long long s = (long long)blockIdx.x * BA_BLOCK + threadIdx.x;
-  const int pi = D.s_pose[s];
-  if (pi < 0) return;
-  const int ci = D.s_cam[s], DC = D.DC;
-  const int po = D.pose_off[pi], co = D.cam_off[ci], nv = D.cam_nvar[ci];
-  const double r0 = D.r[s], r1 = D.r[D.nslots + s];
-  double J0[6 + BA_MAXDK], J1[6 + BA_MAXDK];
-  for (int c = 0; c < DC; ++c) { J0[c] = D.Jc[BA_JC(c, s)]; J1[c] = D.Jc[BA_JC((DC + c), s)]; }
-  if (po >= 0) {
-    double* H = D.Hbb + D.blk_pack[D.off2blk[po]];
-    for (int a = 0; a < 6; ++a) {
-      atomicAdd(&D.gc[po + a], J0[a] * r0 + J1[a] * r1);
-      for (int b = 0; b < 6; ++b) atomicAdd(&H[a * 6 + b], J0[a] * J0[b] + J1[a] * J1[b]);
-    }
-  }
-  if (co >= 0) {
-    double* H = D.Hbb + D.blk_pack[D.off2blk[co]];
-    for (int a = 0; a < nv; ++a) {
-      atomicAdd(&D.gc[co + a], J0[6 + a] * r0 + J1[6 + a] * r1);
-      for (int b = 0; b < nv; ++b) atomicAdd(&H[a * nv + b], J0[6 + a] * J0[6 + b] + J1[6 + a] * J1[6 + b]);
-    }
-  }
 }
 __global__ void ba_diag_from_blocks_kernel(const BaDev D) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -441,8 +504,9 @@ __global__ void ba_gradmax_kernel(const BaDev D) {
 
 // camera-side accumulations without per-observation atomics: one warp per chunk of a block's observations in
 // camera order: g_c and the diagonal block of H_cc (both triangles), reduced with shuffles, one red.add per entry
-__global__ void __launch_bounds__(BA_BLOCK) ba_build_cam_sorted_kernel(const BaDev D) {
-  const int chunk = blockIdx.x * (BA_BLOCK / 32) + (threadIdx.x >> 5);
+#define BA_SC_BLOCK 128
+__global__ void __launch_bounds__(BA_SC_BLOCK) ba_build_cam_sorted_kernel(const BaDev D) {
+  const int chunk = blockIdx.x * (BA_SC_BLOCK / 32) + (threadIdx.x >> 5);
   if (chunk >= D.nchunks) return;
   const int lane = threadIdx.x & 31;
   const int4 ch = D.chunks[chunk];
@@ -450,6 +514,7 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_build_cam_sorted_kernel(const BaD
   double g[6] = {0, 0, 0, 0, 0, 0}, H[21];
 #pragma unroll
   for (int i = 0; i < 21; ++i) H[i] = 0.0;
+#pragma unroll 4
   for (int k = ch.x + lane; k < ch.y; k += 32) {
     const double r0 = D.rC[BA_U(0, k)], r1 = D.rC[BA_U(1, k)];
     double a[6], b[6];
@@ -483,76 +548,104 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_build_cam_sorted_kernel(const BaD
     }
 }
 
-// per slot: u = J_p Hinv g_p (for the reduced right-hand side) and T = V^T Hinv V with V = J_p^T J_c,pose (the
-// point term of the pose's SCHUR_JACOBI block), both written in camera order for the chunk reductions
-__global__ void __launch_bounds__(BA_BLOCK) ba_schur_slot_kernel(const BaDev D) {
-  const long long s = (long long)blockIdx.x * BA_BLOCK + threadIdx.x;
-  const int pi = D.s_pose[s];
-  if (pi < 0) return;
-  const long long cp = D.s2c[s];
-  const int lp = D.s_lpt[s];
-  double u0 = 0.0, u1 = 0.0;
-  double T[21];
+// Point terms of the reduced system, one warp per chunk of a camera-side block's observations (camera order, so
+// every operand streams): for each observation u = J_p Hinv g_p and V = J_p^T J_c,block; accumulated per chunk are
+//   rhs(block)  += J_c,block^T u                       (reduced right-hand side  -g_c + H_cp Hinv g_p)
+//   Mbb(block)  -= V^T Hinv V                          (point term of the block's SCHUR_JACOBI diagonal block)
+// reduced with shuffles, one red.add per entry per chunk.  Nothing per observation is written.  When a track sees the
+// same variable-intrinsics camera twice (shared cameras) the intrinsics blocks also need the cross terms between
+// different observations of the point: those problems set D.intr_by_pt and the intrinsics blocks come from
+// ba_schur_pt_kernel instead.
+__global__ void __launch_bounds__(BA_SC_BLOCK) ba_schur_cam_kernel(const BaDev D) {
+  const int chunk = blockIdx.x * (BA_SC_BLOCK / 32) + (threadIdx.x >> 5);
+  if (chunk >= D.nchunks) return;
+  const int lane = threadIdx.x & 31;
+  const int4 ch = D.chunks[chunk];
+  const int comp0 = ch.w & 0xff, n = ch.w >> 8;
+  const bool want_T = (comp0 == 0) || !D.intr_by_pt;
+  double g[6] = {0, 0, 0, 0, 0, 0}, T[21];
 #pragma unroll
   for (int i = 0; i < 21; ++i) T[i] = 0.0;
-  if (lp >= 0) {
-    const double* I = D.Hpp_inv + 6 * (long long)lp;
-    const double Hi[9] = {I[0], I[1], I[2], I[1], I[3], I[4], I[2], I[4], I[5]};
-    const double g0 = D.gp[3 * (long long)lp], g1 = D.gp[3 * (long long)lp + 1], g2 = D.gp[3 * (long long)lp + 2];
-    const double w0 = Hi[0] * g0 + Hi[1] * g1 + Hi[2] * g2, w1 = Hi[3] * g0 + Hi[4] * g1 + Hi[5] * g2, w2 = Hi[6] * g0 + Hi[7] * g1 + Hi[8] * g2;
-    double a[3], b[3];
+  // Software pipeline: a warp walks its chunk 32 observations at a time and every step has a dependent gather
+  // (observation -> point -> Hinv, g_p).  The point index is fetched two steps ahead, the point data and the Jacobian
+  // rows one step ahead, so no step waits for a memory round trip.
+  int k = ch.x + lane;
+  int lp_n = (k < ch.y) ? D.c_pack[k].y : -1;                 // point of step 0
+  int lp_nn = (k + 32 < ch.y) ? D.c_pack[k + 32].y : -1;      // point of step 1
+  double Hn[6], gn[3];
+  float an[3], bn[3], j0n[6], j1n[6];
+  auto fetch = [&](int kk, int lp) {
+    if (lp >= 0) {
+      const double* I = D.Hpp_inv + 6 * (long long)lp;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { a[c] = D.Jp[BA_JP(c, s)]; b[c] = D.Jp[BA_JP(3 + c, s)]; }
-    u0 = a[0] * w0 + a[1] * w1 + a[2] * w2;
-    u1 = b[0] * w0 + b[1] * w1 + b[2] * w2;
-    if (D.pose_off[pi] >= 0) {
-      double V[18], G[18];
+      for (int c = 0; c < 6; ++c) Hn[c] = I[c];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gn[c] = D.gp[3 * (long long)lp + c];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { an[c] = D.JpC[BA_JP(c, kk)]; bn[c] = D.JpC[BA_JP(3 + c, kk)]; }
 #pragma unroll
       for (int c = 0; c < 6; ++c) {
-        const double j0 = D.Jc[BA_JC(c, s)], j1 = D.Jc[BA_JC(D.DC + c, s)];
-#pragma unroll
-        for (int t = 0; t < 3; ++t) V[t * 6 + c] = a[t] * j0 + b[t] * j1;
+        j0n[c] = (c < n) ? D.JcC[BA_JC(comp0 + c, kk)] : 0.f;
+        j1n[c] = (c < n) ? D.JcC[BA_JC(D.DC + comp0 + c, kk)] : 0.f;
       }
+    }
+  };
+  fetch(k, lp_n);
+  for (; k < ch.y; k += 32) {
+    const int lp = lp_n;
+    double I[6], gq[3], a[3], b[3], j0[6], j1[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { I[c] = Hn[c]; j0[c] = (double)j0n[c]; j1[c] = (double)j1n[c]; }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { gq[c] = gn[c]; a[c] = (double)an[c]; b[c] = (double)bn[c]; }
+    // next steps' loads go out before this step's arithmetic
+    lp_n = lp_nn;
+    lp_nn = (k + 64 < ch.y) ? D.c_pack[k + 64].y : -1;
+    fetch(k + 32, lp_n);
+    if (lp < 0) continue;
+    const double Hi[9] = {I[0], I[1], I[2], I[1], I[3], I[4], I[2], I[4], I[5]};
+    const double w0 = Hi[0] * gq[0] + Hi[1] * gq[1] + Hi[2] * gq[2], w1 = Hi[3] * gq[0] + Hi[4] * gq[1] + Hi[5] * gq[2],
+                 w2 = Hi[6] * gq[0] + Hi[7] * gq[1] + Hi[8] * gq[2];
+    const double u0 = a[0] * w0 + a[1] * w1 + a[2] * w2;
+    const double u1 = b[0] * w0 + b[1] * w1 + b[2] * w2;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) g[c] += j0[c] * u0 + j1[c] * u1;
+    if (want_T) {
+      double V[18];
 #pragma unroll
       for (int c = 0; c < 6; ++c)
 #pragma unroll
-        for (int t = 0; t < 3; ++t) G[t * 6 + c] = Hi[3 * t] * V[c] + Hi[3 * t + 1] * V[6 + c] + Hi[3 * t + 2] * V[12 + c];
+        for (int t = 0; t < 3; ++t) V[t * 6 + c] = a[t] * j0[c] + b[t] * j1[c];
       int idx = 0;
 #pragma unroll
-      for (int r = 0; r < 6; ++r)
+      for (int r = 0; r < 6; ++r) {
+        // row r of V^T Hinv, then its products with the columns c >= r of V
+        const double G0 = V[r] * Hi[0] + V[6 + r] * Hi[3] + V[12 + r] * Hi[6];
+        const double G1 = V[r] * Hi[1] + V[6 + r] * Hi[4] + V[12 + r] * Hi[7];
+        const double G2 = V[r] * Hi[2] + V[6 + r] * Hi[5] + V[12 + r] * Hi[8];
 #pragma unroll
-        for (int c = r; c < 6; ++c) T[idx++] = V[r] * G[c] + V[6 + r] * G[6 + c] + V[12 + r] * G[12 + c];
+        for (int c = r; c < 6; ++c) T[idx++] += G0 * V[c] + G1 * V[6 + c] + G2 * V[12 + c];
+      }
     }
   }
-  D.u[BA_U(0, cp)] = (float)u0;
-  D.u[BA_U(1, cp)] = (float)u1;
 #pragma unroll
-  for (int i = 0; i < 21; ++i) D.T21[BA_T(i, cp)] = T[i];
-}
-// Mbb(pose block) -= sum over the pose's observations of T
-__global__ void __launch_bounds__(BA_BLOCK) ba_pose_block_reduce_kernel(const BaDev D) {
-  const int chunk = blockIdx.x * (BA_BLOCK / 32) + (threadIdx.x >> 5);
-  if (chunk >= D.nchunks) return;
-  const int4 ch = D.chunks[chunk];
-  if ((ch.w & 0xff) != 0) return;  // pose chunks only
-  const int lane = threadIdx.x & 31;
-  double T[21];
-#pragma unroll
-  for (int i = 0; i < 21; ++i) T[i] = 0.0;
-  for (int k = ch.x + lane; k < ch.y; k += 32) {
-#pragma unroll
-    for (int i = 0; i < 21; ++i) T[i] += D.T21[BA_T(i, k)];
+  for (int c = 0; c < 6; ++c) {
+    double t = g[c];
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0 && c < n) atomicAdd(&D.rhs[ch.z + c], t);
   }
-  double* M = D.Mbb + D.blk_pack[D.off2blk[ch.z]];
-  int idx = 0;
+  if (want_T) {
+    double* M = D.Mbb + D.blk_pack[D.off2blk[ch.z]];
+    int idx = 0;
 #pragma unroll
-  for (int r = 0; r < 6; ++r)
+    for (int r = 0; r < 6; ++r)
 #pragma unroll
-    for (int c = r; c < 6; ++c) {
-      double t = T[idx++];
-      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if (lane == 0) { atomicAdd(&M[r * 6 + c], -t); if (c != r) atomicAdd(&M[c * 6 + r], -t); }
-    }
+      for (int c = r; c < 6; ++c) {
+        double t = T[idx++];
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0 && r < n && c < n) { atomicAdd(&M[r * n + c], -t); if (c != r) atomicAdd(&M[c * n + r], -t); }
+      }
+  }
 }
 
 // (H_pp + D_p^2)^-1 per point
@@ -580,8 +673,8 @@ __global__ void ba_damp_cam_kernel(const BaDev D, double inv_radius, double dmin
   for (int c = 0; c < n; ++c) D.Mbb[D.blk_pack[b] + l * n + c] = D.Hbb[D.blk_pack[b] + l * n + c] + (c == l ? d : 0.0);
 }
 // per point: the point term of the INTRINSICS blocks of SCHUR_JACOBI, -= V^T Hinv V with V summed over every
-// observation of the track made with the same camera (exact cross terms for shared intrinsics).  The pose blocks
-// and the reduced right-hand side are handled by ba_schur_slot_kernel + the camera-order reductions.
+// observation of the track made with the same camera (exact cross terms for shared intrinsics).  Only launched when
+// some track sees a variable-intrinsics camera more than once (D.intr_by_pt); otherwise ba_schur_cam_kernel has them.
 __global__ void ba_schur_pt_kernel(const BaDev D) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= D.nvpt) return;
@@ -692,28 +785,29 @@ __device__ __forceinline__ double ba_shfl_down_f64(double v, int off) { return _
 __device__ __forceinline__ double ba_shfl_f64(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
 template <int DC>
-__global__ void __launch_bounds__(BA_BLOCK) ba_schur_spmv_warp_kernel(const BaDev D, const double* __restrict__ pvec) {
-  if (D.ctl->done) return;
-  const long long s = (long long)blockIdx.x * BA_BLOCK + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  const int4 pk = D.s_pack[s];                  // all per-slot indices in one coalesced 16-byte load
+__device__ __forceinline__ void ba_spmv_slot(const BaDev& D, const long long s, const int lane, const double* __restrict__ pvec) {
+  const int4 pk = __ldg(D.s_pack + s);          // all per-slot indices in one coalesced 16-byte load
   const unsigned pky = (unsigned)pk.y;
   const int po = pk.x, co = (int)(pky & 0x7ffffu) - 1, nv = (int)((pky >> 19) & 7u);
   const int lp = pk.z;
   const long long cp = pk.w;                     // -1 on padding slots
   int head = lane, last = lane;
   double y0 = 0.0, y1 = 0.0;
-  float jp[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  // the Jacobian rows are fetched unconditionally (padding slots hold zeros) so that their loads are in flight
+  // together with the index load instead of behind it
+  float J0[DC], J1[DC], jp[6];
+#pragma unroll
+  for (int c = 0; c < DC; ++c) { J0[c] = D.Jc[BA_JC(c, s)]; J1[c] = D.Jc[BA_JC(DC + c, s)]; }
+#pragma unroll
+  for (int c = 0; c < 6; ++c) jp[c] = D.Jp[BA_JP(c, s)];
   if (cp >= 0) {
-    float J0[DC], J1[DC];
-#pragma unroll
-    for (int c = 0; c < DC; ++c) { J0[c] = D.Jc[BA_JC(c, s)]; J1[c] = D.Jc[BA_JC(DC + c, s)]; }
-#pragma unroll
-    for (int c = 0; c < 6; ++c) jp[c] = D.Jp[BA_JP(c, s)];
     head = (int)((pky >> 22) & 31u); last = (int)((pky >> 27) & 31u);
-    if (po >= 0) {
+    if (po >= 0) {   // pose blocks are 6 doubles wide: the offset is 16-byte aligned -> three 128-bit loads
+      const double2* v2 = reinterpret_cast<const double2*>(pvec + po);
+      const double2 va = v2[0], vb = v2[1], vc = v2[2];
+      const double v[6] = {va.x, va.y, vb.x, vb.y, vc.x, vc.y};
 #pragma unroll
-      for (int c = 0; c < 6; ++c) { const double v = pvec[po + c]; y0 += (double)J0[c] * v; y1 += (double)J1[c] * v; }
+      for (int c = 0; c < 6; ++c) { y0 += (double)J0[c] * v[c]; y1 += (double)J1[c] * v[c]; }
     }
     if (co >= 0) {
 #pragma unroll
@@ -744,10 +838,29 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_schur_spmv_warp_kernel(const BaDe
   }
 }
 
+template <int DC>
+__global__ void __launch_bounds__(BA_BLOCK) ba_schur_spmv_warp_kernel(const BaDev D, const double* __restrict__ pvec) {
+  if (D.ctl->done) return;
+  ba_spmv_slot<DC>(D, (long long)blockIdx.x * BA_BLOCK + threadIdx.x, threadIdx.x & 31, pvec);
+}
+// Persistent form with the camera-side vector staged in shared memory: the per-lane gathers p[pose], p[camera] (every
+// lane of a warp looks at a different camera) cost one L1 wavefront per lane and instruction from global memory, a few
+// bank-conflict cycles from shared memory.  Grid = SMs x resident CTAs, each CTA loads p once and walks the slot blocks.
+template <int DC>
+__global__ void __launch_bounds__(BA_BLOCK) ba_schur_spmv_warp_smem_kernel(const BaDev D, const double* __restrict__ pvec) {
+  extern __shared__ double2 ba_sp2[];
+  double* sp = reinterpret_cast<double*>(ba_sp2);
+  if (D.ctl->done) return;
+  for (int i = threadIdx.x; i < D.nc; i += BA_BLOCK) sp[i] = pvec[i];
+  __syncthreads();
+  for (int blk = blockIdx.x; blk < D.nblocks_warp; blk += gridDim.x)
+    ba_spmv_slot<DC>(D, (long long)blk * BA_BLOCK + threadIdx.x, threadIdx.x & 31, sp);
+}
+
 // THE ROOFLINE KERNEL, pass 1 of 2: u_o = J_c p - J_p (H_pp + D_p^2)^-1 sum_track J_p^T J_c p per observation.
 // One thread per observation slot; a block holds whole tracks, so the point-block elimination
 // (z_p = sum J_p^T y, w_p = Hinv z_p) is a shared-memory exchange.  u is written in camera-sorted order and
-// reduced per camera-side block by ba_cam_reduce_kernel (no atomics on the hot data, deterministic).
+// reduced per camera-side block by ba_cam_stream_kernel.
 template <int DC>
 __global__ void __launch_bounds__(BA_BLOCK) ba_schur_spmv_kernel(const BaDev D, const double* __restrict__ pvec,
                                                                  double* __restrict__ qvec) {
@@ -811,98 +924,226 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_schur_spmv_kernel(const BaDev D, 
   }
 }
 
-// Second SpMV pass (also used for the reduced right-hand side): out[block] += sum over the block's observations
-// of Jc^T u, observations in camera-sorted order so every block (pose or intrinsics) owns contiguous ranges.
-// One CTA per chunk of <= BA_CHUNK observations; deterministic tree inside the chunk, one red.add per output.
-__global__ void __launch_bounds__(BA_BLOCK) ba_cam_reduce_kernel(const BaDev D, double* __restrict__ out, int respect_done) {
-  if (respect_done && D.ctl->done) return;
-  const int chunk = blockIdx.x * (BA_BLOCK / 32) + (threadIdx.x >> 5);   // one warp per chunk: shuffles only, no barrier
-  if (chunk >= D.nchunks) return;
-  const int lane = threadIdx.x & 31;
-  const int4 ch = D.chunks[chunk];
-  const int comp0 = ch.w & 0xff, ncomp = ch.w >> 8;
-  double acc[6] = {0, 0, 0, 0, 0, 0};
-#pragma unroll 4
-  for (int k = ch.x + lane; k < ch.y; k += 32) {
-    const double u0 = D.u[BA_U(0, k)], u1 = D.u[BA_U(1, k)];
+// Second SpMV pass (streaming): out[block] += sum over the block's observations of J_c^T u, observations in camera
+// order.  A warp owns BA_CS_TILES (template parameter; B200BA_CS_TILES = 1 | 2 | 4, default 2) consecutive 32-observation tiles; all their loads are issued up front (fully
+// coalesced tile lines), the products are accumulated per lane while the tiles stay inside one (camera, pose) run —
+// runs are thousands of observations long — and reduced with shuffles once per run change / at the end: 6 + nv
+// red.adds per warp.  No shared memory, no barrier.
+template <int DC>
+__device__ __forceinline__ void ba_cam_stream_flush(double* acc, int run, const BaDev& D, double* __restrict__ out, int lane) {
+  if (run < 0) return;
+  const int4 rd = D.runs[run];
+  double mine = 0.0;
 #pragma unroll
-    for (int c = 0; c < 6; ++c)
-      if (c < ncomp) acc[c] += (double)D.JcC[BA_JC((comp0 + c), k)] * u0 + (double)D.JcC[BA_JC((D.DC + comp0 + c), k)] * u1;
+  for (int c = 0; c < DC; ++c) {
+    double t = acc[c];
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == c) mine = t;
+    acc[c] = 0.0;
   }
+  if (lane < 6) { if (rd.x >= 0) atomicAdd(&out[rd.x + lane], mine); }
+  else if (lane < 6 + rd.z) { if (rd.y >= 0) atomicAdd(&out[rd.y + lane - 6], mine); }
+}
+template <int DC, int BA_CS_TILES>
+__global__ void __launch_bounds__(BA_BLOCK) ba_cam_stream_kernel(const BaDev D, double* __restrict__ out, int respect_done) {
+  if (respect_done && D.ctl->done) return;
+  const int lane = threadIdx.x & 31;
+  const long long tile0 = ((long long)blockIdx.x * (BA_BLOCK / 32) + (threadIdx.x >> 5)) * BA_CS_TILES;
+  const long long ntiles = (D.nobs_c + 31) >> 5;
+  int run[BA_CS_TILES];
+  float j0[BA_CS_TILES][DC], j1[BA_CS_TILES][DC], uf0[BA_CS_TILES], uf1[BA_CS_TILES];
 #pragma unroll
-  for (int c = 0; c < 6; ++c) {
-    if (c < ncomp) {
-      double t = acc[c];
-      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if (lane == 0) atomicAdd(&out[ch.z + c], t);
+  for (int t = 0; t < BA_CS_TILES; ++t) {
+    const long long k = (tile0 + t) * 32 + lane;
+    if (tile0 + t < ntiles) {   // warp-uniform; the padded tail of the last tile is allocated (run = -1 there)
+      run[t] = D.c_run[k];
+#pragma unroll
+      for (int c = 0; c < DC; ++c) { j0[t][c] = D.JcC[BA_JC(c, k)]; j1[t][c] = D.JcC[BA_JC(DC + c, k)]; }
+      uf0[t] = D.u[BA_U(0, k)]; uf1[t] = D.u[BA_U(1, k)];
+    } else {
+      run[t] = -1;
+#pragma unroll
+      for (int c = 0; c < DC; ++c) { j0[t][c] = 0.f; j1[t][c] = 0.f; }
+      uf0[t] = 0.f; uf1[t] = 0.f;
     }
   }
+  double acc[DC];
+#pragma unroll
+  for (int c = 0; c < DC; ++c) acc[c] = 0.0;
+  int cur = -1;
+#pragma unroll
+  for (int t = 0; t < BA_CS_TILES; ++t) {
+    const int r0 = __shfl_sync(0xffffffffu, run[t], 0);
+    const bool uniform = __all_sync(0xffffffffu, run[t] == r0);
+    if (uniform) {
+      if (r0 != cur) { ba_cam_stream_flush<DC>(acc, cur, D, out, lane); cur = r0; }
+      if (r0 >= 0) {
+#pragma unroll
+        for (int c = 0; c < DC; ++c) acc[c] += (double)j0[t][c] * (double)uf0[t] + (double)j1[t][c] * (double)uf1[t];
+      }
+    } else {  // the tile straddles a run boundary (or is the ragged tail): per-observation adds (rare)
+      ba_cam_stream_flush<DC>(acc, cur, D, out, lane); cur = -1;
+      if (run[t] >= 0) {
+        const int4 rd = D.runs[run[t]];
+#pragma unroll
+        for (int c = 0; c < DC; ++c) {
+          const double v = (double)j0[t][c] * (double)uf0[t] + (double)j1[t][c] * (double)uf1[t];
+          if (c < 6) { if (rd.x >= 0) atomicAdd(&out[rd.x + c], v); }
+          else if (c < 6 + rd.z) { if (rd.y >= 0) atomicAdd(&out[rd.y + c - 6], v); }
+        }
+      }
+    }
+  }
+  ba_cam_stream_flush<DC>(acc, cur, D, out, lane);
 }
 
-// Streaming form of the second SpMV pass: one thread per observation in camera order.  A warp covers one 32-observation
-// tile (fully coalesced tile loads); when the whole warp belongs to one (camera, pose) run — the normal case, runs are
-// thousands of observations long — the 6 + nv products are reduced with shuffles and lanes 0..5+nv issue one red.add each.
+// Looped form of the second pass: a warp walks a contiguous range of tiles, the next tile's loads are issued before the
+// current tile is accumulated (register double buffer), and the shuffle reduction happens only when the (camera, pose)
+// run changes or the range ends — instead of once per tile.
 template <int DC>
-__global__ void __launch_bounds__(BA_BLOCK) ba_cam_stream_kernel(const BaDev D, double* __restrict__ out, int respect_done) {
-  __shared__ double part[BA_BLOCK / 32][DC];
-  __shared__ int run0;
+__global__ void __launch_bounds__(BA_BLOCK) ba_cam_stream_loop_kernel(const BaDev D, double* __restrict__ out, int respect_done,
+                                                                      int tiles_per_warp) {
   if (respect_done && D.ctl->done) return;
-  const long long k = (long long)blockIdx.x * BA_BLOCK + threadIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // all loads are issued up front, independent of the run lookup (the padded tail of the arrays is allocated)
-  const int run = D.c_run[k];   // -1 on the padding of the last tile
-  float j0[DC], j1[DC];
+  const int lane = threadIdx.x & 31;
+  const long long ntiles = (D.nobs_c + 31) >> 5;
+  long long t = ((long long)blockIdx.x * (BA_BLOCK / 32) + (threadIdx.x >> 5)) * tiles_per_warp;
+  const long long t1 = (t + tiles_per_warp < ntiles) ? t + tiles_per_warp : ntiles;
+  if (t >= t1) return;
+  int run_c;
+  float j0c[DC], j1c[DC], u0c, u1c;
+  {
+    const long long k = t * 32 + lane;
+    run_c = D.c_run[k];
 #pragma unroll
-  for (int c = 0; c < DC; ++c) { j0[c] = D.JcC[BA_JC(c, k)]; j1[c] = D.JcC[BA_JC(DC + c, k)]; }
-  const float uf0 = D.u[BA_U(0, k)], uf1 = D.u[BA_U(1, k)];
-  double v[DC];
-  int4 rd = make_int4(-1, -1, 0, 0);
-  if (run >= 0) {
-    rd = D.runs[run];
-#pragma unroll
-    for (int c = 0; c < DC; ++c) v[c] = (double)j0[c] * (double)uf0 + (double)j1[c] * (double)uf1;
-  } else {
-#pragma unroll
-    for (int c = 0; c < DC; ++c) v[c] = 0.0;
+    for (int c = 0; c < DC; ++c) { j0c[c] = D.JcC[BA_JC(c, k)]; j1c[c] = D.JcC[BA_JC(DC + c, k)]; }
+    u0c = D.u[BA_U(0, k)]; u1c = D.u[BA_U(1, k)];
   }
-  if (threadIdx.x == 0) run0 = run;
+  double acc[DC];
+#pragma unroll
+  for (int c = 0; c < DC; ++c) acc[c] = 0.0;
+  int cur = -1;
+  for (; t < t1; ++t) {
+    int run_n = -1;
+    float j0n[DC], j1n[DC], u0n = 0.f, u1n = 0.f;
+    if (t + 1 < t1) {
+      const long long k = (t + 1) * 32 + lane;
+      run_n = D.c_run[k];
+#pragma unroll
+      for (int c = 0; c < DC; ++c) { j0n[c] = D.JcC[BA_JC(c, k)]; j1n[c] = D.JcC[BA_JC(DC + c, k)]; }
+      u0n = D.u[BA_U(0, k)]; u1n = D.u[BA_U(1, k)];
+    } else {
+#pragma unroll
+      for (int c = 0; c < DC; ++c) { j0n[c] = 0.f; j1n[c] = 0.f; }
+    }
+    const int r0 = __shfl_sync(0xffffffffu, run_c, 0);
+    const bool uniform = __all_sync(0xffffffffu, run_c == r0);
+    if (uniform) {
+      if (r0 != cur) { ba_cam_stream_flush<DC>(acc, cur, D, out, lane); cur = r0; }
+      if (r0 >= 0) {
+#pragma unroll
+        for (int c = 0; c < DC; ++c) acc[c] += (double)j0c[c] * (double)u0c + (double)j1c[c] * (double)u1c;
+      }
+    } else {  // the tile straddles a run boundary (or is the ragged tail): per-observation adds (rare)
+      ba_cam_stream_flush<DC>(acc, cur, D, out, lane); cur = -1;
+      if (run_c >= 0) {
+        const int4 rd = D.runs[run_c];
+#pragma unroll
+        for (int c = 0; c < DC; ++c) {
+          const double v = (double)j0c[c] * (double)u0c + (double)j1c[c] * (double)u1c;
+          if (c < 6) { if (rd.x >= 0) atomicAdd(&out[rd.x + c], v); }
+          else if (c < 6 + rd.z) { if (rd.y >= 0) atomicAdd(&out[rd.y + c - 6], v); }
+        }
+      }
+    }
+    run_c = run_n; u0c = u0n; u1c = u1n;
+#pragma unroll
+    for (int c = 0; c < DC; ++c) { j0c[c] = j0n[c]; j1c[c] = j1n[c]; }
+  }
+  ba_cam_stream_flush<DC>(acc, cur, D, out, lane);
+}
+
+// ---- PCG vector work between two SpMVs in one single-CTA kernel (camera-side dimension is small: a few thousand) ----
+#define BA_PCG_T 1024
+#define BA_PCG_FUSED_MAX 65536
+__device__ __forceinline__ double ba_cta_allsum(double v, double* sm /* [33] */) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sm[w] = v;
   __syncthreads();
-  // the whole CTA (256 consecutive observations) inside one (camera, pose) run: one red.add per component per CTA
-  const bool cta_uniform = __syncthreads_and(run == run0) && run0 >= 0;
-  const bool warp_uniform = __all_sync(0xffffffffu, run == __shfl_sync(0xffffffffu, run, 0));
-  if (cta_uniform || warp_uniform) {
-#pragma unroll
-    for (int c = 0; c < DC; ++c) {
-      double t = v[c];
-      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      v[c] = t;
-    }
+  if (threadIdx.x < 32) {
+    double t = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) sm[32] = t;
   }
-  if (cta_uniform) {
-    if (lane == 0) {
-#pragma unroll
-      for (int c = 0; c < DC; ++c) part[warp][c] = v[c];
+  __syncthreads();
+  const double t = sm[32];
+  __syncthreads();
+  return t;  // valid in every thread
+}
+// One launch between two SpMVs: the tail of PCG iteration i (pq = p.q ; x += alpha p ; r -= alpha q ; Q1 = -x.(b + r) ;
+// |r|^2 ; termination, see ba_pcg_step_kernel) followed by the head of iteration i + 1 (z = M^-1 r ; rho = r.z ;
+// p = z + beta p ; q = D_c^2 p — the SpMV adds the rest).  do_post = 0 for the very first call of a solve.
+__global__ void __launch_bounds__(BA_PCG_T) ba_pcg_mid_kernel(const BaDev D, double q_tolerance, double r_tolerance,
+                                                              int max_iters, int zero_q, int do_post) {
+  __shared__ double sm[33];
+  __shared__ int s_done;
+  BaCtl* c = D.ctl;
+  if (c->done) return;
+  int it = c->it;
+  double last_rho = c->last_rho;
+  if (do_post) {
+    double v = 0.0;
+    for (int i = threadIdx.x; i < D.nc; i += BA_PCG_T) v += D.p[i] * D.q[i];
+    const double pq = ba_cta_allsum(v, sm);
+    if (!(pq > 0.0)) { if (threadIdx.x == 0) c->done = 1; return; }
+    const double rho = c->rho, alpha = rho / pq;
+    double a = 0.0, w = 0.0;
+    for (int i = threadIdx.x; i < D.nc; i += BA_PCG_T) {
+      const double x = D.x[i] + alpha * D.p[i];
+      const double r = D.rr[i] - alpha * D.q[i];
+      D.x[i] = x; D.rr[i] = r;
+      a += -x * (D.rhs[i] + r);
+      w += r * r;
     }
-    __syncthreads();
-    if (threadIdx.x < DC) {
-      double t = 0.0;
-#pragma unroll
-      for (int w = 0; w < BA_BLOCK / 32; ++w) t += part[w][threadIdx.x];
-      const int c = threadIdx.x;
-      if (c < 6) { if (rd.x >= 0) atomicAdd(&out[rd.x + c], t); }
-      else if (c < 6 + rd.z) { if (rd.y >= 0) atomicAdd(&out[rd.y + c - 6], t); }
+    const double Q1 = ba_cta_allsum(a, sm);
+    const double rnorm2 = ba_cta_allsum(w, sm);
+    it += 1;
+    if (threadIdx.x == 0) {
+      int done = 0;
+      c->it = it; c->iters_total += 1;
+      if (r_tolerance > 0.0) {
+        if (rnorm2 <= r_tolerance * r_tolerance * c->norm_b || it >= max_iters) done = 1;
+      } else {
+        const double zeta = it * (Q1 - c->Q0) / Q1;
+        if (zeta < q_tolerance || it >= max_iters) done = 1;
+      }
+      c->Q0 = Q1; c->Q1 = 0.0; c->rnorm2 = 0.0;
+      c->last_rho = rho; c->rho = 0.0; c->pq = 0.0;
+      c->done = done;
+      s_done = done;
     }
-  } else if (warp_uniform) {
-    if (run < 0) return;
-    double mine = 0.0;
-#pragma unroll
-    for (int c = 0; c < DC; ++c) if (lane == c) mine = v[c];
-    if (lane < 6) { if (rd.x >= 0) atomicAdd(&out[rd.x + lane], mine); }
-    else if (lane < 6 + rd.z) { if (rd.y >= 0) atomicAdd(&out[rd.y + lane - 6], mine); }
-  } else if (run >= 0) {  // tile straddles a run boundary: per-observation adds (rare)
-    if (rd.x >= 0) for (int c = 0; c < 6; ++c) atomicAdd(&out[rd.x + c], v[c]);
-    if (rd.y >= 0) for (int c = 0; c < rd.z; ++c) atomicAdd(&out[rd.y + c], v[6 + c]);
+    __syncthreads();   // also orders the rr stores above before the preconditioner reads below
+    if (s_done) return;
+    last_rho = rho;
   }
+  double v = 0.0;
+  for (int i = threadIdx.x; i < D.nc; i += BA_PCG_T) {
+    const int4 ri = D.row_info[i];   // {first row of the block, offset of this row of Minv, block size}
+    const double* M = D.Minv + ri.y;
+    double t = 0;
+    for (int k = 0; k < ri.z; ++k) t += M[k] * D.rr[ri.x + k];
+    D.z[i] = t;
+    v += t * D.rr[i];
+  }
+  const double rho = ba_cta_allsum(v, sm);
+  const bool first = (it == 0);   // first iteration: p = z (never reads the uninitialised / recycled p buffer)
+  const double beta = first ? 0.0 : rho / last_rho;
+  for (int i = threadIdx.x; i < D.nc; i += BA_PCG_T) {
+    const double p = first ? D.z[i] : D.z[i] + beta * D.p[i];
+    D.p[i] = p;
+    D.q[i] = zero_q ? 0.0 : D.Dc2[i] * p;
+  }
+  if (threadIdx.x == 0) c->rho = rho;
 }
 
 __global__ void ba_pcg_dot_pq_kernel(const BaDev D) {
@@ -1001,12 +1242,13 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_giant_finish_kernel(const BaDev D
 
 // d_p = Hinv (-g_p - H_pc d_c); also the model cost change -(Jd)^T (r + Jd/2), one thread per slot block-wise
 template <int DC>
-__global__ void __launch_bounds__(BA_BLOCK) ba_backsub_model_kernel(const BaDev D) {
+__global__ void __launch_bounds__(BA_BLOCK) ba_backsub_model_kernel(const BaDev D, int blk0) {
   __shared__ double sy[2][BA_BLOCK];
   __shared__ double sw[3][BA_BLOCK];
   __shared__ double sm[8];
-  if ((int)blockIdx.x >= D.nblocks_giant0 && (int)blockIdx.x < D.nblocks_giant1) return;
-  const long long s = (long long)blockIdx.x * BA_BLOCK + threadIdx.x;
+  const int blk = blockIdx.x + blk0;
+  if (blk >= D.nblocks_giant0 && blk < D.nblocks_giant1) return;
+  const long long s = (long long)blk * BA_BLOCK + threadIdx.x;
   const int pi = D.s_pose[s];
   double y0 = 0.0, y1 = 0.0;
   if (pi >= 0) {
@@ -1015,14 +1257,14 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_backsub_model_kernel(const BaDev 
     if (po >= 0) for (int c = 0; c < 6; ++c) { const double v = D.x[po + c]; y0 += D.Jc[BA_JC(c, s)] * v; y1 += D.Jc[BA_JC((DC + c), s)] * v; }
     if (co >= 0) for (int c = 0; c < nv; ++c) { const double v = D.x[co + c]; y0 += D.Jc[BA_JC((6 + c), s)] * v; y1 += D.Jc[BA_JC((DC + 6 + c), s)] * v; }
   }
-  if (blockIdx.x < D.nblocks_var) {
+  if (blk < D.nblocks_var) {
     sy[0][threadIdx.x] = y0; sy[1][threadIdx.x] = y1;
     __syncthreads();
-    if (threadIdx.x < D.blk_npt[blockIdx.x]) {
-      const int k = D.blk_pt0[blockIdx.x] + threadIdx.x;
+    if (threadIdx.x < D.blk_npt[blk]) {
+      const int k = D.blk_pt0[blk] + threadIdx.x;
       double t0 = -D.gp[3 * (long long)k], t1 = -D.gp[3 * (long long)k + 1], t2 = -D.gp[3 * (long long)k + 2];
       for (int t = D.vpt_s0[k]; t < D.vpt_s1[k]; ++t) {
-        const int l = t - blockIdx.x * BA_BLOCK;
+        const int l = t - blk * BA_BLOCK;
         const double a0 = sy[0][l], a1 = sy[1][l];
         t0 -= D.Jp[BA_JP(0, t)] * a0 + D.Jp[BA_JP(3, t)] * a1;
         t1 -= D.Jp[BA_JP(1, t)] * a0 + D.Jp[BA_JP(4, t)] * a1;
@@ -1036,7 +1278,7 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_backsub_model_kernel(const BaDev 
     __syncthreads();
     const int lp = (pi >= 0) ? D.s_lpt[s] : -1;
     if (lp >= 0) {
-      const int lt = lp - D.blk_pt0[blockIdx.x];
+      const int lt = lp - D.blk_pt0[blk];
       const double w0 = sw[0][lt], w1 = sw[1][lt], w2 = sw[2][lt];
       y0 += D.Jp[BA_JP(0, s)] * w0 + D.Jp[BA_JP(1, s)] * w1 + D.Jp[BA_JP(2, s)] * w2;
       y1 += D.Jp[BA_JP(3, s)] * w0 + D.Jp[BA_JP(4, s)] * w1 + D.Jp[BA_JP(5, s)] * w2;
@@ -1044,6 +1286,63 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_backsub_model_kernel(const BaDev 
   }
   double m = 0.0;
   if (pi >= 0) m = -(y0 * (D.r[s] + 0.5 * y0) + y1 * (D.r[D.nslots + s] + 0.5 * y1));
+  const double t = ba_block_sum(m, sm);
+  if (threadIdx.x == 0) atomicAdd(&D.ctl->model, t);
+}
+
+// Warp-packed blocks (tracks of <= 32 observations): the same step with the per-track sums as segmented shuffle
+// reductions (cf. ba_spmv_slot) — no shared-memory exchange, no per-track serial loop.
+template <int DC>
+__global__ void __launch_bounds__(BA_BLOCK) ba_backsub_warp_kernel(const BaDev D) {
+  __shared__ double sm[8];
+  const long long s = (long long)blockIdx.x * BA_BLOCK + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int4 pk = __ldg(D.s_pack + s);
+  const unsigned pky = (unsigned)pk.y;
+  const int po = pk.x, co = (int)(pky & 0x7ffffu) - 1, nv = (int)((pky >> 19) & 7u);
+  const int lp = pk.z;
+  const long long cp = pk.w;
+  float J0[DC], J1[DC], jp[6];
+#pragma unroll
+  for (int c = 0; c < DC; ++c) { J0[c] = D.Jc[BA_JC(c, s)]; J1[c] = D.Jc[BA_JC(DC + c, s)]; }
+#pragma unroll
+  for (int c = 0; c < 6; ++c) jp[c] = D.Jp[BA_JP(c, s)];
+  const double r0 = D.r[s], r1 = D.r[D.nslots + s];
+  int head = lane, last = lane;
+  double y0 = 0.0, y1 = 0.0;
+  if (cp >= 0) {
+    head = (int)((pky >> 22) & 31u); last = (int)((pky >> 27) & 31u);
+    if (po >= 0) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { const double v = D.x[po + c]; y0 += (double)J0[c] * v; y1 += (double)J1[c] * v; }
+    }
+    if (co >= 0) {
+#pragma unroll
+      for (int c = 0; c < DC - 6; ++c) if (c < nv) { const double v = D.x[co + c]; y0 += (double)J0[6 + c] * v; y1 += (double)J1[6 + c] * v; }
+    }
+  }
+  double z0 = (double)jp[0] * y0 + (double)jp[3] * y1, z1 = (double)jp[1] * y0 + (double)jp[4] * y1, z2 = (double)jp[2] * y0 + (double)jp[5] * y1;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const double t0 = ba_shfl_down_f64(z0, off), t1 = ba_shfl_down_f64(z1, off), t2 = ba_shfl_down_f64(z2, off);
+    if (lane + off <= last) { z0 += t0; z1 += t1; z2 += t2; }
+  }
+  double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+  if (lane == head && lp >= 0 && cp >= 0) {
+    const double t0 = -D.gp[3 * (long long)lp] - z0, t1 = -D.gp[3 * (long long)lp + 1] - z1, t2 = -D.gp[3 * (long long)lp + 2] - z2;
+    const double* I = D.Hpp_inv + 6 * (long long)lp;
+    d0 = I[0] * t0 + I[1] * t1 + I[2] * t2; d1 = I[1] * t0 + I[3] * t1 + I[4] * t2; d2 = I[2] * t0 + I[4] * t1 + I[5] * t2;
+    D.dp[3 * (long long)lp] = d0; D.dp[3 * (long long)lp + 1] = d1; D.dp[3 * (long long)lp + 2] = d2;
+  }
+  d0 = ba_shfl_f64(d0, head); d1 = ba_shfl_f64(d1, head); d2 = ba_shfl_f64(d2, head);
+  double m = 0.0;
+  if (cp >= 0) {
+    if (lp >= 0) {
+      y0 += (double)jp[0] * d0 + (double)jp[1] * d1 + (double)jp[2] * d2;
+      y1 += (double)jp[3] * d0 + (double)jp[4] * d1 + (double)jp[5] * d2;
+    }
+    m = -(y0 * (r0 + 0.5 * y0) + y1 * (r1 + 0.5 * y1));
+  }
   const double t = ba_block_sum(m, sm);
   if (threadIdx.x == 0) atomicAdd(&D.ctl->model, t);
 }
@@ -1101,24 +1400,71 @@ struct BaPool {
   void release() { cudaDeviceSynchronize(); for (auto& a : ptrs) B200DeviceCache::get().free(a.first, a.second); ptrs.clear(); }
 };
 
+static int g_ba_cs_tiles = 0;   // ba_cam_stream: 0 = looped kernel (default), 1 | 2 | 4 = tiles per warp of the one-shot kernel (B200BA_CS_TILES)
+static int g_ba_spmv_smem = 1;  // pass 1 with p staged in shared memory when it fits (B200BA_SPMV_SMEM=0 disables)
+static int g_ba_sms = 0;
+#define BA_SPMV_SMEM_MAX (72 * 1024)
 template <int DC>
 static void ba_launch_spmv(const BaDev& D, cudaStream_t s) {
-  if (D.nblocks_warp) ba_schur_spmv_warp_kernel<DC><<<D.nblocks_warp, BA_BLOCK, 0, s>>>(D, D.p);
+  if (D.nblocks_warp) {
+    const size_t smem = sizeof(double) * (size_t)D.nc;
+    if (g_ba_spmv_smem && smem <= BA_SPMV_SMEM_MAX) {
+      static bool attr_set = false;   // per instantiation
+      if (!attr_set) { cudaFuncSetAttribute(ba_schur_spmv_warp_smem_kernel<DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, BA_SPMV_SMEM_MAX); attr_set = true; }
+      if (!g_ba_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_ba_sms, cudaDevAttrMultiProcessorCount, dev); }
+      const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(5, (size_t)(216 * 1024) / (smem + 1024)));
+      const int grid = std::min(D.nblocks_warp, g_ba_sms * per_sm);
+      ba_schur_spmv_warp_smem_kernel<DC><<<grid, BA_BLOCK, smem, s>>>(D, D.p);
+    } else {
+      ba_schur_spmv_warp_kernel<DC><<<D.nblocks_warp, BA_BLOCK, 0, s>>>(D, D.p);
+    }
+  }
   if (D.nblocks > D.nblocks_warp) ba_schur_spmv_kernel<DC><<<D.nblocks - D.nblocks_warp, BA_BLOCK, 0, s>>>(D, D.p, D.q);
   if (D.nblocks_giant1 > D.nblocks_giant0) {
     cudaMemsetAsync(D.zg, 0, sizeof(double) * 3 * (size_t)D.nvpt, s);
     ba_giant_accumulate_kernel<0><<<D.nblocks_giant1 - D.nblocks_giant0, BA_BLOCK, 0, s>>>(D, D.p);
     ba_giant_finish_kernel<0><<<D.nblocks_giant1 - D.nblocks_giant0, BA_BLOCK, 0, s>>>(D, D.p);
   }
-  if (D.nobs_c) ba_cam_stream_kernel<DC><<<(unsigned)((D.nobs_c + BA_BLOCK - 1) / BA_BLOCK), BA_BLOCK, 0, s>>>(D, D.q, 1);
+  if (D.nobs_c) {
+    if (g_ba_cs_tiles == 0) {
+      if (!g_ba_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_ba_sms, cudaDevAttrMultiProcessorCount, dev); }
+      const long long ntiles = (D.nobs_c + 31) / 32;
+      const long long warps = (long long)g_ba_sms * 2 * (BA_BLOCK / 32) * 2;   // two waves of two resident CTAs per SM
+      const int tpw = (int)std::max<long long>(4, (ntiles + warps - 1) / warps);
+      const unsigned grid = (unsigned)((ntiles + (long long)tpw * (BA_BLOCK / 32) - 1) / ((long long)tpw * (BA_BLOCK / 32)));
+      ba_cam_stream_loop_kernel<DC><<<grid, BA_BLOCK, 0, s>>>(D, D.q, 1, tpw);
+    } else {
+      const unsigned per = BA_BLOCK * (unsigned)g_ba_cs_tiles;
+      const unsigned grid = (unsigned)((D.nobs_c + per - 1) / per);
+      if (g_ba_cs_tiles == 4) ba_cam_stream_kernel<DC, 4><<<grid, BA_BLOCK, 0, s>>>(D, D.q, 1);
+      else if (g_ba_cs_tiles == 2) ba_cam_stream_kernel<DC, 2><<<grid, BA_BLOCK, 0, s>>>(D, D.q, 1);
+      else ba_cam_stream_kernel<DC, 1><<<grid, BA_BLOCK, 0, s>>>(D, D.q, 1);
+    }
+  }
 }
 template <int DC>
 static void ba_launch_backsub(const BaDev& D, cudaStream_t s) {
-  ba_backsub_model_kernel<DC><<<D.nblocks, BA_BLOCK, 0, s>>>(D);
+  if (D.nblocks_warp) ba_backsub_warp_kernel<DC><<<D.nblocks_warp, BA_BLOCK, 0, s>>>(D);
+  if (D.nblocks > D.nblocks_warp) ba_backsub_model_kernel<DC><<<D.nblocks - D.nblocks_warp, BA_BLOCK, 0, s>>>(D, D.nblocks_warp);
   if (D.nblocks_giant1 > D.nblocks_giant0) {
     cudaMemsetAsync(D.zg, 0, sizeof(double) * 3 * (size_t)D.nvpt, s);
     ba_giant_accumulate_kernel<1><<<D.nblocks_giant1 - D.nblocks_giant0, BA_BLOCK, 0, s>>>(D, D.x);
     ba_giant_finish_kernel<1><<<D.nblocks_giant1 - D.nblocks_giant0, BA_BLOCK, 0, s>>>(D, D.x);
+  }
+}
+template <int DC>
+static void ba_launch_linearize_dc(const BaDev& D, int apply_scale, cudaStream_t s) {
+  ba_linearize_slot_kernel<DC><<<D.nblocks, BA_BLOCK, 0, s>>>(D, apply_scale, &D.ctl->cost);
+  if (D.nobs_c) ba_linearize_cam_kernel<DC><<<(unsigned)((D.nobs_c + BA_BLOCK - 1) / BA_BLOCK), BA_BLOCK, 0, s>>>(D, apply_scale);
+}
+static void ba_launch_linearize(const BaDev& D, int apply_scale, cudaStream_t s) {
+  switch (D.DC) {
+    case 6: ba_launch_linearize_dc<6>(D, apply_scale, s); break;
+    case 7: ba_launch_linearize_dc<7>(D, apply_scale, s); break;
+    case 8: ba_launch_linearize_dc<8>(D, apply_scale, s); break;
+    case 9: ba_launch_linearize_dc<9>(D, apply_scale, s); break;
+    case 10: ba_launch_linearize_dc<10>(D, apply_scale, s); break;
+    default: ba_launch_linearize_dc<11>(D, apply_scale, s); break;
   }
 }
 #define BA_DISPATCH_DC(FN, D, s)                 \
@@ -1498,6 +1844,14 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   const long long nobs_c_pad = (nobs_c + BA_BLOCK - 1) / BA_BLOCK * BA_BLOCK;
   std::vector<int> c_run(nobs_c_pad, -1);
   std::vector<int4> runs, chunks;
+  std::vector<int2> runs_pc, c_pack((size_t)nobs_c_pad, make_int2(0, -1));
+  std::vector<double> xyC(2 * (size_t)nobs_c_pad, 0.0);
+  for (long long k = 0; k < nobs_c; ++k) {
+    const int sl = c2s[k];
+    c_pack[k] = make_int2(s_pt[sl], s_lpt[sl]);
+    xyC[((k >> 5) * 2 + 0) * 32 + (k & 31)] = sx[sl];
+    xyC[((k >> 5) * 2 + 1) * 32 + (k & 31)] = sy[sl];
+  }
   {
     std::vector<int> cpose((size_t)nobs_c), ccam((size_t)nobs_c);
     for (long long k = 0; k < nobs_c; ++k) { const int sl = c2s[k]; cpose[k] = s_pose[sl]; ccam[k] = s_cam[sl]; }
@@ -1512,6 +1866,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
       const int rid = (int)runs.size();
       for (long long j = k; j < e; ++j) c_run[j] = rid;
       runs.push_back(make_int4(pose_off[pose], cam_off[cam], cam_nvar[cam], 0));
+      runs_pc.push_back(make_int2(pose, cam));
       if (pose_off[pose] >= 0) add_chunks(k, e, pose_off[pose], 0, 6);
       if (e == nobs_c || ccam[e] != cam) {  // end of this camera's range
         if (cam_off[cam] >= 0) add_chunks(cam_start, e, cam_off[cam], 6, cam_nvar[cam]);
@@ -1527,6 +1882,19 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
     const unsigned head_ = (unsigned)(s_seg[sl] & 0xff), last_ = (unsigned)(s_seg[sl] >> 8);
     const unsigned y = (unsigned)(co_ + 1) | ((unsigned)nv_ << 19) | (head_ << 22) | (last_ << 27);
     s_pack[sl] = make_int4(po_, (int)y, s_lpt[sl], s2c[sl]);
+  }
+  // does any track see the same variable-intrinsics camera twice?  (shared cameras: the intrinsics blocks of the
+  // preconditioner then need cross terms between observations of one point)
+  int intr_by_pt = 0;
+  {
+    std::vector<int> seen((size_t)NCAM, -1);
+    for (int n = 0; n < nvpt && !intr_by_pt; ++n)
+      for (int sl = vpt_s0[n]; sl < vpt_s1[n]; ++sl) {
+        const int cam = s_cam[sl];
+        if (cam_off[cam] < 0) continue;
+        if (seen[cam] == n) { intr_by_pt = 1; break; }
+        seen[cam] = n;
+      }
   }
   tick("camera order, runs, chunks");
   if (host_only) {
@@ -1565,8 +1933,20 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   { int* t; BA_CUDA(pool.upload(&t, blk_start, st)); D.blk_start = t; }
   { int* t; BA_CUDA(pool.upload(&t, blk_pack, st)); D.blk_pack = t; }
   { int* t; BA_CUDA(pool.upload(&t, off2blk, st)); D.off2blk = t; }
+  {
+    std::vector<int4> row_info((size_t)nc);
+    for (int i = 0; i < nc; ++i) {
+      const int b = off2blk[i], n = blk_start[b + 1] - blk_start[b], l = i - blk_start[b];
+      row_info[i] = make_int4(blk_start[b], blk_pack[b] + l * n, n, 0);
+    }
+    int4* t; BA_CUDA(pool.upload(&t, row_info, st)); D.row_info = t;
+  }
   BA_CUDA(pool.alloc(&D.Jc, (size_t)2 * D.DC * nslots)); BA_CUDA(pool.alloc(&D.Jp, (size_t)6 * nslots));
-  BA_CUDA(pool.alloc(&D.JcC, (size_t)2 * D.DC * nobs_c_pad)); BA_CUDA(pool.alloc(&D.u, (size_t)2 * nobs_c_pad)); BA_CUDA(pool.alloc(&D.rC, (size_t)2 * nobs_c_pad)); BA_CUDA(pool.alloc(&D.T21, (size_t)21 * nobs_c_pad));
+  BA_CUDA(pool.alloc(&D.JcC, (size_t)2 * D.DC * nobs_c_pad)); BA_CUDA(pool.alloc(&D.u, (size_t)2 * nobs_c_pad)); BA_CUDA(pool.alloc(&D.rC, (size_t)2 * nobs_c_pad)); BA_CUDA(pool.alloc(&D.JpC, (size_t)6 * nobs_c_pad));
+  { double* t; BA_CUDA(pool.upload(&t, xyC, st)); D.xyC = t; }
+  { int2* t; BA_CUDA(pool.upload(&t, c_pack, st)); D.c_pack = t; }
+  { int2* t; BA_CUDA(pool.upload(&t, runs_pc, st)); D.runs_pc = t; }
+  D.intr_by_pt = intr_by_pt;
   { int* t; BA_CUDA(pool.upload(&t, s2c, st)); D.s2c = t; }
   { int* t; BA_CUDA(pool.upload(&t, s_seg, st)); D.s_seg = t; }
   { int4* t; BA_CUDA(pool.upload(&t, s_pack, st)); D.s_pack = t; }
@@ -1600,9 +1980,9 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   auto zero_field = [&](double* field) { return cudaMemsetAsync(field, 0, sizeof(double), st); };
   auto linearize_current = [&](int apply_scale) {
     zero_field(&D.ctl->cost);
-    ba_linearize_kernel<1><<<nblocks, BA_BLOCK, 0, st>>>(D, D.poses, D.cams, D.pts, apply_scale, &D.ctl->cost);
+    ba_launch_linearize(D, apply_scale, st);
     allreduce(&D.ctl->cost, 1, ncclDouble, ncclSum);
-    ++launches;
+    launches += 2;
   };
 
   BA_CUDA(cudaEventRecord(ev0, st));
@@ -1628,13 +2008,16 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   const int max_cg = exact ? std::max(10 * nc + 100, o->max_linear_solver_iterations) : o->max_linear_solver_iterations;
   bool finished = false;
   const bool verbose = getenv("B200BA_VERBOSE") != nullptr;
+  const bool fused_pcg = nc <= BA_PCG_FUSED_MAX && getenv("B200BA_PCG_MULTI") == nullptr;
+  if (const char* e = getenv("B200BA_CS_TILES")) { const int t = atoi(e); g_ba_cs_tiles = (t == 4 || t == 2 || t == 1) ? t : 0; }
+  if (const char* e = getenv("B200BA_SPMV_SMEM")) g_ba_spmv_smem = atoi(e) != 0;
   double last_gmax = 0.0;
   while (!finished) {
     // normal equations from the current (scaled) Jacobian
     BA_CUDA(cudaMemsetAsync(D.gc, 0, sizeof(double) * (nc ? nc : 1), st));
     BA_CUDA(cudaMemsetAsync(D.Hbb, 0, sizeof(double) * (pack ? pack : 1), st));
     BA_CUDA(zero_field(&D.ctl->gmax));
-    if (D.nchunks) ba_build_cam_sorted_kernel<<<(D.nchunks + 7) / 8, BA_BLOCK, 0, st>>>(D);
+    if (D.nchunks) ba_build_cam_sorted_kernel<<<(D.nchunks + BA_SC_BLOCK / 32 - 1) / (BA_SC_BLOCK / 32), BA_SC_BLOCK, 0, st>>>(D);
     BA_CUDA(allreduce(D.gc, nc, ncclDouble, ncclSum));
     BA_CUDA(allreduce(D.Hbb, pack, ncclDouble, ncclSum));
     if (nc) ba_diag_from_blocks_kernel<<<gc_blocks, 256, 0, st>>>(D);
@@ -1657,11 +2040,9 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
         BA_CUDA(cudaMemsetAsync(D.Mbb, 0, sizeof(double) * (pack ? pack : 1), st));
       }
       if (nvpt && nc) {
-        ba_schur_slot_kernel<<<nblocks, BA_BLOCK, 0, st>>>(D);
-        ba_cam_reduce_kernel<<<(D.nchunks + 7) / 8, BA_BLOCK, 0, st>>>(D, D.rhs, 0);
-        ba_pose_block_reduce_kernel<<<(D.nchunks + 7) / 8, BA_BLOCK, 0, st>>>(D);
-        if (dkmax > 0) ba_schur_pt_kernel<<<gp_blocks, 256, 0, st>>>(D);
-        launches += 3;
+        if (D.nchunks) ba_schur_cam_kernel<<<(D.nchunks + BA_SC_BLOCK / 32 - 1) / (BA_SC_BLOCK / 32), BA_SC_BLOCK, 0, st>>>(D);
+        if (dkmax > 0 && intr_by_pt) ba_schur_pt_kernel<<<gp_blocks, 256, 0, st>>>(D);
+        launches += 1 + (dkmax > 0 && intr_by_pt ? 1 : 0);
       }
       BA_CUDA(allreduce(D.rhs, nc, ncclDouble, ncclSum));
       BA_CUDA(allreduce(D.Mbb, pack, ncclDouble, ncclSum));
@@ -1675,20 +2056,29 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
         ba_pcg_init_kernel<<<gc_blocks, 256, 0, st>>>(D);
         ++launches;
         int issued = 0;
+        const bool zero_q = sharded && comm->rank != 0;   // D_c^2 p is contributed by rank 0 only
+        if (fused_pcg) { ba_pcg_mid_kernel<<<1, BA_PCG_T, 0, st>>>(D, q_tol, r_tol, max_cg, zero_q ? 1 : 0, 0); ++launches; }
         for (;;) {
           const int batch = std::min(8, max_cg - issued);
           for (int b = 0; b < batch; ++b) {
-            ba_pcg_precond_kernel<<<gc_blocks, 256, 0, st>>>(D);
-            ba_pcg_direction_kernel<<<gc_blocks, 256, 0, st>>>(D);
-            if (sharded && comm->rank != 0) BA_CUDA(cudaMemsetAsync(D.q, 0, sizeof(double) * nc, st));  // D_c^2 p from rank 0 only
+            if (!fused_pcg) {
+              ba_pcg_precond_kernel<<<gc_blocks, 256, 0, st>>>(D);
+              ba_pcg_direction_kernel<<<gc_blocks, 256, 0, st>>>(D);
+              if (zero_q) BA_CUDA(cudaMemsetAsync(D.q, 0, sizeof(double) * nc, st));
+            }
             if (b == 0) BA_CUDA(cudaEventRecord(evs0, st));  // first SpMV of a batch always does real work
             BA_DISPATCH_DC(ba_launch_spmv, D, st);
             if (b == 0) BA_CUDA(cudaEventRecord(evs1, st));
             BA_CUDA(allreduce(D.q, nc, ncclDouble, ncclSum));  // the one data-path collective of a PCG iteration
-            ba_pcg_dot_pq_kernel<<<gc_blocks, 256, 0, st>>>(D);
-            ba_pcg_update_kernel<<<gc_blocks, 256, 0, st>>>(D);
-            ba_pcg_step_kernel<<<1, 1, 0, st>>>(D, q_tol, r_tol, max_cg);
-            launches += 6;
+            if (fused_pcg) {
+              ba_pcg_mid_kernel<<<1, BA_PCG_T, 0, st>>>(D, q_tol, r_tol, max_cg, zero_q ? 1 : 0, 1);
+              launches += 3;
+            } else {
+              ba_pcg_dot_pq_kernel<<<gc_blocks, 256, 0, st>>>(D);
+              ba_pcg_update_kernel<<<gc_blocks, 256, 0, st>>>(D);
+              ba_pcg_step_kernel<<<1, 1, 0, st>>>(D, q_tol, r_tol, max_cg);
+              launches += 7;
+            }
           }
           issued += batch;
           BA_CUDA(read_ctl());
@@ -1701,7 +2091,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
       { const long long n = (long long)NP + NCAM + NPT; ba_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(D); }
       BA_CUDA(zero_field(&D.ctl->new_cost));
       BA_CUDA(zero_field(&D.ctl->cost_delta));
-      ba_linearize_kernel<0><<<nblocks, BA_BLOCK, 0, st>>>(D, D.nposes_, D.ncams_, D.npts_, 0, &D.ctl->new_cost);
+      ba_cost_kernel<<<nblocks, BA_BLOCK, 0, st>>>(D, D.nposes_, D.ncams_, D.npts_, &D.ctl->new_cost);
       BA_CUDA(allreduce(&D.ctl->model, 1, ncclDouble, ncclSum));
       BA_CUDA(allreduce(&D.ctl->new_cost, 1, ncclDouble, ncclSum));
       BA_CUDA(allreduce(&D.ctl->cost_delta, 1, ncclDouble, ncclSum));
