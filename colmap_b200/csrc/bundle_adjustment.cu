@@ -514,16 +514,33 @@ __global__ void __launch_bounds__(BA_SC_BLOCK) ba_build_cam_sorted_kernel(const 
   double g[6] = {0, 0, 0, 0, 0, 0}, H[21];
 #pragma unroll
   for (int i = 0; i < 21; ++i) H[i] = 0.0;
-#pragma unroll 4
-  for (int k = ch.x + lane; k < ch.y; k += 32) {
-    const double r0 = D.rC[BA_U(0, k)], r1 = D.rC[BA_U(1, k)];
+  // register double buffer: the next step's loads are issued before this step's 27 accumulations
+  float an[6], bn[6];
+  double r0n = 0.0, r1n = 0.0;
+  auto fetch = [&](int kk) {
+    if (kk < ch.y) {
+      r0n = D.rC[BA_U(0, kk)]; r1n = D.rC[BA_U(1, kk)];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        an[c] = (c < n) ? D.JcC[BA_JC(comp0 + c, kk)] : 0.f;
+        bn[c] = (c < n) ? D.JcC[BA_JC(D.DC + comp0 + c, kk)] : 0.f;
+      }
+    } else {
+      r0n = 0.0; r1n = 0.0;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { an[c] = 0.f; bn[c] = 0.f; }
+    }
+  };
+  int k = ch.x + lane;
+  fetch(k);
+  for (; k < ch.y; k += 32) {
+    const double r0 = r0n, r1 = r1n;
     double a[6], b[6];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) {
-      a[c] = (c < n) ? (double)D.JcC[BA_JC(comp0 + c, k)] : 0.0;
-      b[c] = (c < n) ? (double)D.JcC[BA_JC(D.DC + comp0 + c, k)] : 0.0;
-      g[c] += a[c] * r0 + b[c] * r1;
-    }
+    for (int c = 0; c < 6; ++c) { a[c] = (double)an[c]; b[c] = (double)bn[c]; }
+    fetch(k + 32);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) g[c] += a[c] * r0 + b[c] * r1;
     int idx = 0;
 #pragma unroll
     for (int r = 0; r < 6; ++r)
@@ -1083,65 +1100,99 @@ __device__ __forceinline__ double ba_cta_allsum(double v, double* sm /* [33] */)
 // One launch between two SpMVs: the tail of PCG iteration i (pq = p.q ; x += alpha p ; r -= alpha q ; Q1 = -x.(b + r) ;
 // |r|^2 ; termination, see ba_pcg_step_kernel) followed by the head of iteration i + 1 (z = M^-1 r ; rho = r.z ;
 // p = z + beta p ; q = D_c^2 p — the SpMV adds the rest).  do_post = 0 for the very first call of a solve.
+#define BA_PCG_EPT 4   // elements per thread handled from registers (nc <= BA_PCG_T * BA_PCG_EPT takes the fast path)
 __global__ void __launch_bounds__(BA_PCG_T) ba_pcg_mid_kernel(const BaDev D, double q_tolerance, double r_tolerance,
                                                               int max_iters, int zero_q, int do_post) {
   __shared__ double sm[33];
   __shared__ int s_done;
   BaCtl* c = D.ctl;
   if (c->done) return;
+  // independent restrict views: the vectors never alias, which lets the loads of all elements go out together
+  double* __restrict__ X = D.x; double* __restrict__ R = D.rr; double* __restrict__ P = D.p; double* __restrict__ Q = D.q;
+  double* __restrict__ Z = D.z;
+  const double* __restrict__ RHS = D.rhs; const double* __restrict__ DC2 = D.Dc2; const double* __restrict__ MI = D.Minv;
+  const int nc = D.nc;
   int it = c->it;
   double last_rho = c->last_rho;
+  const double rho_in = c->rho, norm_b = c->norm_b, Q0 = c->Q0;
   if (do_post) {
-    double v = 0.0;
-    for (int i = threadIdx.x; i < D.nc; i += BA_PCG_T) v += D.p[i] * D.q[i];
+    double pv[BA_PCG_EPT], qv[BA_PCG_EPT], v = 0.0;
+    const bool small = nc <= BA_PCG_T * BA_PCG_EPT;
+    if (small) {
+#pragma unroll
+      for (int e = 0; e < BA_PCG_EPT; ++e) { const int i = threadIdx.x + e * BA_PCG_T; pv[e] = i < nc ? P[i] : 0.0; qv[e] = i < nc ? Q[i] : 0.0; v += pv[e] * qv[e]; }
+    } else {
+      for (int i = threadIdx.x; i < nc; i += BA_PCG_T) v += P[i] * Q[i];
+    }
     const double pq = ba_cta_allsum(v, sm);
     if (!(pq > 0.0)) { if (threadIdx.x == 0) c->done = 1; return; }
-    const double rho = c->rho, alpha = rho / pq;
+    const double alpha = rho_in / pq;
     double a = 0.0, w = 0.0;
-    for (int i = threadIdx.x; i < D.nc; i += BA_PCG_T) {
-      const double x = D.x[i] + alpha * D.p[i];
-      const double r = D.rr[i] - alpha * D.q[i];
-      D.x[i] = x; D.rr[i] = r;
-      a += -x * (D.rhs[i] + r);
-      w += r * r;
-    }
-    const double Q1 = ba_cta_allsum(a, sm);
-    const double rnorm2 = ba_cta_allsum(w, sm);
-    it += 1;
-    if (threadIdx.x == 0) {
-      int done = 0;
-      c->it = it; c->iters_total += 1;
-      if (r_tolerance > 0.0) {
-        if (rnorm2 <= r_tolerance * r_tolerance * c->norm_b || it >= max_iters) done = 1;
-      } else {
-        const double zeta = it * (Q1 - c->Q0) / Q1;
-        if (zeta < q_tolerance || it >= max_iters) done = 1;
+    if (small) {
+      double xv[BA_PCG_EPT], rv[BA_PCG_EPT], bv[BA_PCG_EPT];
+#pragma unroll
+      for (int e = 0; e < BA_PCG_EPT; ++e) { const int i = threadIdx.x + e * BA_PCG_T; xv[e] = i < nc ? X[i] : 0.0; rv[e] = i < nc ? R[i] : 0.0; bv[e] = i < nc ? RHS[i] : 0.0; }
+#pragma unroll
+      for (int e = 0; e < BA_PCG_EPT; ++e) {
+        const int i = threadIdx.x + e * BA_PCG_T;
+        const double x = xv[e] + alpha * pv[e], r = rv[e] - alpha * qv[e];
+        if (i < nc) { X[i] = x; R[i] = r; a += -x * (bv[e] + r); w += r * r; }
       }
-      c->Q0 = Q1; c->Q1 = 0.0; c->rnorm2 = 0.0;
-      c->last_rho = rho; c->rho = 0.0; c->pq = 0.0;
-      c->done = done;
-      s_done = done;
+    } else {
+      for (int i = threadIdx.x; i < nc; i += BA_PCG_T) {
+        const double x = X[i] + alpha * P[i];
+        const double r = R[i] - alpha * Q[i];
+        X[i] = x; R[i] = r;
+        a += -x * (RHS[i] + r);
+        w += r * r;
+      }
     }
-    __syncthreads();   // also orders the rr stores above before the preconditioner reads below
+    // two sums in one pass through the barriers
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); w += __shfl_xor_sync(0xffffffffu, w, o); }
+    __shared__ double sm2[2][33];
+    const int wid = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sm2[0][wid] = a; sm2[1][wid] = w; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      double ta = sm2[0][threadIdx.x], tw = sm2[1][threadIdx.x];   // BA_PCG_T / 32 == 32 warps
+      for (int o = 16; o > 0; o >>= 1) { ta += __shfl_xor_sync(0xffffffffu, ta, o); tw += __shfl_xor_sync(0xffffffffu, tw, o); }
+      if (threadIdx.x == 0) {
+        const double Q1 = ta, rnorm2 = tw;
+        int done = 0;
+        c->it = it + 1; c->iters_total += 1;
+        if (r_tolerance > 0.0) {
+          if (rnorm2 <= r_tolerance * r_tolerance * norm_b || it + 1 >= max_iters) done = 1;
+        } else {
+          const double zeta = (it + 1) * (Q1 - Q0) / Q1;
+          if (zeta < q_tolerance || it + 1 >= max_iters) done = 1;
+        }
+        c->Q0 = Q1; c->Q1 = 0.0; c->rnorm2 = 0.0;
+        c->last_rho = rho_in; c->rho = 0.0; c->pq = 0.0;
+        c->done = done;
+        s_done = done;
+      }
+    }
+    __syncthreads();   // also orders the R stores above before the preconditioner reads below
     if (s_done) return;
-    last_rho = rho;
+    it += 1;
+    last_rho = rho_in;
   }
   double v = 0.0;
-  for (int i = threadIdx.x; i < D.nc; i += BA_PCG_T) {
+  for (int i = threadIdx.x; i < nc; i += BA_PCG_T) {
     const int4 ri = D.row_info[i];   // {first row of the block, offset of this row of Minv, block size}
-    const double* M = D.Minv + ri.y;
+    const double* __restrict__ M = MI + ri.y;
     double t = 0;
-    for (int k = 0; k < ri.z; ++k) t += M[k] * D.rr[ri.x + k];
-    D.z[i] = t;
-    v += t * D.rr[i];
+    for (int k = 0; k < ri.z; ++k) t += M[k] * R[ri.x + k];
+    Z[i] = t;
+    v += t * R[i];
   }
   const double rho = ba_cta_allsum(v, sm);
   const bool first = (it == 0);   // first iteration: p = z (never reads the uninitialised / recycled p buffer)
   const double beta = first ? 0.0 : rho / last_rho;
-  for (int i = threadIdx.x; i < D.nc; i += BA_PCG_T) {
-    const double p = first ? D.z[i] : D.z[i] + beta * D.p[i];
-    D.p[i] = p;
-    D.q[i] = zero_q ? 0.0 : D.Dc2[i] * p;
+  for (int i = threadIdx.x; i < nc; i += BA_PCG_T) {
+    const double p = first ? Z[i] : Z[i] + beta * P[i];
+    P[i] = p;
+    Q[i] = zero_q ? 0.0 : DC2[i] * p;
   }
   if (threadIdx.x == 0) c->rho = rho;
 }
