@@ -186,9 +186,12 @@ BA_HD void ba_loss(int type, double a, double s, double rho[3]) {
 // device problem
 // ------------------------------------------------------------------------------------------------
 struct BaCtl {          // device-resident scalars of the LM / PCG loops
-  double cost, new_cost, model, gmax, cost_delta;
+  double cost, new_cost, model, cost_delta;
   double rho, last_rho, pq, Q0, Q1, norm_b, rnorm2;
-  int it, done, iters_total, pad;
+  int it, done;
+  // everything above is cleared before each linear solve; the fields below persist
+  int iters_total, fail;
+  double gmax;
 };
 
 struct BaDev {
@@ -219,7 +222,7 @@ struct BaDev {
   int nblocks_warp;                   // leading blocks whose tracks never cross a warp (tracks <= 32 observations)
   int nblocks_giant0, nblocks_giant1; // block range of the tracks longer than a block (> 256 observations): generic two-kernel path
   double* zg;                         // [3*nvpt] scratch of the generic path (sum J_p^T y per point)
-  float* u;                           // [2][nobs_c] per-observation 2-vector exchanged between the two SpMV passes (fp32 like the operator)
+  float2* u;                          // [nobs_c] per-observation 2-vector exchanged between the two SpMV passes (fp32 like the operator)
   double* rC;                         // [2][nobs_c] residuals in camera order
   float* JpC;                         // [6][nobs_c] point-side Jacobian in camera order
   const double* xyC;                  // [2][nobs_c] observed image points in camera order
@@ -839,10 +842,11 @@ __device__ __forceinline__ void ba_spmv_slot(const BaDev& D, const long long s, 
   }
   double w0 = 0.0, w1 = 0.0, w2 = 0.0;
   if (lane == head && lp >= 0) {
-    const double* I = D.Hpp_inv + 6 * (long long)lp;
-    w0 = I[0] * z0 + I[1] * z1 + I[2] * z2;
-    w1 = I[1] * z0 + I[3] * z1 + I[4] * z2;
-    w2 = I[2] * z0 + I[4] * z1 + I[5] * z2;
+    const double2* I2 = reinterpret_cast<const double2*>(D.Hpp_inv + 6 * (long long)lp);   // 48-byte records: 16-byte aligned
+    const double2 ia = I2[0], ib = I2[1], ic = I2[2];
+    w0 = ia.x * z0 + ia.y * z1 + ib.x * z2;
+    w1 = ia.y * z0 + ib.y * z1 + ic.x * z2;
+    w2 = ib.x * z0 + ic.x * z1 + ic.y * z2;
   }
   w0 = ba_shfl_f64(w0, head); w1 = ba_shfl_f64(w1, head); w2 = ba_shfl_f64(w2, head);
   if (cp >= 0) {
@@ -850,8 +854,7 @@ __device__ __forceinline__ void ba_spmv_slot(const BaDev& D, const long long s, 
       y0 -= (double)jp[0] * w0 + (double)jp[1] * w1 + (double)jp[2] * w2;
       y1 -= (double)jp[3] * w0 + (double)jp[4] * w1 + (double)jp[5] * w2;
     }
-    D.u[BA_U(0, cp)] = (float)y0;
-    D.u[BA_U(1, cp)] = (float)y1;
+    D.u[cp] = make_float2((float)y0, (float)y1);   // one 8-byte scattered store per observation
   }
 }
 
@@ -936,8 +939,7 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_schur_spmv_kernel(const BaDev D, 
   }
   if (pi >= 0) {
     const long long cp = D.s2c[s];
-    D.u[BA_U(0, cp)] = (float)y0;
-    D.u[BA_U(1, cp)] = (float)y1;
+    D.u[cp] = make_float2((float)y0, (float)y1);   // one 8-byte scattered store per observation
   }
 }
 
@@ -976,7 +978,7 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_cam_stream_kernel(const BaDev D, 
       run[t] = D.c_run[k];
 #pragma unroll
       for (int c = 0; c < DC; ++c) { j0[t][c] = D.JcC[BA_JC(c, k)]; j1[t][c] = D.JcC[BA_JC(DC + c, k)]; }
-      uf0[t] = D.u[BA_U(0, k)]; uf1[t] = D.u[BA_U(1, k)];
+      { const float2 uu = D.u[k]; uf0[t] = uu.x; uf1[t] = uu.y; }
     } else {
       run[t] = -1;
 #pragma unroll
@@ -1033,7 +1035,7 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_cam_stream_loop_kernel(const BaDe
     run_c = D.c_run[k];
 #pragma unroll
     for (int c = 0; c < DC; ++c) { j0c[c] = D.JcC[BA_JC(c, k)]; j1c[c] = D.JcC[BA_JC(DC + c, k)]; }
-    u0c = D.u[BA_U(0, k)]; u1c = D.u[BA_U(1, k)];
+    { const float2 uu = D.u[k]; u0c = uu.x; u1c = uu.y; }
   }
   double acc[DC];
 #pragma unroll
@@ -1047,7 +1049,7 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_cam_stream_loop_kernel(const BaDe
       run_n = D.c_run[k];
 #pragma unroll
       for (int c = 0; c < DC; ++c) { j0n[c] = D.JcC[BA_JC(c, k)]; j1n[c] = D.JcC[BA_JC(DC + c, k)]; }
-      u0n = D.u[BA_U(0, k)]; u1n = D.u[BA_U(1, k)];
+      { const float2 uu = D.u[k]; u0n = uu.x; u1n = uu.y; }
     } else {
 #pragma unroll
       for (int c = 0; c < DC; ++c) { j0n[c] = 0.f; j1n[c] = 0.f; }
@@ -1277,8 +1279,7 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_giant_finish_kernel(const BaDev D
     const double j1 = D.Jp[BA_JP(3, s)] * w0 + D.Jp[BA_JP(4, s)] * w1 + D.Jp[BA_JP(5, s)] * w2;
     if (MODE == 0) {
       const long long cp = D.s2c[s];
-      D.u[BA_U(0, cp)] = (float)(y0 - j0);
-      D.u[BA_U(1, cp)] = (float)(y1 - j1);
+      D.u[cp] = make_float2((float)(y0 - j0), (float)(y1 - j1));
     } else {
       if ((int)s == D.vpt_s0[lp]) { D.dp[3 * (long long)lp] = w0; D.dp[3 * (long long)lp + 1] = w1; D.dp[3 * (long long)lp + 2] = w2; }
       y0 += j0; y1 += j1;
@@ -1993,7 +1994,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
     int4* t; BA_CUDA(pool.upload(&t, row_info, st)); D.row_info = t;
   }
   BA_CUDA(pool.alloc(&D.Jc, (size_t)2 * D.DC * nslots)); BA_CUDA(pool.alloc(&D.Jp, (size_t)6 * nslots));
-  BA_CUDA(pool.alloc(&D.JcC, (size_t)2 * D.DC * nobs_c_pad)); BA_CUDA(pool.alloc(&D.u, (size_t)2 * nobs_c_pad)); BA_CUDA(pool.alloc(&D.rC, (size_t)2 * nobs_c_pad)); BA_CUDA(pool.alloc(&D.JpC, (size_t)6 * nobs_c_pad));
+  BA_CUDA(pool.alloc(&D.JcC, (size_t)2 * D.DC * nobs_c_pad)); BA_CUDA(pool.alloc(&D.u, (size_t)nobs_c_pad)); BA_CUDA(pool.alloc(&D.rC, (size_t)2 * nobs_c_pad)); BA_CUDA(pool.alloc(&D.JpC, (size_t)6 * nobs_c_pad));
   { double* t; BA_CUDA(pool.upload(&t, xyC, st)); D.xyC = t; }
   { int2* t; BA_CUDA(pool.upload(&t, c_pack, st)); D.c_pack = t; }
   { int2* t; BA_CUDA(pool.upload(&t, runs_pc, st)); D.runs_pc = t; }
@@ -2014,7 +2015,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   BA_CUDA(pool.alloc(&D.Hbb, (size_t)pack)); BA_CUDA(pool.alloc(&D.Mbb, (size_t)pack)); BA_CUDA(pool.alloc(&D.Minv, (size_t)pack));
   BA_CUDA(pool.alloc(&D.x, (size_t)nc)); BA_CUDA(pool.alloc(&D.rr, (size_t)nc)); BA_CUDA(pool.alloc(&D.z, (size_t)nc)); BA_CUDA(pool.alloc(&D.p, (size_t)nc)); BA_CUDA(pool.alloc(&D.q, (size_t)nc));
   BA_CUDA(pool.alloc(&D.ctl, 1));
-  int* d_fail; BA_CUDA(pool.alloc(&d_fail, 1));
+  int* d_fail = &D.ctl->fail;   // part of the control block: travels with the per-iteration read
   BA_CUDA(cudaMemsetAsync(D.ctl, 0, sizeof(BaCtl), st));
   BA_CUDA(cudaMemsetAsync(D.x, 0, sizeof(double) * (nc ? nc : 1), st));
   BA_CUDA(cudaMemsetAsync(D.dp, 0, sizeof(double) * (nvpt ? 3 * (size_t)nvpt : 1), st));
@@ -2063,6 +2064,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   if (const char* e = getenv("B200BA_CS_TILES")) { const int t = atoi(e); g_ba_cs_tiles = (t == 4 || t == 2 || t == 1) ? t : 0; }
   if (const char* e = getenv("B200BA_SPMV_SMEM")) g_ba_spmv_smem = atoi(e) != 0;
   double last_gmax = 0.0;
+  int discarded_pcg = 0;
   while (!finished) {
     // normal equations from the current (scaled) Jacobian
     BA_CUDA(cudaMemsetAsync(D.gc, 0, sizeof(double) * (nc ? nc : 1), st));
@@ -2076,12 +2078,15 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
     { const long long n = (long long)NP + NCAM + 3LL * nvpt; ba_gradmax_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(D); }
     launches += 4;
     BA_CUDA(allreduce(&D.ctl->gmax, 1, ncclDouble, ncclMax));
-    BA_CUDA(read_ctl());
-    last_gmax = h.gmax;
-    if (h.gmax <= o->gradient_tolerance) { sum->termination_type = B200BA_CONVERGENCE; break; }
+    // The gradient-norm test of this iteration is read back together with the first linear-solve batch (one host
+    // round trip less per LM iteration); if it says "converged" the enqueued solve is discarded.
+    bool check_gmax = true;
     bool accepted = false;
     while (!accepted) {
-      if (iter >= o->max_num_iterations) { finished = true; break; }
+      if (iter >= o->max_num_iterations) {
+        if (check_gmax) { BA_CUDA(read_ctl()); last_gmax = h.gmax; if (h.gmax <= o->gradient_tolerance) sum->termination_type = B200BA_CONVERGENCE; }
+        finished = true; break;
+      }
       ++iter;
       BA_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
       if (nvpt) ba_damp_pt_kernel<<<gp_blocks, 256, 0, st>>>(D, 1.0 / radius, o->min_lm_diagonal, o->max_lm_diagonal, d_fail);
@@ -2137,6 +2142,15 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
           if (h.done || issued >= max_cg) break;
         }
       }
+      if (check_gmax) {
+        check_gmax = false;
+        if (!nc) BA_CUDA(read_ctl());
+        last_gmax = h.gmax;
+        if (h.gmax <= o->gradient_tolerance) {
+          --iter; discarded_pcg = nc ? h.it : 0;
+          sum->termination_type = B200BA_CONVERGENCE; finished = true; break;
+        }
+      }
       BA_CUDA(zero_field(&D.ctl->model));
       BA_DISPATCH_DC(ba_launch_backsub, D, st);
       { const long long n = (long long)NP + NCAM + NPT; ba_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(D); }
@@ -2148,8 +2162,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
       BA_CUDA(allreduce(&D.ctl->cost_delta, 1, ncclDouble, ncclSum));
       launches += 3;
       BA_CUDA(read_ctl());
-      int failed = 0;
-      BA_CUDA(cudaMemcpy(&failed, d_fail, sizeof(int), cudaMemcpyDeviceToHost));
+      const int failed = h.fail;
       const double model = h.model, new_cost = h.new_cost;
       // cost change summed residual by residual (same quantity as cost - new_cost, without the cancellation)
       const double cost_change_acc = -h.cost_delta;
@@ -2183,7 +2196,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   BA_CUDA(cudaEventElapsedTime(&solve_ms, ev0, ev1));
   sum->solve_ms = solve_ms;
   sum->final_cost = cost;
-  sum->num_linear_solver_iterations = h.iters_total;
+  sum->num_linear_solver_iterations = h.iters_total - discarded_pcg;
   sum->kernel_launches = launches;
   sum->spmv_launches = spmv_launches;
   sum->spmv_ms_total = spmv_ms;
