@@ -29,6 +29,9 @@
 #include "../../include/b200_bundle_adjustment.h"
 #include "device_cache.h"
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
 #define BA_MAXDK 5
 #define BA_BLOCK 256
 #define BA_CHUNK 512
@@ -1426,6 +1429,67 @@ __global__ void ba_update_kernel(const BaDev D) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// problem set-up on the device: the host decides only which observation sits in which slot (s_obs); the per-slot
+// arrays, the (camera, pose) order and everything indexed by it are produced here from the caller's raw arrays.
+// ------------------------------------------------------------------------------------------------
+__global__ void ba_setup_slot_kernel(long long nslots, const int* __restrict__ s_obs, const int* __restrict__ obs_pose,
+                                     const int* __restrict__ obs_cam, const int* __restrict__ obs_pt,
+                                     const double* __restrict__ obs_xy, int* __restrict__ s_pose, int* __restrict__ s_cam,
+                                     int* __restrict__ s_pt, double* __restrict__ s_xy, unsigned long long* __restrict__ key,
+                                     int* __restrict__ val) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nslots) return;
+  const int obs = s_obs[s];
+  val[s] = (int)s;
+  if (obs < 0) {
+    s_pose[s] = -1; s_cam[s] = -1; s_pt[s] = -1; s_xy[s] = 0.0; s_xy[nslots + s] = 0.0;
+    key[s] = ~0ull;   // padding sorts behind every observation
+    return;
+  }
+  const int pose = obs_pose[obs], cam = obs_cam[obs];
+  s_pose[s] = pose; s_cam[s] = cam; s_pt[s] = obs_pt[obs];
+  const double2 xy = reinterpret_cast<const double2*>(obs_xy)[obs];
+  s_xy[s] = xy.x; s_xy[nslots + s] = xy.y;
+  key[s] = ((unsigned long long)(unsigned)cam << 32) | (unsigned)pose;   // (camera, pose) lexicographic
+}
+// k = position in (camera, pose) order; c2s / keys are the sorted (stable) slot indices and keys
+__global__ void ba_setup_cam_kernel(long long nobs_c, long long nobs_c_pad, long long nslots, const unsigned long long* __restrict__ keys,
+                                    const int* __restrict__ c2s, const int* __restrict__ s_pt, const int* __restrict__ s_lpt,
+                                    const double* __restrict__ s_xy, int* __restrict__ s2c, int2* __restrict__ c_pack,
+                                    double* __restrict__ xyC, int* __restrict__ head) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nobs_c_pad) return;
+  if (k >= nobs_c) { c_pack[k] = make_int2(0, -1); xyC[BA_U(0, k)] = 0.0; xyC[BA_U(1, k)] = 0.0; return; }
+  const int sl = c2s[k];
+  s2c[sl] = (int)k;
+  c_pack[k] = make_int2(s_pt[sl], s_lpt[sl]);
+  xyC[BA_U(0, k)] = s_xy[sl]; xyC[BA_U(1, k)] = s_xy[nslots + sl];
+  head[k] = (k == 0 || keys[k] != keys[k - 1]) ? 1 : 0;
+}
+__global__ void ba_setup_run_kernel(long long nobs_c, const int* __restrict__ run_incl, int* __restrict__ c_run,
+                                    const int* __restrict__ head, const unsigned long long* __restrict__ keys,
+                                    int* __restrict__ run_start, unsigned long long* __restrict__ run_key) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nobs_c) return;
+  const int r = run_incl[k] - 1;
+  c_run[k] = r;
+  if (head[k]) { run_start[r] = (int)k; run_key[r] = keys[k]; }
+}
+__global__ void ba_setup_pack_kernel(long long nslots, const int* __restrict__ s_pose, const int* __restrict__ s_cam,
+                                     const int* __restrict__ s_lpt, const int* __restrict__ s_seg, const int* __restrict__ s2c,
+                                     const int* __restrict__ pose_off, const int* __restrict__ cam_off,
+                                     const int* __restrict__ cam_nvar, int4* __restrict__ s_pack) {
+  const long long sl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (sl >= nslots) return;
+  const int pose = s_pose[sl];
+  if (pose < 0) { s_pack[sl] = make_int4(-1, 0, -1, -1); return; }
+  const int cam = s_cam[sl];
+  const unsigned seg = (unsigned)s_seg[sl];
+  const unsigned y = (unsigned)(cam_off[cam] + 1) | ((unsigned)cam_nvar[cam] << 19) | ((seg & 0xffu) << 22) | ((seg >> 8) << 27);
+  s_pack[sl] = make_int4(pose_off[pose], (int)y, s_lpt[sl], s2c[sl]);
+}
+
+// ------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_ba_error;
@@ -1774,18 +1838,15 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
     for (long long i = 0; i < NOBS; ++i) { const int pv = pt_var[p->obs_point_idx[i]]; if (pv >= 0) vobs[cur[pv]++] = i; }
   }
   tick("group observations by point");
-  // pack whole tracks into blocks of BA_BLOCK slots
-  std::vector<int> s_pose, s_cam, s_pt, s_lpt, blk_pt0, blk_npt, vpt_s0(nvpt), vpt_s1(nvpt), vpt_point(nvpt);
-  std::vector<double> sx, sy;
+  // pack whole tracks into blocks of BA_BLOCK slots.  The host only decides WHICH observation sits in which slot
+  // (s_obs); every per-slot / per-camera-order array is then built on the device from the caller's raw arrays.
+  std::vector<int> s_obs, s_lpt, blk_pt0, blk_npt, vpt_s0(nvpt), vpt_s1(nvpt), vpt_point(nvpt);
   {
     const size_t cap = (size_t)(nobs_eff + nobs_eff / 8 + 4 * BA_BLOCK);
-    s_pose.reserve(cap); s_cam.reserve(cap); s_pt.reserve(cap); s_lpt.reserve(cap); sx.reserve(cap); sy.reserve(cap);
+    s_obs.reserve(cap); s_lpt.reserve(cap);
   }
-  auto push_slot = [&](long long obs, int lpt) {
-    if (obs < 0) { s_pose.push_back(-1); s_cam.push_back(-1); s_pt.push_back(-1); s_lpt.push_back(-1); sx.push_back(0); sy.push_back(0); return; }
-    s_pose.push_back(p->obs_pose_idx[obs]); s_cam.push_back(p->obs_camera_idx[obs]); s_pt.push_back(p->obs_point_idx[obs]);
-    s_lpt.push_back(lpt); sx.push_back(p->obs_xy[2 * obs]); sy.push_back(p->obs_xy[2 * obs + 1]);
-  };
+  if (NOBS >= (1LL << 31)) return ba_fail(-3, "problem too large for 32-bit observation indices");
+  auto push_slot = [&](long long obs, int lpt) { s_obs.push_back((int)obs); s_lpt.push_back(obs < 0 ? -1 : lpt); };
   // variable points are renumbered: tracks of <= 32 observations first (packed so that none crosses a warp),
   // then the longer ones (packed so that none crosses a block)
   std::vector<int> s_seg;
@@ -1821,134 +1882,56 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
     for (int n = 0; n < nvpt; ++n) newidx[order_pts[n]] = n;
     for (long long i = 0; i < NPT; ++i) if (pt_var[i] >= 0) pt_var[i] = newidx[pt_var[i]];
     for (long long i = 0; i < NPT; ++i) if (pt_var[i] >= 0) vpt_point[pt_var[i]] = (int)i;
-    auto pad_to = [&](size_t mult) { while (s_pose.size() % mult) { push_slot(-1, -1); s_seg.push_back(0); } };
+    auto pad_to = [&](size_t mult) { while (s_obs.size() % mult) { push_slot(-1, -1); s_seg.push_back(0); } };
     int cur_blk = -1;
     auto note_block = [&](int k) {
-      const int b = (int)(s_pose.size() / BA_BLOCK);
+      const int b = (int)(s_obs.size() / BA_BLOCK);
       while ((int)blk_pt0.size() <= b) { blk_pt0.push_back(k); blk_npt.push_back(0); }
       blk_npt[b]++; cur_blk = b;
     };
     for (int n = 0; n < nshort; ++n) {
       const int k = order_pts[n], len = (int)olen[k];
-      const int used = (int)(s_pose.size() % 32);
+      const int used = (int)(s_obs.size() % 32);
       if (used + len > 32) pad_to(32);
       note_block(n);
-      vpt_s0[n] = (int)s_pose.size();
-      const int head = (int)(s_pose.size() % 32), last = head + len - 1;
+      vpt_s0[n] = (int)s_obs.size();
+      const int head = (int)(s_obs.size() % 32), last = head + len - 1;
       for (long long j = ostart[k]; j < ostart[k] + len; ++j) { push_slot(vobs[j], n); s_seg.push_back(head | (last << 8)); }
-      vpt_s1[n] = (int)s_pose.size();
+      vpt_s1[n] = (int)s_obs.size();
     }
     pad_to(BA_BLOCK);
-    nblocks_warp = (int)(s_pose.size() / BA_BLOCK);
+    nblocks_warp = (int)(s_obs.size() / BA_BLOCK);
     for (int n = nshort; n < nmid; ++n) {
       const int k = order_pts[n], len = (int)olen[k];
-      const int used = (int)(s_pose.size() % BA_BLOCK);
+      const int used = (int)(s_obs.size() % BA_BLOCK);
       if (used + len > BA_BLOCK) pad_to(BA_BLOCK);
       note_block(n);
-      vpt_s0[n] = (int)s_pose.size();
+      vpt_s0[n] = (int)s_obs.size();
       for (long long j = ostart[k]; j < ostart[k] + len; ++j) { push_slot(vobs[j], n); s_seg.push_back(0); }
-      vpt_s1[n] = (int)s_pose.size();
+      vpt_s1[n] = (int)s_obs.size();
     }
     pad_to(BA_BLOCK);
-    nblocks_giant0 = (int)(s_pose.size() / BA_BLOCK);
+    nblocks_giant0 = (int)(s_obs.size() / BA_BLOCK);
     for (int n = nmid; n < nvpt; ++n) {   // tracks longer than a block: laid out back to back, generic kernels
       const int k = order_pts[n];
-      vpt_s0[n] = (int)s_pose.size();
+      vpt_s0[n] = (int)s_obs.size();
       for (long long j = ostart[k]; j < ostart[k] + olen[k]; ++j) { push_slot(vobs[j], n); s_seg.push_back(0); }
-      vpt_s1[n] = (int)s_pose.size();
+      vpt_s1[n] = (int)s_obs.size();
     }
     pad_to(BA_BLOCK);
-    nblocks_giant1 = (int)(s_pose.size() / BA_BLOCK);
+    nblocks_giant1 = (int)(s_obs.size() / BA_BLOCK);
     (void)cur_blk;
   }
   tick("pack tracks into slots");
   const int nblocks_var = nblocks_giant0;   // blocks whose tracks are eliminated in shared memory / by shuffles
   for (long long i : const_obs) { push_slot(i, -1); s_seg.push_back(0); }
-  while (s_pose.size() % BA_BLOCK) { push_slot(-1, -1); s_seg.push_back(0); }
-  const long long nslots = (long long)s_pose.size();
+  while (s_obs.size() % BA_BLOCK) { push_slot(-1, -1); s_seg.push_back(0); }
+  const long long nslots = (long long)s_obs.size();
   const int nblocks = (int)(nslots / BA_BLOCK);
   blk_pt0.resize(nblocks, nvpt); blk_npt.resize(nblocks, 0);
   if (nslots >= (1LL << 31)) return ba_fail(-3, "problem too large for 32-bit slot indices");
   if (nc >= (1 << 19) - 1) return ba_fail(-3, "camera-side dimension above 2^19 is not supported");
-  std::vector<double> s_xy(2 * nslots);
-  for (long long s = 0; s < nslots; ++s) { s_xy[s] = sx[s]; s_xy[nslots + s] = sy[s]; }
   tick("slot arrays");
-  // camera order: observations sorted by (camera, pose) so that every camera-side block owns contiguous ranges
-  std::vector<int> c2s;
-  {  // two stable counting sorts (by pose, then by camera) = lexicographic (camera, pose) order in O(n)
-    std::vector<int> tmp;
-    tmp.reserve((size_t)nobs_eff);
-    std::vector<long long> cnt((size_t)std::max(NP, NCAM) + 1, 0);
-    for (long long s2 = 0; s2 < nslots; ++s2) if (s_pose[s2] >= 0) cnt[s_pose[s2] + 1]++;
-    for (int i = 0; i < NP; ++i) cnt[i + 1] += cnt[i];
-    tmp.resize((size_t)cnt[NP]);
-    for (long long s2 = 0; s2 < nslots; ++s2) if (s_pose[s2] >= 0) tmp[cnt[s_pose[s2]]++] = (int)s2;
-    std::fill(cnt.begin(), cnt.end(), 0);
-    for (int v : tmp) cnt[s_cam[v] + 1]++;
-    for (int i = 0; i < NCAM; ++i) cnt[i + 1] += cnt[i];
-    c2s.resize(tmp.size());
-    for (int v : tmp) c2s[cnt[s_cam[v]]++] = v;
-  }
-  const long long nobs_c = (long long)c2s.size();
-  std::vector<int> s2c(nslots, -1);
-  for (long long k = 0; k < nobs_c; ++k) s2c[c2s[k]] = (int)k;
-  // runs of equal (camera, pose) in camera order; chunks (<= BA_CHUNK observations of one pose / one camera)
-  const long long nobs_c_pad = (nobs_c + BA_BLOCK - 1) / BA_BLOCK * BA_BLOCK;
-  std::vector<int> c_run(nobs_c_pad, -1);
-  std::vector<int4> runs, chunks;
-  std::vector<int2> runs_pc, c_pack((size_t)nobs_c_pad, make_int2(0, -1));
-  std::vector<double> xyC(2 * (size_t)nobs_c_pad, 0.0);
-  for (long long k = 0; k < nobs_c; ++k) {
-    const int sl = c2s[k];
-    c_pack[k] = make_int2(s_pt[sl], s_lpt[sl]);
-    xyC[((k >> 5) * 2 + 0) * 32 + (k & 31)] = sx[sl];
-    xyC[((k >> 5) * 2 + 1) * 32 + (k & 31)] = sy[sl];
-  }
-  {
-    std::vector<int> cpose((size_t)nobs_c), ccam((size_t)nobs_c);
-    for (long long k = 0; k < nobs_c; ++k) { const int sl = c2s[k]; cpose[k] = s_pose[sl]; ccam[k] = s_cam[sl]; }
-    auto add_chunks = [&](long long k0, long long k1, int out, int comp0, int ncomp) {
-      for (long long c0 = k0; c0 < k1; c0 += BA_CHUNK) chunks.push_back(make_int4((int)c0, (int)std::min<long long>(c0 + BA_CHUNK, k1), out, comp0 | (ncomp << 8)));
-    };
-    long long cam_start = 0;
-    for (long long k = 0; k < nobs_c;) {
-      long long e = k;
-      const int pose = cpose[k], cam = ccam[k];
-      while (e < nobs_c && cpose[e] == pose && ccam[e] == cam) ++e;
-      const int rid = (int)runs.size();
-      for (long long j = k; j < e; ++j) c_run[j] = rid;
-      runs.push_back(make_int4(pose_off[pose], cam_off[cam], cam_nvar[cam], 0));
-      runs_pc.push_back(make_int2(pose, cam));
-      if (pose_off[pose] >= 0) add_chunks(k, e, pose_off[pose], 0, 6);
-      if (e == nobs_c || ccam[e] != cam) {  // end of this camera's range
-        if (cam_off[cam] >= 0) add_chunks(cam_start, e, cam_off[cam], 6, cam_nvar[cam]);
-        cam_start = e;
-      }
-      k = e;
-    }
-  }
-  std::vector<int4> s_pack(nslots);
-  for (long long sl = 0; sl < nslots; ++sl) {
-    if (s_pose[sl] < 0) { s_pack[sl] = make_int4(-1, 0, -1, -1); continue; }
-    const int po_ = pose_off[s_pose[sl]], co_ = cam_off[s_cam[sl]], nv_ = cam_nvar[s_cam[sl]];
-    const unsigned head_ = (unsigned)(s_seg[sl] & 0xff), last_ = (unsigned)(s_seg[sl] >> 8);
-    const unsigned y = (unsigned)(co_ + 1) | ((unsigned)nv_ << 19) | (head_ << 22) | (last_ << 27);
-    s_pack[sl] = make_int4(po_, (int)y, s_lpt[sl], s2c[sl]);
-  }
-  // does any track see the same variable-intrinsics camera twice?  (shared cameras: the intrinsics blocks of the
-  // preconditioner then need cross terms between observations of one point)
-  int intr_by_pt = 0;
-  {
-    std::vector<int> seen((size_t)NCAM, -1);
-    for (int n = 0; n < nvpt && !intr_by_pt; ++n)
-      for (int sl = vpt_s0[n]; sl < vpt_s1[n]; ++sl) {
-        const int cam = s_cam[sl];
-        if (cam_off[cam] < 0) continue;
-        if (seen[cam] == n) { intr_by_pt = 1; break; }
-        seen[cam] = n;
-      }
-  }
-  tick("camera order, runs, chunks");
   if (host_only) {
     sum->setup_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_setup0).count();
     return ba_fail(-102, "B200BA_HOST_ONLY: stopped after the host flattening");
@@ -1973,11 +1956,85 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   { signed char* t; BA_CUDA(pool.upload(&t, cam_var, st)); D.cam_var = t; }
   { int* t; BA_CUDA(pool.upload(&t, pt_var, st)); D.pt_var = t; }
   { int* t; BA_CUDA(pool.upload(&t, vpt_point, st)); D.vpt_point = t; }
-  { int* t; BA_CUDA(pool.upload(&t, s_pose, st)); D.s_pose = t; }
-  { int* t; BA_CUDA(pool.upload(&t, s_cam, st)); D.s_cam = t; }
-  { int* t; BA_CUDA(pool.upload(&t, s_pt, st)); D.s_pt = t; }
   { int* t; BA_CUDA(pool.upload(&t, s_lpt, st)); D.s_lpt = t; }
-  { double* t; BA_CUDA(pool.upload(&t, s_xy, st)); D.s_xy = t; }
+  { int* t; BA_CUDA(pool.upload(&t, s_seg, st)); D.s_seg = t; }
+  // per-slot arrays, (camera, pose) order, runs: built on the device from the caller's arrays
+  const long long nobs_c = nobs_eff;   // every non-padding slot is an observation connected to a variable block
+  const long long nobs_c_pad = (nobs_c + BA_BLOCK - 1) / BA_BLOCK * BA_BLOCK;
+  std::vector<int4> runs, chunks;
+  std::vector<int2> runs_pc;
+  int intr_by_pt = 0;
+  {
+    int *d_sobs, *d_opose, *d_ocam, *d_opt, *d_val, *d_c2s, *d_head, *d_incl, *d_run_start;
+    double* d_oxy;
+    unsigned long long *d_key, *d_key_sorted, *d_run_key;
+    BA_CUDA(pool.upload(&d_sobs, s_obs, st));
+    BA_CUDA(pool.alloc(&d_opose, (size_t)NOBS)); BA_CUDA(pool.alloc(&d_ocam, (size_t)NOBS)); BA_CUDA(pool.alloc(&d_opt, (size_t)NOBS)); BA_CUDA(pool.alloc(&d_oxy, 2 * (size_t)NOBS));
+    BA_CUDA(cudaMemcpyAsync(d_opose, p->obs_pose_idx, sizeof(int) * (size_t)NOBS, cudaMemcpyHostToDevice, st));
+    BA_CUDA(cudaMemcpyAsync(d_ocam, p->obs_camera_idx, sizeof(int) * (size_t)NOBS, cudaMemcpyHostToDevice, st));
+    BA_CUDA(cudaMemcpyAsync(d_opt, p->obs_point_idx, sizeof(int) * (size_t)NOBS, cudaMemcpyHostToDevice, st));
+    BA_CUDA(cudaMemcpyAsync(d_oxy, p->obs_xy, sizeof(double) * 2 * (size_t)NOBS, cudaMemcpyHostToDevice, st));
+    int *t_pose, *t_cam, *t_pt, *t_s2c, *t_crun; double *t_xy, *t_xyC; int2* t_cpack; int4* t_spack;
+    BA_CUDA(pool.alloc(&t_pose, (size_t)nslots)); BA_CUDA(pool.alloc(&t_cam, (size_t)nslots)); BA_CUDA(pool.alloc(&t_pt, (size_t)nslots));
+    BA_CUDA(pool.alloc(&t_xy, 2 * (size_t)nslots)); BA_CUDA(pool.alloc(&t_s2c, (size_t)nslots)); BA_CUDA(pool.alloc(&t_spack, (size_t)nslots));
+    BA_CUDA(pool.alloc(&t_crun, (size_t)nobs_c_pad)); BA_CUDA(pool.alloc(&t_xyC, 2 * (size_t)nobs_c_pad)); BA_CUDA(pool.alloc(&t_cpack, (size_t)nobs_c_pad));
+    BA_CUDA(pool.alloc(&d_key, (size_t)nslots)); BA_CUDA(pool.alloc(&d_key_sorted, (size_t)nslots)); BA_CUDA(pool.alloc(&d_val, (size_t)nslots)); BA_CUDA(pool.alloc(&d_c2s, (size_t)nslots));
+    BA_CUDA(pool.alloc(&d_head, (size_t)nobs_c_pad)); BA_CUDA(pool.alloc(&d_incl, (size_t)nobs_c_pad));
+    const unsigned sb = (unsigned)((nslots + 255) / 256), cb = (unsigned)((nobs_c_pad + 255) / 256);
+    ba_setup_slot_kernel<<<sb, 256, 0, st>>>(nslots, d_sobs, d_opose, d_ocam, d_opt, d_oxy, t_pose, t_cam, t_pt, t_xy, d_key, d_val);
+    // stable radix sort by (camera, pose): ties keep slot order, padding (key = ~0) ends up behind the nobs_c observations
+    int cam_bits = 1; while ((1LL << cam_bits) < NCAM) ++cam_bits;
+    size_t tmp_bytes = 0, tmp2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_key, d_key_sorted, d_val, d_c2s, (int)nslots, 0, 64, st);
+    cub::DeviceScan::InclusiveSum(nullptr, tmp2, d_head, d_incl, (int)nobs_c_pad, st);
+    tmp_bytes = std::max(tmp_bytes, tmp2);
+    unsigned char* d_tmp; BA_CUDA(pool.alloc(&d_tmp, tmp_bytes));
+    BA_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_key, d_key_sorted, d_val, d_c2s, (int)nslots, 0, 64, st));
+    (void)cam_bits;
+    BA_CUDA(cudaMemsetAsync(t_s2c, 0xff, sizeof(int) * (size_t)nslots, st));
+    BA_CUDA(cudaMemsetAsync(d_head, 0, sizeof(int) * (size_t)nobs_c_pad, st));
+    BA_CUDA(cudaMemsetAsync(t_crun, 0xff, sizeof(int) * (size_t)nobs_c_pad, st));
+    if (nobs_c_pad) ba_setup_cam_kernel<<<cb, 256, 0, st>>>(nobs_c, nobs_c_pad, nslots, d_key_sorted, d_c2s, t_pt, D.s_lpt, t_xy, t_s2c, t_cpack, t_xyC, d_head);
+    if (nobs_c) BA_CUDA(cub::DeviceScan::InclusiveSum(d_tmp, tmp_bytes, d_head, d_incl, (int)nobs_c, st));
+    int nruns = 0;
+    if (nobs_c) {
+      BA_CUDA(cudaMemcpyAsync(&nruns, d_incl + (nobs_c - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+      BA_CUDA(cudaStreamSynchronize(st));
+    }
+    BA_CUDA(pool.alloc(&d_run_start, (size_t)nruns + 1)); BA_CUDA(pool.alloc(&d_run_key, (size_t)nruns + 1));
+    if (nobs_c) ba_setup_run_kernel<<<cb, 256, 0, st>>>(nobs_c, d_incl, t_crun, d_head, d_key_sorted, d_run_start, d_run_key);
+    ba_setup_pack_kernel<<<sb, 256, 0, st>>>(nslots, t_pose, t_cam, D.s_lpt, D.s_seg, t_s2c, D.pose_off, D.cam_off, D.cam_nvar, t_spack);
+    std::vector<int> run_start((size_t)nruns + 1);
+    std::vector<unsigned long long> run_key((size_t)nruns + 1);
+    if (nruns) {
+      BA_CUDA(cudaMemcpyAsync(run_start.data(), d_run_start, sizeof(int) * (size_t)nruns, cudaMemcpyDeviceToHost, st));
+      BA_CUDA(cudaMemcpyAsync(run_key.data(), d_run_key, sizeof(unsigned long long) * (size_t)nruns, cudaMemcpyDeviceToHost, st));
+      BA_CUDA(cudaStreamSynchronize(st));
+    }
+    run_start[nruns] = (int)nobs_c;
+    // runs of equal (camera, pose); chunks (<= BA_CHUNK observations of one pose block / one intrinsics block)
+    auto add_chunks = [&](long long k0, long long k1, int out, int comp0, int ncomp) {
+      for (long long c0 = k0; c0 < k1; c0 += BA_CHUNK) chunks.push_back(make_int4((int)c0, (int)std::min<long long>(c0 + BA_CHUNK, k1), out, comp0 | (ncomp << 8)));
+    };
+    long long cam_start = 0;
+    for (int r = 0; r < nruns; ++r) {
+      const int pose = (int)(run_key[r] & 0xffffffffu), cam = (int)(run_key[r] >> 32);
+      const long long k = run_start[r], e = run_start[r + 1];
+      runs.push_back(make_int4(pose_off[pose], cam_off[cam], cam_nvar[cam], 0));
+      runs_pc.push_back(make_int2(pose, cam));
+      if (pose_off[pose] >= 0) add_chunks(k, e, pose_off[pose], 0, 6);
+      const bool cam_ends = (r + 1 == nruns) || (int)(run_key[r + 1] >> 32) != cam;
+      // a variable-intrinsics camera seen from several poses: some track may see it twice -> the intrinsics blocks of
+      // the preconditioner need the cross terms between observations of one point (ba_schur_pt_kernel)
+      if (!cam_ends && cam_off[cam] >= 0) intr_by_pt = 1;
+      if (cam_ends) {
+        if (cam_off[cam] >= 0) add_chunks(cam_start, e, cam_off[cam], 6, cam_nvar[cam]);
+        cam_start = e;
+      }
+    }
+    D.s_pose = t_pose; D.s_cam = t_cam; D.s_pt = t_pt; D.s_xy = t_xy; D.s2c = t_s2c; D.s_pack = t_spack;
+    D.c_run = t_crun; D.xyC = t_xyC; D.c_pack = t_cpack;
+  }
   { int* t; BA_CUDA(pool.upload(&t, blk_pt0, st)); D.blk_pt0 = t; }
   { int* t; BA_CUDA(pool.upload(&t, blk_npt, st)); D.blk_npt = t; }
   { int* t; BA_CUDA(pool.upload(&t, vpt_s0, st)); D.vpt_s0 = t; }
@@ -1995,17 +2052,11 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   }
   BA_CUDA(pool.alloc(&D.Jc, (size_t)2 * D.DC * nslots)); BA_CUDA(pool.alloc(&D.Jp, (size_t)6 * nslots));
   BA_CUDA(pool.alloc(&D.JcC, (size_t)2 * D.DC * nobs_c_pad)); BA_CUDA(pool.alloc(&D.u, (size_t)nobs_c_pad)); BA_CUDA(pool.alloc(&D.rC, (size_t)2 * nobs_c_pad)); BA_CUDA(pool.alloc(&D.JpC, (size_t)6 * nobs_c_pad));
-  { double* t; BA_CUDA(pool.upload(&t, xyC, st)); D.xyC = t; }
-  { int2* t; BA_CUDA(pool.upload(&t, c_pack, st)); D.c_pack = t; }
   { int2* t; BA_CUDA(pool.upload(&t, runs_pc, st)); D.runs_pc = t; }
   D.intr_by_pt = intr_by_pt;
-  { int* t; BA_CUDA(pool.upload(&t, s2c, st)); D.s2c = t; }
-  { int* t; BA_CUDA(pool.upload(&t, s_seg, st)); D.s_seg = t; }
-  { int4* t; BA_CUDA(pool.upload(&t, s_pack, st)); D.s_pack = t; }
   D.nblocks_warp = nblocks_warp; D.nblocks_giant0 = nblocks_giant0; D.nblocks_giant1 = nblocks_giant1;
   BA_CUDA(pool.alloc(&D.zg, (size_t)3 * nvpt));
   { int4* t; BA_CUDA(pool.upload(&t, chunks, st)); D.chunks = t; }
-  { int* t; BA_CUDA(pool.upload(&t, c_run, st)); D.c_run = t; }
   { int4* t; BA_CUDA(pool.upload(&t, runs, st)); D.runs = t; }
   D.nchunks = (int)chunks.size(); D.nobs_c = nobs_c; BA_CUDA(pool.alloc(&D.r, (size_t)2 * nslots)); BA_CUDA(pool.alloc(&D.cost_slot, (size_t)nslots));
   BA_CUDA(pool.alloc(&D.scale_c, (size_t)nc)); BA_CUDA(pool.alloc(&D.scale_p, (size_t)3 * nvpt));
