@@ -179,7 +179,7 @@ def bench_ba(steps, warmup, peak, peak_src, with_cpu):
            "e2e": {"value": lm / (wall_ms * 1e-3), "unit": "LM iterations/s", "h2d_bytes_per_step": int(h2d),
                    "d2h_bytes_per_step": int(d2h), "ms_per_step": wall_ms / steps},
            "final_cost": s.final_cost, "termination_type": s.termination_type, "gpu_launches": int(launches),
-           "roofline": {"bound": "hbm", "kernel": "ba_schur_spmv_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+           "roofline": {"bound": "hbm", "kernel": "ba_schur_spmv_warp_smem_kernel + ba_cam_stream_loop_kernel (one implicit-Schur product)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "traffic": _ncu_traffic("ba_schur_spmv_kernel"), "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": alg, "launch_ms": spmv_launch_ms}}
     if with_cpu:
@@ -425,7 +425,7 @@ def main():
                                           "serial": pass_ms[2] / args.steps / n_sweeps},
                     "taps_per_s": taps_per_sweep / (sweep_launch_ms * 1e-3),
                     "note": "the faithful sweep is instruction-issue bound, not HBM bound (DESIGN.md §2): 177 algorithmic "
-                            "bytes but 3872 bilinear taps (~50 instructions each) per pixel per sweep; ncu: 65-69% issue-slot "
+                            "bytes but 3872 bilinear taps (~45 instructions each) per pixel per sweep; ncu: 70% issue-slot "
                             "utilisation in the dominant kernel"}
         line = {"metric": "patchmatch_mpixels_per_s", "value": world * mpix / (ms_per_step * 1e-3), "unit": "Mpixels/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
