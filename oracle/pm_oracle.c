@@ -969,6 +969,15 @@ void pm_oracle_compose_inverse_projection_matrix(const float K[9], const float R
   compose_pose_row(I3, Z3, K, R, T, row);
   memcpy(iP, row + 31, 48);
 }
+/* RotatePose (mvs/image.cc:144-150): R <- RR R, T <- RR T, fp32 */
+void pm_oracle_rotate_pose(const float RR[9], float R[9], float T[3]) {
+  float nR[9], nT[3];
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) nR[3 * r + c] = RR[3 * r] * R[c] + RR[3 * r + 1] * R[3 + c] + RR[3 * r + 2] * R[6 + c];
+    nT[r] = RR[3 * r] * T[0] + RR[3 * r + 1] * T[1] + RR[3 * r + 2] * T[2];
+  }
+  memcpy(R, nR, sizeof(nR)); memcpy(T, nT, sizeof(nT));
+}
 void pm_oracle_projection_center(const float R[9], const float T[3], float C[3]) {
   const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Z3[3] = {0, 0, 0};
   const float K[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};

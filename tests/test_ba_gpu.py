@@ -159,3 +159,17 @@ def test_long_tracks_use_the_generic_path():
     a, sg, b, sr = _both(BundleAdjustmentOptions(linear_solver_type=ITERATIVE_SCHUR, max_num_iterations=15), noisy)
     assert sg.num_residuals == 2 * int(lens.sum())
     _assert_parity(a, sg, b, sr, param_rel=1e-4)
+
+
+def test_golden_fixture_solution():
+    """tests/golden/ba_case_small.npz (problem + the oracle's frozen solution): the GPU solver lands on the stored
+    solution within the 1e-5 relative tolerance, without the oracle being run."""
+    from test_golden_cpu import ba_case
+    z, o, flat = ba_case()
+    s = solve_flat(o, flat)
+    assert s.num_residuals == int(z["num_residuals"]) and s.num_effective_parameters == int(z["num_effective_parameters"])
+    assert abs(s.initial_cost - float(z["initial_cost"])) <= 1e-9 * float(z["initial_cost"])
+    assert abs(s.final_cost - float(z["final_cost"])) <= 1e-5 * float(z["final_cost"])
+    assert np.allclose(flat.poses, z["sol_poses"], rtol=1e-5, atol=1e-5)
+    assert np.allclose(flat.points, z["sol_points"], rtol=1e-5, atol=1e-5)
+    assert np.allclose(flat.cam_params, z["sol_cam_params"], rtol=1e-5, atol=1e-5)

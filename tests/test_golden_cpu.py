@@ -1,0 +1,137 @@
+"""The oracles against the committed golden fixtures (tests/golden/, generator: tests/golden/make_golden.py):
+the reference's own known-answer vectors, and the frozen oracle outputs that the CUDA path is compared with."""
+import json
+import os
+
+import numpy as np
+
+import oracle_ba
+import oracle_pm
+from colmap_b200.bundle_adjustment import (BundleAdjustmentOptions, FlatProblem, ITERATIVE_SCHUR, SIMPLE_PINHOLE,
+                                           PINHOLE)
+from colmap_b200.patch_match import PatchMatchOptions, _f32p
+from colmap_b200.synthetic import synthesize_ba_problem
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+KA = json.load(open(os.path.join(GOLDEN, "reference_known_answers.json")))
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+def _p(a):
+    return a.ctypes.data_as(_f32p)
+
+
+def test_known_answers_mvs_image():
+    """mvs/image_test.cc vectors (see the fixture for file:line)."""
+    L = oracle_pm.lib()
+    c = KA["mvs_image"]["compose_projection_matrix"]
+    K, R, T, P = _f32(c["K"]), _f32(c["R"]), _f32(c["T"]), np.empty(12, np.float32)
+    L.pm_oracle_compose_projection_matrix(_p(K), _p(R), _p(T), _p(P))
+    assert np.array_equal(P, _f32(c["P"]))
+    c = KA["mvs_image"]["compute_projection_center"]
+    R, T, C = _f32(c["R"]), _f32(c["T"]), np.empty(3, np.float32)
+    L.pm_oracle_projection_center(_p(R), _p(T), _p(C))
+    assert np.array_equal(C, _f32(c["C"]))
+    L.pm_oracle_rotate_pose.argtypes = [_f32p, _f32p, _f32p]
+    for c in KA["mvs_image"]["rotate_pose"]:
+        RR, R, T = _f32(c["RR"]), _f32(c["R"]), _f32(c["T"])
+        L.pm_oracle_rotate_pose(_p(RR), _p(R), _p(T))
+        assert np.allclose(R, c["R_out"], atol=1e-7) and np.allclose(T, c["T_out"], atol=1e-7)
+
+
+def test_known_answers_rotate_convention():
+    """mvs/gpu_mat_test.cu: rotated(d, W-1-c, r) == original(d, r, c)."""
+    L = oracle_pm.lib()
+    rng = np.random.default_rng(0)
+    for w, h, d in KA["gpu_mat_rotate"]["sizes"]:
+        src = rng.random((d, h, w)).astype(np.float32)
+        dst = np.empty((d, w, h), np.float32)
+        L.pm_oracle_rotate_f32(_p(src), w, h, d, _p(dst))
+        r, c = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+        assert np.array_equal(dst[:, w - 1 - c, r], src[:, r, c])
+
+
+def test_known_answers_reprojection_error():
+    """cost_functions/reprojection_error_test.cc: residual = projection - observation."""
+    c = KA["reprojection_error"]
+    for case in c["cases"]:
+        ok, res, *_ = oracle_ba.reproj(SIMPLE_PINHOLE, case["point"], c["pose"], case["params"], c["xy"])
+        assert np.array_equal(res, np.asarray(case["residual"], np.float64)), case
+
+
+def test_known_answers_bundle_adjustment_counts():
+    """bundle_adjustment_test.cc MinimumTrackLength (594) and ConstantPoints3D (80, points bit-identical)."""
+    from colmap_b200.bundle_adjustment import BundleAdjustmentConfig, flatten_reconstruction
+    from colmap_b200.synthetic import flat_to_reconstruction
+    cases = {c["name"]: c for c in KA["bundle_adjustment_counts"]["cases"]}
+    c = cases["ConstantPoints3D"]
+    gt, noisy = synthesize_ba_problem(c["num_images"], c["num_points"], c["track_length"], models=(PINHOLE,), seed=1)
+    before = noisy.points.copy()
+    s = oracle_ba.solve(BundleAdjustmentOptions(refine_points3D=False, max_num_iterations=5), noisy)
+    assert s.num_residuals == c["num_residuals"]
+    assert np.array_equal(noisy.points, before)
+    c = cases["MinimumTrackLength"]
+    gt, noisy = synthesize_ba_problem(c["num_images"], c["num_points"], c["track_length"], models=(PINHOLE,), seed=1)
+    rec = flat_to_reconstruction(noisy)
+    # delete one observation: its point is left with a two-observation track and drops out at min_track_length = 3
+    pid = next(iter(rec.points3D))
+    image_id, p2_idx = rec.points3D[pid].track.pop()
+    rec.images[image_id].points2D[p2_idx].point3D_id = -1
+    cfg = BundleAdjustmentConfig()
+    for image_id in rec.images:
+        cfg.AddImage(image_id)
+    o = BundleAdjustmentOptions(min_track_length=c["min_track_length"], max_num_iterations=3)
+    flat = flatten_reconstruction(o, cfg, rec)[0]
+    s = oracle_ba.solve(o, flat)
+    assert s.num_residuals == c["num_residuals"]
+
+
+def test_known_answers_option_defaults():
+    d = KA["options_defaults"]
+    o = PatchMatchOptions()
+    for k, v in d["patch_match"].items():
+        assert getattr(o, k) == v, k
+    b = BundleAdjustmentOptions()
+    for k, v in d["bundle_adjustment"].items():
+        assert getattr(b, k) == v, k
+
+
+def _pm_case():
+    import make_golden  # noqa: F401  (tests/golden is put on sys.path by conftest)
+    z = np.load(os.path.join(GOLDEN, "pm_case_96x64.npz"))
+    problem = make_golden.pm_problem_from_arrays(z)
+    o = PatchMatchOptions(depth_min=float(z["depth_min"]), depth_max=float(z["depth_max"]), **json.loads(str(z["options"])))
+    return z, o, problem
+
+
+def test_pm_oracle_reproduces_the_frozen_fixture():
+    """The fp32 contract is frozen by pm_case_96x64.npz: any change of the oracle's arithmetic shows up here."""
+    z, o, problem = _pm_case()
+    out = oracle_pm.run(o, problem)
+    for k in ("depth", "normal", "sel_prob"):
+        assert np.array_equal(out[k].view(np.uint32), z[k].view(np.uint32)), k
+    assert np.array_equal(out["mask"], z["mask"])
+    assert (z["depth"] > 0).mean() > 0.5
+
+
+def ba_case():
+    z = np.load(os.path.join(GOLDEN, "ba_case_small.npz"))
+    flat = FlatProblem(z["poses"], z["pose_constant"], z["pose_fixed_dim"], z["cam_model"], z["cam_off"], z["cam_params"],
+                       z["cam_constant"], z["points"], z["point_constant"], z["obs_pose"], z["obs_cam"], z["obs_point"],
+                       z["obs_xy"])
+    o = BundleAdjustmentOptions(linear_solver_type=ITERATIVE_SCHUR, max_num_iterations=int(z["max_num_iterations"]))
+    return z, o, flat
+
+
+def test_ba_oracle_reproduces_the_frozen_fixture():
+    z, o, flat = ba_case()
+    s = oracle_ba.solve(o, flat)
+    assert s.num_residuals == int(z["num_residuals"]) and s.num_effective_parameters == int(z["num_effective_parameters"])
+    assert abs(s.initial_cost - float(z["initial_cost"])) <= 1e-9 * float(z["initial_cost"])
+    assert abs(s.final_cost - float(z["final_cost"])) <= 1e-7 * float(z["final_cost"])
+    assert np.allclose(flat.poses, z["sol_poses"], rtol=0, atol=1e-7)
+    assert np.allclose(flat.points, z["sol_points"], rtol=0, atol=1e-7)
+    assert np.allclose(flat.cam_params, z["sol_cam_params"], rtol=1e-8, atol=1e-7)
