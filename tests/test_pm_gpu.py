@@ -208,7 +208,7 @@ def test_golden_reference_cuda_fixture_statistics():
     assert both.mean() > 0.8
     err_ours = np.median(np.abs(ours[both] - gt[both]) / gt[both])
     err_ref = np.median(np.abs(ref[both] - gt[both]) / gt[both])
-    assert err_ours < 2e-4 and err_ours < 3 * err_ref + 1e-5
+    assert err_ours < 1e-3 and err_ours < 1.5 * err_ref + 1e-5   # 160x120: both sit at ~3.5e-4 (pixel footprint)
     rel = np.abs(ours[both] - ref[both]) / ref[both]
     assert np.median(rel) < 1e-4                    # 5 m scene: 1e-4 relative = 0.5 mm
     assert (rel < 1e-3).mean() > 0.9
