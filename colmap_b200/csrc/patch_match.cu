@@ -663,8 +663,8 @@ __global__ void __launch_bounds__(128, 8) pm_pixel_kernel(const PmParams P, cons
   }
 }
 
-template <int WPC, bool GEOM>
-__global__ void __launch_bounds__(32 * WPC) pm_serial_kernel(const PmParams P, const PmSweepArgs A) {
+template <int WPC, bool GEOM, int MINB>
+__global__ void __launch_bounds__(32 * WPC, MINB) pm_serial_kernel(const PmParams P, const PmSweepArgs A) {
   extern __shared__ float4 smem4[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col = blockIdx.x;
@@ -927,6 +927,9 @@ struct b200pm_context {
   PmParams P;
   int device = 0;
   int wpc = 2;
+  bool wpc_auto = true;   // B200PM_WPC unset: the serial pass picks its schedule per sweep (one wave of columns)
+  bool serial_cap = false; // B200PM_SERIAL_CAP=1: allow the register-capped (72 regs, 13 CTAs/SM, small spills) WPC = 2 variant
+  int num_sms = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<std::pair<void*, size_t>> allocs;
@@ -1084,8 +1087,10 @@ int b200pm_create(const b200pm_options* o, const b200pm_problem* p, b200pm_handl
   PM_CUDA(cudaSetDevice(c->device));
   PM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 4; ++i) PM_CUDA(cudaEventCreate(&c->ev[i]));
-  if (const char* e = getenv("B200PM_WPC")) c->wpc = atoi(e);
+  if (const char* e = getenv("B200PM_WPC")) { c->wpc = atoi(e); c->wpc_auto = false; }
   if (c->wpc != 1 && c->wpc != 2 && c->wpc != 4) c->wpc = 2;
+  if (const char* e = getenv("B200PM_SERIAL_CAP")) c->serial_cap = atoi(e) != 0;   // measured: 237 ms vs 233 ms of serial pass per run without it
+  cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device);
 
   PmParams& P = c->P;
   memset(&P, 0, sizeof(P));
@@ -1207,12 +1212,12 @@ static void pm_launch_sweep(b200pm_context* c, const PmSweepArgs& A, int fw) {
   else
     pm_sweep_kernel<WPC, false><<<fw, 32 * WPC, c->smem_sweep, c->stream>>>(c->P, A);
 }
-template <int WPC>
+template <int WPC, int MINB>
 static void pm_launch_serial(b200pm_context* c, const PmSweepArgs& A, int fw) {
   if (c->P.geom)
-    pm_serial_kernel<WPC, true><<<fw, 32 * WPC, c->smem_serial, c->stream>>>(c->P, A);
+    pm_serial_kernel<WPC, true, MINB><<<fw, 32 * WPC, c->smem_serial, c->stream>>>(c->P, A);
   else
-    pm_serial_kernel<WPC, false><<<fw, 32 * WPC, c->smem_serial, c->stream>>>(c->P, A);
+    pm_serial_kernel<WPC, false, MINB><<<fw, 32 * WPC, c->smem_serial, c->stream>>>(c->P, A);
 }
 
 extern "C" {
@@ -1289,9 +1294,22 @@ int b200pm_run(b200pm_handle c) {
         if (P.geom) pm_pixel_kernel<true><<<pgrid, 128, c->smem_init, s>>>(P, A);
         else pm_pixel_kernel<false><<<pgrid, 128, c->smem_init, s>>>(P, A);
         mark(2);
-        if (c->wpc == 1) pm_launch_serial<1>(c, A, fw);
-        else if (c->wpc == 2) pm_launch_serial<2>(c, A, fw);
-        else pm_launch_serial<4>(c, A, fw);
+        // The serial pass is one CTA per column marching down all rows: a second wave of CTAs lengthens its critical
+        // path.  Pick the widest schedule whose resident capacity covers all fw columns in ONE wave (register-file
+        // bound: 128 registers x 32*WPC threads per CTA).  C2: 1920-column sweeps run WPC = 1, 1080-column sweeps
+        // WPC = 2 (serial pass 246 -> 233 ms per run against a fixed WPC = 2).
+        int wpc = c->wpc, capped = 0;
+        if (c->wpc_auto) {
+          const int sms = c->num_sms;
+          if (fw <= sms * 4) wpc = 4;
+          else if (fw <= sms * 8) wpc = 2;
+          else if (fw <= sms * 13 && c->serial_cap) { wpc = 2; capped = 1; }
+          else wpc = 1;
+        }
+        if (wpc == 1) pm_launch_serial<1, 16>(c, A, fw);
+        else if (wpc == 2 && capped) pm_launch_serial<2, 13>(c, A, fw);
+        else if (wpc == 2) pm_launch_serial<2, 8>(c, A, fw);
+        else pm_launch_serial<4, 4>(c, A, fw);
         launches += 3;
         mark(3);
       }
