@@ -2,16 +2,17 @@
 //
 // Reference behaviour: DefaultBundleAdjuster + ceres::Solve (src/colmap/estimators/bundle_adjustment_ceres.cc),
 // residual/Jacobian arithmetic of cost_functions/reprojection_error.h, quaternion_utils.h, sensor/models_jacobian.h.
-// Design: everything of an LM iteration runs on the GPU in fp64 —
-//   linearize      one thread per observation slot: residual + analytic Jacobians in the tangent space,
-//                  written component-major (SoA) so every later pass streams them fully coalesced;
-//   build          Schur blocks: H_pp (3x3 per point), g_p, g_c, diag(J'J), block-Jacobi blocks of H_cc;
-//   damp           (H_pp + D_p^2)^-1, SCHUR_JACOBI preconditioner blocks, reduced right-hand side;
-//   PCG            implicit Schur complement product S p in ONE pass over the stored Jacobians per iteration
-//                  ("SpMV", the roofline kernel), device-side alpha/beta/termination (no host sync per iteration);
+// Design: everything of an LM iteration runs on the GPU, fp64 arithmetic over fp32-stored Jacobians —
+//   set-up         the host decides which observation sits in which slot (whole tracks per warp / block); the per-slot
+//                  arrays, the (camera, pose) order (radix sort), runs and packed index words are built on the device;
+//   linearize      residual + analytic Jacobians in the tangent space, evaluated once per storage order (slot order
+//                  = track order, and (camera, pose) order), tiles of 32 observations x components;
+//   build          H_pp (3x3 per point), g_p, g_c, diag(J'J), diagonal blocks of H_cc (chunk reductions in camera order);
+//   damp           (H_pp + D_p^2)^-1, exact SCHUR_JACOBI blocks and the reduced right-hand side (camera order, no
+//                  per-observation scratch);
+//   PCG            implicit Schur complement product S p in two streaming passes ("SpMV", the roofline kernels) +
+//                  one single-CTA launch for all vector work of an iteration; alpha/beta/termination live on the device;
 //   backsub/update point step, model cost change, candidate evaluation, manifold retraction.
-// Observations are packed into blocks of 256 slots such that a track never crosses a block, so the point-block
-// elimination of the SpMV happens in shared memory.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stddef.h>
