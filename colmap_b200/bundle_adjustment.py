@@ -21,7 +21,8 @@ import numpy as np
 from ._lib import load_library
 
 SIMPLE_PINHOLE, PINHOLE, SIMPLE_RADIAL, RADIAL = 0, 1, 2, 3
-MODEL_NUM_PARAMS = {0: 3, 1: 4, 2: 4, 3: 5}
+SIMPLE_RADIAL_FISHEYE, RADIAL_FISHEYE = 8, 9      # CameraModelId (sensor/models.h:90-109)
+MODEL_NUM_PARAMS = {0: 3, 1: 4, 2: 4, 3: 5, 8: 4, 9: 5}
 AUTO, DENSE_SCHUR, SPARSE_SCHUR, ITERATIVE_SCHUR = 0, 1, 2, 3
 TRIVIAL, SOFT_L1, CAUCHY, HUBER = 0, 1, 2, 3
 CONVERGENCE, NO_CONVERGENCE, FAILURE = 0, 1, 2

@@ -46,7 +46,7 @@
 // ------------------------------------------------------------------------------------------------
 // camera models + reprojection (host/device so the CPU test tier can check them without a GPU)
 // ------------------------------------------------------------------------------------------------
-BA_HD int ba_model_num_params(int id) { return id == 0 ? 3 : (id == 1 ? 4 : (id == 2 ? 4 : (id == 3 ? 5 : -1))); }
+BA_HD int ba_model_num_params(int id) { return id == 0 ? 3 : (id == 1 ? 4 : (id == 2 ? 4 : (id == 3 ? 5 : (id == 8 ? 4 : (id == 9 ? 5 : -1))))); }
 BA_HD int ba_param_group(int id, int k) {  // 0 focal, 1 principal point, 2 extra (models.h:462-520)
   switch (id) {
     case 0: return k == 0 ? 0 : 1;
@@ -80,6 +80,26 @@ BA_HD bool ba_img_from_cam(int id, const double* q, double u, double v, double w
     Juvw[0] = fi * (alpha + two_k * uu2); Juvw[1] = fi * cross; Juvw[2] = -fi * uu * beta;
     Juvw[3] = fi * cross; Juvw[4] = fi * (alpha + two_k * vv2); Juvw[5] = -fi * vv * beta;
     Jp[0] = xd; Jp[1] = 1; Jp[2] = 0; Jp[3] = f * uu * r2; Jp[5] = yd; Jp[6] = 0; Jp[7] = 1; Jp[8] = f * vv * r2;
+  } else if (id == 8 || id == 9) {
+    // SIMPLE_RADIAL_FISHEYE {f, cx, cy, k} / RADIAL_FISHEYE {f, cx, cy, k1, k2} (models_jacobian.h:44-83, 725-851):
+    // equidistant mapping (a, b) -> (theta / r)(a, b) with theta = atan r, then radial distortion in fisheye coordinates
+    const double f = q[0], k1 = q[3], k2 = (id == 9) ? q[4] : 0.0;
+    const double r2 = uu * uu + vv * vv, r = sqrt(r2);
+    double s = 1.0, g = 0.0;   // s = theta / r, g = (ds/dr) / r; identity in the limit r -> 0
+    if (r >= 2.220446049250313e-16) { const double th = atan(r); s = th / r; g = (r / (1.0 + r2) - th) / (r2 * r); }
+    const double fu = s * uu, fv = s * vv;
+    const double F00 = s + uu * uu * g, F01 = uu * vv * g, F11 = s + vv * vv * g;          // d(fu, fv) / d(a, b)
+    const double fu2 = fu * fu, fv2 = fv * fv, t2 = fu2 + fv2, t4 = t2 * t2, radial = k1 * t2 + k2 * t4;
+    const double xd = fu + fu * radial, yd = fv + fv * radial;
+    *x = f * xd + q[1]; *y = f * yd + q[2];
+    const double dr = k1 + 2.0 * k2 * t2, cross = 2.0 * fu * fv * dr;
+    const double D00 = 1.0 + radial + 2.0 * fu2 * dr, D11 = 1.0 + radial + 2.0 * fv2 * dr;   // I + d(distortion) / d(fu, fv)
+    const double a00 = f * (D00 * F00 + cross * F01), a01 = f * (D00 * F01 + cross * F11);
+    const double a10 = f * (cross * F00 + D11 * F01), a11 = f * (cross * F01 + D11 * F11);
+    Juvw[0] = a00 * iw; Juvw[1] = a01 * iw; Juvw[2] = -(a00 * uu + a01 * vv) * iw;
+    Juvw[3] = a10 * iw; Juvw[4] = a11 * iw; Juvw[5] = -(a10 * uu + a11 * vv) * iw;
+    Jp[0] = xd; Jp[1] = 1; Jp[2] = 0; Jp[3] = f * fu * t2; Jp[4] = f * fu * t4;
+    Jp[5] = yd; Jp[6] = 0; Jp[7] = 1; Jp[8] = f * fv * t2; Jp[9] = f * fv * t4;
   } else {
     const double f = q[0], k1 = q[3], k2 = q[4];
     const double uu2 = uu * uu, vv2 = vv * vv, r2 = uu2 + vv2, r4 = r2 * r2, radial = k1 * r2 + k2 * r4;
@@ -1736,7 +1756,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   // ---------------------------------------------------------------- flatten (host)
   const int NP = p->num_poses, NCAM = p->num_cameras;
   const long long NPT = p->num_points, NOBS = p->num_observations;
-  for (int c = 0; c < NCAM; ++c) if (ba_model_num_params(p->camera_model_id[c]) < 0) return ba_fail(-2, "unsupported camera model (supported: SIMPLE_PINHOLE, PINHOLE, SIMPLE_RADIAL, RADIAL)");
+  for (int c = 0; c < NCAM; ++c) if (ba_model_num_params(p->camera_model_id[c]) < 0) return ba_fail(-2, "unsupported camera model (supported: SIMPLE_PINHOLE, PINHOLE, SIMPLE_RADIAL, RADIAL, SIMPLE_RADIAL_FISHEYE, RADIAL_FISHEYE)");
   for (long long i = 0; i < NOBS; ++i)
     if (p->obs_pose_idx[i] < 0 || p->obs_pose_idx[i] >= NP || p->obs_camera_idx[i] < 0 || p->obs_camera_idx[i] >= NCAM || p->obs_point_idx[i] < 0 || p->obs_point_idx[i] >= NPT)
       return ba_fail(-2, "observation index out of range");

@@ -157,7 +157,7 @@ def _quat_rotate(q, p):
 
 
 _MODEL_DEFAULTS = {0: [1280.0, 512.0, 384.0], 1: [1280.0, 1280.0, 512.0, 384.0], 2: [1280.0, 512.0, 384.0, 0.05],
-                   3: [1280.0, 512.0, 384.0, 0.05, 0.01]}
+                   3: [1280.0, 512.0, 384.0, 0.05, 0.01], 8: [1280.0, 512.0, 384.0, 0.05], 9: [1280.0, 512.0, 384.0, 0.05, 0.01]}
 
 
 def _project(model, params, pc):
@@ -167,8 +167,12 @@ def _project(model, params, pc):
         return np.stack([params[..., 0] * uu + params[..., 1], params[..., 0] * vv + params[..., 2]], -1)
     if model == 1:
         return np.stack([params[..., 0] * uu + params[..., 2], params[..., 1] * vv + params[..., 3]], -1)
+    if model in (8, 9):   # equidistant fisheye: (uu, vv) <- (atan r / r)(uu, vv), then the radial polynomial
+        r = np.sqrt(uu * uu + vv * vv)
+        s = np.where(r > 1e-12, np.arctan(r) / np.maximum(r, 1e-300), 1.0)
+        uu, vv = s * uu, s * vv
     r2 = uu * uu + vv * vv
-    rad = params[..., 3] * r2 if model == 2 else params[..., 3] * r2 + params[..., 4] * r2 * r2
+    rad = params[..., 3] * r2 if model in (2, 8) else params[..., 3] * r2 + params[..., 4] * r2 * r2
     return np.stack([params[..., 0] * uu * (1 + rad) + params[..., 1], params[..., 0] * vv * (1 + rad) + params[..., 2]], -1)
 
 

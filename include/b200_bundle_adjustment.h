@@ -28,8 +28,10 @@
 extern "C" {
 #endif
 
-/* CameraModelId values (src/colmap/sensor/models.h:93-97).  Supported here: the radial pinhole family. */
-enum { B200BA_SIMPLE_PINHOLE = 0, B200BA_PINHOLE = 1, B200BA_SIMPLE_RADIAL = 2, B200BA_RADIAL = 3 };
+/* CameraModelId values (src/colmap/sensor/models.h:90-109).  Supported here: the radial pinhole family and its two
+ * equidistant-fisheye counterparts (models with <= 5 parameters). */
+enum { B200BA_SIMPLE_PINHOLE = 0, B200BA_PINHOLE = 1, B200BA_SIMPLE_RADIAL = 2, B200BA_RADIAL = 3,
+       B200BA_SIMPLE_RADIAL_FISHEYE = 8, B200BA_RADIAL_FISHEYE = 9 };
 
 /* ceres::LinearSolverType subset COLMAP selects (bundle_adjustment_ceres.cc:202-212). */
 enum { B200BA_AUTO = 0, B200BA_DENSE_SCHUR = 1, B200BA_SPARSE_SCHUR = 2, B200BA_ITERATIVE_SCHUR = 3 };

@@ -38,7 +38,17 @@
 #define JC (6 + MAXDK)
 
 /* ------------------------------------------------------------------------- camera models */
-static int model_num_params(int id) { return id == 0 ? 3 : (id == 1 ? 4 : (id == 2 ? 4 : (id == 3 ? 5 : -1))); }
+static int model_num_params(int id) {
+  switch (id) { case 0: return 3; case 1: case 2: case 8: return 4; case 3: case 9: return 5; default: return -1; }
+}
+/* FisheyeProjectionWithJac (models_jacobian.h:44-83): (a, b) -> (atan r / r)(a, b); J = d(out) / d(a, b), row-major */
+static void fisheye_with_jac(double a, double b, double* fa, double* fb, double J[4]) {
+  const double r2 = a * a + b * b, r = sqrt(r2);
+  if (r < 2.220446049250313e-16) { *fa = a; *fb = b; J[0] = 1; J[1] = 0; J[2] = 0; J[3] = 1; return; }
+  const double theta = atan(r), s = theta / r, g = (r / (1.0 + r2) - theta) / (r2 * r);
+  *fa = s * a; *fb = s * b;
+  J[0] = s + a * a * g; J[1] = a * b * g; J[2] = J[1]; J[3] = s + b * b * g;
+}
 /* parameter groups (focal, principal point, extra): models.h:462-520 */
 static int param_group(int id, int k) { /* 0 focal, 1 pp, 2 extra */
   switch (id) {
@@ -73,6 +83,25 @@ static int img_from_cam(int id, const double* q, double u, double v, double w, d
     Juvw[0] = fi * (alpha + two_k * uu2); Juvw[1] = fi * cross; Juvw[2] = -fi * uu * beta;
     Juvw[3] = fi * cross; Juvw[4] = fi * (alpha + two_k * vv2); Juvw[5] = -fi * vv * beta;
     Jp[0] = xd; Jp[1] = 1; Jp[2] = 0; Jp[3] = f * uu * r2; Jp[4] = yd; Jp[5] = 0; Jp[6] = 1; Jp[7] = f * vv * r2;
+  } else if (id == 8 || id == 9) { /* SIMPLE_RADIAL_FISHEYE / RADIAL_FISHEYE (models_jacobian.h:725-851) */
+    const int P = id == 8 ? 4 : 5;
+    const double f = q[0], k1 = q[3], k2 = id == 9 ? q[4] : 0.0;
+    double fa, fb, Jf[4];
+    fisheye_with_jac(uu, vv, &fa, &fb, Jf);
+    const double t2 = fa * fa + fb * fb, t4 = t2 * t2, radial = k1 * t2 + k2 * t4;
+    const double xd = fa + fa * radial, yd = fb + fb * radial;
+    *x = f * xd + q[1]; *y = f * yd + q[2];
+    const double dr = k1 + 2.0 * k2 * t2;
+    const double D[4] = {1.0 + radial + 2.0 * fa * fa * dr, 2.0 * fa * fb * dr, 2.0 * fa * fb * dr, 1.0 + radial + 2.0 * fb * fb * dr};
+    double Jab[4];
+    for (int r = 0; r < 2; ++r) for (int c = 0; c < 2; ++c) Jab[2 * r + c] = f * (D[2 * r] * Jf[c] + D[2 * r + 1] * Jf[2 + c]);
+    for (int r = 0; r < 2; ++r) {
+      Juvw[3 * r] = Jab[2 * r] * iw; Juvw[3 * r + 1] = Jab[2 * r + 1] * iw;
+      Juvw[3 * r + 2] = -(Jab[2 * r] * uu + Jab[2 * r + 1] * vv) * iw;
+    }
+    Jp[0] = xd; Jp[1] = 1; Jp[2] = 0; Jp[3] = f * fa * t2;
+    Jp[P] = yd; Jp[P + 1] = 0; Jp[P + 2] = 1; Jp[P + 3] = f * fb * t2;
+    if (id == 9) { Jp[4] = f * fa * t4; Jp[P + 4] = f * fb * t4; }
   } else {
     const double f = q[0], k1 = q[3], k2 = q[4];
     const double uu2 = uu * uu, vv2 = vv * vv, r2 = uu2 + vv2, r4 = r2 * r2, radial = k1 * r2 + k2 * r4;

@@ -9,7 +9,8 @@ import pytest
 
 import oracle_ba
 from colmap_b200 import load_library
-from colmap_b200.bundle_adjustment import (DENSE_SCHUR, ITERATIVE_SCHUR, PINHOLE, RADIAL, SIMPLE_PINHOLE,
+from colmap_b200.bundle_adjustment import (DENSE_SCHUR, ITERATIVE_SCHUR, PINHOLE, RADIAL, RADIAL_FISHEYE, SIMPLE_PINHOLE,
+                                           SIMPLE_RADIAL_FISHEYE,
                                            SIMPLE_RADIAL, SOFT_L1, BundleAdjustmentOptions, _CProblem, _COptions,
                                            _bind, _f64p, _i8p, _u8p)
 from colmap_b200.synthetic import synthesize_ba_problem
@@ -35,7 +36,9 @@ def test_reprojection_known_answers():
 
 
 @pytest.mark.parametrize("model,params", [(SIMPLE_PINHOLE, [600., 320, 240]), (PINHOLE, [600., 610, 320, 240]),
-                                          (SIMPLE_RADIAL, [600., 320, 240, 0.08]), (RADIAL, [600., 320, 240, 0.08, -0.02])])
+                                          (SIMPLE_RADIAL, [600., 320, 240, 0.08]), (RADIAL, [600., 320, 240, 0.08, -0.02]),
+                                          (SIMPLE_RADIAL_FISHEYE, [600., 320, 240, 0.08]),
+                                          (RADIAL_FISHEYE, [600., 320, 240, 0.08, -0.02])])
 def test_analytic_jacobians_match_finite_differences(model, params):
     """The property reprojection_error_test.cc:211-323 pins with autodiff (tolerance 1e-4), restated with
     central differences over a grid of points and a non-trivial pose."""
@@ -182,8 +185,9 @@ def test_product_reprojection_arithmetic_matches_oracle():
     lib = load_library()
     lib.b200ba_test_reproj.argtypes = [ctypes.c_int] + [_f64p] * 8
     rng = np.random.default_rng(5)
-    prm = {0: [600., 320, 240], 1: [600., 610, 320, 240], 2: [600., 320, 240, 0.08], 3: [600., 320, 240, 0.08, -0.02]}
-    for model in range(4):
+    prm = {0: [600., 320, 240], 1: [600., 610, 320, 240], 2: [600., 320, 240, 0.08], 3: [600., 320, 240, 0.08, -0.02],
+           8: [600., 320, 240, 0.08], 9: [600., 320, 240, 0.08, -0.02]}
+    for model in prm:
         for _ in range(50):
             q = rng.normal(size=4); q /= np.linalg.norm(q)
             pose = np.concatenate([q, rng.uniform(-1, 1, 2), [4.0]])

@@ -5,7 +5,8 @@ import numpy as np
 import pytest
 
 import oracle_ba
-from colmap_b200.bundle_adjustment import (CAUCHY, DENSE_SCHUR, HUBER, ITERATIVE_SCHUR, PINHOLE, RADIAL, SIMPLE_PINHOLE,
+from colmap_b200.bundle_adjustment import (CAUCHY, DENSE_SCHUR, HUBER, ITERATIVE_SCHUR, PINHOLE, RADIAL, RADIAL_FISHEYE,
+                                           SIMPLE_PINHOLE, SIMPLE_RADIAL_FISHEYE,
                                            SIMPLE_RADIAL, SOFT_L1, TWO_CAMS_FROM_WORLD, BundleAdjustmentConfig,
                                            BundleAdjustmentOptions, CreateDefaultBundleAdjuster, solve_flat)
 from colmap_b200.synthetic import flat_to_reconstruction, synthesize_ba_problem
@@ -59,6 +60,8 @@ def test_b1_config_dense_schur():
     ((PINHOLE, SIMPLE_RADIAL), False, ITERATIVE_SCHUR),          # mixed models (config B5 style)
     ((SIMPLE_PINHOLE, RADIAL, PINHOLE, SIMPLE_RADIAL), False, DENSE_SCHUR),
     ((RADIAL,), True, ITERATIVE_SCHUR),                          # shared intrinsics block: exact SCHUR_JACOBI cross terms
+    ((SIMPLE_RADIAL_FISHEYE, RADIAL_FISHEYE, SIMPLE_RADIAL), False, ITERATIVE_SCHUR),   # equidistant-fisheye models
+    ((RADIAL_FISHEYE,), True, DENSE_SCHUR),
 ])
 def test_model_grid_parity(models, shared, lst):
     gt, noisy = synthesize_ba_problem(24, 1500, 6, models=models, shared_camera=shared, seed=7)
