@@ -390,8 +390,9 @@ __device__ __forceinline__ double ba_obs_linearize(const BaDev& D, const double*
 }
 
 // Linearisation, pass 1 (slot order = track order): scaled Jacobians Jc / Jp (fp32), residual, per-slot cost.
+// (two CTAs per SM: the register cap of 128 matters - at 130 the occupancy halves)
 template <int DC>
-__global__ void __launch_bounds__(BA_BLOCK) ba_linearize_slot_kernel(const BaDev D, int apply_scale, double* cost_out) {
+__global__ void __launch_bounds__(BA_BLOCK, 2) ba_linearize_slot_kernel(const BaDev D, int apply_scale, double* cost_out) {
   __shared__ double sm[8];
   const long long s = (long long)blockIdx.x * BA_BLOCK + threadIdx.x;
   double cost = 0.0;
@@ -419,7 +420,7 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_linearize_slot_kernel(const BaDev
 // Linearisation, pass 2 (camera order): the same rows again, written as JcC / JpC / rC for the passes that reduce per
 // camera-side block.  Recomputing (one 24-byte point gather per observation) replaces 2*DC + 2 scattered stores.
 template <int DC>
-__global__ void __launch_bounds__(BA_BLOCK) ba_linearize_cam_kernel(const BaDev D, int apply_scale) {
+__global__ void __launch_bounds__(BA_BLOCK, 2) ba_linearize_cam_kernel(const BaDev D, int apply_scale) {
   const long long k = (long long)blockIdx.x * BA_BLOCK + threadIdx.x;
   const int run = D.c_run[k];
   if (run < 0) return;
