@@ -1547,8 +1547,9 @@ static void ba_launch_spmv(const BaDev& D, cudaStream_t s) {
   if (D.nblocks_warp) {
     const size_t smem = sizeof(double) * (size_t)D.nc;
     if (g_ba_spmv_smem && smem <= BA_SPMV_SMEM_MAX) {
-      static bool attr_set = false;   // per instantiation
-      if (!attr_set) { cudaFuncSetAttribute(ba_schur_spmv_warp_smem_kernel<DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, BA_SPMV_SMEM_MAX); attr_set = true; }
+      // function attributes are per device: set on every launch that needs more than the default 48 KB (a process may
+      // drive several GPUs)
+      if (smem > 48 * 1024) cudaFuncSetAttribute(ba_schur_spmv_warp_smem_kernel<DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, BA_SPMV_SMEM_MAX);
       if (!g_ba_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_ba_sms, cudaDevAttrMultiProcessorCount, dev); }
       const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(5, (size_t)(216 * 1024) / (smem + 1024)));
       const int grid = std::min(D.nblocks_warp, g_ba_sms * per_sm);
