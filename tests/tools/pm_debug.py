@@ -1,7 +1,7 @@
 """First-contact debugging: compare the CUDA path with the oracle after 0,1,2,... sweeps."""
 import ctypes, os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle_pm
 from colmap_b200.patch_match import PatchMatch, PatchMatchOptions, _f32p

@@ -4,7 +4,7 @@ filtering, PRNG use is identical in law but not in float detail), so agreement i
 analytic ground truth and against each other."""
 import json, os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import ref_pm
 from colmap_b200.patch_match import PatchMatch, PatchMatchOptions

@@ -1,8 +1,8 @@
-"""Timing of the BA configs (B1 / B3) on the GPU; optional oracle comparison."""
+"""Timing of the BA configs (B1 / B3) on the GPU (the oracle comparison lives in tests/)."""
 import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 from colmap_b200.bundle_adjustment import BundleAdjustmentOptions, ITERATIVE_SCHUR, SIMPLE_RADIAL, PINHOLE, solve_flat
 from colmap_b200.synthetic import synthesize_ba_problem
 
@@ -22,9 +22,3 @@ for rep in range(3):
     t = time.time(); s = solve_flat(o, f); wall = time.time() - t
     steps = s.num_successful_steps + s.num_unsuccessful_steps
     print(f"rep{rep}: term {s.termination_type} cost {s.initial_cost:.6g}->{s.final_cost:.6g} LM steps {steps} pcg {s.num_linear_solver_iterations} solve_ms {s.solve_ms:.1f} setup_ms {s.setup_ms:.1f} wall {wall*1e3:.1f} -> {steps/(s.solve_ms/1e3):.1f} LM it/s; spmv avg {s.spmv_ms_total/max(s.spmv_launches,1)*1e3:.1f} us over {s.spmv_launches} samples; launches {s.kernel_launches}", flush=True)
-if len(sys.argv) > 2:
-    import oracle_ba
-    f = noisy.copy(); f.pose_constant, f.pose_fixed_dim = noisy.pose_constant, noisy.pose_fixed_dim
-    t = time.time(); s = oracle_ba.solve(o, f); wall = time.time() - t
-    steps = s.num_successful_steps + s.num_unsuccessful_steps
-    print(f"oracle: term {s.termination_type} cost {s.initial_cost:.6g}->{s.final_cost:.6g} LM steps {steps} pcg {s.num_linear_solver_iterations} wall {wall:.1f}s -> {steps/wall:.3f} LM it/s")

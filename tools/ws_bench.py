@@ -2,7 +2,7 @@
 import os, sys, tempfile, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, ROOT)
 from colmap_b200.mvs_workspace import Model, ModelPoint, read_mat, write_mat
 
 rng = np.random.default_rng(0)
@@ -29,7 +29,3 @@ for name, fn in (("ComputeDepthRanges", m.ComputeDepthRanges), ("ComputeSharedPo
                  ("ComputeTriangulationAngles(75)", lambda: m.ComputeTriangulationAngles(75.0)),
                  ("GetMaxOverlappingImages(20, 1 deg)", lambda: m.GetMaxOverlappingImages(20, 1.0))):
     t = time.time(); fn(); print(f"{name}: {1e3*(time.time()-t):.0f} ms  ({n_img} images, {n_pts} points; incl. {tm*1e3:.0f} ms Python->C marshalling)")
-if len(sys.argv) > 1:
-    import ws_oracle
-    imgs = [(im.R, im.T) for im in m.images]; pts = [((p.x, p.y, p.z), p.track) for p in m.points[:5000]]
-    t = time.time(); ws_oracle.triangulation_angles(imgs, pts, 75.0); print(f"oracle ComputeTriangulationAngles on 5000 points: {1e3*(time.time()-t):.0f} ms")
