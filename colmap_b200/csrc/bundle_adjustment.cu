@@ -1741,14 +1741,21 @@ void b200ba_comm_destroy(b200ba_comm_t c) {
 
 }  // extern "C"
 
+// Host-side slot layout handed to the CPU test tier (b200ba_test_pack): filled when set and the solve runs host-only.
+struct BaHostLayout {
+  std::vector<int> s_obs, s_lpt, s_seg, vpt_s0, vpt_s1, vpt_point;
+  int nblocks_warp = 0, nblocks_var = 0, nblocks_giant0 = 0, nblocks_giant1 = 0, nc = 0, nvpt = 0, dkmax = 0;
+};
+static thread_local BaHostLayout* g_ba_layout_out = nullptr;
+
 static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum, b200ba_comm* comm) {
   if (!o || !p || !sum) return ba_fail(-1, "null argument");
   memset(sum, 0, sizeof(*sum));
   sum->termination_type = B200BA_FAILURE;
   BaPool pool;
   const auto t_setup0 = std::chrono::steady_clock::now();
-  const bool host_only = getenv("B200BA_HOST_ONLY") != nullptr;   // diagnostic: time the host flattening, then stop
-  auto tick = [&](const char* what) { if (host_only) fprintf(stderr, "[b200ba host] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_setup0).count()); };
+  const bool host_only = getenv("B200BA_HOST_ONLY") != nullptr || g_ba_layout_out != nullptr;   // diagnostic / CPU tests: stop after the host flattening
+  auto tick = [&](const char* what) { if (host_only && !g_ba_layout_out) fprintf(stderr, "[b200ba host] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_setup0).count()); };
   int ndev = 0;
   if (!host_only && (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)) return ba_fail(-101, "no CUDA device: colmap_b200 has no CPU fallback");
   if (!host_only && o->gpu_index >= 0) {
@@ -1956,6 +1963,12 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   if (nc >= (1 << 19) - 1) return ba_fail(-3, "camera-side dimension above 2^19 is not supported");
   tick("slot arrays");
   if (host_only) {
+    if (g_ba_layout_out) {
+      BaHostLayout& L = *g_ba_layout_out;
+      L.s_obs = s_obs; L.s_lpt = s_lpt; L.s_seg = s_seg; L.vpt_s0 = vpt_s0; L.vpt_s1 = vpt_s1; L.vpt_point = vpt_point;
+      L.nblocks_warp = nblocks_warp; L.nblocks_var = nblocks_var; L.nblocks_giant0 = nblocks_giant0; L.nblocks_giant1 = nblocks_giant1;
+      L.nc = nc; L.nvpt = nvpt; L.dkmax = dkmax;
+    }
     sum->setup_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_setup0).count();
     return ba_fail(-102, "B200BA_HOST_ONLY: stopped after the host flattening");
   }
@@ -2295,5 +2308,29 @@ int b200ba_test_reproj(int model_id, const double* point, const double* pose, co
   return ba_reproj(model_id, point, pose, params, xy[0], xy[1], res, J_point, J_pose, J_params) ? 1 : 0;
 }
 void b200ba_test_quat_plus(const double* q, const double* d, double* out) { ba_quat_plus(q, d, out); }
+
+// The host flattening of b200ba_solve without a GPU: which observation sits in which slot.  Two-call pattern: with
+// capacity 0 only the sizes come back.  info[8] = {nslots, nvpt, nblocks_warp, nblocks_var, nblocks_giant0,
+// nblocks_giant1, camera-side dimension, max variable intrinsics}.
+int b200ba_test_pack(const b200ba_options* o, b200ba_problem* p, int64_t capacity, int32_t* s_obs, int32_t* s_lpt,
+                     int32_t* s_seg, int32_t* vpt_s0, int32_t* vpt_s1, int32_t* vpt_point, int64_t* info) {
+  BaHostLayout L;
+  b200ba_summary sum;
+  g_ba_layout_out = &L;
+  const int rc = ba_solve_impl(o, p, &sum, nullptr);
+  g_ba_layout_out = nullptr;
+  if (rc != -102) return rc;   // -102 = "stopped after the host flattening" (the expected outcome here)
+  info[0] = (int64_t)L.s_obs.size(); info[1] = L.nvpt; info[2] = L.nblocks_warp; info[3] = L.nblocks_var;
+  info[4] = L.nblocks_giant0; info[5] = L.nblocks_giant1; info[6] = L.nc; info[7] = L.dkmax;
+  if (capacity == 0) return 0;
+  if (capacity < (int64_t)L.s_obs.size()) return -12;
+  memcpy(s_obs, L.s_obs.data(), sizeof(int) * L.s_obs.size());
+  memcpy(s_lpt, L.s_lpt.data(), sizeof(int) * L.s_lpt.size());
+  memcpy(s_seg, L.s_seg.data(), sizeof(int) * L.s_seg.size());
+  memcpy(vpt_s0, L.vpt_s0.data(), sizeof(int) * L.vpt_s0.size());
+  memcpy(vpt_s1, L.vpt_s1.data(), sizeof(int) * L.vpt_s1.size());
+  memcpy(vpt_point, L.vpt_point.data(), sizeof(int) * L.vpt_point.size());
+  return 0;
+}
 
 }  // extern "C"

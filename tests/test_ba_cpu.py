@@ -242,3 +242,81 @@ def test_point_sharding_covers_and_balances():
             assert np.array_equal(s.points, noisy.points[s.point_ids])
             assert len(s.obs_pose) == np.isin(noisy.obs_point, s.point_ids).sum()
             assert np.array_equal(s.poses, noisy.poses)
+
+
+# ---------------------------------------------------------------- host flattening of the product (no GPU needed)
+def _pack(flat, options=None):
+    """b200ba_test_pack: the slot layout b200ba_solve builds on the host before anything touches the GPU."""
+    lib = _bind(load_library())
+    i32p, i64p = ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64)
+    lib.b200ba_test_pack.argtypes = [ctypes.POINTER(_COptions), ctypes.POINTER(_CProblem), ctypes.c_int64, i32p, i32p, i32p, i32p,
+                                     i32p, i32p, i64p]
+    co, cp = (options or BundleAdjustmentOptions(linear_solver_type=ITERATIVE_SCHUR)).to_c(), flat.to_c()
+    info = np.zeros(8, np.int64)
+    assert lib.b200ba_test_pack(ctypes.byref(co), ctypes.byref(cp), 0, None, None, None, None, None, None, info.ctypes.data_as(i64p)) == 0
+    n, nvpt = int(info[0]), int(info[1])
+    a = {k: np.empty(n, np.int32) for k in ("s_obs", "s_lpt", "s_seg")}
+    v = {k: np.empty(max(nvpt, 1), np.int32) for k in ("vpt_s0", "vpt_s1", "vpt_point")}
+    p = lambda x: x.ctypes.data_as(i32p)
+    assert lib.b200ba_test_pack(ctypes.byref(co), ctypes.byref(cp), n, p(a["s_obs"]), p(a["s_lpt"]), p(a["s_seg"]), p(v["vpt_s0"]),
+                                p(v["vpt_s1"]), p(v["vpt_point"]), info.ctypes.data_as(i64p)) == 0
+    return dict(a, **{k: x[:nvpt] for k, x in v.items()}, nslots=n, nvpt=nvpt, nblocks_warp=int(info[2]), nblocks_var=int(info[3]),
+                nblocks_giant0=int(info[4]), nblocks_giant1=int(info[5]), nc=int(info[6]), dkmax=int(info[7]))
+
+
+def test_product_slot_packing_invariants():
+    """Tracks of <= 32 observations never cross a 32-slot warp (with the head / last lane recorded for the segmented
+    shuffle reductions), tracks of <= 256 never cross a block, longer ones are contiguous; every observation that
+    touches a variable block sits in exactly one slot; observations of constant points follow the variable blocks."""
+    rng = np.random.default_rng(4)
+    lens = np.concatenate([rng.integers(2, 12, 4000), rng.integers(33, 200, 30), [300, 700]])
+    gt, noisy = synthesize_ba_problem(900, len(lens), 0, models=(SIMPLE_RADIAL,), shared_camera=True, seed=9, track_lengths=lens)
+    _gauge(noisy)
+    noisy.point_constant = noisy.point_constant.copy(); noisy.point_constant[:50] = 1     # some constant points
+    L = _pack(noisy)
+    s_obs, s_lpt, s_seg = L["s_obs"], L["s_lpt"], L["s_seg"]
+    assert L["nslots"] % 256 == 0
+    valid = s_obs >= 0
+    assert np.array_equal(np.sort(s_obs[valid]), np.arange(len(noisy.obs_pose)))           # every observation exactly once
+    assert np.all(s_lpt[~valid] == -1)
+    # slot -> point consistency
+    pt_of_slot = noisy.obs_point[s_obs[valid]]
+    lpt = s_lpt[valid]
+    const_slots = lpt < 0
+    assert np.all(noisy.point_constant[pt_of_slot[const_slots]] == 1) and np.all(noisy.point_constant[pt_of_slot[~const_slots]] == 0)
+    assert np.array_equal(L["vpt_point"][lpt[~const_slots]], pt_of_slot[~const_slots])
+    assert L["nvpt"] == int((noisy.point_constant == 0).sum())
+    slots = np.arange(L["nslots"])
+    for n in range(L["nvpt"]):
+        s0, s1 = int(L["vpt_s0"][n]), int(L["vpt_s1"][n])
+        assert np.all(s_lpt[s0:s1] == n) and s1 - s0 == lens[L["vpt_point"][n]]
+        blk0, blk1 = s0 // 256, (s1 - 1) // 256
+        if s1 - s0 <= 32:
+            assert blk0 < L["nblocks_warp"] and s0 // 32 == (s1 - 1) // 32                # inside one warp
+            assert np.all((s_seg[s0:s1] & 0xff) == s0 % 32) and np.all((s_seg[s0:s1] >> 8) == (s1 - 1) % 32)
+        elif s1 - s0 <= 256:
+            assert L["nblocks_warp"] <= blk0 == blk1 < L["nblocks_giant0"]                # inside one block
+        else:
+            assert L["nblocks_giant0"] <= blk0 and blk1 < L["nblocks_giant1"]
+    # constant-point observations sit behind the variable blocks
+    assert np.all(slots[valid][const_slots] >= L["nblocks_giant1"] * 256) and L["nblocks_var"] == L["nblocks_giant0"]
+    # the length-bucket packing wastes little: >= 95 % of the warp-packed slots carry an observation
+    warp_region = valid[:L["nblocks_warp"] * 256]
+    assert warp_region.mean() > 0.95
+    assert L["nc"] == 6 * 899 + 2 and L["dkmax"] == 2          # 899 variable poses (the gauge-fixed coordinate is masked, the block stays 6 wide) + f, k of the shared camera
+
+
+def test_product_rejects_unsupported_inputs_without_a_gpu():
+    gt, noisy = synthesize_ba_problem(4, 30, 3, models=(SIMPLE_RADIAL,), seed=1)
+    bad = noisy.copy(); bad.cam_model = noisy.cam_model.copy(); bad.cam_model[0] = 4       # OPENCV: 8 parameters, not supported
+    lib = _bind(load_library())
+    info = np.zeros(8, np.int64)
+    lib.b200ba_test_pack.argtypes = [ctypes.POINTER(_COptions), ctypes.POINTER(_CProblem), ctypes.c_int64] + [ctypes.c_void_p] * 6 + [ctypes.POINTER(ctypes.c_int64)]
+    co, cp = BundleAdjustmentOptions().to_c(), bad.to_c()
+    assert lib.b200ba_test_pack(ctypes.byref(co), ctypes.byref(cp), 0, None, None, None, None, None, None,
+                                info.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))) == -2
+    assert b"unsupported camera model" in lib.b200ba_last_error()
+    bad2 = noisy.copy(); bad2.obs_pose = noisy.obs_pose.copy(); bad2.obs_pose[0] = 99
+    cp = bad2.to_c()
+    assert lib.b200ba_test_pack(ctypes.byref(co), ctypes.byref(cp), 0, None, None, None, None, None, None,
+                                info.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))) == -2
