@@ -488,21 +488,36 @@ class PatchMatchController:
             ConsistencyGraph(out["depth"].shape[1], out["depth"].shape[0], rec).Write(gp)
         return True
 
-    def Run(self, runner: Optional[Runner] = None) -> int:
-        """Returns the number of problems processed (skipped outputs not counted)."""
+    def Run(self, runner: Optional[Runner] = None, rank: int = 0, world: int = 1) -> int:
+        """Returns the number of problems THIS rank processed (skipped outputs not counted).
+
+        Multi-GPU: one process per GPU; every rank reads the workspace, takes its share of the
+        problems (largest reference image first onto the least loaded rank, `assign_problems`) and writes its maps.
+        The photometric problems need no communication; the geometric phase reads the photometric maps of its source
+        images, which other ranks may have produced, so the phases are separated by one barrier - the same hand-over
+        through the workspace files the reference uses between its two thread-pool passes (patch_match.cc:182-205).
+        (`colmap_b200/workspace.py` is the variant that keeps the maps on the GPUs and all-gathers them over NCCL.)"""
+        from .sharding import assign_problems
         runner = runner or _default_runner
         self.ReadWorkspace()
         self.ReadProblems()
+        costs = [float(self.model.images[ref].width * self.model.images[ref].height * max(len(srcs), 1)) for ref, srcs in self.problems]
+        mine = assign_problems(costs, world)[rank]
+
+        def barrier():
+            if world > 1:
+                import torch.distributed as dist
+                dist.barrier()
+
         done = 0
         if self.options.geom_consistency:
             photo = PatchMatchOptions(**{**self.options.__dict__})
             photo.geom_consistency = False
             photo.filter = False
-            for k in range(len(self.problems)):
+            for k in mine:
                 done += bool(self._process(photo, k, runner))
-            for k in range(len(self.problems)):
-                done += bool(self._process(self.options, k, runner))
-        else:
-            for k in range(len(self.problems)):
-                done += bool(self._process(self.options, k, runner))
+            barrier()
+        for k in mine:
+            done += bool(self._process(self.options, k, runner))
+        barrier()
         return done

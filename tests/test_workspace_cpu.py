@@ -240,3 +240,48 @@ def test_library_exports_every_declared_workspace_symbol():
     assert len(names) >= 12
     for n in names:
         assert hasattr(lib, n), n
+
+
+# ---------------------------------------------------------------- two ranks (gloo) share one workspace
+def _controller_worker(rank, world, port, tmp, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from colmap_b200.mvs_workspace import PatchMatchController as C
+    from colmap_b200.patch_match import PatchMatchOptions as O
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    seen = []
+
+    def runner(o, problem):
+        hh, ww = problem.images[0].bitmap.shape
+        if o.geom_consistency:      # the photometric maps of ALL source images must be on disk by now, whoever wrote them
+            assert problem.depth_maps is not None and all(float(d[0, 0]) >= 100.0 for d in problem.depth_maps)
+        seen.append(o.geom_consistency)
+        v = float(np.float32(100 + rank)) if not o.geom_consistency else float(np.float32(200 + rank))
+        return dict(depth=np.full((hh, ww), v, np.float32), normal=np.full((3, hh, ww), v, np.float32))
+
+    n = C(O(geom_consistency=True), tmp).Run(runner, rank=rank, world=world)
+    dist.destroy_process_group()
+    q.put((rank, n, seen))
+
+
+def test_controller_two_ranks_share_a_workspace(tmp_path):
+    import socket
+    import torch.multiprocessing as mp
+    tmp = str(tmp_path)
+    _write_workspace(tmp, n_img=5)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_controller_worker, args=(r, 2, port, tmp, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] + res[1][1] == 10 and {res[0][1], res[1][1]} == {4, 6}          # 5 photometric + 5 geometric, split 3 / 2
+    for _, n, seen in res:
+        assert seen == [False] * (n // 2) + [True] * (n // 2)                        # phase order on every rank
+    for i in range(5):
+        d = read_depth_map(os.path.join(tmp, "stereo", "depth_maps", f"view{i}.png.geometric.bin"))
+        assert d.shape == (36, 48) and float(d[0, 0]) in (200.0, 201.0)
