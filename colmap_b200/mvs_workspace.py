@@ -418,6 +418,7 @@ class PatchMatchController:
         self.problems: List[Tuple[int, List[int]]] = []
         self.depth_ranges: List[Tuple[float, float]] = []
         self._bitmaps: Dict[int, np.ndarray] = {}
+        self.gpu_indices: List[int] = []
 
     # -- ReadWorkspace / ReadProblems
     def ReadWorkspace(self):
@@ -428,6 +429,22 @@ class PatchMatchController:
         path = self.config_path or os.path.join(self.workspace_path, self.stereo_folder, "patch-match.cfg")
         with open(path) as f:
             self.problems = read_problems(f.read(), self.model, self.options.min_triangulation_angle)
+
+    def ReadGpuIndices(self, num_devices: Optional[int] = None) -> List[int]:
+        """PatchMatchController::ReadGpuIndices (patch_match.cc:375-384): one worker thread per entry of
+        `options.gpu_index`; "-1" = every visible device.  Listing a device twice ("0,0") runs two problems on it at a
+        time - the latency-bound serial pass of one overlaps the pixel pass of the other."""
+        idx = [int(v) for v in str(self.options.gpu_index).replace(";", ",").split(",") if v.strip()]
+        if len(idx) == 1 and idx[0] == -1:
+            if num_devices is None:
+                try:
+                    import torch
+                    num_devices = torch.cuda.device_count()
+                except Exception:
+                    num_devices = 0
+            idx = list(range(max(int(num_devices), 1)))
+        self.gpu_indices = idx
+        return idx
 
     def _out_paths(self, image_name: str, output_type: str):
         base = os.path.join(self.workspace_path, self.stereo_folder)
@@ -448,7 +465,7 @@ class PatchMatchController:
             K[0, 0] *= sx; K[0, 2] *= sx; K[1, 1] *= sy; K[1, 2] *= sy
         return Image(bitmap=bm, K=K.astype(np.float32), R=mi.R, T=mi.T)
 
-    def _process(self, options: PatchMatchOptions, problem_idx: int, runner: Runner):
+    def _process(self, options: PatchMatchOptions, problem_idx: int, runner: Runner, gpu_index: int = -1):
         ref, srcs = self.problems[problem_idx]
         output_type = "geometric" if options.geom_consistency else "photometric"
         name = self.model.GetImageName(ref)
@@ -462,6 +479,7 @@ class PatchMatchController:
                 raise WorkspaceError("You must manually set the minimum and maximum depth, since no sparse model is provided in the workspace.")
         if o.sigma_spatial <= 0:
             o.sigma_spatial = float(o.window_radius)
+        o.gpu_index = str(gpu_index)
         used = [ref] + list(srcs)
         local = {g: k for k, g in enumerate(used)}
         images = [self._image(g) for g in used]
@@ -497,10 +515,31 @@ class PatchMatchController:
         images, which other ranks may have produced, so the phases are separated by one barrier - the same hand-over
         through the workspace files the reference uses between its two thread-pool passes (patch_match.cc:182-205).
         (`colmap_b200/workspace.py` is the variant that keeps the maps on the GPUs and all-gathers them over NCCL.)"""
+        import threading
+        from concurrent.futures import ThreadPoolExecutor
         from .sharding import assign_problems
         runner = runner or _default_runner
         self.ReadWorkspace()
         self.ReadProblems()
+        gpu_indices = getattr(self, "gpu_indices", None) or self.ReadGpuIndices()
+        tls = threading.local()
+        free = list(gpu_indices)
+        lock = threading.Lock()
+
+        def run_phase(options, indices):   # the reference's thread pool: one thread per GPU-index entry
+            def work(k):
+                if not hasattr(tls, "gpu"):
+                    with lock:
+                        tls.gpu = free.pop(0)
+                return bool(self._process(options, k, runner, tls.gpu))
+            if len(gpu_indices) == 1:
+                return sum(bool(self._process(options, k, runner, gpu_indices[0])) for k in indices)
+            with lock:
+                free[:] = list(gpu_indices)
+            with ThreadPoolExecutor(max_workers=len(gpu_indices)) as pool:
+                for t in list(vars(tls)):
+                    delattr(tls, t)
+                return sum(pool.map(work, indices))
         costs = [float(self.model.images[ref].width * self.model.images[ref].height * max(len(srcs), 1)) for ref, srcs in self.problems]
         mine = assign_problems(costs, world)[rank]
 
@@ -514,10 +553,8 @@ class PatchMatchController:
             photo = PatchMatchOptions(**{**self.options.__dict__})
             photo.geom_consistency = False
             photo.filter = False
-            for k in mine:
-                done += bool(self._process(photo, k, runner))
+            done += run_phase(photo, mine)
             barrier()
-        for k in mine:
-            done += bool(self._process(self.options, k, runner))
+        done += run_phase(self.options, mine)
         barrier()
         return done

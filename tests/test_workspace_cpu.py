@@ -285,3 +285,33 @@ def test_controller_two_ranks_share_a_workspace(tmp_path):
     for i in range(5):
         d = read_depth_map(os.path.join(tmp, "stereo", "depth_maps", f"view{i}.png.geometric.bin"))
         assert d.shape == (36, 48) and float(d[0, 0]) in (200.0, 201.0)
+
+
+def test_controller_thread_pool_follows_gpu_index_list(tmp_path):
+    """`gpu_index = "0,0"`: two worker threads on device 0 (patch_match.cc:375-384 + the thread pool of :176-205); every
+    problem carries the device of its worker; the photometric phase still completes before the geometric one starts."""
+    import threading
+    import time
+    tmp = str(tmp_path)
+    _write_workspace(tmp, n_img=6)
+    lock, state = threading.Lock(), dict(active=0, peak=0, log=[])
+
+    def runner(o, problem):
+        with lock:
+            state["active"] += 1; state["peak"] = max(state["peak"], state["active"])
+            state["log"].append((o.geom_consistency, o.gpu_index, threading.get_ident()))
+        time.sleep(0.05)
+        with lock:
+            state["active"] -= 1
+        hh, ww = problem.images[0].bitmap.shape
+        return dict(depth=np.ones((hh, ww), np.float32), normal=np.ones((3, hh, ww), np.float32))
+
+    c = PatchMatchController(PatchMatchOptions(geom_consistency=True, gpu_index="0,0"), tmp)
+    assert c.ReadGpuIndices() == [0, 0]
+    assert c.Run(runner) == 12
+    assert state["peak"] == 2
+    assert [g for g, _, _ in state["log"]] == [False] * 6 + [True] * 6
+    assert {i for _, i, _ in state["log"]} == {"0"}
+    assert len({t for _, _, t in state["log"][:6]}) == 2
+    c2 = PatchMatchController(PatchMatchOptions(gpu_index="-1"), tmp)
+    assert c2.ReadGpuIndices(num_devices=4) == [0, 1, 2, 3] and PatchMatchController(PatchMatchOptions(gpu_index="1, 3"), tmp).ReadGpuIndices() == [1, 3]
