@@ -23,6 +23,10 @@
  * (reprojection_error_test.cc:211-323), ground-truth recovery tolerances and residual counts of
  * bundle_adjustment_test.cc:303-411, constants bit-identical.
  *
+ * Every loop over observations / points is OpenMP-parallel (per-thread partial sums for the camera-side quantities,
+ * one thread per point for the point-side ones), because this file is also the CPU baseline bench.py times beside
+ * the GPU path: a serial oracle would flatter the GPU numbers.
+ *
  * Build: gcc -O2 -fopenmp -shared -fPIC (Makefile).
  */
 #define _GNU_SOURCE
@@ -477,6 +481,11 @@ static void schur_jacobi(const ba_flat* F, const ba_lin* L, const int* blk_start
                          const int* blk_pack) {
   double* M = (double*)calloc((size_t)blk_pack[nblk] + 1, sizeof(double));
   /* exact: M_b = Hcc_bb + Dc2_b - sum_p V_b(p)^T Hpp_inv(p) V_b(p),  V_b(p) = sum_{o in p, b in o} Jp_o^T Jc_o,b */
+  const size_t msize = (size_t)blk_pack[nblk] + 1;
+#pragma omp parallel
+  {
+  double* Mloc = (double*)calloc(msize, sizeof(double));   /* per-thread partial blocks, joined below */
+#pragma omp for schedule(static) nowait
   for (int64_t j = 0; j < F->nobs; ++j) {
     int po, co, nv; obs_blocks(F, j, &po, &co, &nv);
     const double* Jc = F->Jc + 2 * JC * j;
@@ -485,14 +494,14 @@ static void schur_jacobi(const ba_flat* F, const ba_lin* L, const int* blk_start
       if (off < 0) continue;
       int b = 0; /* block index by binary search */
       { int lo = 0, hi = nblk - 1; while (lo < hi) { const int mid = (lo + hi + 1) / 2; if (blk_start[mid] <= off) lo = mid; else hi = mid - 1; } b = lo; }
-      double* Mb = M + blk_pack[b];
+      double* Mb = Mloc + blk_pack[b];
       for (int r = 0; r < n; ++r)
         for (int c = 0; c < n; ++c)
           Mb[r * n + c] += F->scale_c[off + r] * F->scale_c[off + c] * (Jc[jo + r] * Jc[jo + c] + Jc[JC + jo + r] * Jc[JC + jo + c]);
     }
   }
-  for (int b = 0; b < nblk; ++b) { const int n = blk_start[b + 1] - blk_start[b]; for (int r = 0; r < n; ++r) M[blk_pack[b] + r * n + r] += L->Dc2[blk_start[b] + r]; }
   /* point terms */
+#pragma omp for schedule(static) nowait
   for (int64_t k = 0; k < F->nvpt; ++k) {
     const int64_t s = F->pt_start[k], e2 = F->pt_start[k + 1];
     const double* Hi = L->Hpp_inv + 9 * k;
@@ -517,7 +526,7 @@ static void schur_jacobi(const ba_flat* F, const ba_lin* L, const int* blk_start
               V[a * n + c] += F->scale_p[3 * k + a] * F->scale_c[off + c] * (Jp[a] * Jc[jo + c] + Jp[3 + a] * Jc[JC + jo + c]);
         }
         int b; { int lo = 0, hi = nblk - 1; while (lo < hi) { const int mid = (lo + hi + 1) / 2; if (blk_start[mid] <= off) lo = mid; else hi = mid - 1; } b = lo; }
-        double* Mb = M + blk_pack[b];
+        double* Mb = Mloc + blk_pack[b];
         for (int r = 0; r < n; ++r)
           for (int c = 0; c < n; ++c) {
             double t = 0;
@@ -527,7 +536,13 @@ static void schur_jacobi(const ba_flat* F, const ba_lin* L, const int* blk_start
       }
     }
   }
+#pragma omp critical
+  for (size_t i = 0; i < msize; ++i) M[i] += Mloc[i];
+  free(Mloc);
+  }
+  for (int b = 0; b < nblk; ++b) { const int n = blk_start[b + 1] - blk_start[b]; for (int r = 0; r < n; ++r) M[blk_pack[b] + r * n + r] += L->Dc2[blk_start[b] + r]; }
   /* invert each block (Cholesky based) */
+#pragma omp parallel for schedule(static)
   for (int b = 0; b < nblk; ++b) {
     const int n = blk_start[b + 1] - blk_start[b];
     double A[36], col[6];
@@ -626,12 +641,27 @@ int ba_oracle_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* 
     /* jacobi scaling from the first Jacobian */
     if (!have_scale) {
       for (int i = 0; i < nc; ++i) F.scale_c[i] = 0; for (int64_t i = 0; i < np3; ++i) F.scale_p[i] = 0;
-      for (int64_t j = 0; j < F.nobs; ++j) {
-        int po, co, nv; obs_blocks(&F, j, &po, &co, &nv); const double* Jc = F.Jc + 2 * JC * j; const double* Jp = F.Jp + 6 * j;
-        if (po >= 0) for (int c = 0; c < 6; ++c) F.scale_c[po + c] += Jc[c] * Jc[c] + Jc[JC + c] * Jc[JC + c];
-        if (co >= 0) for (int c = 0; c < nv; ++c) F.scale_c[co + c] += Jc[6 + c] * Jc[6 + c] + Jc[JC + 6 + c] * Jc[JC + 6 + c];
-        if (j < F.nobs_var) { const int pv = F.pt_var[p->obs_point_idx[F.obs[j]]]; for (int c = 0; c < 3; ++c) F.scale_p[3 * (int64_t)pv + c] += Jp[c] * Jp[c] + Jp[3 + c] * Jp[3 + c]; }
+      /* camera side: per-thread partial sums joined afterwards; point side: one thread per point (observations are
+       * grouped by point) */
+#pragma omp parallel
+      {
+        double* loc = (double*)calloc(nc + 1, sizeof(double));
+#pragma omp for schedule(static) nowait
+        for (int64_t j = 0; j < F.nobs; ++j) {
+          int po, co, nv; obs_blocks(&F, j, &po, &co, &nv); const double* Jc = F.Jc + 2 * JC * j;
+          if (po >= 0) for (int c = 0; c < 6; ++c) loc[po + c] += Jc[c] * Jc[c] + Jc[JC + c] * Jc[JC + c];
+          if (co >= 0) for (int c = 0; c < nv; ++c) loc[co + c] += Jc[6 + c] * Jc[6 + c] + Jc[JC + 6 + c] * Jc[JC + 6 + c];
+        }
+#pragma omp critical
+        for (int i = 0; i < nc; ++i) F.scale_c[i] += loc[i];
+        free(loc);
       }
+#pragma omp parallel for schedule(static)
+      for (int64_t k = 0; k < F.nvpt; ++k)
+        for (int64_t j = F.pt_start[k]; j < F.pt_start[k + 1]; ++j) {
+          const double* Jp = F.Jp + 6 * j;
+          for (int c = 0; c < 3; ++c) F.scale_p[3 * k + c] += Jp[c] * Jp[c] + Jp[3 + c] * Jp[3 + c];
+        }
       for (int i = 0; i < nc; ++i) F.scale_c[i] = o->jacobi_scaling ? 1.0 / (1.0 + sqrt(F.scale_c[i])) : 1.0;
       for (int64_t i = 0; i < np3; ++i) F.scale_p[i] = o->jacobi_scaling ? 1.0 / (1.0 + sqrt(F.scale_p[i])) : 1.0;
       have_scale = 1;
@@ -639,20 +669,30 @@ int ba_oracle_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* 
     /* gradient (scaled space) and diag(J_s^T J_s) */
     memset(gc, 0, sizeof(double) * nc); memset(gp, 0, sizeof(double) * np3);
     memset(diag_c, 0, sizeof(double) * nc); memset(diag_p, 0, sizeof(double) * np3);
-    for (int64_t j = 0; j < F.nobs; ++j) {
-      jct_times_add(&F, j, F.r + 2 * j, gc);
-      int po, co, nv; obs_blocks(&F, j, &po, &co, &nv); const double* Jc = F.Jc + 2 * JC * j; const double* Jp = F.Jp + 6 * j;
-      if (po >= 0) for (int c = 0; c < 6; ++c) diag_c[po + c] += F.scale_c[po + c] * F.scale_c[po + c] * (Jc[c] * Jc[c] + Jc[JC + c] * Jc[JC + c]);
-      if (co >= 0) for (int c = 0; c < nv; ++c) diag_c[co + c] += F.scale_c[co + c] * F.scale_c[co + c] * (Jc[6 + c] * Jc[6 + c] + Jc[JC + 6 + c] * Jc[JC + 6 + c]);
-      if (j < F.nobs_var) {
-        const int64_t pv = F.pt_var[p->obs_point_idx[F.obs[j]]];
+#pragma omp parallel
+    {
+      double* lg = (double*)calloc(2 * (size_t)nc + 2, sizeof(double)); double* ld = lg + nc + 1;
+#pragma omp for schedule(static) nowait
+      for (int64_t j = 0; j < F.nobs; ++j) {
+        jct_times_add(&F, j, F.r + 2 * j, lg);
+        int po, co, nv; obs_blocks(&F, j, &po, &co, &nv); const double* Jc = F.Jc + 2 * JC * j;
+        if (po >= 0) for (int c = 0; c < 6; ++c) ld[po + c] += F.scale_c[po + c] * F.scale_c[po + c] * (Jc[c] * Jc[c] + Jc[JC + c] * Jc[JC + c]);
+        if (co >= 0) for (int c = 0; c < nv; ++c) ld[co + c] += F.scale_c[co + c] * F.scale_c[co + c] * (Jc[6 + c] * Jc[6 + c] + Jc[JC + 6 + c] * Jc[JC + 6 + c]);
+      }
+#pragma omp critical
+      for (int i = 0; i < nc; ++i) { gc[i] += lg[i]; diag_c[i] += ld[i]; }
+      free(lg);
+    }
+#pragma omp parallel for schedule(static)
+    for (int64_t pv = 0; pv < F.nvpt; ++pv)
+      for (int64_t j = F.pt_start[pv]; j < F.pt_start[pv + 1]; ++j) {
+        const double* Jp = F.Jp + 6 * j;
         for (int c = 0; c < 3; ++c) {
           const double s = F.scale_p[3 * pv + c];
           gp[3 * pv + c] += s * (Jp[c] * F.r[2 * j] + Jp[3 + c] * F.r[2 * j + 1]);
           diag_p[3 * pv + c] += s * s * (Jp[c] * Jp[c] + Jp[3 + c] * Jp[3 + c]);
         }
       }
-    }
     if (iter == 0 || 1) {
       /* gradient tolerance is tested on the unscaled gradient */
       double* ugc = dc; double* ugp = dp;
@@ -669,6 +709,7 @@ int ba_oracle_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* 
       for (int64_t i = 0; i < np3; ++i) L.Dp2[i] = fmin(fmax(diag_p[i], o->min_lm_diagonal), o->max_lm_diagonal) / radius;
       /* point blocks */
       int ok = 1;
+#pragma omp parallel for schedule(static) reduction(&& : ok)
       for (int64_t k = 0; k < F.nvpt; ++k) {
         double H[9] = {0};
         for (int64_t j = F.pt_start[k]; j < F.pt_start[k + 1]; ++j) {
@@ -680,14 +721,22 @@ int ba_oracle_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* 
       }
       /* reduced right-hand side: -g_c + H_cp Hpp^-1 g_p */
       for (int i = 0; i < nc; ++i) rhs[i] = -gc[i];
-      for (int64_t k = 0; k < F.nvpt; ++k) {
-        const double* Hi = L.Hpp_inv + 9 * k; double w[3];
-        for (int c = 0; c < 3; ++c) w[c] = Hi[3 * c] * gp[3 * k] + Hi[3 * c + 1] * gp[3 * k + 1] + Hi[3 * c + 2] * gp[3 * k + 2];
-        for (int64_t j = F.pt_start[k]; j < F.pt_start[k + 1]; ++j) {
-          const double* Jp = F.Jp + 6 * j; double u[2];
-          for (int r = 0; r < 2; ++r) { double t = 0; for (int c = 0; c < 3; ++c) t += Jp[3 * r + c] * F.scale_p[3 * k + c] * w[c]; u[r] = t; }
-          jct_times_add(&F, j, u, rhs);
+#pragma omp parallel
+      {
+        double* loc = (double*)calloc(nc + 1, sizeof(double));
+#pragma omp for schedule(static) nowait
+        for (int64_t k = 0; k < F.nvpt; ++k) {
+          const double* Hi = L.Hpp_inv + 9 * k; double w[3];
+          for (int c = 0; c < 3; ++c) w[c] = Hi[3 * c] * gp[3 * k] + Hi[3 * c + 1] * gp[3 * k + 1] + Hi[3 * c + 2] * gp[3 * k + 2];
+          for (int64_t j = F.pt_start[k]; j < F.pt_start[k + 1]; ++j) {
+            const double* Jp = F.Jp + 6 * j; double u[2];
+            for (int r = 0; r < 2; ++r) { double t = 0; for (int c = 0; c < 3; ++c) t += Jp[3 * r + c] * F.scale_p[3 * k + c] * w[c]; u[r] = t; }
+            jct_times_add(&F, j, u, loc);
+          }
         }
+#pragma omp critical
+        for (int i = 0; i < nc; ++i) rhs[i] += loc[i];
+        free(loc);
       }
       /* reduced solve */
       memset(dc, 0, sizeof(double) * nc);
@@ -728,6 +777,7 @@ int ba_oracle_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* 
         }
       }
       /* back-substitution: dp = Hpp^-1 (-g_p - H_pc dc) */
+#pragma omp parallel for schedule(static)
       for (int64_t k = 0; k < F.nvpt; ++k) {
         double t[3] = {-gp[3 * k], -gp[3 * k + 1], -gp[3 * k + 2]};
         for (int64_t j = F.pt_start[k]; j < F.pt_start[k + 1]; ++j) {
@@ -739,6 +789,7 @@ int ba_oracle_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* 
       }
       /* model cost change = -(J d)^T (r + J d / 2) */
       double model = 0;
+#pragma omp parallel for schedule(static) reduction(+ : model)
       for (int64_t j = 0; j < F.nobs; ++j) {
         double y[2]; jc_times(&F, j, dc, y);
         if (j < F.nobs_var) { const int64_t pv = F.pt_var[p->obs_point_idx[F.obs[j]]]; const double* Jp = F.Jp + 6 * j;
