@@ -138,7 +138,7 @@ def _fresh(noisy):
     return f
 
 
-def _oracle_ba_sample(noisy, max_iters=3):
+def _oracle_ba_sample(noisy, max_iters=10):
     """Bounded CPU sample: the same B3 problem, first `max_iters` LM iterations, oracle port, all host threads."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_ba
