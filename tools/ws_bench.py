@@ -29,3 +29,14 @@ for name, fn in (("ComputeDepthRanges", m.ComputeDepthRanges), ("ComputeSharedPo
                  ("ComputeTriangulationAngles(75)", lambda: m.ComputeTriangulationAngles(75.0)),
                  ("GetMaxOverlappingImages(20, 1 deg)", lambda: m.GetMaxOverlappingImages(20, 1.0))):
     t = time.time(); fn(); print(f"{name}: {1e3*(time.time()-t):.0f} ms  ({n_img} images, {n_pts} points; incl. {tm*1e3:.0f} ms Python->C marshalling)")
+
+# ---- stereo fusion at a workspace-like size (ground-truth maps of the synthetic scene, 1 + 4 views)
+from colmap_b200.mvs_fusion import FusionImage, StereoFusionOptions, fuse
+from colmap_b200.synthetic import make_patch_match_scene
+W, H = 640, 360
+sc = make_patch_match_scene(W, H, 4, seed=0, with_gt_maps=True)
+views = [FusionImage(im.K, im.R, im.T, W, H, sc["depth_maps"][k].astype(np.float32), sc["normal_maps"][k].astype(np.float32),
+                     np.stack([im.bitmap] * 3, -1)) for k, im in enumerate(sc["images"])]
+overlap = [[j for j in range(5) if j != i] for i in range(5)]
+t = time.time(); pts = fuse(StereoFusionOptions(), views, overlap); dt = time.time() - t
+print(f"stereo fusion: 5 views {W}x{H} ({5*W*H/1e6:.2f} Mpx of depth) -> {len(pts.xyz)} points in {dt*1e3:.0f} ms ({5*W*H/1e6/dt:.1f} Mpx/s, one host thread)")
