@@ -393,6 +393,77 @@ def flatten_reconstruction(options: BundleAdjustmentOptions, config: BundleAdjus
     return flat, image_ids, camera_ids, point_ids
 
 
+class _CScene(ctypes.Structure):
+    _fields_ = [("num_images", ctypes.c_int), ("image_id", ctypes.POINTER(ctypes.c_uint32)), ("image_camera", _i32p),
+                ("cam_from_world", _f64p), ("point2D_offset", ctypes.POINTER(ctypes.c_int64)), ("point2D_xy", _f64p),
+                ("point2D_point3D", ctypes.POINTER(ctypes.c_int64)), ("num_cameras", ctypes.c_int), ("camera_model_id", _i32p),
+                ("camera_param_offset", _i32p), ("camera_params", _f64p), ("num_points3D", ctypes.c_int64), ("xyz", _f64p),
+                ("track_offset", ctypes.POINTER(ctypes.c_int64)), ("track_image", _i32p), ("track_point2D", _i32p)]
+
+
+class _CConfig(ctypes.Structure):
+    _fields_ = [("image_in_config", _u8p), ("image_constant_pose", _u8p), ("camera_constant", _u8p), ("point_variable", _u8p),
+                ("point_constant", _u8p), ("point_ignored", _u8p), ("fixed_gauge", ctypes.c_int), ("min_track_length", ctypes.c_int)]
+
+
+def assemble_reconstruction(options: BundleAdjustmentOptions, config: BundleAdjustmentConfig, rec: Reconstruction):
+    """b200ba_assemble: the C++ problem assembly (DefaultBundleAdjuster's constructor incl. the two-cams gauge) on flat
+    views of the reconstruction.  Returns (flat, image_ids, camera_ids, point_ids) like flatten_reconstruction."""
+    lib = _bind(load_library())
+    i64p, u32p = ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_uint32)
+    lib.b200ba_assemble.argtypes = [ctypes.POINTER(_COptions), ctypes.POINTER(_CScene), ctypes.POINTER(_CConfig), ctypes.POINTER(ctypes.c_void_p)]
+    lib.b200ba_assembly_problem.argtypes = [ctypes.c_void_p]; lib.b200ba_assembly_problem.restype = ctypes.POINTER(_CProblem)
+    lib.b200ba_assembly_free.argtypes = [ctypes.c_void_p]
+    image_ids, camera_ids, point_ids = sorted(rec.images), sorted(rec.cameras), sorted(rec.points3D)
+    img_idx = {i: k for k, i in enumerate(image_ids)}; cam_idx = {c: k for k, c in enumerate(camera_ids)}; pt_idx = {p: k for k, p in enumerate(point_ids)}
+    c = np.ascontiguousarray
+    ids = c(image_ids, np.uint32); icam = c([cam_idx[rec.images[i].camera_id] for i in image_ids], np.int32)
+    poses = c(np.stack([rec.images[i].cam_from_world for i in image_ids]) if image_ids else np.zeros((0, 7)), np.float64)
+    p2off = np.zeros(len(image_ids) + 1, np.int64)
+    p2off[1:] = np.cumsum([len(rec.images[i].points2D) for i in image_ids])
+    p2xy = c([p.xy for i in image_ids for p in rec.images[i].points2D], np.float64).reshape(-1, 2)
+    p2pt = c([pt_idx.get(p.point3D_id, -1) if p.point3D_id >= 0 else -1 for i in image_ids for p in rec.images[i].points2D], np.int64)
+    cmodel = c([rec.cameras[k].model_id for k in camera_ids], np.int32)
+    coff = np.zeros(len(camera_ids), np.int32); off = 0
+    for k, cid in enumerate(camera_ids):
+        coff[k] = off; off += MODEL_NUM_PARAMS[rec.cameras[cid].model_id]
+    cparams = c(np.concatenate([rec.cameras[k].params for k in camera_ids]) if camera_ids else np.zeros(0), np.float64)
+    xyz = c(np.stack([rec.points3D[p].xyz for p in point_ids]) if point_ids else np.zeros((0, 3)), np.float64)
+    toff = np.zeros(len(point_ids) + 1, np.int64)
+    toff[1:] = np.cumsum([len(rec.points3D[p].track) for p in point_ids])
+    timg = c([img_idx[i] for p in point_ids for i, _ in rec.points3D[p].track], np.int32)
+    tp2 = c([k for p in point_ids for _, k in rec.points3D[p].track], np.int32)
+    flags = lambda keys, pred: c([1 if pred(k) else 0 for k in keys], np.uint8)
+    f_in = flags(image_ids, config.HasImage); f_cp = flags(image_ids, config.HasConstantRigFromWorldPose)
+    f_cc = flags(camera_ids, config.HasConstantCamIntrinsics)
+    f_pv = flags(point_ids, lambda p: p in config.VariablePoints()); f_pc = flags(point_ids, lambda p: p in config.ConstantPoints())
+    f_pi = flags(point_ids, config.IsIgnoredPoint)
+    P = lambda a, t: a.ctypes.data_as(t)
+    sc = _CScene(len(image_ids), P(ids, u32p), P(icam, _i32p), P(poses, _f64p), P(p2off, i64p), P(p2xy, _f64p), P(p2pt, i64p),
+                 len(camera_ids), P(cmodel, _i32p), P(coff, _i32p), P(cparams, _f64p), len(point_ids), P(xyz, _f64p), P(toff, i64p),
+                 P(timg, _i32p), P(tp2, _i32p))
+    cf = _CConfig(P(f_in, _u8p), P(f_cp, _u8p), P(f_cc, _u8p), P(f_pv, _u8p), P(f_pc, _u8p), P(f_pi, _u8p), int(config.FixedGauge()),
+                  int(options.min_track_length))
+    co, h = options.to_c(), ctypes.c_void_p()
+    rc = lib.b200ba_assemble(ctypes.byref(co), ctypes.byref(sc), ctypes.byref(cf), ctypes.byref(h))
+    if rc != 0:
+        raise BundleAdjustmentError(f"b200ba_assemble failed ({rc}): {lib.b200ba_last_error().decode()}")
+    try:
+        pr = lib.b200ba_assembly_problem(h).contents
+        n_obs, n_cam, n_pt, n_img = pr.num_observations, pr.num_cameras, pr.num_points, pr.num_poses
+        arr = lambda ptr, n, dt: np.ctypeslib.as_array(ptr, shape=(max(n, 1),))[:n].astype(dt, copy=True) if n else np.zeros(0, dt)
+        flat = FlatProblem(arr(pr.poses, 7 * n_img, np.float64), arr(pr.pose_constant, n_img, np.uint8),
+                           arr(pr.pose_fixed_translation_dim, n_img, np.int8), arr(pr.camera_model_id, n_cam, np.int32),
+                           arr(pr.camera_param_offset, n_cam, np.int32), arr(pr.camera_params, len(cparams), np.float64),
+                           arr(pr.camera_constant, n_cam, np.uint8), arr(pr.points, 3 * n_pt, np.float64),
+                           arr(pr.point_constant, n_pt, np.uint8), arr(pr.obs_pose_idx, n_obs, np.int32),
+                           arr(pr.obs_camera_idx, n_obs, np.int32), arr(pr.obs_point_idx, n_obs, np.int32),
+                           arr(pr.obs_xy, 2 * n_obs, np.float64))
+    finally:
+        lib.b200ba_assembly_free(h)
+    return flat, image_ids, camera_ids, point_ids
+
+
 class BundleAdjuster:
     """BundleAdjuster (bundle_adjustment.h:212-226), B200 backend: Solve() updates the reconstruction in place."""
 

@@ -1706,6 +1706,109 @@ int b200ba_fix_gauge_two_cams_from_world(const b200ba_problem* p, const b200ba_o
   return 0;
 }
 
+// ---- problem assembly (see the header): DefaultBundleAdjuster's constructor on flat views ----
+}  // extern "C"
+struct b200ba_assembly {
+  std::vector<double> poses, cam_params, points, obs_xy;
+  std::vector<uint8_t> pose_constant, cam_constant, point_constant;
+  std::vector<int8_t> pose_fixed_dim;
+  std::vector<int32_t> cam_model, cam_off, obs_pose, obs_cam, obs_point;
+  b200ba_problem problem;
+};
+extern "C" {
+
+int b200ba_assemble(const b200ba_options* o, const b200ba_scene* sc, const b200ba_config* cfg, b200ba_assembly_t* out) {
+  if (!o || !sc || !cfg || !out) return ba_fail(-1, "null argument");
+  const int NI = sc->num_images, NC = sc->num_cameras;
+  const int64_t NPT = sc->num_points3D;
+  auto flag = [](const uint8_t* f, int64_t i) { return f && f[i]; };
+  for (int i = 0; i < NI; ++i) if (sc->image_camera[i] < 0 || sc->image_camera[i] >= NC) return ba_fail(-2, "image references a camera outside the scene");
+  for (int c = 0; c < NC; ++c) if (ba_model_num_params(sc->camera_model_id[c]) < 0) return ba_fail(-2, "unsupported camera model");
+  b200ba_assembly* A = new b200ba_assembly();
+  std::vector<int64_t> point_num_obs((size_t)NPT, 0);
+  auto track_len = [&](int64_t pid) { return sc->track_offset[pid + 1] - sc->track_offset[pid]; };
+  auto push = [&](int img, int64_t pid, const double* xy) {
+    A->obs_pose.push_back(img); A->obs_cam.push_back(sc->image_camera[img]); A->obs_point.push_back((int32_t)pid);
+    A->obs_xy.push_back(xy[0]); A->obs_xy.push_back(xy[1]);
+    point_num_obs[pid] += 1;
+  };
+  // AddImageToProblem: every observation of the config's images (:688-751)
+  for (int i = 0; i < NI; ++i) {
+    if (!flag(cfg->image_in_config, i)) continue;
+    for (int64_t k = sc->point2D_offset[i]; k < sc->point2D_offset[i + 1]; ++k) {
+      const int64_t pid = sc->point2D_point3D[k];
+      if (pid < 0) continue;
+      if (pid >= NPT) { delete A; return ba_fail(-2, "point2D references a point outside the scene"); }
+      if (flag(cfg->point_ignored, pid)) continue;
+      if (track_len(pid) < cfg->min_track_length) continue;
+      push(i, pid, sc->point2D_xy + 2 * k);
+    }
+  }
+  // AddPointToProblem: explicit config points bring the observations made by images outside the config (:829-888)
+  for (int64_t pid = 0; pid < NPT; ++pid) {
+    if (!flag(cfg->point_variable, pid) && !flag(cfg->point_constant, pid)) continue;
+    if (point_num_obs[pid] == track_len(pid)) continue;
+    for (int64_t t = sc->track_offset[pid]; t < sc->track_offset[pid + 1]; ++t) {
+      const int img = sc->track_image[t];
+      if (img < 0 || img >= NI) { delete A; return ba_fail(-2, "track references an image outside the scene"); }
+      if (flag(cfg->image_in_config, img)) continue;
+      const int64_t k = sc->point2D_offset[img] + sc->track_point2D[t];
+      if (k < sc->point2D_offset[img] || k >= sc->point2D_offset[img + 1]) { delete A; return ba_fail(-2, "track references a point2D outside its image"); }
+      push(img, pid, sc->point2D_xy + 2 * k);
+    }
+  }
+  A->poses.assign(sc->cam_from_world, sc->cam_from_world + 7 * (size_t)NI);
+  A->pose_constant.assign(NI, 1);
+  A->pose_fixed_dim.assign(NI, -1);
+  std::vector<uint8_t> cam_in_cfg(NC, 0);
+  for (int i = 0; i < NI; ++i)
+    if (flag(cfg->image_in_config, i)) {
+      cam_in_cfg[sc->image_camera[i]] = 1;
+      if (!flag(cfg->image_constant_pose, i)) A->pose_constant[i] = 0;
+    }
+  // cameras seen only through constant-pose factors of outside images stay constant (:863-878)
+  A->cam_constant.resize(NC);
+  for (int c = 0; c < NC; ++c) A->cam_constant[c] = (!cam_in_cfg[c] || flag(cfg->camera_constant, c)) ? 1 : 0;
+  A->cam_model.assign(sc->camera_model_id, sc->camera_model_id + NC);
+  A->cam_off.assign(sc->camera_param_offset, sc->camera_param_offset + NC);
+  int64_t nparams = 0;
+  for (int c = 0; c < NC; ++c) nparams = std::max<int64_t>(nparams, sc->camera_param_offset[c] + ba_model_num_params(sc->camera_model_id[c]));
+  A->cam_params.assign(sc->camera_params, sc->camera_params + nparams);
+  // ParameterizePoints (:540-565): variable iff refined and fully observed inside the problem; explicit constants win
+  A->points.assign(sc->xyz, sc->xyz + 3 * (size_t)NPT);
+  A->point_constant.assign((size_t)NPT, 1);
+  for (int64_t pid = 0; pid < NPT; ++pid) {
+    if (point_num_obs[pid] > 0 && o->refine_points3D && track_len(pid) <= point_num_obs[pid]) A->point_constant[pid] = 0;
+    if (flag(cfg->point_constant, pid)) A->point_constant[pid] = 1;
+  }
+  b200ba_problem& P = A->problem;
+  memset(&P, 0, sizeof(P));
+  P.num_poses = NI; P.poses = A->poses.data(); P.pose_constant = A->pose_constant.data(); P.pose_fixed_translation_dim = A->pose_fixed_dim.data();
+  P.num_cameras = NC; P.camera_model_id = A->cam_model.data(); P.camera_param_offset = A->cam_off.data(); P.camera_params = A->cam_params.data();
+  P.camera_constant = A->cam_constant.data();
+  P.num_points = NPT; P.points = A->points.data(); P.point_constant = A->point_constant.data();
+  P.num_observations = (int64_t)A->obs_pose.size();
+  P.obs_pose_idx = A->obs_pose.data(); P.obs_camera_idx = A->obs_cam.data(); P.obs_point_idx = A->obs_point.data(); P.obs_xy = A->obs_xy.data();
+  // FixGauge (:270-417), TWO_CAMS_FROM_WORLD: the search runs over the config's images in ascending image id
+  if (cfg->fixed_gauge == 1 && o->refine_rig_from_world) {
+    std::vector<int> idx;
+    for (int i = 0; i < NI; ++i) if (flag(cfg->image_in_config, i)) idx.push_back(i);
+    std::vector<double> sp(7 * idx.size());
+    std::vector<uint8_t> sc_in(idx.size()), sc_out(idx.size());
+    std::vector<int8_t> sd_in(idx.size(), -1), sd_out(idx.size());
+    for (size_t k = 0; k < idx.size(); ++k) { memcpy(sp.data() + 7 * k, A->poses.data() + 7 * (size_t)idx[k], 56); sc_in[k] = A->pose_constant[idx[k]]; }
+    b200ba_problem sub;
+    memset(&sub, 0, sizeof(sub));
+    sub.num_poses = (int)idx.size(); sub.poses = sp.data(); sub.pose_constant = sc_in.data(); sub.pose_fixed_translation_dim = sd_in.data();
+    b200ba_fix_gauge_two_cams_from_world(&sub, o, sc_out.data(), sd_out.data());
+    for (size_t k = 0; k < idx.size(); ++k) { A->pose_constant[idx[k]] = sc_out[k]; A->pose_fixed_dim[idx[k]] = sd_out[k]; }
+  }
+  *out = A;
+  return 0;
+}
+b200ba_problem* b200ba_assembly_problem(b200ba_assembly_t a) { return a ? &a->problem : nullptr; }
+void b200ba_assembly_free(b200ba_assembly_t a) { delete a; }
+
 int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum) { return ba_solve_impl(o, p, sum, nullptr); }
 
 // Point-sharded solve: every rank passes the SAME poses / cameras and its own shard of points with all their

@@ -131,6 +131,48 @@ int b200ba_comm_init(const void* id128, int rank, int world_size, b200ba_comm_t*
 void b200ba_comm_destroy(b200ba_comm_t comm);
 int b200ba_solve_sharded(const b200ba_options* o, b200ba_problem* local_shard, b200ba_comm_t comm, b200ba_summary* out);
 
+/* ---- problem assembly from a Reconstruction + BundleAdjustmentConfig ----
+ * DefaultBundleAdjuster's constructor (bundle_adjustment_ceres.cc:606-664: AddImageToProblem :688-751, AddPointToProblem
+ * :829-888, ParameterizeCameras / ParameterizePoints :478-565, FixGauge :270-417) for trivial frames, on flat views of the
+ * reference's containers.  The adapter fills the views with plain loops over Reconstruction (no hash-map walks remain on
+ * the solve path), calls b200ba_assemble, b200ba_solve on the assembled problem, and copies the three in/out arrays back. */
+typedef struct b200ba_scene {
+  int num_images;                   /* every image of the reconstruction, ascending image id */
+  const uint32_t* image_id;
+  const int32_t* image_camera;      /* [num_images] index into the camera arrays */
+  const double* cam_from_world;     /* [7*num_images] qx qy qz qw tx ty tz */
+  const int64_t* point2D_offset;    /* [num_images+1] into the two arrays below */
+  const double* point2D_xy;         /* [2*total] */
+  const int64_t* point2D_point3D;   /* [total] index into the point arrays, -1 = no 3D point */
+  int num_cameras;
+  const int32_t* camera_model_id;
+  const int32_t* camera_param_offset;
+  const double* camera_params;
+  int64_t num_points3D;             /* ascending point3D id */
+  const double* xyz;                /* [3*num_points3D] */
+  const int64_t* track_offset;      /* [num_points3D+1] */
+  const int32_t* track_image;       /* image INDEX of every track element */
+  const int32_t* track_point2D;     /* index of the element inside that image's point2D list */
+} b200ba_scene;
+
+typedef struct b200ba_config {      /* BundleAdjustmentConfig (bundle_adjustment.h:77-151) as flags over the scene arrays */
+  const uint8_t* image_in_config;       /* [num_images] */
+  const uint8_t* image_constant_pose;   /* HasConstantRigFromWorldPose */
+  const uint8_t* camera_constant;       /* [num_cameras] HasConstantCamIntrinsics */
+  const uint8_t* point_variable;        /* [num_points3D] AddVariablePoint */
+  const uint8_t* point_constant;        /* AddConstantPoint */
+  const uint8_t* point_ignored;         /* IgnorePoint */
+  int fixed_gauge;                      /* 0 UNSPECIFIED, 1 TWO_CAMS_FROM_WORLD, 2 THREE_POINTS (bundle_adjustment.h:44-48) */
+  int min_track_length;                 /* BundleAdjustmentOptions::min_track_length */
+} b200ba_config;
+
+typedef struct b200ba_assembly* b200ba_assembly_t;
+int b200ba_assemble(const b200ba_options* o, const b200ba_scene* scene, const b200ba_config* config, b200ba_assembly_t* out);
+/* the assembled problem; flat pose / camera / point indices equal the scene's image / camera / point indices.  The
+ * arrays belong to the assembly; poses, camera_params and points are copies that b200ba_solve updates in place. */
+b200ba_problem* b200ba_assembly_problem(b200ba_assembly_t a);
+void b200ba_assembly_free(b200ba_assembly_t a);
+
 const char* b200ba_last_error(void);
 
 #ifdef __cplusplus

@@ -320,3 +320,70 @@ def test_product_rejects_unsupported_inputs_without_a_gpu():
     cp = bad2.to_c()
     assert lib.b200ba_test_pack(ctypes.byref(co), ctypes.byref(cp), 0, None, None, None, None, None, None,
                                 info.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))) == -2
+
+
+# ---------------------------------------------------------------- C++ problem assembly == the Python mirror's
+def _apply_two_cams_gauge(options, config, flat, image_ids):
+    """what BundleAdjuster.Solve does after flatten_reconstruction (gauge search over the config's images)."""
+    from colmap_b200.bundle_adjustment import FlatProblem, TWO_CAMS_FROM_WORLD
+    if not (config.FixedGauge() == TWO_CAMS_FROM_WORLD and options.refine_rig_from_world):
+        return flat
+    lib = _bind(load_library())
+    in_cfg = np.array([1 if i in config.Images() else 0 for i in image_ids], np.uint8)
+    sub = FlatProblem(flat.poses[in_cfg == 1], flat.pose_constant[in_cfg == 1], flat.pose_fixed_dim[in_cfg == 1], flat.cam_model,
+                      flat.cam_off, flat.cam_params, flat.cam_constant, flat.points, flat.point_constant, np.zeros(0, np.int32),
+                      np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros((0, 2)))
+    out_c = np.zeros(len(sub.poses), np.uint8); out_d = -np.ones(len(sub.poses), np.int8)
+    co, csub = options.to_c(), sub.to_c()
+    lib.b200ba_fix_gauge_two_cams_from_world(ctypes.byref(csub), ctypes.byref(co), out_c.ctypes.data_as(_u8p), out_d.ctypes.data_as(_i8p))
+    idx = np.nonzero(in_cfg)[0]
+    flat.pose_constant = flat.pose_constant.copy(); flat.pose_fixed_dim = flat.pose_fixed_dim.copy()
+    flat.pose_constant[idx] = out_c; flat.pose_fixed_dim[idx] = out_d
+    return flat
+
+
+@pytest.mark.parametrize("case", ["all_images", "subset_with_config_points", "constants_and_ignored", "min_track_length", "no_points_refined"])
+def test_cpp_assembly_equals_the_python_mirror(case):
+    from colmap_b200.bundle_adjustment import (BundleAdjustmentConfig, TWO_CAMS_FROM_WORLD, assemble_reconstruction,
+                                               flatten_reconstruction)
+    from colmap_b200.synthetic import flat_to_reconstruction
+    gt, noisy = synthesize_ba_problem(7, 90, 4, models=(SIMPLE_RADIAL, PINHOLE), seed=6)
+    rec = flat_to_reconstruction(noisy)
+    cfg = BundleAdjustmentConfig()
+    o = BundleAdjustmentOptions()
+    ids = sorted(rec.images)
+    if case == "all_images":
+        for i in ids: cfg.AddImage(i)
+        cfg.FixGauge(TWO_CAMS_FROM_WORLD)
+    elif case == "subset_with_config_points":
+        for i in ids[:4]: cfg.AddImage(i)
+        for p in list(rec.points3D)[:10]: cfg.AddVariablePoint(p)
+        for p in list(rec.points3D)[10:15]: cfg.AddConstantPoint(p)
+        cfg.FixGauge(TWO_CAMS_FROM_WORLD)
+    elif case == "constants_and_ignored":
+        for i in ids: cfg.AddImage(i)
+        cfg.SetConstantRigFromWorldPose(ids[2]); cfg.SetConstantCamIntrinsics(rec.images[ids[1]].camera_id)
+        for p in list(rec.points3D)[:7]: cfg.IgnorePoint(p)
+        cfg.FixGauge(TWO_CAMS_FROM_WORLD)
+    elif case == "min_track_length":
+        for i in ids: cfg.AddImage(i)
+        o = BundleAdjustmentOptions(min_track_length=5)        # tracks have 4 observations: nothing is left
+    else:
+        for i in ids[1:]: cfg.AddImage(i)
+        o = BundleAdjustmentOptions(refine_points3D=False, refine_rig_from_world=False)
+        cfg.FixGauge(TWO_CAMS_FROM_WORLD)
+    a, ia, ca, pa = assemble_reconstruction(o, cfg, rec)
+    b, ib, cb, pb = flatten_reconstruction(o, cfg, rec)
+    b = _apply_two_cams_gauge(o, cfg, b, ib)
+    assert (ia, ca, pa) == (ib, cb, pb)
+    for name in ("poses", "pose_constant", "pose_fixed_dim", "cam_model", "cam_off", "cam_params", "cam_constant", "points",
+                 "point_constant", "obs_pose", "obs_cam", "obs_point", "obs_xy"):
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+    if case == "min_track_length":
+        assert len(a.obs_pose) == 0
+    if case == "subset_with_config_points":
+        assert np.any(~np.isin(a.obs_pose, [0, 1, 2, 3]))       # observations brought in by the config points
+    # the assembled problem is what the solver's host flattening accepts
+    if len(a.obs_pose):
+        L = _pack(a, o)
+        assert L["nslots"] >= len(a.obs_pose) or (L["s_obs"] >= 0).sum() <= len(a.obs_pose)

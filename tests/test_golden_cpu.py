@@ -87,6 +87,9 @@ def test_known_answers_bundle_adjustment_counts():
     flat = flatten_reconstruction(o, cfg, rec)[0]
     s = oracle_ba.solve(o, flat)
     assert s.num_residuals == c["num_residuals"]
+    from colmap_b200.bundle_adjustment import assemble_reconstruction
+    flat_cpp = assemble_reconstruction(o, cfg, rec)[0]               # the C++ assembly gives the same count
+    assert oracle_ba.solve(o, flat_cpp).num_residuals == c["num_residuals"]
 
 
 def test_known_answers_option_defaults():
