@@ -29,6 +29,7 @@
 
 #include "../../include/b200_bundle_adjustment.h"
 #include "device_cache.h"
+#include "ba_models.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -2411,6 +2412,17 @@ int b200ba_test_reproj(int model_id, const double* point, const double* pose, co
   return ba_reproj(model_id, point, pose, params, xy[0], xy[1], res, J_point, J_pose, J_params) ? 1 : 0;
 }
 void b200ba_test_quat_plus(const double* q, const double* d, double* out) { ba_quat_plus(q, d, out); }
+
+// Camera models with more than five parameters (ba_models.cuh: formulas + dual numbers), host evaluation for the CPU
+// test tier: xy[2], J_uvw[2x3], J_params[2xP].  Returns 1 / 0 (depth guard) / -1 (unknown model).
+int b200ba_test_project_wide(int model_id, const double* params, const double* uvw, double* xy, double* J_uvw, double* J_params) {
+  switch (ba_wide_model_num_params(model_id)) {
+    case 5: return ba_project_wide_with_jac<5>(model_id, params, uvw[0], uvw[1], uvw[2], xy, J_uvw, J_params) ? 1 : 0;
+    case 8: return ba_project_wide_with_jac<8>(model_id, params, uvw[0], uvw[1], uvw[2], xy, J_uvw, J_params) ? 1 : 0;
+    case 12: return ba_project_wide_with_jac<12>(model_id, params, uvw[0], uvw[1], uvw[2], xy, J_uvw, J_params) ? 1 : 0;
+    default: return -1;
+  }
+}
 
 // The host flattening of b200ba_solve without a GPU: which observation sits in which slot.  Two-call pattern: with
 // capacity 0 only the sizes come back.  info[8] = {nslots, nvpt, nblocks_warp, nblocks_var, nblocks_giant0,

@@ -30,6 +30,7 @@
  * Build: gcc -O2 -fopenmp -shared -fPIC (Makefile).
  */
 #define _GNU_SOURCE
+#include <complex.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -118,6 +119,70 @@ static int img_from_cam(int id, const double* q, double u, double v, double w, d
     Juvw[3] = a10 * iw; Juvw[4] = a11 * iw; Juvw[5] = -(a10 * uu + a11 * vv) * iw;
     Jp[0] = xd; Jp[1] = 1; Jp[2] = 0; Jp[3] = f * uu * r2; Jp[4] = f * uu * r4;
     Jp[5] = yd; Jp[6] = 0; Jp[7] = 1; Jp[8] = f * vv * r2; Jp[9] = f * vv * r4;
+  }
+  return 1;
+}
+
+/* ---- camera models with more than five parameters (groundwork for SURVEY 8f-4): ImgFromCam of OPENCV, OPENCV_FISHEYE,
+ * FULL_OPENCV, FOV, THIN_PRISM_FISHEYE (sensor/models.h:1513-1885, 2180-2238) written over complex numbers; the Jacobians
+ * come from the complex-step method  df/dx = Im f(x + ih) / h  (exact to rounding for analytic f, h = 1e-40) - an
+ * independent route from the product's dual numbers (colmap_b200/csrc/ba_models.cuh) and from the reference's
+ * hand-derived formulas (sensor/models_jacobian.h:401-1565). */
+typedef double complex cplx;
+static int wide_num_params(int id) { switch (id) { case 4: case 5: return 8; case 6: case 10: return 12; case 7: return 5; default: return -1; } }
+static void c_fisheye(cplx a, cplx b, cplx* fa, cplx* fb) {
+  const cplx r = csqrt(a * a + b * b);
+  if (creal(r) > 2.220446049250313e-16) { const cplx s = catan(r) / r; *fa = a * s; *fb = b * s; } else { *fa = a; *fb = b; }
+}
+static int c_project_wide(int id, const cplx* q, cplx u, cplx v, cplx w, cplx* x, cplx* y) {
+  if (!(creal(w) >= 2.220446049250313e-16)) return 0;
+  const cplx a = u / w, b = v / w;
+  if (id == 4) {
+    const cplx r2 = a * a + b * b, radial = q[4] * r2 + q[5] * r2 * r2;
+    *x = q[0] * (a + a * radial + 2.0 * q[6] * a * b + q[7] * (r2 + 2.0 * a * a)) + q[2];
+    *y = q[1] * (b + b * radial + 2.0 * q[7] * a * b + q[6] * (r2 + 2.0 * b * b)) + q[3];
+  } else if (id == 5) {
+    cplx fa, fb; c_fisheye(a, b, &fa, &fb);
+    const cplx t2 = fa * fa + fb * fb;
+    const cplx radial = t2 * (q[4] + t2 * (q[5] + t2 * (q[6] + t2 * q[7])));
+    *x = q[0] * fa * (1.0 + radial) + q[2]; *y = q[1] * fb * (1.0 + radial) + q[3];
+  } else if (id == 6) {
+    const cplx r2 = a * a + b * b;
+    const cplx radial = (1.0 + r2 * (q[4] + r2 * (q[5] + r2 * q[8]))) / (1.0 + r2 * (q[9] + r2 * (q[10] + r2 * q[11])));
+    *x = q[0] * (a * radial + 2.0 * q[6] * a * b + q[7] * (r2 + 2.0 * a * a)) + q[2];
+    *y = q[1] * (b * radial + 2.0 * q[7] * a * b + q[6] * (r2 + 2.0 * b * b)) + q[3];
+  } else if (id == 7) {
+    const cplx om = q[4], r2 = a * a + b * b, o2 = om * om;
+    cplx f;
+    if (creal(o2) < 1e-4) f = o2 * r2 / 3.0 - o2 / 12.0 + 1.0;
+    else if (creal(r2) < 1e-4) { const cplx t = ctan(om / 2.0); f = -2.0 * t * (4.0 * r2 * t * t - 3.0) / (3.0 * om); }
+    else { const cplx r = csqrt(r2); f = catan(r * 2.0 * ctan(om / 2.0)) / (r * om); }
+    *x = q[0] * a * f + q[2]; *y = q[1] * b * f + q[3];
+  } else if (id == 10) {
+    cplx fa, fb; c_fisheye(a, b, &fa, &fb);
+    const cplx r2 = fa * fa + fb * fb;
+    const cplx radial = r2 * (q[4] + r2 * (q[5] + r2 * (q[8] + r2 * q[9])));
+    *x = q[0] * (fa + fa * radial + 2.0 * q[6] * fa * fb + q[7] * (r2 + 2.0 * fa * fa) + q[10] * r2) + q[2];
+    *y = q[1] * (fb + fb * radial + 2.0 * q[7] * fa * fb + q[6] * (r2 + 2.0 * fb * fb) + q[11] * r2) + q[3];
+  } else return 0;
+  return 1;
+}
+int ba_oracle_project_wide(int id, const double* params, const double* uvw, double* xy, double* J_uvw, double* J_params) {
+  const int P = wide_num_params(id);
+  if (P < 0) return -1;
+  const double h = 1e-40;
+  cplx in[3 + 12], x, y;
+  for (int k = 0; k < 3; ++k) in[k] = uvw[k];
+  for (int k = 0; k < P; ++k) in[3 + k] = params[k];
+  if (!c_project_wide(id, in + 3, in[0], in[1], in[2], &x, &y)) return 0;
+  xy[0] = creal(x); xy[1] = creal(y);
+  for (int k = 0; k < 3 + P; ++k) {
+    const cplx keep = in[k];
+    in[k] = keep + h * I;
+    c_project_wide(id, in + 3, in[0], in[1], in[2], &x, &y);
+    in[k] = keep;
+    if (k < 3) { J_uvw[k] = cimag(x) / h; J_uvw[3 + k] = cimag(y) / h; }
+    else { J_params[k - 3] = cimag(x) / h; J_params[P + k - 3] = cimag(y) / h; }
   }
   return 1;
 }

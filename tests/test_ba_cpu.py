@@ -388,3 +388,63 @@ def test_cpp_assembly_equals_the_python_mirror(case):
     if len(a.obs_pose):
         L = _pack(a, o)
         assert L["nslots"] >= len(a.obs_pose) or (L["s_obs"] >= 0).sum() <= len(a.obs_pose)
+
+
+# ---------------------------------------------------------------- camera models with > 5 parameters (groundwork)
+_WIDE = {4: [600., 610., 320., 240., 0.08, -0.02, 0.001, -0.0015],                                    # OPENCV
+         5: [600., 610., 320., 240., 0.05, -0.01, 0.004, -0.001],                                      # OPENCV_FISHEYE
+         6: [600., 610., 320., 240., 0.08, -0.02, 0.001, -0.0015, 0.004, 0.03, -0.01, 0.002],          # FULL_OPENCV
+         7: [600., 610., 320., 240., 0.9],                                                             # FOV
+         10: [600., 610., 320., 240., 0.05, -0.01, 0.001, -0.0015, 0.004, -0.001, 0.002, -0.003]}      # THIN_PRISM_FISHEYE
+
+
+def _project_wide(fn, model, params, uvw):
+    P = len(params)
+    xy, Juvw, Jp = np.zeros(2), np.zeros((2, 3)), np.zeros((2, P))
+    prm, p3 = np.ascontiguousarray(params, np.float64), np.ascontiguousarray(uvw, np.float64)
+    rc = fn(model, prm.ctypes.data_as(_f64p), p3.ctypes.data_as(_f64p), xy.ctypes.data_as(_f64p), Juvw.ctypes.data_as(_f64p),
+            Jp.ctypes.data_as(_f64p))
+    return rc, xy, Juvw, Jp
+
+
+@pytest.mark.parametrize("model", sorted(_WIDE))
+def test_wide_models_dual_numbers_vs_complex_step_oracle(model):
+    """Product: formulas + forward-mode dual numbers (ba_models.cuh); oracle: the same models over complex numbers with
+    complex-step derivatives; plus central finite differences of the product's own value.  Known answer: with all
+    distortion parameters zero OPENCV / FULL_OPENCV reduce to PINHOLE (sensor/models.h:1513-1543)."""
+    lib = load_library()
+    lib.b200ba_test_project_wide.argtypes = [ctypes.c_int] + [_f64p] * 5
+    ol = oracle_ba.lib()
+    ol.ba_oracle_project_wide.argtypes = [ctypes.c_int] + [_f64p] * 5
+    rng = np.random.default_rng(model)
+    params = np.asarray(_WIDE[model])
+    cases = [rng.uniform(-1.2, 1.2, 3) * [1, 1, 0] + [0, 0, rng.uniform(2, 6)] for _ in range(40)]
+    cases += [np.array([1e-9, -1e-9, 3.0]), np.array([0.0, 0.0, 2.0])]        # r -> 0 branches
+    if model == 7:
+        cases += [np.array([0.001, 0.002, 1.0])]                              # FOV small-radius branch
+    for uvw in cases:
+        rc, xy, Juvw, Jp = _project_wide(lib.b200ba_test_project_wide, model, params, uvw)
+        rc2, xy2, Juvw2, Jp2 = _project_wide(ol.ba_oracle_project_wide, model, params, uvw)
+        assert rc == rc2 == 1
+        assert np.allclose(xy, xy2, rtol=1e-13, atol=1e-10)
+        assert np.allclose(Juvw, Juvw2, rtol=1e-9, atol=1e-9) and np.allclose(Jp, Jp2, rtol=1e-9, atol=1e-9)
+        if np.hypot(uvw[0], uvw[1]) > 1e-3:       # finite differences (away from the non-smooth point of sqrt)
+            for k in range(3):
+                e = np.zeros(3); e[k] = 1e-6
+                fd = (_project_wide(lib.b200ba_test_project_wide, model, params, uvw + e)[1] -
+                      _project_wide(lib.b200ba_test_project_wide, model, params, uvw - e)[1]) / 2e-6
+                assert np.allclose(Juvw[:, k], fd, rtol=1e-5, atol=1e-4)
+            for k in range(len(params)):
+                e = np.zeros(len(params)); e[k] = 1e-6 * max(1.0, abs(params[k]))
+                fd = (_project_wide(lib.b200ba_test_project_wide, model, params + e, uvw)[1] -
+                      _project_wide(lib.b200ba_test_project_wide, model, params - e, uvw)[1]) / (2 * e[k])
+                assert np.allclose(Jp[:, k], fd, rtol=1e-5, atol=1e-4)
+    # depth guard and unknown ids
+    assert _project_wide(lib.b200ba_test_project_wide, model, params, [0.1, 0.1, 0.0])[0] == 0
+    assert _project_wide(ol.ba_oracle_project_wide, model, params, [0.1, 0.1, -1.0])[0] == 0
+    assert _project_wide(lib.b200ba_test_project_wide, 99, params, [0, 0, 1.0])[0] == -1
+    if model in (4, 6):
+        zero = params.copy(); zero[4:] = 0.0
+        uvw = np.array([0.3, -0.2, 2.0])
+        xy = _project_wide(lib.b200ba_test_project_wide, model, zero, uvw)[1]
+        assert np.allclose(xy, [zero[0] * 0.15 + zero[2], zero[1] * -0.1 + zero[3]], rtol=1e-15)
