@@ -2413,10 +2413,15 @@ int b200ba_test_reproj(int model_id, const double* point, const double* pose, co
 }
 void b200ba_test_quat_plus(const double* q, const double* d, double* out) { ba_quat_plus(q, d, out); }
 
-// Camera models with more than five parameters (ba_models.cuh: formulas + dual numbers), host evaluation for the CPU
+// The twelve camera models outside the radial pinhole family (ba_models.cuh: formulas + dual numbers), host evaluation for the CPU
 // test tier: xy[2], J_uvw[2x3], J_params[2xP].  Returns 1 / 0 (depth guard) / -1 (unknown model).
 int b200ba_test_project_wide(int model_id, const double* params, const double* uvw, double* xy, double* J_uvw, double* J_params) {
   switch (ba_wide_model_num_params(model_id)) {
+    case 2: return ba_project_wide_with_jac<2>(model_id, params, uvw[0], uvw[1], uvw[2], xy, J_uvw, J_params) ? 1 : 0;
+    case 3: return ba_project_wide_with_jac<3>(model_id, params, uvw[0], uvw[1], uvw[2], xy, J_uvw, J_params) ? 1 : 0;
+    case 4: return ba_project_wide_with_jac<4>(model_id, params, uvw[0], uvw[1], uvw[2], xy, J_uvw, J_params) ? 1 : 0;
+    case 6: return ba_project_wide_with_jac<6>(model_id, params, uvw[0], uvw[1], uvw[2], xy, J_uvw, J_params) ? 1 : 0;
+    case 16: return ba_project_wide_with_jac<16>(model_id, params, uvw[0], uvw[1], uvw[2], xy, J_uvw, J_params) ? 1 : 0;
     case 5: return ba_project_wide_with_jac<5>(model_id, params, uvw[0], uvw[1], uvw[2], xy, J_uvw, J_params) ? 1 : 0;
     case 8: return ba_project_wide_with_jac<8>(model_id, params, uvw[0], uvw[1], uvw[2], xy, J_uvw, J_params) ? 1 : 0;
     case 12: return ba_project_wide_with_jac<12>(model_id, params, uvw[0], uvw[1], uvw[2], xy, J_uvw, J_params) ? 1 : 0;

@@ -129,14 +129,46 @@ static int img_from_cam(int id, const double* q, double u, double v, double w, d
  * independent route from the product's dual numbers (colmap_b200/csrc/ba_models.cuh) and from the reference's
  * hand-derived formulas (sensor/models_jacobian.h:401-1565). */
 typedef double complex cplx;
-static int wide_num_params(int id) { switch (id) { case 4: case 5: return 8; case 6: case 10: return 12; case 7: return 5; default: return -1; } }
+static int wide_num_params(int id) {
+  switch (id) { case 4: case 5: return 8; case 6: case 10: return 12; case 7: case 13: return 5; case 11: return 16; case 12: case 15: return 4;
+                case 14: return 3; case 16: return 6; case 17: return 2; default: return -1; }
+}
 static void c_fisheye(cplx a, cplx b, cplx* fa, cplx* fb) {
   const cplx r = csqrt(a * a + b * b);
   if (creal(r) > 2.220446049250313e-16) { const cplx s = catan(r) / r; *fa = a * s; *fb = b * s; } else { *fa = a; *fb = b; }
 }
 static int c_project_wide(int id, const cplx* q, cplx u, cplx v, cplx w, cplx* x, cplx* y) {
+  if (id == 12 || id == 13) { /* division models (models.h:2406-2530) */
+    const cplx k = q[id == 12 ? 3 : 4], dsq = w * w - 4.0 * k * (u * u + v * v);
+    if (creal(dsq) < 0) return 0;
+    const cplx r = 2.0 / (w + csqrt(dsq));
+    *x = q[0] * r * u + q[id == 12 ? 1 : 2]; *y = q[id == 12 ? 0 : 1] * r * v + q[id == 12 ? 2 : 3];
+    return 1;
+  }
   if (!(creal(w) >= 2.220446049250313e-16)) return 0;
+  if (id == 16) { /* EUCM (models.h:2758-2792) */
+    const cplx rho2 = q[5] * (u * u + v * v) + w * w;
+    if (creal(rho2) < 0) return 0;
+    const cplx den = q[4] * csqrt(rho2) + (1.0 - q[4]) * w;
+    if (!(creal(den) >= 2.220446049250313e-16)) return 0;
+    *x = q[0] * u / den + q[2]; *y = q[1] * v / den + q[3];
+    return 1;
+  }
   const cplx a = u / w, b = v / w;
+  if (id == 14 || id == 15) { /* (SIMPLE_)FISHEYE (models.h:2608-2720) */
+    cplx fa, fb; c_fisheye(a, b, &fa, &fb);
+    *x = q[0] * fa + q[id == 14 ? 1 : 2]; *y = q[id == 14 ? 0 : 1] * fb + q[id == 14 ? 2 : 3];
+    return 1;
+  }
+  if (id == 11) { /* RAD_TAN_THIN_PRISM_FISHEYE (models.h:2300-2376) */
+    cplx fa, fb; c_fisheye(a, b, &fa, &fb);
+    const cplx t2 = fa * fa + fb * fb;
+    const cplx radial = 1.0 + t2 * (q[4] + t2 * (q[5] + t2 * (q[6] + t2 * (q[7] + t2 * (q[8] + t2 * q[9])))));
+    const cplx px = radial * fa, py = radial * fb, r2 = px * px + py * py;
+    *x = q[0] * (px + 2.0 * q[11] * px * py + q[10] * (r2 + 2.0 * px * px) + q[12] * r2 + q[13] * r2 * r2) + q[2];
+    *y = q[1] * (py + 2.0 * q[10] * px * py + q[11] * (r2 + 2.0 * py * py) + q[14] * r2 + q[15] * r2 * r2) + q[3];
+    return 1;
+  }
   if (id == 4) {
     const cplx r2 = a * a + b * b, radial = q[4] * r2 + q[5] * r2 * r2;
     *x = q[0] * (a + a * radial + 2.0 * q[6] * a * b + q[7] * (r2 + 2.0 * a * a)) + q[2];
@@ -167,11 +199,40 @@ static int c_project_wide(int id, const cplx* q, cplx u, cplx v, cplx w, cplx* x
   } else return 0;
   return 1;
 }
+/* EQUIRECTANGULAR (models.h:2853-2875) uses atan2, which has no complex-step form: value in real arithmetic, Jacobians by
+ * Richardson-extrapolated central differences */
+static int equirect(const double* q, const double* p, double* xy) {
+  const double hor = sqrt(p[0] * p[0] + p[2] * p[2]);
+  if (hor + fabs(p[1]) < 2.220446049250313e-16) return 0;
+  xy[0] = (atan2(p[0], p[2]) / (2.0 * M_PI) + 0.5) * q[0];
+  xy[1] = (0.5 - atan2(-p[1], hor) / M_PI) * q[1];
+  return 1;
+}
 int ba_oracle_project_wide(int id, const double* params, const double* uvw, double* xy, double* J_uvw, double* J_params) {
   const int P = wide_num_params(id);
   if (P < 0) return -1;
+  if (id == 17) {
+    if (!equirect(params, uvw, xy)) return 0;
+    double in[5] = {uvw[0], uvw[1], uvw[2], params[0], params[1]};
+    for (int k = 0; k < 5; ++k) {
+      double d[2][2];
+      for (int lvl = 0; lvl < 2; ++lvl) {
+        const double h = (lvl ? 0.5e-4 : 1e-4) * fmax(1.0, fabs(in[k])), keep = in[k];
+        double a[2], b[2];
+        in[k] = keep + h; equirect(in + 3, in, a);
+        in[k] = keep - h; equirect(in + 3, in, b);
+        in[k] = keep;
+        d[lvl][0] = (a[0] - b[0]) / (2 * h); d[lvl][1] = (a[1] - b[1]) / (2 * h);
+      }
+      for (int r = 0; r < 2; ++r) {
+        const double v = (4.0 * d[1][r] - d[0][r]) / 3.0;
+        if (k < 3) J_uvw[3 * r + k] = v; else J_params[2 * r + k - 3] = v;
+      }
+    }
+    return 1;
+  }
   const double h = 1e-40;
-  cplx in[3 + 12], x, y;
+  cplx in[3 + 16], x, y;
   for (int k = 0; k < 3; ++k) in[k] = uvw[k];
   for (int k = 0; k < P; ++k) in[3 + k] = params[k];
   if (!c_project_wide(id, in + 3, in[0], in[1], in[2], &x, &y)) return 0;

@@ -395,7 +395,14 @@ _WIDE = {4: [600., 610., 320., 240., 0.08, -0.02, 0.001, -0.0015],              
          5: [600., 610., 320., 240., 0.05, -0.01, 0.004, -0.001],                                      # OPENCV_FISHEYE
          6: [600., 610., 320., 240., 0.08, -0.02, 0.001, -0.0015, 0.004, 0.03, -0.01, 0.002],          # FULL_OPENCV
          7: [600., 610., 320., 240., 0.9],                                                             # FOV
-         10: [600., 610., 320., 240., 0.05, -0.01, 0.001, -0.0015, 0.004, -0.001, 0.002, -0.003]}      # THIN_PRISM_FISHEYE
+         10: [600., 610., 320., 240., 0.05, -0.01, 0.001, -0.0015, 0.004, -0.001, 0.002, -0.003],      # THIN_PRISM_FISHEYE
+         11: [600., 610., 320., 240., 0.05, -0.01, 0.004, -0.001, 0.0005, -0.0002, 0.001, -0.0015, 0.002, -0.001, 0.0015, 0.0007],  # RAD_TAN_THIN_PRISM_FISHEYE
+         12: [600., 320., 240., -0.05],                                                                # SIMPLE_DIVISION
+         13: [600., 610., 320., 240., -0.05],                                                          # DIVISION
+         14: [600., 320., 240.],                                                                       # SIMPLE_FISHEYE
+         15: [600., 610., 320., 240.],                                                                 # FISHEYE
+         16: [600., 610., 320., 240., 0.6, 1.2],                                                       # EUCM
+         17: [1000., 500.]}                                                                            # EQUIRECTANGULAR
 
 
 def _project_wide(fn, model, params, uvw):
@@ -427,7 +434,8 @@ def test_wide_models_dual_numbers_vs_complex_step_oracle(model):
         rc2, xy2, Juvw2, Jp2 = _project_wide(ol.ba_oracle_project_wide, model, params, uvw)
         assert rc == rc2 == 1
         assert np.allclose(xy, xy2, rtol=1e-13, atol=1e-10)
-        assert np.allclose(Juvw, Juvw2, rtol=1e-9, atol=1e-9) and np.allclose(Jp, Jp2, rtol=1e-9, atol=1e-9)
+        tol = 1e-6 if model == 17 else 1e-9          # the equirectangular oracle differentiates numerically
+        assert np.allclose(Juvw, Juvw2, rtol=tol, atol=tol) and np.allclose(Jp, Jp2, rtol=tol, atol=tol)
         if np.hypot(uvw[0], uvw[1]) > 1e-3:       # finite differences (away from the non-smooth point of sqrt)
             for k in range(3):
                 e = np.zeros(3); e[k] = 1e-6
@@ -440,8 +448,15 @@ def test_wide_models_dual_numbers_vs_complex_step_oracle(model):
                       _project_wide(lib.b200ba_test_project_wide, model, params - e, uvw)[1]) / (2 * e[k])
                 assert np.allclose(Jp[:, k], fd, rtol=1e-5, atol=1e-4)
     # depth guard and unknown ids
-    assert _project_wide(lib.b200ba_test_project_wide, model, params, [0.1, 0.1, 0.0])[0] == 0
-    assert _project_wide(ol.ba_oracle_project_wide, model, params, [0.1, 0.1, -1.0])[0] == 0
+    if model not in (12, 13, 17):                 # the division and equirectangular models have no depth guard
+        assert _project_wide(lib.b200ba_test_project_wide, model, params, [0.1, 0.1, 0.0])[0] == 0
+        assert _project_wide(ol.ba_oracle_project_wide, model, params, [0.1, 0.1, -1.0])[0] == 0
+    if model == 17:
+        assert _project_wide(lib.b200ba_test_project_wide, model, params, [0.0, 0.0, 0.0])[0] == 0
+        assert _project_wide(lib.b200ba_test_project_wide, model, params, [0.3, 0.2, -1.0])[0] == 1      # behind the camera is fine on a sphere
+    if model in (12, 13):
+        pos = list(params); pos[-1] = 0.5
+        assert _project_wide(lib.b200ba_test_project_wide, model, pos, [3.0, 3.0, 1.0])[0] == 0          # negative discriminant
     assert _project_wide(lib.b200ba_test_project_wide, 99, params, [0, 0, 1.0])[0] == -1
     if model in (4, 6):
         zero = params.copy(); zero[4:] = 0.0
