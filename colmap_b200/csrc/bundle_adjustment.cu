@@ -1870,11 +1870,12 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   const int NP = p->num_poses, NCAM = p->num_cameras;
   const long long NPT = p->num_points, NOBS = p->num_observations;
   for (int c = 0; c < NCAM; ++c) if (ba_model_num_params(p->camera_model_id[c]) < 0) return ba_fail(-2, "unsupported camera model (supported: SIMPLE_PINHOLE, PINHOLE, SIMPLE_RADIAL, RADIAL, SIMPLE_RADIAL_FISHEYE, RADIAL_FISHEYE)");
-  for (long long i = 0; i < NOBS; ++i)
-    if (p->obs_pose_idx[i] < 0 || p->obs_pose_idx[i] >= NP || p->obs_camera_idx[i] < 0 || p->obs_camera_idx[i] >= NCAM || p->obs_point_idx[i] < 0 || p->obs_point_idx[i] >= NPT)
-      return ba_fail(-2, "observation index out of range");
   std::vector<unsigned char> pose_used(NP, 0), cam_used(NCAM, 0), pt_used(NPT, 0);
-  for (long long i = 0; i < NOBS; ++i) { pose_used[p->obs_pose_idx[i]] = 1; cam_used[p->obs_camera_idx[i]] = 1; pt_used[p->obs_point_idx[i]] = 1; }
+  for (long long i = 0; i < NOBS; ++i) {   // range check and "block appears in an observation" in one pass
+    const int a = p->obs_pose_idx[i], b = p->obs_camera_idx[i], c = p->obs_point_idx[i];
+    if ((unsigned)a >= (unsigned)NP || (unsigned)b >= (unsigned)NCAM || c < 0 || c >= NPT) return ba_fail(-2, "observation index out of range");
+    pose_used[a] = 1; cam_used[b] = 1; pt_used[c] = 1;
+  }
   const bool sharded = comm != nullptr && comm->world > 1;
   cudaStream_t st = nullptr;
   if (!host_only) BA_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
@@ -2007,6 +2008,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
         }
       }
     }
+    tick("  buckets");
     const int nshort = (int)order_pts.size();
     for (int k = 0; k < nvpt; ++k) if (olen[k] > 32 && olen[k] <= BA_BLOCK) order_pts.push_back(k);
     const int nmid = (int)order_pts.size();
@@ -2016,7 +2018,16 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
     for (int n = 0; n < nvpt; ++n) newidx[order_pts[n]] = n;
     for (long long i = 0; i < NPT; ++i) if (pt_var[i] >= 0) pt_var[i] = newidx[pt_var[i]];
     for (long long i = 0; i < NPT; ++i) if (pt_var[i] >= 0) vpt_point[pt_var[i]] = (int)i;
-    auto pad_to = [&](size_t mult) { while (s_obs.size() % mult) { push_slot(-1, -1); s_seg.push_back(0); } };
+    tick("  renumber");
+    auto pad_to = [&](size_t mult) {
+      const size_t r = s_obs.size() % mult;
+      if (r) { const size_t add = mult - r; s_obs.insert(s_obs.end(), add, -1); s_lpt.insert(s_lpt.end(), add, -1); s_seg.insert(s_seg.end(), add, 0); }
+    };
+    auto append_track = [&](long long first, long long len, int n, int seg) {   // one track: observations vobs[first .. first + len)
+      const size_t at = s_obs.size();
+      s_obs.resize(at + (size_t)len); s_lpt.insert(s_lpt.end(), (size_t)len, n); s_seg.insert(s_seg.end(), (size_t)len, seg);
+      for (long long j = 0; j < len; ++j) s_obs[at + (size_t)j] = (int)vobs[first + j];
+    };
     int cur_blk = -1;
     auto note_block = [&](int k) {
       const int b = (int)(s_obs.size() / BA_BLOCK);
@@ -2030,7 +2041,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
       note_block(n);
       vpt_s0[n] = (int)s_obs.size();
       const int head = (int)(s_obs.size() % 32), last = head + len - 1;
-      for (long long j = ostart[k]; j < ostart[k] + len; ++j) { push_slot(vobs[j], n); s_seg.push_back(head | (last << 8)); }
+      append_track(ostart[k], len, n, head | (last << 8));
       vpt_s1[n] = (int)s_obs.size();
     }
     pad_to(BA_BLOCK);
@@ -2041,7 +2052,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
       if (used + len > BA_BLOCK) pad_to(BA_BLOCK);
       note_block(n);
       vpt_s0[n] = (int)s_obs.size();
-      for (long long j = ostart[k]; j < ostart[k] + len; ++j) { push_slot(vobs[j], n); s_seg.push_back(0); }
+      append_track(ostart[k], len, n, 0);
       vpt_s1[n] = (int)s_obs.size();
     }
     pad_to(BA_BLOCK);
@@ -2049,7 +2060,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
     for (int n = nmid; n < nvpt; ++n) {   // tracks longer than a block: laid out back to back, generic kernels
       const int k = order_pts[n];
       vpt_s0[n] = (int)s_obs.size();
-      for (long long j = ostart[k]; j < ostart[k] + olen[k]; ++j) { push_slot(vobs[j], n); s_seg.push_back(0); }
+      append_track(ostart[k], olen[k], n, 0);
       vpt_s1[n] = (int)s_obs.size();
     }
     pad_to(BA_BLOCK);
