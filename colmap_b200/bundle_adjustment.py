@@ -464,6 +464,39 @@ def assemble_reconstruction(options: BundleAdjustmentOptions, config: BundleAdju
     return flat, image_ids, camera_ids, point_ids
 
 
+def fix_gauge_three_points(flat: FlatProblem) -> int:
+    """FixGaugeWithThreePoints (bundle_adjustment_ceres.cc:270-306) on a flat problem: already-constant observed points
+    count first, then variable ones are fixed, until three linearly independent coordinate vectors are held (ascending
+    point index; the reference walks a hash map).  Returns the number of points holding the gauge."""
+    observed = np.zeros(len(flat.points), bool)
+    observed[flat.obs_point] = True
+    basis, max_pivot = [], 0.0
+    flat.point_constant = flat.point_constant.copy()
+
+    def maybe_add(X):
+        nonlocal max_pivot
+        if len(basis) >= 3:
+            return False
+        r = np.array(X, np.float64)
+        for q in basis:
+            r = r - (r @ q) * q
+        nr, nx = float(np.sqrt(r @ r)), float(np.sqrt(X @ X))
+        if not nr > 3.0 * 2.220446049250313e-16 * max(max_pivot, nx):
+            return False
+        basis.append(r / nr); max_pivot = max(max_pivot, nx)
+        return True
+
+    for k in np.nonzero(observed & (flat.point_constant != 0))[0]:
+        if len(basis) < 3:
+            maybe_add(flat.points[k])
+    for k in np.nonzero(observed & (flat.point_constant == 0))[0]:
+        if len(basis) >= 3:
+            break
+        if maybe_add(flat.points[k]):
+            flat.point_constant[k] = 1
+    return len(basis)
+
+
 class BundleAdjuster:
     """BundleAdjuster (bundle_adjustment.h:212-226), B200 backend: Solve() updates the reconstruction in place."""
 
@@ -494,6 +527,8 @@ class BundleAdjuster:
             idx = np.nonzero(in_cfg)[0]
             flat.pose_constant[idx] = out_c
             flat.pose_fixed_dim[idx] = out_d
+        elif self.config_.FixedGauge() == THREE_POINTS:
+            fix_gauge_three_points(flat)
         summary = solve_flat(self.options_, flat)
         # write back in place (variable blocks only changed)
         for k, i in enumerate(image_ids):

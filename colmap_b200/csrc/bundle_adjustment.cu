@@ -1804,6 +1804,34 @@ int b200ba_assemble(const b200ba_options* o, const b200ba_scene* sc, const b200b
     b200ba_fix_gauge_two_cams_from_world(&sub, o, sc_out.data(), sd_out.data());
     for (size_t k = 0; k < idx.size(); ++k) { A->pose_constant[idx[k]] = sc_out[k]; A->pose_fixed_dim[idx[k]] = sd_out[k]; }
   }
+  // FixGaugeWithThreePoints (:270-306): three points whose coordinate vectors are linearly independent stay fixed; points
+  // that are already constant count first.  The reference walks a hash map (unspecified order); here ascending point id.
+  if (cfg->fixed_gauge == 2) {
+    double basis[9];
+    int nfixed = 0;
+    double max_pivot = 0.0;
+    auto maybe_add = [&](const double* X) {   // rank test of [fixed points | X] by Gram-Schmidt, Eigen's default threshold
+      if (nfixed >= 3) return false;
+      double r[3] = {X[0], X[1], X[2]};
+      for (int b = 0; b < nfixed; ++b) {
+        const double* q = basis + 3 * b;
+        const double d = r[0] * q[0] + r[1] * q[1] + r[2] * q[2];
+        for (int c = 0; c < 3; ++c) r[c] -= d * q[c];
+      }
+      const double nr = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+      const double nx = sqrt(X[0] * X[0] + X[1] * X[1] + X[2] * X[2]);
+      if (!(nr > 3.0 * 2.220446049250313e-16 * std::max(max_pivot, nx))) return false;
+      for (int c = 0; c < 3; ++c) basis[3 * nfixed + c] = r[c] / nr;
+      max_pivot = std::max(max_pivot, nx);
+      ++nfixed;
+      return true;
+    };
+    for (int64_t pid = 0; pid < NPT && nfixed < 3; ++pid)
+      if (point_num_obs[pid] > 0 && A->point_constant[pid]) maybe_add(A->points.data() + 3 * pid);
+    for (int64_t pid = 0; pid < NPT && nfixed < 3; ++pid)
+      if (point_num_obs[pid] > 0 && !A->point_constant[pid] && maybe_add(A->points.data() + 3 * pid)) A->point_constant[pid] = 1;
+    if (nfixed < 3) g_ba_error = "Failed to fix Gauge due to insufficient number of fixed points";   // warning, like the reference
+  }
   *out = A;
   return 0;
 }

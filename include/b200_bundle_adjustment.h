@@ -162,7 +162,8 @@ typedef struct b200ba_config {      /* BundleAdjustmentConfig (bundle_adjustment
   const uint8_t* point_variable;        /* [num_points3D] AddVariablePoint */
   const uint8_t* point_constant;        /* AddConstantPoint */
   const uint8_t* point_ignored;         /* IgnorePoint */
-  int fixed_gauge;                      /* 0 UNSPECIFIED, 1 TWO_CAMS_FROM_WORLD, 2 THREE_POINTS (bundle_adjustment.h:44-48) */
+  int fixed_gauge;                      /* 0 UNSPECIFIED, 1 TWO_CAMS_FROM_WORLD (:308-417), 2 THREE_POINTS (:270-306; points in
+                                         * ascending id, the reference walks a hash map) - enum at bundle_adjustment.h:44-48 */
   int min_track_length;                 /* BundleAdjustmentOptions::min_track_length */
 } b200ba_config;
 

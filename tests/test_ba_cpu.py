@@ -463,3 +463,33 @@ def test_wide_models_dual_numbers_vs_complex_step_oracle(model):
         uvw = np.array([0.3, -0.2, 2.0])
         xy = _project_wide(lib.b200ba_test_project_wide, model, zero, uvw)[1]
         assert np.allclose(xy, [zero[0] * 0.15 + zero[2], zero[1] * -0.1 + zero[3]], rtol=1e-15)
+
+
+def test_three_points_gauge_assembly_and_oracle_solve():
+    """FixGaugeWithThreePoints (bundle_adjustment_ceres.cc:270-306): C++ assembly == Python mirror; already-constant points
+    count first; collinear-with-origin candidates are skipped; the oracle converges under that gauge."""
+    from colmap_b200.bundle_adjustment import (BundleAdjustmentConfig, THREE_POINTS, assemble_reconstruction, fix_gauge_three_points,
+                                               flatten_reconstruction)
+    from colmap_b200.synthetic import flat_to_reconstruction
+    gt, noisy = synthesize_ba_problem(6, 80, 4, models=(PINHOLE,), shared_camera=True, seed=12)
+    noisy.points[1] = 2.0 * noisy.points[0]            # same direction as point 0: adds no rank
+    rec = flat_to_reconstruction(noisy)
+    ids = sorted(rec.points3D)
+    cfg = BundleAdjustmentConfig()
+    for i in rec.images: cfg.AddImage(i)
+    cfg.AddConstantPoint(ids[5])                       # an explicit constant point is used first
+    cfg.FixGauge(THREE_POINTS)
+    o = BundleAdjustmentOptions(max_num_iterations=50)
+    a = assemble_reconstruction(o, cfg, rec)[0]
+    b = flatten_reconstruction(o, cfg, rec)[0]
+    assert fix_gauge_three_points(b) == 3
+    assert np.array_equal(a.point_constant, b.point_constant)
+    fixed = np.nonzero(a.point_constant)[0]
+    assert list(fixed) == [0, 2, 5]                    # 5 (already constant), then 0, skip collinear 1, then 2
+    assert np.linalg.matrix_rank(a.points[fixed].T) == 3
+    assert not a.pose_constant.any() and np.all(a.pose_fixed_dim == -1)      # no camera is touched by this gauge
+    before = a.points[fixed].copy()
+    s = oracle_ba.solve(o, a)
+    assert s.termination_type in (0, 1) and s.final_cost < 1e-2 * s.initial_cost
+    assert np.array_equal(a.points[fixed], before)
+    assert s.num_effective_parameters == 6 * 6 + 2 + 3 * (80 - 3)             # fx, fy of the shared camera
