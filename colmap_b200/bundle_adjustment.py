@@ -522,11 +522,14 @@ class BundleAdjuster:
                               np.zeros((0, 2)))
             out_c = np.zeros(len(sub.poses), np.uint8); out_d = -np.ones(len(sub.poses), np.int8)
             csub = sub.to_c()
-            lib.b200ba_fix_gauge_two_cams_from_world(ctypes.byref(csub), ctypes.byref(co), out_c.ctypes.data_as(_u8p),
-                                                     out_d.ctypes.data_as(_i8p))
-            idx = np.nonzero(in_cfg)[0]
-            flat.pose_constant[idx] = out_c
-            flat.pose_fixed_dim[idx] = out_d
+            rc = lib.b200ba_fix_gauge_two_cams_from_world(ctypes.byref(csub), ctypes.byref(co), out_c.ctypes.data_as(_u8p),
+                                                          out_d.ctypes.data_as(_i8p))
+            if rc == 1:     # no valid pair: the reference falls back to three fixed points (bundle_adjustment_ceres.cc:390-394)
+                fix_gauge_three_points(flat)
+            else:
+                idx = np.nonzero(in_cfg)[0]
+                flat.pose_constant[idx] = out_c
+                flat.pose_fixed_dim[idx] = out_d
         elif self.config_.FixedGauge() == THREE_POINTS:
             fix_gauge_three_points(flat)
         summary = solve_flat(self.options_, flat)

@@ -1791,6 +1791,7 @@ int b200ba_assemble(const b200ba_options* o, const b200ba_scene* sc, const b200b
   P.num_observations = (int64_t)A->obs_pose.size();
   P.obs_pose_idx = A->obs_pose.data(); P.obs_camera_idx = A->obs_cam.data(); P.obs_point_idx = A->obs_point.data(); P.obs_xy = A->obs_xy.data();
   // FixGauge (:270-417), TWO_CAMS_FROM_WORLD: the search runs over the config's images in ascending image id
+  bool three_points = cfg->fixed_gauge == 2;
   if (cfg->fixed_gauge == 1 && o->refine_rig_from_world) {
     std::vector<int> idx;
     for (int i = 0; i < NI; ++i) if (flag(cfg->image_in_config, i)) idx.push_back(i);
@@ -1801,12 +1802,15 @@ int b200ba_assemble(const b200ba_options* o, const b200ba_scene* sc, const b200b
     b200ba_problem sub;
     memset(&sub, 0, sizeof(sub));
     sub.num_poses = (int)idx.size(); sub.poses = sp.data(); sub.pose_constant = sc_in.data(); sub.pose_fixed_translation_dim = sd_in.data();
-    b200ba_fix_gauge_two_cams_from_world(&sub, o, sc_out.data(), sd_out.data());
-    for (size_t k = 0; k < idx.size(); ++k) { A->pose_constant[idx[k]] = sc_out[k]; A->pose_fixed_dim[idx[k]] = sd_out[k]; }
+    if (b200ba_fix_gauge_two_cams_from_world(&sub, o, sc_out.data(), sd_out.data()) == 1) {
+      three_points = true;   // "Failed to fix Gauge with two cameras. Falling back to fixing Gauge with three points." (:390-394)
+    } else {
+      for (size_t k = 0; k < idx.size(); ++k) { A->pose_constant[idx[k]] = sc_out[k]; A->pose_fixed_dim[idx[k]] = sd_out[k]; }
+    }
   }
   // FixGaugeWithThreePoints (:270-306): three points whose coordinate vectors are linearly independent stay fixed; points
   // that are already constant count first.  The reference walks a hash map (unspecified order); here ascending point id.
-  if (cfg->fixed_gauge == 2) {
+  if (three_points) {
     double basis[9];
     int nfixed = 0;
     double max_pivot = 0.0;

@@ -493,3 +493,19 @@ def test_three_points_gauge_assembly_and_oracle_solve():
     assert s.termination_type in (0, 1) and s.final_cost < 1e-2 * s.initial_cost
     assert np.array_equal(a.points[fixed], before)
     assert s.num_effective_parameters == 6 * 6 + 2 + 3 * (80 - 3)             # fx, fy of the shared camera
+
+
+def test_two_cams_gauge_falls_back_to_three_points():
+    """One image in the config: no second camera exists, so the reference fixes three points instead
+    (bundle_adjustment_ceres.cc:386-394)."""
+    from colmap_b200.bundle_adjustment import BundleAdjustmentConfig, TWO_CAMS_FROM_WORLD, assemble_reconstruction
+    from colmap_b200.synthetic import flat_to_reconstruction
+    gt, noisy = synthesize_ba_problem(3, 40, 3, models=(PINHOLE,), seed=2)
+    rec = flat_to_reconstruction(noisy)
+    cfg = BundleAdjustmentConfig()
+    cfg.AddImage(sorted(rec.images)[0])
+    cfg.FixGauge(TWO_CAMS_FROM_WORLD)
+    a = assemble_reconstruction(BundleAdjustmentOptions(), cfg, rec)[0]
+    assert a.pose_constant[0] == 0 and np.all(a.pose_fixed_dim == -1)
+    # points observed only partly inside the config are constant anyway (ParameterizePoints): the gauge is already held
+    assert a.point_constant.sum() >= 3
