@@ -138,3 +138,64 @@ def test_ba_oracle_reproduces_the_frozen_fixture():
     assert np.allclose(flat.poses, z["sol_poses"], rtol=0, atol=1e-7)
     assert np.allclose(flat.points, z["sol_points"], rtol=0, atol=1e-7)
     assert np.allclose(flat.cam_params, z["sol_cam_params"], rtol=1e-8, atol=1e-7)
+
+
+def test_known_answers_partially_contained_tracks():
+    """bundle_adjustment_ceres_test.cc:674-807: residual / parameter counts and which blocks stay constant when only part of
+    a track lies inside the config, through the C++ assembly and the oracle."""
+    from colmap_b200.bundle_adjustment import BundleAdjustmentConfig, SIMPLE_RADIAL, assemble_reconstruction
+    from colmap_b200.synthetic import flat_to_reconstruction
+    cases = {c["name"]: c for c in KA["bundle_adjustment_partial_tracks"]["cases"]}
+    for name in ("PartiallyContainedTracks", "PartiallyContainedTracksForceToOptimizePoint"):
+        gt, noisy = synthesize_ba_problem(3, 100, 3, models=(SIMPLE_RADIAL,), seed=3, point3D_stddev=0.0, translation_stddev=0.0,
+                                          rotation_stddev_deg=0.0)
+        rec = flat_to_reconstruction(noisy)
+        im3 = rec.images[3]
+        pid_var, pid_add_var, pid_add_const = im3.points2D[0].point3D_id, im3.points2D[1].point3D_id, im3.points2D[2].point3D_id
+        rec.points3D[pid_var].track = [t for t in rec.points3D[pid_var].track if t != (3, 0)]      # DeleteObservation(3, 0)
+        im3.points2D[0].point3D_id = -1
+        cfg = BundleAdjustmentConfig()
+        cfg.AddImage(1); cfg.AddImage(2)
+        cfg.SetConstantRigFromWorldPose(1); cfg.SetConstantRigFromWorldPose(2)
+        if name.endswith("ForceToOptimizePoint"):
+            cfg.AddVariablePoint(pid_add_var); cfg.AddConstantPoint(pid_add_const)
+        o = BundleAdjustmentOptions(max_num_iterations=20)
+        flat, image_ids, camera_ids, point_ids = assemble_reconstruction(o, cfg, rec)
+        before = flat.copy()
+        s = oracle_ba.solve(o, flat)
+        assert s.termination_type in (0, 1)
+        assert s.num_residuals == cases[name]["num_residuals_reduced"]
+        assert s.num_effective_parameters == cases[name]["num_effective_parameters_reduced"]
+        # poses constant; cameras 1, 2 variable (f and k move, principal point fixed), camera 3 constant
+        assert np.array_equal(flat.poses, before.poses)
+        cp, cb = flat.cam_params.reshape(3, 4), before.cam_params.reshape(3, 4)
+        assert np.array_equal(cp[2], cb[2]) and np.array_equal(cp[:2, 1:3], cb[:2, 1:3])
+        assert np.all(cp[:2, 0] != cb[:2, 0]) and np.all(cp[:2, 3] != cb[:2, 3])
+        moved = {point_ids[k] for k in np.nonzero(np.any(flat.points != before.points, axis=1))[0]}
+        expect = {pid_var, pid_add_var} if name.endswith("ForceToOptimizePoint") else {pid_var}
+        assert moved == expect
+
+
+def test_known_answers_bundle_adjustment_scenarios():
+    """The variable / constant matrix of bundle_adjustment_ceres_test.cc (twelve scenarios): residual and effective-parameter
+    counts of the problem the C++ assembly builds, as counted by the oracle."""
+    from colmap_b200.bundle_adjustment import (BundleAdjustmentConfig, SIMPLE_RADIAL, THREE_POINTS, TWO_CAMS_FROM_WORLD,
+                                               assemble_reconstruction)
+    from colmap_b200.synthetic import flat_to_reconstruction
+    gauges = {"TWO_CAMS_FROM_WORLD": TWO_CAMS_FROM_WORLD, "THREE_POINTS": THREE_POINTS}
+    for c in KA["bundle_adjustment_scenarios"]["cases"]:
+        gt, noisy = synthesize_ba_problem(c["num_images"], 100, c["num_images"], models=(SIMPLE_RADIAL,), seed=5)
+        rec = flat_to_reconstruction(noisy)
+        cfg = BundleAdjustmentConfig()
+        for i in range(1, c["num_images"] + 1):
+            cfg.AddImage(i)
+        for i in c.get("constant_poses", []): cfg.SetConstantRigFromWorldPose(i)
+        for i in c.get("constant_cameras", []): cfg.SetConstantCamIntrinsics(i)
+        for p in c.get("constant_points", []): cfg.AddConstantPoint(p)
+        for p in c.get("ignored_points", []): cfg.IgnorePoint(p)
+        if "gauge" in c:
+            cfg.FixGauge(gauges[c["gauge"]])
+        o = BundleAdjustmentOptions(max_num_iterations=2, **c.get("options", {}))
+        flat = assemble_reconstruction(o, cfg, rec)[0]
+        s = oracle_ba.solve(o, flat)
+        assert (s.num_residuals, s.num_effective_parameters) == (c["num_residuals"], c["num_effective_parameters"]), c["name"]
