@@ -1881,6 +1881,7 @@ void b200ba_comm_destroy(b200ba_comm_t c) {
 struct BaHostLayout {
   std::vector<int> s_obs, s_lpt, s_seg, vpt_s0, vpt_s1, vpt_point;
   int nblocks_warp = 0, nblocks_var = 0, nblocks_giant0 = 0, nblocks_giant1 = 0, nc = 0, nvpt = 0, dkmax = 0;
+  int num_residuals = 0, num_effective_parameters = 0;
 };
 static thread_local BaHostLayout* g_ba_layout_out = nullptr;
 
@@ -2115,6 +2116,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
       L.s_obs = s_obs; L.s_lpt = s_lpt; L.s_seg = s_seg; L.vpt_s0 = vpt_s0; L.vpt_s1 = vpt_s1; L.vpt_point = vpt_point;
       L.nblocks_warp = nblocks_warp; L.nblocks_var = nblocks_var; L.nblocks_giant0 = nblocks_giant0; L.nblocks_giant1 = nblocks_giant1;
       L.nc = nc; L.nvpt = nvpt; L.dkmax = dkmax;
+      L.num_residuals = sum->num_residuals; L.num_effective_parameters = sum->num_effective_parameters;
     }
     sum->setup_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_setup0).count();
     return ba_fail(-102, "B200BA_HOST_ONLY: stopped after the host flattening");
@@ -2473,8 +2475,8 @@ int b200ba_test_project_wide(int model_id, const double* params, const double* u
 }
 
 // The host flattening of b200ba_solve without a GPU: which observation sits in which slot.  Two-call pattern: with
-// capacity 0 only the sizes come back.  info[8] = {nslots, nvpt, nblocks_warp, nblocks_var, nblocks_giant0,
-// nblocks_giant1, camera-side dimension, max variable intrinsics}.
+// capacity 0 only the sizes come back.  info[10] = {nslots, nvpt, nblocks_warp, nblocks_var, nblocks_giant0,
+// nblocks_giant1, camera-side dimension, max variable intrinsics, num_residuals, num_effective_parameters}.
 int b200ba_test_pack(const b200ba_options* o, b200ba_problem* p, int64_t capacity, int32_t* s_obs, int32_t* s_lpt,
                      int32_t* s_seg, int32_t* vpt_s0, int32_t* vpt_s1, int32_t* vpt_point, int64_t* info) {
   BaHostLayout L;
@@ -2485,6 +2487,7 @@ int b200ba_test_pack(const b200ba_options* o, b200ba_problem* p, int64_t capacit
   if (rc != -102) return rc;   // -102 = "stopped after the host flattening" (the expected outcome here)
   info[0] = (int64_t)L.s_obs.size(); info[1] = L.nvpt; info[2] = L.nblocks_warp; info[3] = L.nblocks_var;
   info[4] = L.nblocks_giant0; info[5] = L.nblocks_giant1; info[6] = L.nc; info[7] = L.dkmax;
+  info[8] = L.num_residuals; info[9] = L.num_effective_parameters;
   if (capacity == 0) return 0;
   if (capacity < (int64_t)L.s_obs.size()) return -12;
   memcpy(s_obs, L.s_obs.data(), sizeof(int) * L.s_obs.size());

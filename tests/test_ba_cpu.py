@@ -253,7 +253,7 @@ def _pack(flat, options=None):
     lib.b200ba_test_pack.argtypes = [ctypes.POINTER(_COptions), ctypes.POINTER(_CProblem), ctypes.c_int64, i32p, i32p, i32p, i32p,
                                      i32p, i32p, i64p]
     co, cp = (options or BundleAdjustmentOptions(linear_solver_type=ITERATIVE_SCHUR)).to_c(), flat.to_c()
-    info = np.zeros(8, np.int64)
+    info = np.zeros(10, np.int64)
     assert lib.b200ba_test_pack(ctypes.byref(co), ctypes.byref(cp), 0, None, None, None, None, None, None, info.ctypes.data_as(i64p)) == 0
     n, nvpt = int(info[0]), int(info[1])
     a = {k: np.empty(n, np.int32) for k in ("s_obs", "s_lpt", "s_seg")}
@@ -262,7 +262,8 @@ def _pack(flat, options=None):
     assert lib.b200ba_test_pack(ctypes.byref(co), ctypes.byref(cp), n, p(a["s_obs"]), p(a["s_lpt"]), p(a["s_seg"]), p(v["vpt_s0"]),
                                 p(v["vpt_s1"]), p(v["vpt_point"]), info.ctypes.data_as(i64p)) == 0
     return dict(a, **{k: x[:nvpt] for k, x in v.items()}, nslots=n, nvpt=nvpt, nblocks_warp=int(info[2]), nblocks_var=int(info[3]),
-                nblocks_giant0=int(info[4]), nblocks_giant1=int(info[5]), nc=int(info[6]), dkmax=int(info[7]))
+                nblocks_giant0=int(info[4]), nblocks_giant1=int(info[5]), nc=int(info[6]), dkmax=int(info[7]),
+                num_residuals=int(info[8]), num_effective_parameters=int(info[9]))
 
 
 def test_product_slot_packing_invariants():
@@ -311,7 +312,7 @@ def test_product_rejects_unsupported_inputs_without_a_gpu():
     gt, noisy = synthesize_ba_problem(4, 30, 3, models=(SIMPLE_RADIAL,), seed=1)
     bad = noisy.copy(); bad.cam_model = noisy.cam_model.copy(); bad.cam_model[0] = 4       # OPENCV: 8 parameters, not supported
     lib = _bind(load_library())
-    info = np.zeros(8, np.int64)
+    info = np.zeros(10, np.int64)
     lib.b200ba_test_pack.argtypes = [ctypes.POINTER(_COptions), ctypes.POINTER(_CProblem), ctypes.c_int64] + [ctypes.c_void_p] * 6 + [ctypes.POINTER(ctypes.c_int64)]
     co, cp = BundleAdjustmentOptions().to_c(), bad.to_c()
     assert lib.b200ba_test_pack(ctypes.byref(co), ctypes.byref(cp), 0, None, None, None, None, None, None,

@@ -199,3 +199,7 @@ def test_known_answers_bundle_adjustment_scenarios():
         flat = assemble_reconstruction(o, cfg, rec)[0]
         s = oracle_ba.solve(o, flat)
         assert (s.num_residuals, s.num_effective_parameters) == (c["num_residuals"], c["num_effective_parameters"]), c["name"]
+        # the PRODUCT's own host flattening (what b200ba_solve reports in its summary) counts the same - no oracle involved
+        from test_ba_cpu import _pack
+        L = _pack(flat, o)
+        assert (L["num_residuals"], L["num_effective_parameters"]) == (c["num_residuals"], c["num_effective_parameters"]), c["name"]
