@@ -26,6 +26,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 C2 = dict(width=1920, height=1080, num_src=8, window_radius=5, window_step=1, num_samples=15, num_iterations=5)
+# one string for both arms (the driver compares config.workload of the two lines)
+C2_WORKLOAD = ("PatchMatch C2: 1 ref + 8 src views, 1920x1080, window 11, 15 samples, 5 iters, photometric + filter; "
+               "one reference image per GPU")
+B3_WORKLOAD = ("BA B3: 500 cameras (SIMPLE_RADIAL, own intrinsics), 300k points, 2M observations, ITERATIVE_SCHUR + "
+               "SCHUR_JACOBI, two-cams gauge, trivial loss, 100 LM iterations max")
 
 
 def _env_int(name, default):
@@ -138,8 +143,9 @@ def _fresh(noisy):
     return f
 
 
-def _oracle_ba_sample(noisy, max_iters=10):
-    """Bounded CPU sample: the same B3 problem, first `max_iters` LM iterations, oracle port, all host threads."""
+def _oracle_ba_sample(noisy, max_iters=100):
+    """CPU leg: the same B3 problem and the SAME iteration limit as the GPU arm (100 LM iterations), oracle port, all
+    host threads (about 10-30 s)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_ba
     from colmap_b200.bundle_adjustment import ITERATIVE_SCHUR, BundleAdjustmentOptions
@@ -148,7 +154,7 @@ def _oracle_ba_sample(noisy, max_iters=10):
     s = oracle_ba.solve(o, _fresh(noisy))
     dt = time.time() - t
     steps = s.num_successful_steps + s.num_unsuccessful_steps
-    return steps / dt, dt, f"B3 problem (500 cams, 300k pts, 2M obs), first {max_iters} LM iterations, ITERATIVE_SCHUR, oracle port"
+    return steps / dt, dt, f"B3 problem (500 cams, 300k pts, 2M obs), full solve ({steps} LM iterations, limit {max_iters}), ITERATIVE_SCHUR, oracle port"
 
 
 def bench_ba(steps, warmup, peak, peak_src, with_cpu):
@@ -174,8 +180,7 @@ def bench_ba(steps, warmup, peak, peak_src, with_cpu):
     d2h = f.poses.nbytes + f.cam_params.nbytes + f.points.nbytes
     out = {"metric": "ba_lm_iterations_per_s", "value": lm / (dev_ms * 1e-3), "unit": "LM iterations/s", "dtype": "f64",
            "ms_per_step": dev_ms / steps, "lm_iterations_per_solve": lm / steps,
-           "config": {"workload": "BA B3: 500 cameras (SIMPLE_RADIAL, own intrinsics), 300k points, 2M observations, "
-                                  "ITERATIVE_SCHUR + SCHUR_JACOBI, two-cams gauge, trivial loss"},
+           "config": {"workload": B3_WORKLOAD},
            "e2e": {"value": lm / (wall_ms * 1e-3), "unit": "LM iterations/s", "h2d_bytes_per_step": int(h2d),
                    "d2h_bytes_per_step": int(d2h), "ms_per_step": wall_ms / steps},
            "final_cost": s.final_cost, "termination_type": s.termination_type, "gpu_launches": int(launches),
@@ -225,15 +230,15 @@ def bench_ba_sharded(steps, warmup, rank, world, local_rank):
             "final_cost": s.final_cost, "termination_type": s.termination_type}
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, local_rank):
     """Reference arm.  COLMAP has no CPU implementation of PatchMatch (exe/mvs.cc:260 aborts without CUDA): its
     implementation of this path IS mvs/patch_match_cuda.cu.  When oracle/_ref/libpm_ref.so exists (the reference's
     own CUDA sources compiled in place against stub headers, oracle/build_ref.sh, as compute_90 PTX that the driver
-    JITs — upstream's Blackwell configuration) this arm times it on the full C2 workload through the same host-buffer
-    entry (constructor + Run + GetDepthMap/GetNormalMap).  Otherwise it falls back to the CPU oracle port on a
-    bounded sample.  The BA leg times the fp64 oracle port (Ceres is not installed in this image)."""
-    if rank != 0:
-        return
+    JITs - upstream's Blackwell configuration) this arm times it on the full C2 workload through the same host-buffer
+    entry (constructor + Run + GetDepthMap/GetNormalMap), on EVERY rank (one reference image per GPU, like our arm),
+    max over ranks.  Otherwise it falls back to the CPU oracle port on a bounded sample (rank 0).  The BA leg times
+    (a) the reference's own GPU backend, Caspar (oracle/_ref/libcaspar_ref.so, when built) and (b) the fp64 oracle
+    port on the host threads (Ceres is not installed in this image)."""
     cores = os.cpu_count()
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     line = None
@@ -242,31 +247,51 @@ def run_reference(args, rank, world):
         have_ref = ref_pm.available()
     except Exception:
         have_ref = False
+    torch = None
     if have_ref:
         try:
             import torch
             have_ref = torch.cuda.is_available()
         except Exception:
             have_ref = False
+    if not have_ref and rank != 0:
+        return
+    distributed = have_ref and world > 1
+    if distributed:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if have_ref:
         from colmap_b200.patch_match import PatchMatchOptions
         from colmap_b200.synthetic import make_patch_match_scene
-        sc = make_patch_match_scene(C2["width"], C2["height"], C2["num_src"], seed=0)
+        sc = make_patch_match_scene(C2["width"], C2["height"], C2["num_src"], seed=rank)
         o = PatchMatchOptions(depth_min=sc["depth_min"], depth_max=sc["depth_max"], geom_consistency=False,
                               window_radius=C2["window_radius"], window_step=C2["window_step"],
-                              num_samples=C2["num_samples"], num_iterations=C2["num_iterations"], gpu_index="0")
-        for _ in range(min(args.warmup, 1)):      # first call also pays the PTX JIT (~1 min)
+                              num_samples=C2["num_samples"], num_iterations=C2["num_iterations"], gpu_index=str(local_rank))
+        for _ in range(args.warmup):              # the first call also pays the PTX JIT (~1 min)
             ref_pm.run(o, sc["problem"])
-        ms = [ref_pm.run(o, sc["problem"])["ms"] for _ in range(args.steps)]
-        t = sum(ms) / len(ms)
-        v = C2["width"] * C2["height"] / 1e6 / (t * 1e-3)
-        sample = "full C2 workload; reference PatchMatchCuda (unmodified sources, compute_90 PTX JIT) on the same GPU"
-        line = {"impl": "reference", "metric": "patchmatch_mpixels_per_s", "value": v, "unit": "Mpixels/s", "n_gpus": 1,
-                "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": t, "higher_is_better": True,
+        if distributed:
+            torch.cuda.synchronize(); dist.barrier()
+        t0 = time.time()
+        for _ in range(args.steps):
+            ref_pm.run(o, sc["problem"])
+        if distributed:
+            torch.cuda.synchronize(); dist.barrier()
+        t = (time.time() - t0) * 1e3 / args.steps
+        if distributed:
+            from colmap_b200.sharding import max_over_ranks
+            t = max_over_ranks(t, "cuda")
+        v = world * C2["width"] * C2["height"] / 1e6 / (t * 1e-3)
+        sample = "full C2 workload; reference PatchMatchCuda (unmodified sources, compute_90 PTX JIT) on the same GPU(s)"
+        line = {"impl": "reference", "metric": "patchmatch_mpixels_per_s", "value": v, "unit": "Mpixels/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": t, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "PatchMatch C2: 1 ref + 8 src views, 1920x1080, window 11, 15 samples, 5 iters, "
-                                       "photometric + filter", "note": "the reference implementation of this path is CUDA "
-                                       "(no CPU PatchMatch exists in COLMAP); timed end to end with host buffers"},
+                "config": {"workload": C2_WORKLOAD,
+                           "l2": "inputs larger than L2: cost/sel-prob maps 3 x 66 MB + 66 MB source footprints vs 126 MB L2",
+                           "parallelism": f"problems x{world} (no collective)",
+                           "note": "the reference implementation of this path is CUDA (no CPU PatchMatch exists in "
+                                   "COLMAP); timed end to end with host buffers"},
                 "cpu_baseline": {"value": v, "unit": "Mpixels/s", "cores": 0, "kind": "reference", "sample": sample},
                 "e2e": {"value": v, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -281,21 +306,52 @@ def run_reference(args, rank, world):
         line = {"impl": "reference", "metric": "patchmatch_mpixels_per_s", "value": v, "unit": "Mpixels/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "PatchMatch C2: 1 ref + 8 src, 1920x1080, window 11, 5 iters (bounded sample)",
-                           "sample": sample},
+                "config": {"workload": C2_WORKLOAD, "sample": sample},
                 "cpu_baseline": {"value": v, "unit": "Mpixels/s", "cores": cores, "kind": "port", "sample": sample},
                 "e2e": {"value": v, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-    if not args.no_ba:
+    if rank == 0 and not args.no_ba:
+        ba = {"impl": "reference", "metric": "ba_lm_iterations_per_s", "unit": "LM iterations/s",
+              "config": {"workload": B3_WORKLOAD}}
         try:
-            v, dt, sample = _oracle_ba_sample(_b3_problem())
-            line["ba"] = {"impl": "reference", "metric": "ba_lm_iterations_per_s", "value": v, "unit": "LM iterations/s",
-                          "cpu_baseline": {"value": v, "unit": "LM iterations/s", "cores": cores, "kind": "port",
-                                           "sample": sample},
-                          "note": "Ceres is not installed in this image; the fp64 oracle port restates its algorithm"}
+            noisy = _b3_problem()
+            try:
+                ba["caspar"] = _caspar_ba(noisy, args.steps, args.warmup)
+                ba["value"] = ba["caspar"]["value"]
+            except Exception as e:
+                ba["caspar"] = {"unavailable": repr(e)}
+            v, dt, sample = _oracle_ba_sample(noisy)
+            ba["cpu_baseline"] = {"value": v, "unit": "LM iterations/s", "cores": cores, "kind": "port", "sample": sample,
+                                  "seconds": dt}
+            ba.setdefault("value", v)
+            ba["note"] = ("Ceres is not installed in this image; `caspar` is the reference's own GPU backend (fp32), "
+                          "`cpu_baseline` the fp64 oracle port that restates Ceres' algorithm")
         except Exception as e:
-            line["ba"] = {"error": repr(e)}
-    print(json.dumps(line), flush=True)
+            ba["error"] = repr(e)
+        line["ba"] = ba
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.destroy_process_group()
+
+
+def _caspar_ba(noisy, steps, warmup):
+    """The reference's CasparBundleAdjuster core (thirdparty Symforce-Caspar generated solver, compiled in place into
+    oracle/_ref/libcaspar_ref.so by oracle/build_ref.sh) on the same flat problem."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ref_caspar
+    if not ref_caspar.available():
+        raise RuntimeError("oracle/_ref/libcaspar_ref.so not built")
+    out = None
+    for i in range(max(warmup, 1) + steps):
+        r = ref_caspar.solve(_fresh(noisy))
+        if i == max(warmup, 1):
+            out = dict(lm=0, ms=0.0)
+        if out is not None:
+            out["lm"] += r["iterations"]; out["ms"] += r["solve_ms"]
+    return {"value": out["lm"] / (out["ms"] * 1e-3), "unit": "LM iterations/s", "kind": "reference (Caspar, fp32, GPU)",
+            "lm_iterations_per_solve": out["lm"] / steps, "ms_per_step": out["ms"] / steps, "final_cost": r["final_cost"],
+            "initial_cost": r["initial_cost"]}
 
 
 def main():
@@ -313,7 +369,7 @@ def main():
     local_rank = _env_int("LOCAL_RANK", 0)
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, local_rank)
         return
 
     import numpy as np
@@ -430,8 +486,7 @@ def main():
         line = {"metric": "patchmatch_mpixels_per_s", "value": world * mpix / (ms_per_step * 1e-3), "unit": "Mpixels/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "PatchMatch C2: 1 ref + 8 src views, 1920x1080, window 11, 15 samples, 5 iters, "
-                                       "photometric + filter; one reference image per GPU",
+                "config": {"workload": C2_WORKLOAD,
                            "l2": "inputs larger than L2: cost/sel-prob maps 3 x 66 MB + 66 MB source footprints vs 126 MB L2",
                            "parallelism": f"problems x{world} (no collective)"},
                 "e2e": {"value": world * mpix / (e2e_ms * 1e-3), "unit": "Mpixels/s", "h2d_bytes_per_step": int(h2d),

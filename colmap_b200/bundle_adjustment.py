@@ -55,7 +55,7 @@ class _CProblem(ctypes.Structure):
                 ("camera_param_offset", _i32p), ("camera_params", _f64p), ("camera_constant", _u8p),
                 ("num_points", ctypes.c_int64), ("points", _f64p), ("point_constant", _u8p),
                 ("num_observations", ctypes.c_int64), ("obs_pose_idx", _i32p), ("obs_camera_idx", _i32p),
-                ("obs_point_idx", _i32p), ("obs_xy", _f64p)]
+                ("obs_point_idx", _i32p), ("obs_xy", _f64p), ("num_config_images", ctypes.c_int32)]
 
 
 class _CSummary(ctypes.Structure):
@@ -215,8 +215,14 @@ class FlatProblem:
         self.obs_cam = c(obs_cam, np.int32)
         self.obs_point = c(obs_point, np.int32)
         self.obs_xy = c(obs_xy, np.float64).reshape(-1, 2)
+        self.num_config_images = 0      # config.NumImages(); 0 = poses that appear in observations
 
     def copy(self):
+        f = self._copy()
+        f.num_config_images = self.num_config_images
+        return f
+
+    def _copy(self):
         return FlatProblem(self.poses.copy(), self.pose_constant, self.pose_fixed_dim, self.cam_model, self.cam_off,
                            self.cam_params.copy(), self.cam_constant, self.points.copy(), self.point_constant,
                            self.obs_pose, self.obs_cam, self.obs_point, self.obs_xy)
@@ -235,6 +241,7 @@ class FlatProblem:
         p.num_observations = len(self.obs_pose)
         p.obs_pose_idx = self.obs_pose.ctypes.data_as(_i32p); p.obs_camera_idx = self.obs_cam.ctypes.data_as(_i32p)
         p.obs_point_idx = self.obs_point.ctypes.data_as(_i32p); p.obs_xy = self.obs_xy.ctypes.data_as(_f64p)
+        p.num_config_images = int(self.num_config_images)
         return p
 
 
@@ -287,6 +294,7 @@ def shard_flat_problem(flat: FlatProblem, rank: int, world: int) -> "FlatProblem
                         flat.cam_params.copy(), flat.cam_constant, flat.points[lo:hi].copy(), flat.point_constant[lo:hi],
                         flat.obs_pose[sel], flat.obs_cam[sel], flat.obs_point[sel] - lo, flat.obs_xy[sel])
     local.point_ids = np.arange(lo, hi)
+    local.num_config_images = flat.num_config_images or int(len(np.unique(flat.obs_pose)))
     return local
 
 
@@ -341,6 +349,7 @@ def flatten_reconstruction(options: BundleAdjustmentOptions, config: BundleAdjus
     obs_pose, obs_cam, obs_point, obs_xy = [], [], [], []
     point_num_obs = {}
     # AddImageToProblem (:688-751)
+    parameterized_images = set()                     # images that contributed >= 1 observation (:745-748)
     for image_id in cfg_images:
         im = rec.images[image_id]
         for p2 in im.points2D:
@@ -350,12 +359,15 @@ def flatten_reconstruction(options: BundleAdjustmentOptions, config: BundleAdjus
             if len(rec.points3D[pid].track) < options.min_track_length:
                 continue
             point_num_obs[pid] = point_num_obs.get(pid, 0) + 1
+            parameterized_images.add(image_id)
             obs_pose.append(pose_idx[image_id]); obs_cam.append(cam_idx[im.camera_id]); obs_point.append(pt_idx[pid])
             obs_xy.append(p2.xy)
     # AddPointToProblem (:829-888): explicit config points get the observations from images outside the config
     extra_const_pose = set()
     for pid in sorted(config.VariablePoints() | config.ConstantPoints()):
         pt = rec.points3D[pid]
+        if options.min_track_length > 0 and len(pt.track) < options.min_track_length:   # :835-838
+            continue
         if point_num_obs.get(pid, 0) == len(pt.track):
             continue
         for image_id, p2_idx in pt.track:
@@ -371,7 +383,7 @@ def flatten_reconstruction(options: BundleAdjustmentOptions, config: BundleAdjus
         if not config.HasConstantRigFromWorldPose(image_id):
             pose_constant[pose_idx[image_id]] = 0
     # cameras that only appear through constant-pose factors of outside images stay constant (:863-878)
-    cam_in_cfg = {rec.images[i].camera_id for i in cfg_images}
+    cam_in_cfg = {rec.images[i].camera_id for i in cfg_images if i in parameterized_images}
     cam_constant = np.array([1 if (c not in cam_in_cfg or config.HasConstantCamIntrinsics(c)) else 0 for c in camera_ids], np.uint8)
     # ParameterizePoints (:540-565)
     point_constant = np.ones(len(point_ids), np.uint8)
@@ -390,6 +402,8 @@ def flatten_reconstruction(options: BundleAdjustmentOptions, config: BundleAdjus
         np.concatenate([rec.cameras[c].params for c in camera_ids]) if camera_ids else np.zeros(0), cam_constant,
         np.stack([rec.points3D[p].xyz for p in point_ids]) if point_ids else np.zeros((0, 3)), point_constant,
         obs_pose, obs_cam, obs_point, np.asarray(obs_xy, np.float64).reshape(-1, 2))
+    flat.num_config_images = config.NumImages()
+    flat.parameterized_image_ids = parameterized_images
     return flat, image_ids, camera_ids, point_ids
 
 
@@ -459,6 +473,7 @@ def assemble_reconstruction(options: BundleAdjustmentOptions, config: BundleAdju
                            arr(pr.point_constant, n_pt, np.uint8), arr(pr.obs_pose_idx, n_obs, np.int32),
                            arr(pr.obs_camera_idx, n_obs, np.int32), arr(pr.obs_point_idx, n_obs, np.int32),
                            arr(pr.obs_xy, 2 * n_obs, np.float64))
+        flat.num_config_images = int(pr.num_config_images)
     finally:
         lib.b200ba_assembly_free(h)
     return flat, image_ids, camera_ids, point_ids
@@ -515,7 +530,7 @@ class BundleAdjuster:
             co, cp = self.options_.to_c(), flat.to_c()
             pc = flat.pose_constant.copy()
             # images outside the config are not candidates: mark them "not in problem" for the search
-            in_cfg = np.array([1 if i in self.config_.Images() else 0 for i in image_ids], np.uint8)
+            in_cfg = np.array([1 if (i in self.config_.Images() and i in flat.parameterized_image_ids) else 0 for i in image_ids], np.uint8)
             sub = FlatProblem(flat.poses[in_cfg == 1], flat.pose_constant[in_cfg == 1], flat.pose_fixed_dim[in_cfg == 1],
                               flat.cam_model, flat.cam_off, flat.cam_params, flat.cam_constant, flat.points,
                               flat.point_constant, np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32),

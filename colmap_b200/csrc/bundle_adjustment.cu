@@ -1536,7 +1536,17 @@ struct BaPool {
     if (e != cudaSuccess) return e;
     return cudaMemcpyAsync(*p, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, s);
   }
-  void release() { cudaDeviceSynchronize(); for (auto& a : ptrs) B200DeviceCache::get().free(a.first, a.second); ptrs.clear(); }
+  void release() { if (ptrs.empty()) return; cudaDeviceSynchronize(); for (auto& a : ptrs) B200DeviceCache::get().free(a.first, a.second); ptrs.clear(); }
+  ~BaPool() { release(); }   // every return path of a solve gives its blocks back
+};
+// stream + events of one solve: destroyed on every return path (declared after the pool, so before its release)
+struct BaStreamGuard {
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  ~BaStreamGuard() {
+    for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e);
+    if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+  }
 };
 
 static int g_ba_cs_tiles = 0;   // ba_cam_stream: 0 = looped kernel (default), 1 | 2 | 4 = tiles per warp of the one-shot kernel (B200BA_CS_TILES)
@@ -1733,9 +1743,12 @@ int b200ba_assemble(const b200ba_options* o, const b200ba_scene* sc, const b200b
     A->obs_xy.push_back(xy[0]); A->obs_xy.push_back(xy[1]);
     point_num_obs[pid] += 1;
   };
-  // AddImageToProblem: every observation of the config's images (:688-751)
+  // AddImageToProblem: every observation of the config's images (:688-751); an image (and its camera) counts as
+  // parameterized only if it contributed at least one observation (:745-748)
+  std::vector<uint8_t> image_parameterized(NI, 0);
   for (int i = 0; i < NI; ++i) {
     if (!flag(cfg->image_in_config, i)) continue;
+    const size_t before = A->obs_pose.size();
     for (int64_t k = sc->point2D_offset[i]; k < sc->point2D_offset[i + 1]; ++k) {
       const int64_t pid = sc->point2D_point3D[k];
       if (pid < 0) continue;
@@ -1744,10 +1757,12 @@ int b200ba_assemble(const b200ba_options* o, const b200ba_scene* sc, const b200b
       if (track_len(pid) < cfg->min_track_length) continue;
       push(i, pid, sc->point2D_xy + 2 * k);
     }
+    if (A->obs_pose.size() > before) image_parameterized[i] = 1;
   }
   // AddPointToProblem: explicit config points bring the observations made by images outside the config (:829-888)
   for (int64_t pid = 0; pid < NPT; ++pid) {
     if (!flag(cfg->point_variable, pid) && !flag(cfg->point_constant, pid)) continue;
+    if (cfg->min_track_length > 0 && track_len(pid) < cfg->min_track_length) continue;   // :835-838
     if (point_num_obs[pid] == track_len(pid)) continue;
     for (int64_t t = sc->track_offset[pid]; t < sc->track_offset[pid + 1]; ++t) {
       const int img = sc->track_image[t];
@@ -1764,7 +1779,7 @@ int b200ba_assemble(const b200ba_options* o, const b200ba_scene* sc, const b200b
   std::vector<uint8_t> cam_in_cfg(NC, 0);
   for (int i = 0; i < NI; ++i)
     if (flag(cfg->image_in_config, i)) {
-      cam_in_cfg[sc->image_camera[i]] = 1;
+      if (image_parameterized[i]) cam_in_cfg[sc->image_camera[i]] = 1;
       if (!flag(cfg->image_constant_pose, i)) A->pose_constant[i] = 0;
     }
   // cameras seen only through constant-pose factors of outside images stay constant (:863-878)
@@ -1790,11 +1805,13 @@ int b200ba_assemble(const b200ba_options* o, const b200ba_scene* sc, const b200b
   P.num_points = NPT; P.points = A->points.data(); P.point_constant = A->point_constant.data();
   P.num_observations = (int64_t)A->obs_pose.size();
   P.obs_pose_idx = A->obs_pose.data(); P.obs_camera_idx = A->obs_cam.data(); P.obs_point_idx = A->obs_point.data(); P.obs_xy = A->obs_xy.data();
+  P.num_config_images = 0;
+  for (int i = 0; i < NI; ++i) if (flag(cfg->image_in_config, i)) P.num_config_images += 1;   // config.NumImages() (:131)
   // FixGauge (:270-417), TWO_CAMS_FROM_WORLD: the search runs over the config's images in ascending image id
   bool three_points = cfg->fixed_gauge == 2;
   if (cfg->fixed_gauge == 1 && o->refine_rig_from_world) {
     std::vector<int> idx;
-    for (int i = 0; i < NI; ++i) if (flag(cfg->image_in_config, i)) idx.push_back(i);
+    for (int i = 0; i < NI; ++i) if (flag(cfg->image_in_config, i) && image_parameterized[i]) idx.push_back(i);   // parameterized_image_ids_
     std::vector<double> sp(7 * idx.size());
     std::vector<uint8_t> sc_in(idx.size()), sc_out(idx.size());
     std::vector<int8_t> sd_in(idx.size(), -1), sd_out(idx.size());
@@ -1910,8 +1927,9 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
     pose_used[a] = 1; cam_used[b] = 1; pt_used[c] = 1;
   }
   const bool sharded = comm != nullptr && comm->world > 1;
-  cudaStream_t st = nullptr;
-  if (!host_only) BA_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  BaStreamGuard guard;
+  if (!host_only) BA_CUDA(cudaStreamCreateWithFlags(&guard.st, cudaStreamNonBlocking));
+  const cudaStream_t st = guard.st;
   // all-reduce of a device buffer over the ranks of a sharded solve (no-op otherwise)
   auto allreduce = [&](void* buf, size_t count, ncclDataType_t dt, ncclRedOp_t op) -> cudaError_t {
     if (!sharded || count == 0) return cudaSuccess;
@@ -1994,9 +2012,16 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   sum->num_residuals = (int)(2 * g_nobs_eff);
   sum->num_effective_parameters = neff;
   int lst = o->linear_solver_type;
-  if (lst == B200BA_AUTO) lst = NP <= 50 ? B200BA_DENSE_SCHUR : (NP <= 1000 ? B200BA_SPARSE_SCHUR : B200BA_ITERATIVE_SCHUR);
+  if (lst == B200BA_AUTO) {
+    // config.NumImages() decides (bundle_adjustment_ceres.cc:131,204-210), not the number of poses of the whole model:
+    // a local BA of six images inside a large reconstruction is a DENSE_SCHUR problem.  Flat callers that do not say
+    // get the number of poses that appear in observations.
+    int nimg = p->num_config_images;
+    if (nimg <= 0) for (int i = 0; i < NP; ++i) nimg += pose_used[i] ? 1 : 0;
+    lst = nimg <= 50 ? B200BA_DENSE_SCHUR : (nimg <= 1000 ? B200BA_SPARSE_SCHUR : B200BA_ITERATIVE_SCHUR);
+  }
   sum->linear_solver_type_used = lst;
-  if (g_nobs_eff == 0 || neff == 0) { sum->termination_type = B200BA_CONVERGENCE; cudaStreamDestroy(st); pool.release(); return 0; }
+  if (g_nobs_eff == 0 || neff == 0) { sum->termination_type = B200BA_CONVERGENCE; return 0; }
   for (int k = 0; k < nvpt; ++k) {
     vcount[k + 1] += vcount[k];
   }
@@ -2258,8 +2283,8 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   BA_CUDA(cudaStreamSynchronize(st));
   sum->setup_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_setup0).count();
 
-  cudaEvent_t ev0, ev1, evs0, evs1;
-  BA_CUDA(cudaEventCreate(&ev0)); BA_CUDA(cudaEventCreate(&ev1)); BA_CUDA(cudaEventCreate(&evs0)); BA_CUDA(cudaEventCreate(&evs1));
+  for (int i = 0; i < 4; ++i) BA_CUDA(cudaEventCreate(&guard.ev[i]));
+  const cudaEvent_t ev0 = guard.ev[0], ev1 = guard.ev[1], evs0 = guard.ev[2], evs1 = guard.ev[3];
   int launches = 0, spmv_launches = 0;
   double spmv_ms = 0.0;
   const int gc_blocks = (nc + 255) / 256, gp_blocks = (nvpt + 255) / 256;
@@ -2443,10 +2468,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   for (int i = 0; i < NP; ++i) if (pose_off[i] >= 0) memcpy(p->poses + 7 * (size_t)i, h_poses.data() + 7 * (size_t)i, 56);
   for (int c = 0; c < NCAM; ++c) for (int k = 0; k < cam_nvar[c]; ++k) { const int idx = cam_poff[c] + cam_var[5 * (size_t)c + k]; p->camera_params[idx] = h_cams[idx]; }
   for (long long i = 0; i < NPT; ++i) if (pt_var[i] >= 0) memcpy(p->points + 3 * i, h_pts.data() + 3 * i, 24);
-  cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(evs0); cudaEventDestroy(evs1);
-  cudaStreamDestroy(st);
-  pool.release();
-  return 0;
+  return 0;   // pool, stream and events are released by their guards
 }
 
 extern "C" {

@@ -1251,7 +1251,7 @@ int b200pm_run(b200pm_handle c) {
   c->dirty = true;
   {
     const size_t n = (size_t)P.W0 * P.H0;
-    const int grid = (int)std::min<size_t>((n + 3) / 4, (size_t)148 * 64);
+    const int grid = (int)std::min<size_t>((n + 3) / 4, (size_t)c->num_sms * 64);
     pm_initial_cost_kernel<<<grid, 128, c->smem_init, s>>>(P);
     ++launches;
   }
@@ -1290,7 +1290,7 @@ int b200pm_run(b200pm_handle c) {
         pm_rand_kernel<<<(fw + 63) / 64, 64, 0, s>>>(P, A);
         mark(1);
         const size_t npx = (size_t)P.W0 * P.H0;
-        const int pgrid = (int)std::min<size_t>((npx + 3) / 4, (size_t)148 * 32);
+        const int pgrid = (int)std::min<size_t>((npx + 3) / 4, (size_t)c->num_sms * 32);
         if (P.geom) pm_pixel_kernel<true><<<pgrid, 128, c->smem_init, s>>>(P, A);
         else pm_pixel_kernel<false><<<pgrid, 128, c->smem_init, s>>>(P, A);
         mark(2);

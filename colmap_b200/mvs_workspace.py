@@ -480,7 +480,13 @@ class PatchMatchController:
         if o.sigma_spatial <= 0:
             o.sigma_spatial = float(o.window_radius)
         o.gpu_index = str(gpu_index)
-        used = [ref] + list(srcs)
+        # used_image_idxs is a set in the reference (patch_match.cc:451-458): duplicates collapse, the reference image is
+        # not a source of itself, and the consistency threshold cannot exceed the number of sources (a single-source
+        # problem with the default of 2 would otherwise filter every pixel).  Sources keep their cfg order (the
+        # reference iterates a hash set, i.e. an unspecified order).
+        srcs = [g for g in dict.fromkeys(srcs) if g != ref]
+        o.filter_min_num_consistent = min(len(srcs), o.filter_min_num_consistent)
+        used = [ref] + srcs
         local = {g: k for k, g in enumerate(used)}
         images = [self._image(g) for g in used]
         problem = Problem(ref_image_idx=0, src_image_idxs=[local[g] for g in srcs], images=images)

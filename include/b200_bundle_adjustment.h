@@ -89,6 +89,8 @@ typedef struct b200ba_problem {
   const int32_t* obs_camera_idx;
   const int32_t* obs_point_idx;
   const double* obs_xy;                    /* [2*num_observations] */
+  int32_t num_config_images;               /* config.NumImages(): drives the AUTO linear-solver choice (bundle_adjustment_ceres.cc:131,
+                                            * 204-210); 0 = the number of poses that appear in observations */
 } b200ba_problem;
 
 /* BundleAdjustmentSummary (bundle_adjustment.h:63-74) + the ceres::Solver::Summary fields

@@ -733,7 +733,16 @@ int ba_oracle_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* 
   neff += (int)(3 * F.nvpt);
   sum->num_effective_parameters = neff;
   int lst = o->linear_solver_type;
-  if (lst == B200BA_AUTO) lst = p->num_poses <= 50 ? B200BA_DENSE_SCHUR : (p->num_poses <= 1000 ? B200BA_SPARSE_SCHUR : B200BA_ITERATIVE_SCHUR);
+  if (lst == B200BA_AUTO) {   /* config.NumImages() decides (bundle_adjustment_ceres.cc:131,204-210) */
+    int nimg = p->num_config_images;
+    if (nimg <= 0) {
+      unsigned char* used = (unsigned char*)calloc((size_t)p->num_poses + 1, 1);
+      for (int64_t i = 0; i < p->num_observations; ++i) used[p->obs_pose_idx[i]] = 1;
+      for (int i = 0; i < p->num_poses; ++i) nimg += used[i];
+      free(used);
+    }
+    lst = nimg <= 50 ? B200BA_DENSE_SCHUR : (nimg <= 1000 ? B200BA_SPARSE_SCHUR : B200BA_ITERATIVE_SCHUR);
+  }
   sum->linear_solver_type_used = lst;
   if (F.nobs == 0 || neff == 0) { sum->termination_type = B200BA_CONVERGENCE; return 0; }
 

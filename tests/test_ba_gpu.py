@@ -176,3 +176,83 @@ def test_golden_fixture_solution():
     assert np.allclose(flat.poses, z["sol_poses"], rtol=1e-5, atol=1e-5)
     assert np.allclose(flat.points, z["sol_points"], rtol=1e-5, atol=1e-5)
     assert np.allclose(flat.cam_params, z["sol_cam_params"], rtol=1e-5, atol=1e-5)
+
+
+# ---------------------------------------------------------------- BASELINE sizes
+def test_b3_full_size_parity_vs_oracle():
+    """BASELINE config B3 at FULL size (500 SIMPLE_RADIAL cameras with their own intrinsics, 300k points, 2M
+    observations, ITERATIVE_SCHUR + SCHUR_JACOBI): the first 12 LM iterations of both implementations - cost 1e-5,
+    parameters 1e-4 (inexact Newton steps: the PCG forcing term leaves the weakest directions pinned to ~1e-4)."""
+    gt, noisy = synthesize_ba_problem(500, 300000, 7, models=(SIMPLE_RADIAL,), seed=42, num_obs=2000000)
+    _gauge(noisy)
+    a, sg, b, sr = _both(BundleAdjustmentOptions(linear_solver_type=ITERATIVE_SCHUR, max_num_iterations=12), noisy)
+    assert sg.num_residuals == 4000000
+    assert sg.num_successful_steps + sg.num_unsuccessful_steps == sr.num_successful_steps + sr.num_unsuccessful_steps
+    _assert_parity(a, sg, b, sr, param_rel=1e-4)
+
+
+def test_b5_shaped_mixed_models_parity_vs_oracle():
+    """B5-shaped (mixed camera models, > 1M observations): 400 cameras cycling over four models, 180k points, 1.1M
+    observations, ITERATIVE_SCHUR; 8 LM iterations against the oracle."""
+    gt, noisy = synthesize_ba_problem(400, 180000, 6, models=(PINHOLE, SIMPLE_RADIAL, RADIAL, SIMPLE_RADIAL_FISHEYE),
+                                      seed=5, num_obs=1100000)
+    _gauge(noisy)
+    a, sg, b, sr = _both(BundleAdjustmentOptions(linear_solver_type=ITERATIVE_SCHUR, max_num_iterations=8), noisy)
+    assert sg.num_residuals == 2200000
+    _assert_parity(a, sg, b, sr, param_rel=1e-4)
+
+
+def test_assemble_then_solve_on_the_gpu():
+    """SURVEY 8(a) DefaultBundleAdjuster ctor + 8(f-3): the C++ assembly (b200ba_assemble: observations, constancy rules,
+    two-cams gauge, config.NumImages() for the solver choice) feeding b200ba_solve on the GPU, against the oracle run on
+    the Python mirror's flattening of the same reconstruction: a LOCAL bundle adjustment (6 of 40 images in the config,
+    constant-pose observations from outside images through explicit variable points)."""
+    from colmap_b200.bundle_adjustment import assemble_reconstruction, flatten_reconstruction, BundleAdjuster
+    gt, noisy = synthesize_ba_problem(40, 1500, 8, models=(SIMPLE_RADIAL,), seed=2)
+    rec = flat_to_reconstruction(noisy)
+    cfg = BundleAdjustmentConfig()
+    for i in (3, 4, 5, 9, 10, 11):
+        cfg.AddImage(i)
+    for pid in list(rec.points3D)[:200]:
+        cfg.AddVariablePoint(pid)
+    cfg.FixGauge(TWO_CAMS_FROM_WORLD)
+    o = BundleAdjustmentOptions()
+    flat_c, image_ids, camera_ids, point_ids = assemble_reconstruction(o, cfg, rec)
+    assert flat_c.num_config_images == 6
+    sg = solve_flat(o, flat_c)
+    assert sg.linear_solver_type_used == DENSE_SCHUR          # 6 config images, although the model has 40 (ADVICE r1)
+    # oracle on the Python mirror's flattening + the same gauge the adapter applies
+    rec2 = flat_to_reconstruction(noisy)
+    adj = BundleAdjuster(o, cfg, rec2)
+    flat_p, *_ = flatten_reconstruction(o, cfg, rec2)
+    flat_p.pose_constant, flat_p.pose_fixed_dim = flat_c.pose_constant.copy(), flat_c.pose_fixed_dim.copy()
+    sr = oracle_ba.solve(o, flat_p)
+    assert sg.num_residuals == sr.num_residuals and sg.num_effective_parameters == sr.num_effective_parameters
+    assert abs(sg.final_cost - sr.final_cost) <= REL * sr.final_cost
+    assert np.allclose(flat_c.poses, flat_p.poses, rtol=REL, atol=REL) and np.allclose(flat_c.points, flat_p.points, rtol=REL, atol=REL)
+    outside = [k for k, i in enumerate(image_ids) if i not in cfg.Images()]
+    assert np.array_equal(flat_c.poses[outside], noisy.poses[outside])       # constant blocks bit-identical
+
+
+def test_cross_backend_with_the_reference_caspar_solver():
+    """The reference's own GPU backend (generated Caspar solver, fp32, compiled in place into oracle/_ref) on the same
+    problem - the cross-backend check of bundle_adjustment_caspar_test.cc:957-1022 (MergedCalibMatchesCeres: focal within
+    20, principal point within 10, extra within 1.5e-2 in fp32) with our solver in the role of Ceres, plus the final cost.
+    Caspar fixes one frame only (scale left free), so costs are compared, poses are not."""
+    import ref_caspar
+    if not ref_caspar.available():
+        pytest.skip("oracle/_ref/libcaspar_ref.so not built (needs /root/reference at build time)")
+    gt, noisy = synthesize_ba_problem(30, 3000, 8, models=(SIMPLE_RADIAL,), seed=13)
+    _gauge(noisy)
+    o = BundleAdjustmentOptions(refine_principal_point=True)
+    a, b = noisy.copy(), noisy.copy()
+    for f in (a, b):
+        f.pose_constant, f.pose_fixed_dim = noisy.pose_constant, noisy.pose_fixed_dim
+    sg = solve_flat(o, a)
+    rc = ref_caspar.solve(b, o)
+    assert rc["num_residuals"] == sg.num_residuals
+    assert abs(rc["initial_cost"] - sg.initial_cost) <= 1e-3 * sg.initial_cost          # fp32 residual evaluation
+    assert abs(rc["final_cost"] - sg.final_cost) <= 2e-2 * sg.final_cost
+    pa, pb = a.cam_params.reshape(-1, 4), b.cam_params.reshape(-1, 4)
+    assert np.abs(pa[:, 0] - pb[:, 0]).max() < 20.0 and np.abs(pa[:, 1:3] - pb[:, 1:3]).max() < 10.0
+    assert np.abs(pa[:, 3] - pb[:, 3]).max() < 1.5e-2
