@@ -75,7 +75,13 @@ struct PmSweepArgs {
   float* prior3;           // [pixel][3][N] triangulation / incident / resolution priors of the current hypothesis
   float* tab3;             // [pixel][3][N] NCC of hypotheses 2,3,4 for every source image
   float* gtab2;            // [pixel][2][N] geometric cost at cur / rand depth (geom mode)
+  float* fwd_pred;         // [pixel][N] forward messages of the column over the sweep-START costs (pass M): the pixel pass
+                           // predicts which images the serial pass will sample from them
+  int prune;               // 0: the pixel pass evaluates every (hypothesis, image) pair; 1: prediction + exact early-out;
+                           // 2: (tests) the pixel pass evaluates nothing, the serial pass fills every entry itself
+  int col0, col1;          // column range [col0, col1) of the sweep frame handled by this launch (pixel / serial pass)
 };
+#define PM_NOT_EVALUATED (-1.0f)   // tab3 sentinel (an NCC cost is always in [0, 2])
 
 // ------------------------------------------------------------------------------------------------
 // frame maps: frame k = the reference's buffers after k Rotate() calls (cuda_rotate.h:57-75):
@@ -598,8 +604,51 @@ __global__ void pm_rand_kernel(const PmParams P, const PmSweepArgs A) {
   wslot[0] = rs.v0; wslot[1] = rs.v1; wslot[2] = rs.v2; wslot[3] = rs.v3; wslot[4] = rs.v4; wslot[5] = rs.d;
 }
 
-template <bool GEOM>
-__global__ void __launch_bounds__(128, 8) pm_pixel_kernel(const PmParams P, const PmSweepArgs A) {
+
+// M  pm_msg_kernel: one thread per (column, image).  Backward messages of the whole column (:976-989) - the same
+// recurrence pm_serial_kernel used to run at its start, now available BEFORE the pixel pass - and the forward
+// messages over the sweep-start costs ("nothing above this row changes"), which is what the serial pass will see
+// wherever no new hypothesis won above.  From them the pixel pass predicts the Monte-Carlo samples of every pixel.
+__global__ void pm_msg_kernel(const PmParams P, const PmSweepArgs A) {
+  const int rot = A.rot, N = P.N;
+  const int fw = (rot & 1) ? P.H0 : P.W0, fh = (rot & 1) ? P.W0 : P.H0;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int col = t / N, img = t - col * N;
+  if (col >= fw) return;
+  float beta = 0.5f;
+  {
+    float cn = P.cost[pm_pix0(P.W0, P.H0, rot, fh - 1, col) * N + img];
+    for (int row = fh - 1; row >= 0; --row) {
+      const size_t p = pm_pix0(P.W0, P.H0, rot, row, col);
+      const float c = cn;
+      if (row > 0) cn = P.cost[pm_pix0(P.W0, P.H0, rot, row - 1, col) * N + img];   // next load in flight during the chain step
+      beta = pm_backward_message(P.L, c, beta);
+      A.sel_cur[p * N + img] = beta;
+    }
+  }
+  if (A.fwd_pred == nullptr) return;
+  float f = 0.5f;
+  float cn = P.cost[pm_pix0(P.W0, P.H0, rot, 0, col) * N + img];
+  for (int row = 0; row < fh; ++row) {
+    const size_t p = pm_pix0(P.W0, P.H0, rot, row, col);
+    const float c = cn;
+    if (row + 1 < fh) cn = P.cost[pm_pix0(P.W0, P.H0, rot, row + 1, col) * N + img];
+    f = pm_forward_message(P.L, c, f);
+    A.fwd_pred[p * N + img] = f;
+  }
+}
+
+// P  pm_pixel_kernel.  With A.prune == 1 the pass does not evaluate all 3N (hypothesis, image) pairs of a pixel:
+//   * it PREDICTS the Monte-Carlo samples of the pixel (the uniforms are known from pass R, the CDF from the
+//     sweep-start messages of pass M) and from them how often every image will be sampled;
+//   * per hypothesis it evaluates the sampled images in order of multiplicity and stops as soon as the partial cost
+//     sum exceeds the (predicted) cost sum of the current hypothesis: a sum of non-negative terms only grows, so
+//     that hypothesis can no longer win the argmin (:1175-1182);
+//   * entries it did not evaluate stay PM_NOT_EVALUATED.
+// Exactness does not depend on the prediction: pm_serial_kernel re-checks "partial sum > cost sum of hypothesis 0"
+// with the true samples in the true summation order and evaluates any entry it really needs itself.
+template <bool GEOM, bool PRUNE, int MINB>
+__global__ void __launch_bounds__(128, MINB) pm_pixel_kernel(const PmParams P, const PmSweepArgs A) {
   extern __shared__ float4 smem4[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rot = A.rot, N = P.N;
@@ -611,24 +660,29 @@ __global__ void __launch_bounds__(128, 8) pm_pixel_kernel(const PmParams P, cons
   const float iK[4] = {P.invK[rot][0], P.invK[rot][1], P.invK[rot][2], P.invK[rot][3]};
   const float Kr[4] = {P.K[rot][0], P.K[rot][1], P.K[rot][2], P.K[rot][3]};
   __syncthreads();
-  const size_t npix = (size_t)P.W0 * P.H0;
+  const int cw = A.col1 - A.col0;
+  const size_t npix = (size_t)cw * fh;
   const int g = lane >> 3, sub = lane & 7;
   const unsigned gmask = 0xffu << (8 * g);
-  const int npairs = 3 * N;
+  const unsigned full = 0xffffffffu;
+  const unsigned nmask = (N >= 32) ? 0xffffffffu : ((1u << N) - 1u);
+  const int ns = P.num_samples, nsl = ns < 32 ? ns : 32;
+  const int mode = PRUNE ? A.prune : 0;
+  (void)fw; (void)nsl; (void)full; (void)nmask;
   // (an SM-local tiling of the pixel order was measured: L1 hit rate 67% -> 55%, slower; plain grid stride kept)
   for (size_t q = (size_t)blockIdx.x * 4 + warp; q < npix; q += (size_t)gridDim.x * 4) {
-    const int row = (int)(q / fw), col = (int)(q - (size_t)row * fw);  // sweep-frame pixel
+    const int row = (int)(q / cw), col = A.col0 + (int)(q - (size_t)row * cw);  // sweep-frame pixel
     const size_t p = pm_pix0(P.W0, P.H0, rot, row, col);
     const float rowf = (float)row, colf = (float)col;
     float inv_wsum;
     pm_build_patch(P, rot, fw, fh, row, col, patch, lane, &inv_wsum);
-    __syncwarp();
     const float4 cur4 = P.hyp[p];
     float cn0 = cur4.y, cn1 = cur4.z;
     pm_normal_to_frame(rot, cn0, cn1);
     const float cur_d = cur4.x, cn2 = cur4.w;
     const float4 r4 = A.rand_hyp[p];
     const float rsum = P.ref_sum[p], rsq = P.ref_sqsum[p];
+    float prob = 0.0f, cost_i = 0.0f, gcur = 0.0f, grand = 0.0f;
     if (lane < N) {  // per-image priors of the current hypothesis (:1079-1103)
       const float* pose = poses + lane * PM_POSE_STRIDE;
       const float rx = fmaf(iK[0], colf, iK[1]), ry = fmaf(iK[2], rowf, iK[3]);
@@ -637,26 +691,125 @@ __global__ void __launch_bounds__(128, 8) pm_pixel_kernel(const PmParams P, cons
       float Hm[9];
       pm_compose_homography(pose, iK, rowf, colf, cur_d, cn0, cn1, cn2, Hm);
       // kept as three factors: the serial pass evaluates sel_prob * tri * inc * res left to right (:1103)
-      A.prior3[(p * 3 + 0) * N + lane] = pm_tri_prob(P.L, ct);
-      A.prior3[(p * 3 + 1) * N + lane] = pm_inc_prob(P.L, ci);
-      A.prior3[(p * 3 + 2) * N + lane] = pm_res_prob(Hm, rowf, colf, P.radius);
+      const float pt = pm_tri_prob(P.L, ct), pi = pm_inc_prob(P.L, ci), pr = pm_res_prob(Hm, rowf, colf, P.radius);
+      A.prior3[(p * 3 + 0) * N + lane] = pt;
+      A.prior3[(p * 3 + 1) * N + lane] = pi;
+      A.prior3[(p * 3 + 2) * N + lane] = pr;
       if (GEOM) {
         const PmSrcDesc sd = P.src[lane];
         const float* dm = P.src_depth + sd.depth_off;
-        A.gtab2[(p * 2 + 0) * N + lane] = pm_geom_cost(pose, Kr, iK, dm, sd.w, sd.h, rowf, colf, cur_d, P.geom_max_cost);
-        A.gtab2[(p * 2 + 1) * N + lane] = pm_geom_cost(pose, Kr, iK, dm, sd.w, sd.h, rowf, colf, r4.x, P.geom_max_cost);
+        gcur = pm_geom_cost(pose, Kr, iK, dm, sd.w, sd.h, rowf, colf, cur_d, P.geom_max_cost);
+        grand = pm_geom_cost(pose, Kr, iK, dm, sd.w, sd.h, rowf, colf, r4.x, P.geom_max_cost);
+        A.gtab2[(p * 2 + 0) * N + lane] = gcur;
+        A.gtab2[(p * 2 + 1) * N + lane] = grand;
+      }
+      if (mode == 1) {
+        cost_i = P.cost[p * N + lane];
+        const float sp = pm_sel_prob(A.fwd_pred[p * N + lane], A.sel_cur[p * N + lane], A.sel_prev[p * N + lane], A.prev_w);
+        prob = sp * pt * pi * pr;
       }
     }
-    for (int base = 0; base < npairs; base += 4) {
-      const int pair = base + g;
-      if (pair < npairs) {
-        const int hsel = pair / N, img = pair - hsel * N;  // hsel 0: rand/rand, 1: cur depth + rand normal, 2: rand depth + cur normal
-        const float hd = (hsel == 1) ? cur_d : r4.x;
-        const float hn0 = (hsel == 2) ? cn0 : r4.y, hn1 = (hsel == 2) ? cn1 : r4.z, hn2 = (hsel == 2) ? cn2 : r4.w;
-        const PmSrcDesc sd = P.src[img];
-        const float c = pm_ncc_group(patch, P.ntaps, poses + img * PM_POSE_STRIDE, iK, P.quads + sd.quad_off, sd.pitch,
-                                     sd.w, sd.h, rowf, colf, hd, hn0, hn1, hn2, inv_wsum, rsum, rsq, sub, gmask);
-        if (sub == 0) A.tab3[(p * 3 + hsel) * N + img] = c;
+    if (!PRUNE) {   // every (hypothesis, image) pair, four per round
+      __syncwarp();
+      const int npairs = 3 * N;
+      for (int base = 0; base < npairs; base += 4) {
+        const int pair = base + g;
+        if (pair < npairs) {
+          const int hsel = pair / N, img = pair - hsel * N;
+          const float hd = (hsel == 1) ? cur_d : r4.x;
+          const float hn0 = (hsel == 2) ? cn0 : r4.y, hn1 = (hsel == 2) ? cn1 : r4.z, hn2 = (hsel == 2) ? cn2 : r4.w;
+          const PmSrcDesc sd = P.src[img];
+          const float c = pm_ncc_group(patch, P.ntaps, poses + img * PM_POSE_STRIDE, iK, P.quads + sd.quad_off, sd.pitch,
+                                       sd.w, sd.h, rowf, colf, hd, hn0, hn1, hn2, inv_wsum, rsum, rsq, sub, gmask);
+          if (sub == 0) A.tab3[(p * 3 + hsel) * N + img] = c;
+        }
+      }
+      __syncwarp();
+      continue;
+    }
+    for (int e = lane; e < 3 * N; e += 32) A.tab3[p * 3 * N + e] = PM_NOT_EVALUATED;
+    __syncwarp();   // patch complete; sentinel stores ordered before the result stores of other lanes
+    // ---- which images will be sampled, and how often (prediction; mode 0: every image once)
+    int mult = (lane < N) ? 1 : 0;
+    unsigned rem0 = nmask, rem1 = nmask, rem2 = nmask, ev0 = 0u, ev1 = 0u, ev2 = 0u;
+    bool act0 = true, act1 = true, act2 = true, ext0 = true, ext1 = true, ext2 = true;
+    float thr = 3.0e38f;
+    if (mode == 1) {
+      float sum = 0.0f;
+      for (int i = 0; i < N; ++i) sum += __shfl_sync(full, prob, i);
+      const float inv = 1.0f / sum;
+      float cum = 0.0f, cdf = 0.0f;
+      for (int i = 0; i < N; ++i) {
+        cum += __shfl_sync(full, prob, i) * inv;
+        if (lane == i) cdf = cum;
+      }
+      const float u = (lane < nsl) ? A.usamp[p * ns + lane] : 2.0f;
+      int img = -1;
+      for (int i = 0; i < N; ++i) {
+        const float ci = __shfl_sync(full, cdf, i);
+        if (img < 0 && ci > u) img = i;
+      }
+      mult = 0;
+      for (int s2 = 0; s2 < nsl; ++s2) mult += (__shfl_sync(full, img, s2) == lane) ? 1 : 0;
+      if (lane >= N) mult = 0;
+      const unsigned needed = __ballot_sync(full, mult > 0);
+      float t = (float)mult * (GEOM ? fmaf(P.geom_reg, gcur, cost_i) : cost_i);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(full, t, o);
+      thr = fmaf(t, 1.001f, 1e-3f);   // predicted cost sum of the current hypothesis, with a margin for the true order of summation
+      rem0 = rem1 = rem2 = needed;
+      ext0 = ext1 = ext2 = false;
+      act0 = act1 = act2 = needed != 0u;
+    } else if (mode != 0) {
+      act0 = act1 = act2 = false;
+    }
+    float L0 = 0.0f, L1 = 0.0f, L2 = 0.0f;
+    while (act0 || act1 || act2) {
+      // up to four (hypothesis, image) pairs per round, hypotheses taking turns, images by multiplicity
+      int my_k = -1, my_img = 0, slot = 0;
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const bool a = (k == 0) ? act0 : ((k == 1) ? act1 : act2);
+          const unsigned rem = (k == 0) ? rem0 : ((k == 1) ? rem1 : rem2);
+          if (slot < 4 && a && rem) {
+            const unsigned key = ((rem >> lane) & 1u) ? ((((unsigned)mult) << 5) | (unsigned)(31 - lane)) + 1u : 0u;
+            const unsigned best = __reduce_max_sync(full, key);
+            const int im = 31 - (int)((best - 1u) & 31u);
+            const unsigned bit = 1u << im;
+            if (k == 0) { rem0 &= ~bit; ev0 |= bit; } else if (k == 1) { rem1 &= ~bit; ev1 |= bit; } else { rem2 &= ~bit; ev2 |= bit; }
+            if (slot == g) { my_k = k; my_img = im; }
+            ++slot;
+          }
+        }
+      }
+      if (slot == 0) break;
+      float c = 0.0f;
+      if (my_k >= 0) {   // hsel 0: rand/rand, 1: cur depth + rand normal, 2: rand depth + cur normal
+        const float hd = (my_k == 1) ? cur_d : r4.x;
+        const float hn0 = (my_k == 2) ? cn0 : r4.y, hn1 = (my_k == 2) ? cn1 : r4.z, hn2 = (my_k == 2) ? cn2 : r4.w;
+        const PmSrcDesc sd = P.src[my_img];
+        c = pm_ncc_group(patch, P.ntaps, poses + my_img * PM_POSE_STRIDE, iK, P.quads + sd.quad_off, sd.pitch, sd.w, sd.h,
+                         rowf, colf, hd, hn0, hn1, hn2, inv_wsum, rsum, rsq, sub, gmask);
+        if (sub == 0) A.tab3[(p * 3 + my_k) * N + my_img] = c;
+      }
+      if (mode == 1) {
+#pragma unroll
+        for (int s2 = 0; s2 < 4; ++s2) {
+          const int ks = __shfl_sync(full, my_k, 8 * s2), is = __shfl_sync(full, my_img, 8 * s2);
+          float v = __shfl_sync(full, c, 8 * s2);
+          const float w = (float)__shfl_sync(full, mult, is & 31);
+          if (GEOM) v = fmaf(P.geom_reg, __shfl_sync(full, (ks == 1) ? gcur : grand, is & 31), v);
+          if (ks == 0) L0 = fmaf(w, v, L0); else if (ks == 1) L1 = fmaf(w, v, L1); else if (ks == 2) L2 = fmaf(w, v, L2);
+        }
+        // a hypothesis whose partial sum already exceeds the current hypothesis' sum is out; one that survives all its
+        // sampled images is a likely winner: the images nobody sampled are then needed for the cost map (:1184-1196)
+        if (act0) { if (L0 > thr) act0 = false; else if (!rem0) { if (!ext0) { ext0 = true; rem0 = nmask & ~ev0; } if (!rem0) act0 = false; } }
+        if (act1) { if (L1 > thr) act1 = false; else if (!rem1) { if (!ext1) { ext1 = true; rem1 = nmask & ~ev1; } if (!rem1) act1 = false; } }
+        if (act2) { if (L2 > thr) act2 = false; else if (!rem2) { if (!ext2) { ext2 = true; rem2 = nmask & ~ev2; } if (!rem2) act2 = false; } }
+      } else {
+        act0 = rem0 != 0u; act1 = rem1 != 0u; act2 = rem2 != 0u;
       }
     }
     __syncwarp();
@@ -667,36 +820,32 @@ template <int WPC, bool GEOM, int MINB>
 __global__ void __launch_bounds__(32 * WPC, MINB) pm_serial_kernel(const PmParams P, const PmSweepArgs A) {
   extern __shared__ float4 smem4[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int col = blockIdx.x;
+  const int col = A.col0 + blockIdx.x;
   const int rot = A.rot, N = P.N;
   const int fw = (rot & 1) ? P.H0 : P.W0, fh = (rot & 1) ? P.W0 : P.H0;
-  float4* patch = smem4;
-  float* poses = reinterpret_cast<float*>(patch + P.ntaps_pad);
+  // the reference patch and its scalars are double-buffered by row parity: the last warp builds row + 1 while warp 0
+  // may still evaluate NCCs of row (the rare entries the pixel pass left out)
+  float4* patch2 = smem4;
+  float* poses = reinterpret_cast<float*>(patch2 + 2 * P.ntaps_pad);
   float* tab1 = poses + N * PM_POSE_STRIDE;  // [32] NCC of the propagated hypothesis per image
   float* hyp1 = tab1 + 32;                   // depth, normal of the propagated hypothesis
-  float* fctl = hyp1 + 4;                    // inv_wsum, ref_sum, ref_sqsum
+  float* fctl2 = hyp1 + 4;                   // [2][4] inv_wsum, ref_sum, ref_sqsum
   for (int i = threadIdx.x; i < N * PM_POSE_STRIDE; i += blockDim.x) poses[i] = P.poses[(size_t)rot * N * PM_POSE_STRIDE + i];
-  pm_fill_tap_offsets(P, patch, threadIdx.x, blockDim.x);
+  pm_fill_tap_offsets(P, patch2, threadIdx.x, blockDim.x);
+  pm_fill_tap_offsets(P, patch2 + P.ntaps_pad, threadIdx.x, blockDim.x);
   const float iK[4] = {P.invK[rot][0], P.invK[rot][1], P.invK[rot][2], P.invK[rot][3]};
   const float Kr[4] = {P.K[rot][0], P.K[rot][1], P.K[rot][2], P.K[rot][3]};
   const float colf = (float)col;
   const int g = lane >> 3, sub = lane & 7;
   const unsigned gmask = 0xffu << (8 * g);
+  const unsigned full = 0xffffffffu;
   const bool img_lane = lane < N;
   __syncthreads();
 
   float fwd = 0.5f;
   float prev_d = 0.0f, prev_n0 = 0.0f, prev_n1 = 0.0f, prev_n2 = 0.0f;
   const int ns = P.num_samples;
-  if (warp == 0) {
-    if (img_lane) {  // backward messages (:976-989)
-      float beta = 0.5f;
-      for (int row = fh - 1; row >= 0; --row) {
-        const size_t p = pm_pix0(P.W0, P.H0, rot, row, col);
-        beta = pm_backward_message(P.L, P.cost[p * N + lane], beta);
-        A.sel_cur[p * N + lane] = beta;
-      }
-    }
+  if (warp == 0) {   // (the backward messages of the column, :976-989, were written to sel_cur by pm_msg_kernel)
     int r0, c0;
     pm_frame_to_orig(P.W0, P.H0, rot, 0, col, &r0, &c0);
     const float4 h0 = P.hyp[(size_t)r0 * P.W0 + c0];
@@ -729,6 +878,8 @@ __global__ void __launch_bounds__(32 * WPC, MINB) pm_serial_kernel(const PmParam
   for (int row = 0; row < fh; ++row) {
     const size_t p = pm_pix0(P.W0, P.H0, rot, row, col);
     const float rowf = (float)row;
+    float4* patch = patch2 + (row & 1) * P.ntaps_pad;
+    float* fctl = fctl2 + 4 * (row & 1);
     if (warp == WPC - 1) {
       float inv_wsum;
       pm_build_patch(P, rot, fw, fh, row, col, patch, lane, &inv_wsum);
@@ -757,11 +908,11 @@ __global__ void __launch_bounds__(32 * WPC, MINB) pm_serial_kernel(const PmParam
         if (GEOM) { g_cur = nx_gc; g_rand = nx_gr; }
       }
       float sum = 0.0f;
-      for (int i = 0; i < N; ++i) sum += __shfl_sync(0xffffffffu, prob, i);
+      for (int i = 0; i < N; ++i) sum += __shfl_sync(full, prob, i);
       const float inv = 1.0f / sum;
       float cum = 0.0f;
       for (int i = 0; i < N; ++i) {
-        cum += __shfl_sync(0xffffffffu, prob, i) * inv;
+        cum += __shfl_sync(full, prob, i) * inv;
         if (lane == i) cdf = cum;
       }
       if (lane == 0) { hyp1[0] = prev_d; hyp1[1] = prev_n0; hyp1[2] = prev_n1; hyp1[3] = prev_n2; }
@@ -770,8 +921,8 @@ __global__ void __launch_bounds__(32 * WPC, MINB) pm_serial_kernel(const PmParam
     if (warp == 0 && row + 1 < fh) fetch_row(row + 1);
 
     // ---- phase B (all warps): NCC of the propagated hypothesis against every source image
+    const float inv_wsum = fctl[0], rsum = fctl[1], rsq = fctl[2];
     {
-      const float inv_wsum = fctl[0], rsum = fctl[1], rsq = fctl[2];
       const float hd = hyp1[0], hn0 = hyp1[1], hn1 = hyp1[2], hn2 = hyp1[3];
       for (int img = warp * 4 + g; img < N; img += 4 * WPC) {
         const PmSrcDesc sd = P.src[img];
@@ -791,41 +942,96 @@ __global__ void __launch_bounds__(32 * WPC, MINB) pm_serial_kernel(const PmParam
         g_prev = pm_geom_cost(poses + lane * PM_POSE_STRIDE, Kr, iK, P.src_depth + sd.depth_off, sd.w, sd.h, rowf, colf,
                               prev_d, P.geom_max_cost);
       }
-      // Monte-Carlo accumulation (:1128-1173).  The uniforms were drawn by pass R; lanes pick the sampled image of
-      // one sample each, then the five cost sums are accumulated in sample order (a skipped sample adds +0, exact).
-      float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f, a4 = 0.0f;
-      for (int base = 0; base < ns; base += 32) {
-        const int sidx = base + lane;
-        const float u = (base == 0) ? u_first : ((sidx < ns) ? A.usamp[p * ns + sidx] : 2.0f);
-        int img = -1;
-        for (int i = 0; i < N; ++i) {
-          const float ci = __shfl_sync(0xffffffffu, cdf, i);
-          if (img < 0 && ci > u) img = i;
-        }
-        const int src = img < 0 ? 0 : img;
-        float v0 = __shfl_sync(0xffffffffu, cost_i, src), v1 = __shfl_sync(0xffffffffu, c1, src),
-              v2 = __shfl_sync(0xffffffffu, c2, src), v3 = __shfl_sync(0xffffffffu, c3, src),
-              v4 = __shfl_sync(0xffffffffu, c4, src);
-        float gcv = 0.0f, gpv = 0.0f, grv = 0.0f;
-        if (GEOM) { gcv = __shfl_sync(0xffffffffu, g_cur, src); gpv = __shfl_sync(0xffffffffu, g_prev, src); grv = __shfl_sync(0xffffffffu, g_rand, src); }
-        if (img < 0) { v0 = v1 = v2 = v3 = v4 = 0.0f; gcv = gpv = grv = 0.0f; }
-        const int cnt = min(32, ns - base);
-        for (int j = 0; j < cnt; ++j) {
-          a0 += __shfl_sync(0xffffffffu, v0, j); a1 += __shfl_sync(0xffffffffu, v1, j); a2 += __shfl_sync(0xffffffffu, v2, j);
-          a3 += __shfl_sync(0xffffffffu, v3, j); a4 += __shfl_sync(0xffffffffu, v4, j);
-          if (GEOM) {
-            const float gc = __shfl_sync(0xffffffffu, gcv, j), gp = __shfl_sync(0xffffffffu, gpv, j), gr = __shfl_sync(0xffffffffu, grv, j);
-            a0 = fmaf(P.geom_reg, gc, a0); a1 = fmaf(P.geom_reg, gp, a1); a2 = fmaf(P.geom_reg, gr, a2);
-            a3 = fmaf(P.geom_reg, gc, a3); a4 = fmaf(P.geom_reg, gr, a4);
+      // NCC of hypothesis k (2: rand/rand, 3: cur depth + rand normal, 4: rand depth + cur normal) for the images in
+      // `todo`, by this warp's four groups; the results land in lane == image of c2 / c3 / c4
+      auto evaluate = [&](int k, unsigned todo) {
+        const float hd = (k == 3) ? cur_d : r4.x;
+        const float hn0 = (k == 4) ? cur_n0 : r4.y, hn1 = (k == 4) ? cur_n1 : r4.z, hn2 = (k == 4) ? cur_n2 : r4.w;
+        while (todo) {
+          int my_img = -1;
+#pragma unroll
+          for (int s2 = 0; s2 < 4; ++s2)
+            if (todo) { const int im = __ffs(todo) - 1; todo &= todo - 1; if (s2 == g) my_img = im; }
+          float c = 0.0f;
+          if (my_img >= 0) {
+            const PmSrcDesc sd = P.src[my_img];
+            c = pm_ncc_group(patch, P.ntaps, poses + my_img * PM_POSE_STRIDE, iK, P.quads + sd.quad_off, sd.pitch, sd.w, sd.h,
+                             rowf, colf, hd, hn0, hn1, hn2, inv_wsum, rsum, rsq, sub, gmask);
+          }
+#pragma unroll
+          for (int s2 = 0; s2 < 4; ++s2) {
+            const int is = __shfl_sync(full, my_img, 8 * s2);
+            const float cs = __shfl_sync(full, c, 8 * s2);
+            if (is == lane) { if (k == 2) c2 = cs; else if (k == 3) c3 = cs; else c4 = cs; }
           }
         }
+      };
+      // Monte-Carlo accumulation (:1128-1173).  The uniforms were drawn by pass R; lanes pick the sampled image of
+      // one sample each, then the five cost sums are accumulated in sample order (a skipped sample adds +0, exact).
+      // Entries the pixel pass did not evaluate count as 0: the sums of hypotheses 2..4 are then LOWER bounds
+      // (non-negative terms, monotone rounding), which is enough to rule a hypothesis out when the bound already
+      // exceeds the sum of hypothesis 0; otherwise the missing entries are evaluated here and the sums redone.
+      float a0, a1, a2, a3, a4;
+      unsigned out_mask = 0u;   // bit k: hypothesis k is excluded (lower bound > a0)
+      for (int attempt = 0;; ++attempt) {
+        a0 = a1 = a2 = a3 = a4 = 0.0f;
+        unsigned sampled = 0u;
+        for (int base = 0; base < ns; base += 32) {
+          const int sidx = base + lane;
+          const float u = (base == 0) ? u_first : ((sidx < ns) ? A.usamp[p * ns + sidx] : 2.0f);
+          int img = -1;
+          for (int i = 0; i < N; ++i) {
+            const float ci = __shfl_sync(full, cdf, i);
+            if (img < 0 && ci > u) img = i;
+          }
+          const int src = img < 0 ? 0 : img;
+          float v0 = __shfl_sync(full, cost_i, src), v1 = __shfl_sync(full, c1, src),
+                v2 = __shfl_sync(full, c2, src), v3 = __shfl_sync(full, c3, src),
+                v4 = __shfl_sync(full, c4, src);
+          float gcv = 0.0f, gpv = 0.0f, grv = 0.0f;
+          if (GEOM) { gcv = __shfl_sync(full, g_cur, src); gpv = __shfl_sync(full, g_prev, src); grv = __shfl_sync(full, g_rand, src); }
+          if (img < 0) { v0 = v1 = v2 = v3 = v4 = 0.0f; gcv = gpv = grv = 0.0f; }
+          v2 = fmaxf(v2, 0.0f); v3 = fmaxf(v3, 0.0f); v4 = fmaxf(v4, 0.0f);   // PM_NOT_EVALUATED -> 0
+          if (attempt == 0) {
+            for (int i = 0; i < N; ++i) if (__ballot_sync(full, img == i)) sampled |= 1u << i;
+          }
+          const int cnt = min(32, ns - base);
+          for (int j = 0; j < cnt; ++j) {
+            a0 += __shfl_sync(full, v0, j); a1 += __shfl_sync(full, v1, j); a2 += __shfl_sync(full, v2, j);
+            a3 += __shfl_sync(full, v3, j); a4 += __shfl_sync(full, v4, j);
+            if (GEOM) {
+              const float gc = __shfl_sync(full, gcv, j), gp = __shfl_sync(full, gpv, j), gr = __shfl_sync(full, grv, j);
+              a0 = fmaf(P.geom_reg, gc, a0); a1 = fmaf(P.geom_reg, gp, a1); a2 = fmaf(P.geom_reg, gr, a2);
+              a3 = fmaf(P.geom_reg, gc, a3); a4 = fmaf(P.geom_reg, gr, a4);
+            }
+          }
+        }
+        if (attempt != 0) break;
+        // which sampled entries are missing?
+        const unsigned in_s = img_lane && ((sampled >> lane) & 1u);
+        const unsigned m2 = __ballot_sync(full, in_s && c2 < 0.0f), m3 = __ballot_sync(full, in_s && c3 < 0.0f),
+                       m4 = __ballot_sync(full, in_s && c4 < 0.0f);
+        if (!(m2 | m3 | m4)) break;
+        unsigned t2 = 0u, t3 = 0u, t4 = 0u;
+        if (m2) { if (a2 > a0) out_mask |= 4u; else t2 = m2; }
+        if (m3) { if (a3 > a0) out_mask |= 8u; else t3 = m3; }
+        if (m4) { if (a4 > a0) out_mask |= 16u; else t4 = m4; }
+        if (!(t2 | t3 | t4)) break;
+        if (t2) evaluate(2, t2);
+        if (t3) evaluate(3, t3);
+        if (t4) evaluate(4, t4);
       }
       int best = 0;
       float mn = a0;
       if (a1 <= mn) { mn = a1; best = 1; }
-      if (a2 <= mn) { mn = a2; best = 2; }
-      if (a3 <= mn) { mn = a3; best = 3; }
-      if (a4 <= mn) { mn = a4; best = 4; }
+      if (!(out_mask & 4u) && a2 <= mn) { mn = a2; best = 2; }
+      if (!(out_mask & 8u) && a3 <= mn) { mn = a3; best = 3; }
+      if (!(out_mask & 16u) && a4 <= mn) { mn = a4; best = 4; }
+      if (best >= 2) {   // the winner's cost for EVERY image goes to the cost map (:1184-1196)
+        const float cb = (best == 2) ? c2 : ((best == 3) ? c3 : c4);
+        const unsigned miss = __ballot_sync(full, img_lane && cb < 0.0f);
+        if (miss) evaluate(best, miss);
+      }
       float best_d, bn0, bn1, bn2;
       switch (best) {
         case 0: best_d = cur_d; bn0 = cur_n0; bn1 = cur_n1; bn2 = cur_n2; break;
@@ -863,7 +1069,7 @@ __global__ void __launch_bounds__(32 * WPC, MINB) pm_serial_kernel(const PmParam
             }
           }
         }
-        const int cnt = __popc(__ballot_sync(0xffffffffu, ok));
+        const int cnt = __popc(__ballot_sync(full, ok));
         zero = cnt < P.filter_min_num_consistent;
         if (img_lane) P.mask[p * N + lane] = (ok && !zero) ? 1 : 0;
       }
@@ -931,6 +1137,14 @@ struct b200pm_context {
   bool serial_cap = false; // B200PM_SERIAL_CAP=1: allow the register-capped (72 regs, 13 CTAs/SM, small spills) WPC = 2 variant
   int num_sms = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;     // pass M runs here, next to pass R on the main stream
+  std::vector<cudaStream_t> chunk_stream;   // one high-priority stream per column chunk for the serial pass
+  int pix_minb = 8;                   // resident pixel-pass CTAs per SM the kernel is compiled for (B200PM_PIX_MINB = 6 | 7 | 8)
+  int pix_per_warp = 8;               // pixels a pixel-pass warp handles before its CTA retires (B200PM_PPW)
+  std::vector<cudaEvent_t> chunk_ev;  // pixel chunk i done (main stream) ; [kMaxChunks] = serial pass of the sweep done
+  int chunks = 1;                     // column chunks per sweep (B200PM_CHUNKS); measured on B200 at C2: 1 -> 522 ms, 2 -> 621 ms,
+                                      // 4 -> 688 ms per run (the 128-register serial CTAs starve the pixel pass of registers)
+  int prune = 1, prune_from = 1;      // exact early-out in the pixel pass (B200PM_PRUNE), from this sweep on (B200PM_PRUNE_FROM)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<std::pair<void*, size_t>> allocs;
   float* sel[2] = {nullptr, nullptr};
@@ -944,7 +1158,9 @@ struct b200pm_context {
   size_t smem_sweep = 0, smem_init = 0, smem_serial = 0;
   bool fused = false;
   float4* rand_hyp = nullptr; unsigned char* ntrials = nullptr; float* usamp = nullptr; float* prior3 = nullptr; float* tab3 = nullptr; float* gtab2 = nullptr;
+  float* fwd_pred = nullptr;
 };
+#define PM_MAX_CHUNKS 16
 
 template <typename T>
 static cudaError_t pm_alloc(b200pm_context* c, T** p, size_t count) {
@@ -1087,6 +1303,20 @@ int b200pm_create(const b200pm_options* o, const b200pm_problem* p, b200pm_handl
   PM_CUDA(cudaSetDevice(c->device));
   PM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 4; ++i) PM_CUDA(cudaEventCreate(&c->ev[i]));
+  PM_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically lowest = highest priority
+    c->chunk_stream.resize(PM_MAX_CHUNKS);
+    for (auto& st : c->chunk_stream) PM_CUDA(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, hi));
+  }
+  if (const char* e = getenv("B200PM_PIX_MINB")) { const int v = atoi(e); if (v >= 6 && v <= 8) c->pix_minb = v; }
+  if (const char* e = getenv("B200PM_PPW")) c->pix_per_warp = std::max(1, atoi(e));
+  c->chunk_ev.resize(2 * PM_MAX_CHUNKS + 2);
+  for (auto& e : c->chunk_ev) PM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  if (const char* e = getenv("B200PM_CHUNKS")) c->chunks = std::max(1, std::min(PM_MAX_CHUNKS, atoi(e)));
+  if (const char* e = getenv("B200PM_PRUNE")) c->prune = atoi(e);
+  if (const char* e = getenv("B200PM_PRUNE_FROM")) c->prune_from = atoi(e);
   if (const char* e = getenv("B200PM_WPC")) { c->wpc = atoi(e); c->wpc_auto = false; }
   if (c->wpc != 1 && c->wpc != 2 && c->wpc != 4) c->wpc = 2;
   if (const char* e = getenv("B200PM_SERIAL_CAP")) c->serial_cap = atoi(e) != 0;   // measured: 237 ms vs 233 ms of serial pass per run without it
@@ -1187,7 +1417,7 @@ int b200pm_create(const b200pm_options* o, const b200pm_problem* p, b200pm_handl
   c->smem_sweep = sizeof(float4) * P.ntaps_pad + sizeof(float) * ((size_t)N * PM_POSE_STRIDE + 160 + 96 + 20 + 4) +
                   sizeof(int) * (4 + (size_t)P.num_samples);
   c->smem_init = sizeof(float4) * 4 * P.ntaps_pad + sizeof(float) * (size_t)N * PM_POSE_STRIDE;
-  c->smem_serial = sizeof(float4) * P.ntaps_pad + sizeof(float) * ((size_t)N * PM_POSE_STRIDE + 32 + 4 + 4);
+  c->smem_serial = sizeof(float4) * 2 * P.ntaps_pad + sizeof(float) * ((size_t)N * PM_POSE_STRIDE + 32 + 4 + 8);
   c->fused = getenv("B200PM_FUSED") != nullptr && atoi(getenv("B200PM_FUSED")) != 0;
   if (!c->fused) {
     PM_CUDA(pm_alloc(c, &c->rand_hyp, n));
@@ -1196,6 +1426,7 @@ int b200pm_create(const b200pm_options* o, const b200pm_problem* p, b200pm_handl
     PM_CUDA(pm_alloc(c, &c->prior3, 3 * n * N));
     PM_CUDA(pm_alloc(c, &c->tab3, 3 * n * N));
     if (P.geom) PM_CUDA(pm_alloc(c, &c->gtab2, 2 * n * N));
+    PM_CUDA(pm_alloc(c, &c->fwd_pred, n * N));
   }
   PM_CUDA(cudaStreamSynchronize(s));
   PM_CUDA(cudaGetLastError());
@@ -1213,11 +1444,16 @@ static void pm_launch_sweep(b200pm_context* c, const PmSweepArgs& A, int fw) {
     pm_sweep_kernel<WPC, false><<<fw, 32 * WPC, c->smem_sweep, c->stream>>>(c->P, A);
 }
 template <int WPC, int MINB>
-static void pm_launch_serial(b200pm_context* c, const PmSweepArgs& A, int fw) {
+static void pm_launch_serial(b200pm_context* c, const PmSweepArgs& A, cudaStream_t st) {
+  const int cw = A.col1 - A.col0;
+  if (c->smem_serial > 48 * 1024) {
+    cudaFuncSetAttribute(pm_serial_kernel<WPC, true, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_serial);
+    cudaFuncSetAttribute(pm_serial_kernel<WPC, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_serial);
+  }
   if (c->P.geom)
-    pm_serial_kernel<WPC, true, MINB><<<fw, 32 * WPC, c->smem_serial, c->stream>>>(c->P, A);
+    pm_serial_kernel<WPC, true, MINB><<<cw, 32 * WPC, c->smem_serial, st>>>(c->P, A);
   else
-    pm_serial_kernel<WPC, false, MINB><<<fw, 32 * WPC, c->smem_serial, c->stream>>>(c->P, A);
+    pm_serial_kernel<WPC, false, MINB><<<cw, 32 * WPC, c->smem_serial, st>>>(c->P, A);
 }
 
 extern "C" {
@@ -1238,8 +1474,10 @@ int b200pm_run(b200pm_handle c) {
   }
   if (c->smem_init > 48 * 1024) {
     PM_CUDA(cudaFuncSetAttribute(pm_initial_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_init));
-    PM_CUDA(cudaFuncSetAttribute(pm_pixel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_init));
-    PM_CUDA(cudaFuncSetAttribute(pm_pixel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_init));
+#define PM_ATTR(G, PR, MB) PM_CUDA(cudaFuncSetAttribute(pm_pixel_kernel<G, PR, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_init))
+    PM_ATTR(false, false, 8); PM_ATTR(true, false, 8); PM_ATTR(false, true, 8); PM_ATTR(true, true, 8);
+    PM_ATTR(false, true, 7); PM_ATTR(true, true, 7); PM_ATTR(false, true, 6); PM_ATTR(true, true, 6);
+#undef PM_ATTR
   }
   int launches = 0;
   PM_CUDA(cudaEventRecord(c->ev[0], s));
@@ -1287,13 +1525,17 @@ int b200pm_run(b200pm_handle c) {
         mark(1); mark(2); mark(3);
       } else {
         A.rand_hyp = c->rand_hyp; A.ntrials = c->ntrials; A.usamp = c->usamp; A.prior3 = c->prior3; A.tab3 = c->tab3; A.gtab2 = c->gtab2;
+        A.fwd_pred = c->fwd_pred;
+        A.prune = (c->prune == 1) ? ((t >= c->prune_from) ? 1 : 0) : c->prune;
+        A.col0 = 0; A.col1 = fw;
+        // pass M (messages) runs beside pass R (random hypotheses): both only read the state the last sweep left
+        cudaEventRecord(c->chunk_ev[2 * PM_MAX_CHUNKS], s);
+        cudaStreamWaitEvent(c->stream2, c->chunk_ev[2 * PM_MAX_CHUNKS], 0);
+        pm_msg_kernel<<<(fw * P.N + 127) / 128, 128, 0, c->stream2>>>(P, A);
+        cudaEventRecord(c->chunk_ev[2 * PM_MAX_CHUNKS + 1], c->stream2);
         pm_rand_kernel<<<(fw + 63) / 64, 64, 0, s>>>(P, A);
+        cudaStreamWaitEvent(s, c->chunk_ev[2 * PM_MAX_CHUNKS + 1], 0);
         mark(1);
-        const size_t npx = (size_t)P.W0 * P.H0;
-        const int pgrid = (int)std::min<size_t>((npx + 3) / 4, (size_t)c->num_sms * 32);
-        if (P.geom) pm_pixel_kernel<true><<<pgrid, 128, c->smem_init, s>>>(P, A);
-        else pm_pixel_kernel<false><<<pgrid, 128, c->smem_init, s>>>(P, A);
-        mark(2);
         // The serial pass is one CTA per column marching down all rows: a second wave of CTAs lengthens its critical
         // path.  Pick the widest schedule whose resident capacity covers all fw columns in ONE wave (register-file
         // bound: 128 registers x 32*WPC threads per CTA).  C2: 1920-column sweeps run WPC = 1, 1080-column sweeps
@@ -1306,11 +1548,37 @@ int b200pm_run(b200pm_handle c) {
           else if (fw <= sms * 13 && c->serial_cap) { wpc = 2; capped = 1; }
           else wpc = 1;
         }
-        if (wpc == 1) pm_launch_serial<1, 16>(c, A, fw);
-        else if (wpc == 2 && capped) pm_launch_serial<2, 13>(c, A, fw);
-        else if (wpc == 2) pm_launch_serial<2, 8>(c, A, fw);
-        else pm_launch_serial<4, 4>(c, A, fw);
-        launches += 3;
+        // Columns are independent inside a sweep: the pixel pass runs in column chunks on the main stream (short-lived
+        // CTAs) and the serial pass of a chunk starts on its own high-priority stream as soon as its chunk is done, so
+        // the latency-bound serial pass overlaps the issue-bound pixel pass of the following chunks.
+        const int nchunks = std::max(1, std::min(c->chunks, fw / 32 > 0 ? fw / 32 : 1));
+        const int fh_ = (sweep & 1) ? P.W0 : P.H0;
+        for (int k = 0; k < nchunks; ++k) {
+          PmSweepArgs C = A;
+          C.col0 = (int)((long long)fw * k / nchunks); C.col1 = (int)((long long)fw * (k + 1) / nchunks);
+          const size_t npx = (size_t)(C.col1 - C.col0) * fh_;
+          const size_t per_cta = (size_t)4 * c->pix_per_warp;
+          const int pgrid = (int)((npx + per_cta - 1) / per_cta);
+          const bool pr = C.prune != 0;
+#define PM_LAUNCH_PIXEL(G, PR, MB) pm_pixel_kernel<G, PR, MB><<<pgrid, 128, c->smem_init, s>>>(P, C)
+          if (P.geom) { if (!pr) PM_LAUNCH_PIXEL(true, false, 8); else if (c->pix_minb == 8) PM_LAUNCH_PIXEL(true, true, 8); else if (c->pix_minb == 7) PM_LAUNCH_PIXEL(true, true, 7); else PM_LAUNCH_PIXEL(true, true, 6); }
+          else { if (!pr) PM_LAUNCH_PIXEL(false, false, 8); else if (c->pix_minb == 8) PM_LAUNCH_PIXEL(false, true, 8); else if (c->pix_minb == 7) PM_LAUNCH_PIXEL(false, true, 7); else PM_LAUNCH_PIXEL(false, true, 6); }
+#undef PM_LAUNCH_PIXEL
+          cudaStream_t ss = nchunks > 1 ? c->chunk_stream[k] : s;
+          if (nchunks > 1) {
+            cudaEventRecord(c->chunk_ev[k], s);
+            cudaStreamWaitEvent(ss, c->chunk_ev[k], 0);
+          }
+          if (wpc == 1) pm_launch_serial<1, 16>(c, C, ss);
+          else if (wpc == 2 && capped) pm_launch_serial<2, 13>(c, C, ss);
+          else if (wpc == 2) pm_launch_serial<2, 8>(c, C, ss);
+          else pm_launch_serial<4, 4>(c, C, ss);
+          if (nchunks > 1) cudaEventRecord(c->chunk_ev[PM_MAX_CHUNKS + k], ss);
+          launches += 2;
+        }
+        mark(2);
+        if (nchunks > 1) for (int k = 0; k < nchunks; ++k) cudaStreamWaitEvent(s, c->chunk_ev[PM_MAX_CHUNKS + k], 0);
+        launches += 2;
         mark(3);
       }
       c->final_sel = t & 1;
@@ -1404,6 +1672,9 @@ void b200pm_destroy(b200pm_handle c) {
   for (auto& a : c->allocs) B200DeviceCache::get().free(a.first, a.second);
   for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (cudaEvent_t e : c->sweep_ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->chunk_ev) if (e) cudaEventDestroy(e);
+  for (cudaStream_t st : c->chunk_stream) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+  if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }

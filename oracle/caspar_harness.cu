@@ -218,7 +218,7 @@ extern "C" int caspar_ref_solve(const b200ba_options* o, b200ba_problem* p, int 
       }
     }
     out->iterations = res.iteration_count; out->exit_reason = (int)res.exit_reason;
-    out->initial_cost = res.initial_score; out->final_cost = res.final_score;
+    out->initial_cost = 0.0 /* SolveResult::initial_score is never written by the generated solver */; out->final_cost = res.final_score;
     out->solve_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
     out->setup_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
     out->num_residuals = (int)nres;

@@ -251,7 +251,7 @@ def test_cross_backend_with_the_reference_caspar_solver():
     sg = solve_flat(o, a)
     rc = ref_caspar.solve(b, o)
     assert rc["num_residuals"] == sg.num_residuals
-    assert abs(rc["initial_cost"] - sg.initial_cost) <= 1e-3 * sg.initial_cost          # fp32 residual evaluation
+    # (caspar::SolveResult::initial_score is never written by the generated solver, solver.cc:2408-2410)
     assert abs(rc["final_cost"] - sg.final_cost) <= 2e-2 * sg.final_cost
     pa, pb = a.cam_params.reshape(-1, 4), b.cam_params.reshape(-1, 4)
     assert np.abs(pa[:, 0] - pb[:, 0]).max() < 20.0 and np.abs(pa[:, 1:3] - pb[:, 1:3]).max() < 10.0

@@ -17,7 +17,9 @@ def _bits(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
 
 
-def _run_cuda(o, problem, wpc=None, fused=False):
+def _run_cuda(o, problem, wpc=None, fused=False, env=None):
+    for k, v in (env or {}).items():
+        os.environ[k] = str(v)
     if wpc is not None:
         os.environ["B200PM_WPC"] = str(wpc)
     os.environ.pop("B200PM_MAX_SWEEPS", None)
@@ -31,6 +33,8 @@ def _run_cuda(o, problem, wpc=None, fused=False):
     pm.close()
     os.environ.pop("B200PM_WPC", None)
     os.environ.pop("B200PM_FUSED", None)
+    for k in (env or {}):
+        os.environ.pop(k, None)
     return out
 
 
@@ -62,6 +66,32 @@ def test_photometric_bit_exact_vs_oracle(wpc, fused):
     _assert_bit_exact(got, ref)
     assert np.array_equal(got["mask"], ref["mask"])
     assert np.array_equal(got["list"], consistency_list_from_mask(ref["mask"], sc["problem"].src_image_idxs))
+
+
+@pytest.mark.parametrize("prune,prune_from,chunks,geom", [
+    (0, 0, 1, False),     # the pixel pass evaluates every (hypothesis, image) pair, one chunk: the round-1 schedule
+    (1, 0, 3, False),     # prediction + exact early-out from the very first sweep (poor prediction: many late evaluations)
+    (1, 1, 4, False),     # the default schedule
+    (2, 0, 2, False),     # adversarial: the pixel pass evaluates NOTHING, the serial pass must fill every entry it needs
+    (1, 0, 2, True), (2, 0, 1, True),
+])
+def test_early_out_schedules_are_exact(prune, prune_from, chunks, geom):
+    """The pixel pass may skip (hypothesis, image) pairs - predicted unsampled, or ruled out because the partial cost sum
+    already exceeds the current hypothesis' - and the serial pass re-checks / fills in with the true samples.  Whatever the
+    pixel pass chose to evaluate, the result must be the oracle's, bit for bit."""
+    sc = make_patch_match_scene(96, 72, 5, seed=3, with_gt_maps=geom)
+    prob = sc["problem"]
+    if geom:
+        rng = np.random.default_rng(1)
+        prob.depth_maps = [(d * (1 + 0.002 * rng.standard_normal(d.shape))).astype(np.float32) for d in sc["depth_maps"]]
+        prob.normal_maps = [n.copy() for n in sc["normal_maps"]]
+    o = PatchMatchOptions(depth_min=sc["depth_min"], depth_max=sc["depth_max"], geom_consistency=geom, num_iterations=2,
+                          num_samples=15 if not geom else 37)
+    ref = oracle_pm.run(o, prob)
+    for wpc in (1, 2):
+        got = _run_cuda(o, prob, wpc=wpc, env=dict(B200PM_PRUNE=prune, B200PM_PRUNE_FROM=prune_from, B200PM_CHUNKS=chunks))
+        _assert_bit_exact(got, ref)
+        assert np.array_equal(got["mask"], ref["mask"])
 
 
 @pytest.mark.parametrize("w,h,n,radius,step,samples", [

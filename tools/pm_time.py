@@ -1,24 +1,29 @@
-"""Quick timing of the C2 workload (1 ref + 8 src, 1920x1080, window 11, 5 iterations) per WPC."""
-import os, sys, time
+"""Timing of the PatchMatch run under sets of environment knobs (B200PM_*): per-pass times for each configuration.
+usage: pm_time.py W H N "K1=V1 K2=V2" "K1=V3" ...   (each quoted argument is one configuration)"""
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
 from colmap_b200.patch_match import PatchMatch, PatchMatchOptions
 from colmap_b200.synthetic import make_patch_match_scene
-W, H, N = (int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (1920, 1080, 8)
-iters = int(sys.argv[4]) if len(sys.argv) > 4 else 5
-t = time.time(); sc = make_patch_match_scene(W, H, N, seed=0); print("scene s", time.time() - t, flush=True)
-o = PatchMatchOptions(depth_min=sc["depth_min"], depth_max=sc["depth_max"], geom_consistency=False, num_iterations=iters)
-for wpc in [int(x) for x in os.environ.get("WPCS", "0,1,2,4").split(",")]:   # 0 = automatic per-sweep schedule
-    if wpc: os.environ["B200PM_WPC"] = str(wpc)
-    else: os.environ.pop("B200PM_WPC", None)
+
+w, h, n = (int(v) for v in sys.argv[1:4])
+configs = sys.argv[4:] or [""]
+sc = make_patch_match_scene(w, h, n, seed=0)
+o = PatchMatchOptions(depth_min=sc["depth_min"], depth_max=sc["depth_max"], geom_consistency=False, gpu_index="0")
+for cfg in configs:
+    env = dict(kv.split("=") for kv in cfg.split())
+    for k, v in env.items():
+        os.environ[k] = v
     pm = PatchMatch(o, sc["problem"])
-    t = time.time(); pm.Run(); e2e = time.time() - t
-    ms = [pm.last_run_ms()]
+    pm.Run()
+    ms = []
     for _ in range(2):
-        pm.RunOnly(); ms.append(pm.last_run_ms())
-    d = pm.GetDepthMap(); valid = d > 0
-    rel = np.abs(d - sc["depth_gt"])[valid] / sc["depth_gt"][valid]
-    passes = [pm._lib.b200pm_last_pass_ms(pm._h, k) for k in range(3)] if hasattr(pm, "_lib") else []
-    print(f"WPC={wpc}: passes R/P/S ms {passes} run ms {ms} sweep_ms {pm.last_sweep_ms():.1f} -> {W*H/1e6/(min(ms)/1e3):.2f} Mpx/s; first Run() incl create {e2e:.2f}s; valid {valid.mean():.3f} med rel err {np.median(rel):.2e}", flush=True)
+        pm.RunOnly()
+        ms.append((pm.last_run_ms(), pm.last_pass_ms(0), pm.last_pass_ms(1), pm.last_pass_ms(2)))
+    d = pm.GetDepthMap()
     pm.close()
+    for k in env:
+        os.environ.pop(k, None)
+    m = np.mean(ms, axis=0)
+    print(f"{cfg:60s} run {m[0]:7.1f} ms = {w * h / 1e3 / m[0]:.3f} Mpx/s  rand+msg {m[1]:6.1f} pixel {m[2]:6.1f} serial-tail {m[3]:6.1f}  checksum {float(np.abs(d).sum()):.3f}", flush=True)
