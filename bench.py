@@ -194,7 +194,104 @@ def bench_ba(steps, warmup, peak, peak_src, with_cpu):
     return out
 
 
-def bench_ba_sharded(steps, warmup, rank, world, local_rank):
+
+C4 = dict(width=3840, height=2160, num_src=20, images_total=200, images_per_gpu_default=3)
+C4_WORKLOAD = ("PatchMatch C4: 200-image workspace, 4K frames (3840x2160), 20 source images per reference image, window 11, "
+               "5 iters, geometric consistency (photometric pass, NCCL all-gather of the depth maps, geometric pass + "
+               "filter), 8 GPUs")
+B5 = dict(num_images=2000, num_points=2000000, num_obs=12000000)
+B5_WORKLOAD = ("BA B5: 2000 cameras (PINHOLE / SIMPLE_RADIAL 50/50, own intrinsics), 2M points, 12M observations, "
+               "ITERATIVE_SCHUR + SCHUR_JACOBI, points sharded over the ranks")
+
+
+def bench_c4(rank, world, local_rank, images_total):
+    """C4-shaped leg: `images_total` 4K views of one scene, every view a reference image with its 20 nearest views as
+    sources, the reference's two-phase schedule (patch_match.cc:176-204) sharded over the ranks; the photometric depth
+    maps stay in HBM and cross the ranks in ONE NCCL all-gather (colmap_b200/workspace.py).  Mpixels/s = reference
+    pixels of FINAL (geometric, filtered) maps per second of the whole two-phase run, host bitmaps in, host maps out."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from colmap_b200.patch_match import PatchMatchOptions
+    from colmap_b200.sharding import max_over_ranks
+    from colmap_b200.synthetic import make_workspace_scene
+    from colmap_b200.workspace import run_two_phase
+    dev = torch.device("cuda", local_rank)
+    sc = make_workspace_scene(C4["width"], C4["height"], images_total, seed=7, device=dev)
+    n = images_total
+    cen = sc["centers"]
+    nsrc = min(C4["num_src"], n - 1)
+    srcs = []
+    for i in range(n):
+        order = np.argsort(np.linalg.norm(cen - cen[i], axis=1), kind="stable")
+        srcs.append([int(j) for j in order if j != i][:nsrc])
+    o = PatchMatchOptions(depth_min=sc["depth_min"], depth_max=sc["depth_max"], geom_consistency=True, window_radius=5,
+                          num_samples=15, num_iterations=5, gpu_index=str(local_rank))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.time()
+    out = run_two_phase(sc["images"], srcs, o, rank, world, device=dev)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dt = max_over_ranks(time.time() - t0, "cuda") if world > 1 else time.time() - t0
+    mine = sorted(out)
+    valid = float(np.mean([(out[i][0] > 0).mean() for i in mine])) if mine else 0.0
+    rel = [np.median(np.abs(out[i][0] - sc["depth_gt"][i])[out[i][0] > 0] / sc["depth_gt"][i][out[i][0] > 0]) for i in mine]
+    mpix = n * C4["width"] * C4["height"] / 1e6
+    return {"metric": "patchmatch_mpixels_per_s", "value": mpix / dt, "unit": "Mpixels/s", "n_gpus": world, "seconds": dt,
+            "config": {"workload": C4_WORKLOAD, "images_run": n, "images_of_config": C4["images_total"],
+                       "sources_per_image": nsrc,
+                       "note": ("the full 200-image configuration" if n == C4["images_total"] else
+                                f"bounded sample of the configuration: {n} of its 200 images (same frames, sources, options, "
+                                "schedule and exchange), so that the default bench run ends within minutes")},
+            "exchange": "NCCL all-gather of device-resident depth maps (no host round trip)",
+            "quality": {"valid_frac": valid, "median_rel_depth_err": float(np.median(rel)) if rel else None}}
+
+
+def bench_b5(steps, warmup, rank, world, local_rank, comm):
+    """BA leg on config B5 (2000 cameras, 2M points, 12M observations, mixed models), points sharded over the ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from colmap_b200.bundle_adjustment import (ITERATIVE_SCHUR, PINHOLE, SIMPLE_RADIAL, BundleAdjustmentOptions, shard_flat_problem,
+                                               solve_flat, solve_flat_sharded)
+    from colmap_b200.sharding import max_over_ranks
+    from colmap_b200.synthetic import synthesize_ba_problem
+    gt, noisy = synthesize_ba_problem(B5["num_images"], B5["num_points"], 6, models=(PINHOLE, SIMPLE_RADIAL), seed=42,
+                                      num_obs=B5["num_obs"])
+    noisy.pose_constant = noisy.pose_constant.copy(); noisy.pose_fixed_dim = noisy.pose_fixed_dim.copy()
+    noisy.pose_constant[0] = 1
+    noisy.pose_fixed_dim[1] = int(np.argmax(np.abs(noisy.poses[1, 4:] - noisy.poses[0, 4:])))
+    o = BundleAdjustmentOptions(linear_solver_type=ITERATIVE_SCHUR, gpu_index=local_rank)
+    lm, dev_ms, wall_ms, s = 0, 0.0, 0.0, None
+    for i in range(max(warmup, 1) + steps):
+        if world > 1:
+            local = shard_flat_problem(noisy, rank, world)
+            torch.cuda.synchronize(); dist.barrier()
+            t = time.time()
+            s = solve_flat_sharded(o, local, comm)
+            torch.cuda.synchronize(); dist.barrier()
+        else:
+            local = _fresh(noisy)
+            t = time.time()
+            s = solve_flat(o, local)
+        if i >= max(warmup, 1):
+            wall_ms += (time.time() - t) * 1e3
+            lm += s.num_successful_steps + s.num_unsuccessful_steps
+            dev_ms += s.solve_ms
+    if world > 1:
+        dev_ms = max_over_ranks(dev_ms, "cuda"); wall_ms = max_over_ranks(wall_ms, "cuda")
+    return {"metric": "ba_lm_iterations_per_s", "value": lm / (dev_ms * 1e-3), "unit": "LM iterations/s", "dtype": "f64",
+            "n_gpus": world, "scaling": "strong", "ms_per_step": dev_ms / steps, "lm_iterations_per_solve": lm / steps,
+            "config": {"workload": B5_WORKLOAD},
+            "e2e": {"value": lm / (wall_ms * 1e-3), "unit": "LM iterations/s", "ms_per_step": wall_ms / steps},
+            "final_cost": s.final_cost, "initial_cost": s.initial_cost, "termination_type": s.termination_type,
+            "pcg_iterations_per_solve": s.num_linear_solver_iterations}
+
+
+def bench_ba_sharded(steps, warmup, rank, world, local_rank, with_b5=False):
     """BA leg at N > 1: the same B3 problem, points sharded over the ranks (strong scaling), one NCCL all-reduce of the
     camera-side vector per PCG iteration inside b200ba_solve_sharded."""
     import torch
@@ -219,15 +316,23 @@ def bench_ba_sharded(steps, warmup, rank, world, local_rank):
             wall_ms += (time.time() - t) * 1e3
             lm += s.num_successful_steps + s.num_unsuccessful_steps
             dev_ms += s.solve_ms
+    b5 = None
+    if with_b5:
+        try:
+            b5 = bench_b5(min(steps, 2), 1, rank, world, local_rank, comm)
+        except Exception as e:
+            b5 = {"error": repr(e)}
     comm.close()
     from colmap_b200.sharding import max_over_ranks
     dev_ms = max_over_ranks(dev_ms, "cuda"); wall_ms = max_over_ranks(wall_ms, "cuda")
-    return {"metric": "ba_lm_iterations_per_s", "value": lm / (dev_ms * 1e-3), "unit": "LM iterations/s", "dtype": "f64",
-            "n_gpus": world, "scaling": "strong", "ms_per_step": dev_ms / steps, "lm_iterations_per_solve": lm / steps,
-            "config": {"workload": "BA B3 (500 cameras, 300k points, 2M observations), points sharded over the ranks, "
-                                   "NCCL all-reduce of the camera-side vector per PCG iteration"},
-            "e2e": {"value": lm / (wall_ms * 1e-3), "unit": "LM iterations/s", "ms_per_step": wall_ms / steps},
-            "final_cost": s.final_cost, "termination_type": s.termination_type}
+    out = {"metric": "ba_lm_iterations_per_s", "value": lm / (dev_ms * 1e-3), "unit": "LM iterations/s", "dtype": "f64",
+           "n_gpus": world, "scaling": "strong", "ms_per_step": dev_ms / steps, "lm_iterations_per_solve": lm / steps,
+           "config": {"workload": B3_WORKLOAD + "; points sharded over the ranks"},
+           "e2e": {"value": lm / (wall_ms * 1e-3), "unit": "LM iterations/s", "ms_per_step": wall_ms / steps},
+           "final_cost": s.final_cost, "termination_type": s.termination_type}
+    if b5 is not None:
+        out["b5"] = b5
+    return out
 
 
 def run_reference(args, rank, world, local_rank):
@@ -362,6 +467,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ba", action="store_true")
+    ap.add_argument("--c4-images", type=int, default=-1,
+                    help="images of the C4-shaped workspace leg: -1 = 3 per GPU when 8 GPUs run (the configuration's GPU count), "
+                         "else skipped; 0 = skip; 200 = the full configuration")
+    ap.add_argument("--b5", type=int, default=-1, help="BA config B5 leg: -1 = only when 8 GPUs run, 0 = skip, 1 = run")
     args = ap.parse_args()
 
     rank = _env_int("RANK", 0)
@@ -458,11 +567,19 @@ def main():
     wall_per_step = max_over_ranks(wall_ms / args.steps, "cuda")
 
     ba_sharded = None
+    want_b5 = args.b5 == 1 or (args.b5 == -1 and world == 8)
     if distributed and not args.no_ba:
         try:
-            ba_sharded = bench_ba_sharded(args.steps, args.warmup, rank, world, local_rank)
+            ba_sharded = bench_ba_sharded(args.steps, args.warmup, rank, world, local_rank, with_b5=want_b5)
         except Exception as e:
             ba_sharded = {"error": repr(e)}
+    c4 = None
+    c4_images = args.c4_images if args.c4_images >= 0 else (C4["images_per_gpu_default"] * world if world == 8 else 0)
+    if c4_images > 0:
+        try:
+            c4 = bench_c4(rank, world, local_rank, c4_images)
+        except Exception as e:
+            c4 = {"error": repr(e)}
     if rank == 0:
         n_sweeps = 4 * C2["num_iterations"]
         # one sweep = rand + pixel + serial pass; the dominant kernel is pm_pixel_kernel (NCC of 3 of the 4 alternative
@@ -504,6 +621,13 @@ def main():
                 line["ba"] = {"error": repr(e)}
         if ba_sharded is not None:
             line["ba"] = ba_sharded
+        if want_b5 and not distributed and not args.no_ba:
+            try:
+                line.setdefault("ba", {})["b5"] = bench_b5(min(args.steps, 2), 1, rank, world, local_rank, None)
+            except Exception as e:
+                line.setdefault("ba", {})["b5"] = {"error": repr(e)}
+        if c4 is not None:
+            line["c4"] = c4
         print(json.dumps(line), flush=True)
     if distributed:
         dist.destroy_process_group()

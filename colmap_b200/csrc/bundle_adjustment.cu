@@ -269,6 +269,7 @@ struct BaDev {
   int nblk;
   // PCG vectors
   double *x, *rr, *z, *p, *q, *dp;
+  double* Sd;   // dense reduced camera matrix [nc*nc] (DENSE_SCHUR path), column-major == row-major (symmetric)
   BaCtl* ctl;
 };
 
@@ -1318,6 +1319,131 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_giant_finish_kernel(const BaDev D
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// DENSE_SCHUR: the reduced camera matrix S = H_cc + D_c^2 - H_cp (H_pp + D_p^2)^-1 H_pc formed explicitly and factorised
+// (ceres DENSE_SCHUR = SchurEliminator + dense Cholesky; COLMAP picks it for <= 50 images, bundle_adjustment_ceres.cc:
+// 202-206).  Built from the same fp32-stored scaled Jacobians the implicit operator of the PCG path reads.
+// ------------------------------------------------------------------------------------------------
+template <int DC>
+__device__ __forceinline__ void ba_slot_rows(const BaDev& D, long long s, float* J0, float* J1, int* idx) {
+  const int4 pk = __ldg(D.s_pack + s);
+  const unsigned pky = (unsigned)pk.y;
+  const int po = pk.x, co = (int)(pky & 0x7ffffu) - 1, nv = (int)((pky >> 19) & 7u);
+#pragma unroll
+  for (int c = 0; c < DC; ++c) { J0[c] = D.Jc[BA_JC(c, s)]; J1[c] = D.Jc[BA_JC(DC + c, s)]; }
+#pragma unroll
+  for (int c = 0; c < DC; ++c) idx[c] = (c < 6) ? (po >= 0 ? po + c : -1) : ((co >= 0 && c - 6 < nv) ? co + c - 6 : -1);
+  if (pk.w < 0) {
+#pragma unroll
+    for (int c = 0; c < DC; ++c) idx[c] = -1;
+  }
+}
+// S += J_c^T J_c, one thread per observation slot (pose block, intrinsics block and their coupling)
+template <int DC>
+__global__ void __launch_bounds__(BA_BLOCK) ba_dense_gram_kernel(const BaDev D) {
+  const long long s = (long long)blockIdx.x * BA_BLOCK + threadIdx.x;
+  float J0[DC], J1[DC];
+  int idx[DC];
+  ba_slot_rows<DC>(D, s, J0, J1, idx);
+#pragma unroll
+  for (int r = 0; r < DC; ++r) {
+    if (idx[r] < 0) continue;
+#pragma unroll
+    for (int c = 0; c < DC; ++c)
+      if (idx[c] >= 0 && idx[r] >= idx[c])   // lower triangle only: element (i, j), i >= j, lives at Sd[j * nc + i]
+        atomicAdd(&D.Sd[(long long)idx[c] * D.nc + idx[r]], (double)J0[r] * (double)J0[c] + (double)J1[r] * (double)J1[c]);
+  }
+}
+// S -= sum over the pairs (i, j) of a track of W_i^T Hinv W_j with W_o = J_p(o)^T J_c(o); one warp per variable point
+template <int DC>
+__global__ void __launch_bounds__(BA_BLOCK) ba_dense_schur_kernel(const BaDev D) {
+  const int k = blockIdx.x * (BA_BLOCK / 32) + (threadIdx.x >> 5);
+  if (k >= D.nvpt) return;
+  const int lane = threadIdx.x & 31;
+  const int s0 = D.vpt_s0[k], L = D.vpt_s1[k] - s0;
+  const double* I = D.Hpp_inv + 6 * (long long)k;
+  const double Hi[9] = {I[0], I[1], I[2], I[1], I[3], I[4], I[2], I[4], I[5]};
+  for (long long t = lane; t < (long long)L * L; t += 32) {
+    const int i = (int)(t / L), j = (int)(t - (long long)i * L);
+    float A0[DC], A1[DC], B0[DC], B1[DC];
+    int ia[DC], ib[DC];
+    ba_slot_rows<DC>(D, s0 + i, A0, A1, ia);
+    ba_slot_rows<DC>(D, s0 + j, B0, B1, ib);
+    double pa[6], pb[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { pa[c] = D.Jp[BA_JP(c, s0 + i)]; pb[c] = D.Jp[BA_JP(c, s0 + j)]; }
+    // G = Hinv W_j (3 x DC)
+    double G[3][DC];
+#pragma unroll
+    for (int c = 0; c < DC; ++c) {
+      const double w0 = pb[0] * B0[c] + pb[3] * B1[c], w1 = pb[1] * B0[c] + pb[4] * B1[c], w2 = pb[2] * B0[c] + pb[5] * B1[c];
+      G[0][c] = Hi[0] * w0 + Hi[1] * w1 + Hi[2] * w2;
+      G[1][c] = Hi[3] * w0 + Hi[4] * w1 + Hi[5] * w2;
+      G[2][c] = Hi[6] * w0 + Hi[7] * w1 + Hi[8] * w2;
+    }
+#pragma unroll
+    for (int r = 0; r < DC; ++r) {
+      if (ia[r] < 0) continue;
+      const double v0 = pa[0] * A0[r] + pa[3] * A1[r], v1 = pa[1] * A0[r] + pa[4] * A1[r], v2 = pa[2] * A0[r] + pa[5] * A1[r];
+#pragma unroll
+      for (int c = 0; c < DC; ++c)
+        if (ib[c] >= 0 && ia[r] >= ib[c]) atomicAdd(&D.Sd[(long long)ib[c] * D.nc + ia[r]], -(v0 * G[0][c] + v1 * G[1][c] + v2 * G[2][c]));
+    }
+  }
+}
+// S += D_c^2 on the diagonal, Cholesky S = L L^T in place (lower triangle, left-looking, one CTA), then L L^T x = rhs.
+// The matrix is symmetric, so "row i" is read as column i: consecutive threads touch consecutive addresses.
+#define BA_DENSE_T 1024
+// measured on B200 (tools/ba_small.py): nc = 80 (B1) and 64 (8-image local BA) are 2x / 3x faster than the PCG run to
+// 1e-12, nc = 450 (50 images, 80k observations) is 5.7x SLOWER (41M fp64 atomics per LM iteration) - so dense only below 256
+#define BA_DENSE_MAX 256
+__global__ void __launch_bounds__(BA_DENSE_T) ba_dense_solve_kernel(const BaDev D) {
+  __shared__ double s_d;
+  __shared__ int s_bad;
+  const int n = D.nc, tid = threadIdx.x;
+  double* S = D.Sd;
+  // element (i, j), i >= j, of the lower triangle lives at S[j * n + i]
+  if (tid == 0) s_bad = 0;
+  for (int i = tid; i < n; i += BA_DENSE_T) S[(long long)i * n + i] += D.Dc2[i];
+  __syncthreads();
+  for (int j = 0; j < n; ++j) {
+    // column j: L(i, j) = (S(i, j) - sum_{k < j} L(i, k) L(j, k)) / L(j, j), i = j .. n - 1
+    for (int i = j + tid; i < n; i += BA_DENSE_T) {
+      double acc = S[(long long)j * n + i];
+      for (int k = 0; k < j; ++k) acc -= S[(long long)k * n + i] * S[(long long)k * n + j];
+      S[(long long)j * n + i] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) { const double d = S[(long long)j * n + j]; if (!(d > 0.0)) { s_bad = 1; s_d = 1.0; } else s_d = sqrt(d); }
+    __syncthreads();
+    const double inv = 1.0 / s_d;
+    for (int i = j + tid; i < n; i += BA_DENSE_T) S[(long long)j * n + i] = (i == j) ? s_d : S[(long long)j * n + i] * inv;
+    __syncthreads();
+  }
+  if (s_bad) { if (tid == 0) D.ctl->fail = 1; return; }
+  // forward: L y = b (column-oriented), then backward: L^T x = y
+  double* x = D.x;
+  for (int i = tid; i < n; i += BA_DENSE_T) x[i] = D.rhs[i];
+  __syncthreads();
+  for (int j = 0; j < n; ++j) {
+    if (tid == 0) x[j] = x[j] / S[(long long)j * n + j];
+    __syncthreads();
+    const double xj = x[j];
+    for (int i = j + 1 + tid; i < n; i += BA_DENSE_T) x[i] -= S[(long long)j * n + i] * xj;
+    __syncthreads();
+  }
+  for (int j = n - 1; j >= 0; --j) {
+    // x_j = (y_j - sum_{i > j} L(i, j) x_i) / L(j, j): a dot product over column j
+    double acc = 0.0;
+    for (int i = j + 1 + tid; i < n; i += BA_DENSE_T) acc += S[(long long)j * n + i] * x[i];
+    __shared__ double red[33];
+    const double tot = ba_cta_allsum(acc, red);
+    if (tid == 0) x[j] = (x[j] - tot) / S[(long long)j * n + j];
+    __syncthreads();
+  }
+}
+
 // d_p = Hinv (-g_p - H_pc d_c); also the model cost change -(Jd)^T (r + Jd/2), one thread per slot block-wise
 template <int DC>
 __global__ void __launch_bounds__(BA_BLOCK) ba_backsub_model_kernel(const BaDev D, int blk0) {
@@ -1591,6 +1717,13 @@ static void ba_launch_spmv(const BaDev& D, cudaStream_t s) {
       else ba_cam_stream_kernel<DC, 1><<<grid, BA_BLOCK, 0, s>>>(D, D.q, 1);
     }
   }
+}
+template <int DC>
+static void ba_launch_dense(const BaDev& D, cudaStream_t s) {
+  cudaMemsetAsync(D.Sd, 0, sizeof(double) * (size_t)D.nc * D.nc, s);
+  ba_dense_gram_kernel<DC><<<D.nblocks, BA_BLOCK, 0, s>>>(D);
+  if (D.nvpt) ba_dense_schur_kernel<DC><<<(D.nvpt + BA_BLOCK / 32 - 1) / (BA_BLOCK / 32), BA_BLOCK, 0, s>>>(D);
+  ba_dense_solve_kernel<<<1, BA_DENSE_T, 0, s>>>(D);
 }
 template <int DC>
 static void ba_launch_backsub(const BaDev& D, cudaStream_t s) {
@@ -2275,6 +2408,12 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   BA_CUDA(pool.alloc(&D.gc, (size_t)nc)); BA_CUDA(pool.alloc(&D.diag_c, (size_t)nc)); BA_CUDA(pool.alloc(&D.Dc2, (size_t)nc)); BA_CUDA(pool.alloc(&D.rhs, (size_t)nc));
   BA_CUDA(pool.alloc(&D.Hbb, (size_t)pack)); BA_CUDA(pool.alloc(&D.Mbb, (size_t)pack)); BA_CUDA(pool.alloc(&D.Minv, (size_t)pack));
   BA_CUDA(pool.alloc(&D.x, (size_t)nc)); BA_CUDA(pool.alloc(&D.rr, (size_t)nc)); BA_CUDA(pool.alloc(&D.z, (size_t)nc)); BA_CUDA(pool.alloc(&D.p, (size_t)nc)); BA_CUDA(pool.alloc(&D.q, (size_t)nc));
+  const bool want_exact = (lst != B200BA_ITERATIVE_SCHUR);
+  // exact reduced solves: dense Cholesky of the explicit reduced camera matrix when it is small (camera-side dimension
+  // <= BA_DENSE_MAX: the local bundle adjustments of the mapper); larger exact requests run the PCG to a 1e-12 relative
+  // residual instead
+  const bool dense = want_exact && nc > 0 && nc <= BA_DENSE_MAX && !sharded && getenv("B200BA_NO_DENSE") == nullptr;
+  if (dense) BA_CUDA(pool.alloc(&D.Sd, (size_t)nc * nc));
   BA_CUDA(pool.alloc(&D.ctl, 1));
   int* d_fail = &D.ctl->fail;   // part of the control block: travels with the per-iteration read
   BA_CUDA(cudaMemsetAsync(D.ctl, 0, sizeof(BaCtl), st));
@@ -2369,7 +2508,11 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
       // PCG
       BA_CUDA(cudaMemsetAsync(D.ctl, 0, offsetof(BaCtl, iters_total), st));  // keeps iters_total
       BA_CUDA(cudaMemcpyAsync(&D.ctl->cost, &cost, sizeof(double), cudaMemcpyHostToDevice, st));
-      if (nc) {
+      if (nc && dense) {
+        BA_DISPATCH_DC(ba_launch_dense, D, st);
+        launches += 3;
+        if (check_gmax) BA_CUDA(read_ctl());
+      } else if (nc) {
         ba_pcg_init_kernel<<<gc_blocks, 256, 0, st>>>(D);
         ++launches;
         int issued = 0;

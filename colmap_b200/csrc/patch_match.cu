@@ -95,10 +95,12 @@ __device__ __forceinline__ void pm_frame_to_orig(int W0, int H0, int rot, int r,
     default: *r0 = H0 - 1 - c; *c0 = r; break;
   }
 }
+// The four frame maps are affine in (r, c): pixel index = base + r * stride_r + c * stride_c (two IMADs, no branch)
 __device__ __forceinline__ size_t pm_pix0(int W0, int H0, int rot, int r, int c) {
-  int r0, c0;
-  pm_frame_to_orig(W0, H0, rot, r, c, &r0, &c0);
-  return (size_t)r0 * W0 + c0;
+  const int sr = (rot == 0) ? W0 : ((rot == 1) ? -1 : ((rot == 2) ? -W0 : 1));
+  const int sc = (rot == 0) ? 1 : ((rot == 1) ? W0 : ((rot == 2) ? -1 : -W0));
+  const int base = (rot == 0) ? 0 : ((rot == 1) ? (W0 - 1) : ((rot == 2) ? (H0 * W0 - 1) : ((H0 - 1) * W0)));
+  return (size_t)(base + r * sr + c * sc);
 }
 // RotateNormalMap applied k times / undone (patch_match_cuda.cu:849-861)
 __device__ __forceinline__ void pm_normal_to_frame(int rot, float& nx, float& ny) {
@@ -126,9 +128,20 @@ __host__ __device__ __forceinline__ int pm_border_index(int W0, int H0, int r0, 
   if (c0 == 0) return 2 * W0 + (r0 - 1);
   return 2 * W0 + (H0 - 2) + (r0 - 1);
 }
+// (float)v / 255.0f for v = 0..255, IEEE division done once on the host: the same bits as the division it replaces
+__constant__ float pm_lut255[256];
+static void pm_upload_lut() {
+  static thread_local int done_dev = -1;
+  int dev = 0; cudaGetDevice(&dev);
+  if (done_dev == dev) return;
+  float h[256];
+  for (int i = 0; i < 256; ++i) { volatile float a = (float)i, b = 255.0f; h[i] = a / b; }
+  cudaMemcpyToSymbol(pm_lut255, h, sizeof(h));
+  done_dev = dev;
+}
 __device__ __forceinline__ float pm_ref_color(const PmParams& P, int rot, int fw, int fh, int r, int c) {
   if (r < 0 || c < 0 || r >= fh || c >= fw) return 0.0f;
-  return (float)P.ref_img[pm_pix0(P.W0, P.H0, rot, r, c)] / 255.0f;
+  return pm_lut255[P.ref_img[pm_pix0(P.W0, P.H0, rot, r, c)]];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -241,6 +254,57 @@ __device__ __forceinline__ float pm_ncc_group(const float4* __restrict__ patch, 
     s3 = s3 + __shfl_xor_sync(gmask, s3, o);
   }
   return pm_ncc_finalize(s1, s2, s3, inv_wsum, rsum, rsq);
+}
+
+
+// TransformPDFToCDF (:683-696) over the per-image lanes: sum in image order, then the running sum of prob / sum.
+// For N <= 8 the N values are fetched once and both passes run on registers (lanes >= N hold prob = 0: adding +0.0
+// changes nothing, so the loops can run over all 8 slots); same operations in the same order as the plain loops.
+__device__ __forceinline__ float pm_cdf_lanes(float prob, int N, int lane) {
+  const unsigned full = 0xffffffffu;
+  float cdf = 0.0f;
+  if (N <= 8) {
+    float pv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pv[i] = __shfl_sync(full, prob, i);
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += pv[i];
+    const float inv = 1.0f / sum;
+    float cum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < N) { cum += pv[i] * inv; if (lane == i) cdf = cum; }
+    }
+  } else {
+    float sum = 0.0f;
+    for (int i = 0; i < N; ++i) sum += __shfl_sync(full, prob, i);
+    const float inv = 1.0f / sum;
+    float cum = 0.0f;
+    for (int i = 0; i < N; ++i) {
+      cum += __shfl_sync(full, prob, i) * inv;
+      if (lane == i) cdf = cum;
+    }
+  }
+  return cdf;
+}
+// index of the first image whose CDF value exceeds u (-1: none), per lane
+__device__ __forceinline__ int pm_sample_image(float cdf, float u, int N) {
+  const unsigned full = 0xffffffffu;
+  int img = -1;
+  if (N <= 8) {
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+      const float ci = __shfl_sync(full, cdf, i);
+      if (i < N && ci > u) img = i;     // descending i: the smallest qualifying index wins
+    }
+  } else {
+    for (int i = 0; i < N; ++i) {
+      const float ci = __shfl_sync(full, cdf, i);
+      if (img < 0 && ci > u) img = i;
+    }
+  }
+  return img;
 }
 
 // reference patch of one pixel: bilateral weights + weighted colours + 1/sum(w); executed by one warp.
@@ -735,20 +799,9 @@ __global__ void __launch_bounds__(128, MINB) pm_pixel_kernel(const PmParams P, c
     bool act0 = true, act1 = true, act2 = true, ext0 = true, ext1 = true, ext2 = true;
     float thr = 3.0e38f;
     if (mode == 1) {
-      float sum = 0.0f;
-      for (int i = 0; i < N; ++i) sum += __shfl_sync(full, prob, i);
-      const float inv = 1.0f / sum;
-      float cum = 0.0f, cdf = 0.0f;
-      for (int i = 0; i < N; ++i) {
-        cum += __shfl_sync(full, prob, i) * inv;
-        if (lane == i) cdf = cum;
-      }
+      const float cdf = pm_cdf_lanes(prob, N, lane);
       const float u = (lane < nsl) ? A.usamp[p * ns + lane] : 2.0f;
-      int img = -1;
-      for (int i = 0; i < N; ++i) {
-        const float ci = __shfl_sync(full, cdf, i);
-        if (img < 0 && ci > u) img = i;
-      }
+      const int img = pm_sample_image(cdf, u, N);
       mult = 0;
       for (int s2 = 0; s2 < nsl; ++s2) mult += (__shfl_sync(full, img, s2) == lane) ? 1 : 0;
       if (lane >= N) mult = 0;
@@ -830,6 +883,7 @@ __global__ void __launch_bounds__(32 * WPC, MINB) pm_serial_kernel(const PmParam
   float* tab1 = poses + N * PM_POSE_STRIDE;  // [32] NCC of the propagated hypothesis per image
   float* hyp1 = tab1 + 32;                   // depth, normal of the propagated hypothesis
   float* fctl2 = hyp1 + 4;                   // [2][4] inv_wsum, ref_sum, ref_sqsum
+  float* accb = fctl2 + 8;                   // [8][33] per-sample costs of the five hypotheses (+ three geometric costs)
   for (int i = threadIdx.x; i < N * PM_POSE_STRIDE; i += blockDim.x) poses[i] = P.poses[(size_t)rot * N * PM_POSE_STRIDE + i];
   pm_fill_tap_offsets(P, patch2, threadIdx.x, blockDim.x);
   pm_fill_tap_offsets(P, patch2 + P.ntaps_pad, threadIdx.x, blockDim.x);
@@ -907,14 +961,7 @@ __global__ void __launch_bounds__(32 * WPC, MINB) pm_serial_kernel(const PmParam
         c2 = nx_c2; c3 = nx_c3; c4 = nx_c4;
         if (GEOM) { g_cur = nx_gc; g_rand = nx_gr; }
       }
-      float sum = 0.0f;
-      for (int i = 0; i < N; ++i) sum += __shfl_sync(full, prob, i);
-      const float inv = 1.0f / sum;
-      float cum = 0.0f;
-      for (int i = 0; i < N; ++i) {
-        cum += __shfl_sync(full, prob, i) * inv;
-        if (lane == i) cdf = cum;
-      }
+      cdf = pm_cdf_lanes(prob, N, lane);
       if (lane == 0) { hyp1[0] = prev_d; hyp1[1] = prev_n0; hyp1[2] = prev_n1; hyp1[3] = prev_n2; }
     }
     __syncthreads();  // #1: patch + propagated hypothesis visible
@@ -974,16 +1021,12 @@ __global__ void __launch_bounds__(32 * WPC, MINB) pm_serial_kernel(const PmParam
       float a0, a1, a2, a3, a4;
       unsigned out_mask = 0u;   // bit k: hypothesis k is excluded (lower bound > a0)
       for (int attempt = 0;; ++attempt) {
-        a0 = a1 = a2 = a3 = a4 = 0.0f;
+        float acc = 0.0f;
         unsigned sampled = 0u;
         for (int base = 0; base < ns; base += 32) {
           const int sidx = base + lane;
           const float u = (base == 0) ? u_first : ((sidx < ns) ? A.usamp[p * ns + sidx] : 2.0f);
-          int img = -1;
-          for (int i = 0; i < N; ++i) {
-            const float ci = __shfl_sync(full, cdf, i);
-            if (img < 0 && ci > u) img = i;
-          }
+          const int img = pm_sample_image(cdf, u, N);
           const int src = img < 0 ? 0 : img;
           float v0 = __shfl_sync(full, cost_i, src), v1 = __shfl_sync(full, c1, src),
                 v2 = __shfl_sync(full, c2, src), v3 = __shfl_sync(full, c3, src),
@@ -992,20 +1035,25 @@ __global__ void __launch_bounds__(32 * WPC, MINB) pm_serial_kernel(const PmParam
           if (GEOM) { gcv = __shfl_sync(full, g_cur, src); gpv = __shfl_sync(full, g_prev, src); grv = __shfl_sync(full, g_rand, src); }
           if (img < 0) { v0 = v1 = v2 = v3 = v4 = 0.0f; gcv = gpv = grv = 0.0f; }
           v2 = fmaxf(v2, 0.0f); v3 = fmaxf(v3, 0.0f); v4 = fmaxf(v4, 0.0f);   // PM_NOT_EVALUATED -> 0
-          if (attempt == 0) {
-            for (int i = 0; i < N; ++i) if (__ballot_sync(full, img == i)) sampled |= 1u << i;
-          }
+          if (attempt == 0) sampled |= __reduce_or_sync(full, img < 0 ? 0u : (1u << img));
+          // transpose through shared memory: lane k (k = 0..4) then adds the samples of hypothesis k in sample order
+          // (15 LDS + 15 FADD on five lanes at once instead of 75 shuffles + 75 adds on the whole warp)
+          accb[0 * 33 + lane] = v0; accb[1 * 33 + lane] = v1; accb[2 * 33 + lane] = v2; accb[3 * 33 + lane] = v3; accb[4 * 33 + lane] = v4;
+          if (GEOM) { accb[5 * 33 + lane] = gcv; accb[6 * 33 + lane] = gpv; accb[7 * 33 + lane] = grv; }
+          __syncwarp();
           const int cnt = min(32, ns - base);
-          for (int j = 0; j < cnt; ++j) {
-            a0 += __shfl_sync(full, v0, j); a1 += __shfl_sync(full, v1, j); a2 += __shfl_sync(full, v2, j);
-            a3 += __shfl_sync(full, v3, j); a4 += __shfl_sync(full, v4, j);
-            if (GEOM) {
-              const float gc = __shfl_sync(full, gcv, j), gp = __shfl_sync(full, gpv, j), gr = __shfl_sync(full, grv, j);
-              a0 = fmaf(P.geom_reg, gc, a0); a1 = fmaf(P.geom_reg, gp, a1); a2 = fmaf(P.geom_reg, gr, a2);
-              a3 = fmaf(P.geom_reg, gc, a3); a4 = fmaf(P.geom_reg, gr, a4);
+          if (lane < 5) {
+            const float* vk = accb + lane * 33;
+            const float* gk = accb + ((lane == 1) ? 6 : ((lane == 2 || lane == 4) ? 7 : 5)) * 33;   // cur, prev, rand, cur, rand (:1117-1126)
+            for (int j = 0; j < cnt; ++j) {
+              acc += vk[j];
+              if (GEOM) acc = fmaf(P.geom_reg, gk[j], acc);
             }
           }
+          __syncwarp();
         }
+        a0 = __shfl_sync(full, acc, 0); a1 = __shfl_sync(full, acc, 1); a2 = __shfl_sync(full, acc, 2);
+        a3 = __shfl_sync(full, acc, 3); a4 = __shfl_sync(full, acc, 4);
         if (attempt != 0) break;
         // which sampled entries are missing?
         const unsigned in_s = img_lane && ((sampled >> lane) & 1u);
@@ -1245,6 +1293,7 @@ void b200pm_options_init(b200pm_options* o) {
 }
 
 const char* b200pm_last_error(void) { return g_pm_error.c_str(); }
+void b200pm_internal_set_error(const char* msg) { g_pm_error = msg ? msg : ""; }   // pm_workspace.cu reports through the same channel
 
 int b200pm_check(const b200pm_options* o, const b200pm_problem* p) {
   if (!o || !p) return pm_fail(-1, "null options/problem");
@@ -1301,6 +1350,7 @@ int b200pm_create(const b200pm_options* o, const b200pm_problem* p, b200pm_handl
     cudaGetDevice(&c->device);
   }
   PM_CUDA(cudaSetDevice(c->device));
+  pm_upload_lut();
   PM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 4; ++i) PM_CUDA(cudaEventCreate(&c->ev[i]));
   PM_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
@@ -1394,6 +1444,7 @@ int b200pm_create(const b200pm_options* o, const b200pm_problem* p, b200pm_handl
   P.init_depth = d_init_depth; P.init_normal = d_init_normal;
 
   cudaStream_t s = c->stream;
+  const cudaMemcpyKind map_kind = p->maps_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   PM_CUDA(cudaMemcpyAsync(d_ref_raw, p->ref_gray, n, cudaMemcpyHostToDevice, s));
   PM_CUDA(cudaMemcpyAsync(d_poses, poses.data(), poses.size() * sizeof(float), cudaMemcpyHostToDevice, s));
   PM_CUDA(cudaMemcpyAsync(d_src, descs.data(), sizeof(PmSrcDesc) * N, cudaMemcpyHostToDevice, s));
@@ -1403,11 +1454,11 @@ int b200pm_create(const b200pm_options* o, const b200pm_problem* p, b200pm_handl
     dim3 blk(32, 8), grd((descs[i].w + 4 + 31) / 32, (descs[i].h + 4 + 7) / 8);
     pm_pack_quads_kernel<<<grd, blk, 0, s>>>(d_raw, descs[i].w, descs[i].h, descs[i].pitch, d_quads + descs[i].quad_off);
     if (P.geom)
-      PM_CUDA(cudaMemcpyAsync(d_src_depth + descs[i].depth_off, p->src_depth[i], bytes * sizeof(float), cudaMemcpyHostToDevice, s));
+      PM_CUDA(cudaMemcpyAsync(d_src_depth + descs[i].depth_off, p->src_depth[i], bytes * sizeof(float), map_kind, s));
   }
   if (P.geom) {
-    PM_CUDA(cudaMemcpyAsync(d_init_depth, p->ref_depth_init, n * sizeof(float), cudaMemcpyHostToDevice, s));
-    PM_CUDA(cudaMemcpyAsync(d_init_normal, p->ref_normal_init, 3 * n * sizeof(float), cudaMemcpyHostToDevice, s));
+    PM_CUDA(cudaMemcpyAsync(d_init_depth, p->ref_depth_init, n * sizeof(float), map_kind, s));
+    PM_CUDA(cudaMemcpyAsync(d_init_normal, p->ref_normal_init, 3 * n * sizeof(float), map_kind, s));
   }
   {
     dim3 blk(32, 8), grd((P.W0 + 31) / 32, (P.H0 + 7) / 8);
@@ -1417,7 +1468,7 @@ int b200pm_create(const b200pm_options* o, const b200pm_problem* p, b200pm_handl
   c->smem_sweep = sizeof(float4) * P.ntaps_pad + sizeof(float) * ((size_t)N * PM_POSE_STRIDE + 160 + 96 + 20 + 4) +
                   sizeof(int) * (4 + (size_t)P.num_samples);
   c->smem_init = sizeof(float4) * 4 * P.ntaps_pad + sizeof(float) * (size_t)N * PM_POSE_STRIDE;
-  c->smem_serial = sizeof(float4) * 2 * P.ntaps_pad + sizeof(float) * ((size_t)N * PM_POSE_STRIDE + 32 + 4 + 8);
+  c->smem_serial = sizeof(float4) * 2 * P.ntaps_pad + sizeof(float) * ((size_t)N * PM_POSE_STRIDE + 32 + 4 + 8 + 272);
   c->fused = getenv("B200PM_FUSED") != nullptr && atoi(getenv("B200PM_FUSED")) != 0;
   if (!c->fused) {
     PM_CUDA(pm_alloc(c, &c->rand_hyp, n));
@@ -1628,6 +1679,19 @@ static int pm_export(b200pm_handle c, float* depth, float* normal, float* sel, u
   return 0;
 }
 
+// device-to-device export: the maps never leave HBM (geometric phase of a workspace run)
+static int pm_export_device(b200pm_handle c, float* d_depth, float* d_normal) {
+  if (!c) return pm_fail(-1, "null handle");
+  if (!d_depth && !d_normal) return pm_fail(-1, "null device buffer");
+  PM_CUDA(cudaSetDevice(c->device));
+  const size_t n = (size_t)c->P.W0 * c->P.H0;
+  pm_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->P, c->sel[c->ran ? c->final_sel : 1], d_depth, d_normal, nullptr, nullptr);
+  PM_CUDA(cudaStreamSynchronize(c->stream));
+  PM_CUDA(cudaGetLastError());
+  return 0;
+}
+int b200pm_get_depth_device(b200pm_handle c, float* d_depth) { return pm_export_device(c, d_depth, nullptr); }
+int b200pm_get_normal_device(b200pm_handle c, float* d_normal) { return pm_export_device(c, nullptr, d_normal); }
 int b200pm_get_depth(b200pm_handle c, float* depth) { return pm_export(c, depth, nullptr, nullptr, nullptr); }
 int b200pm_get_normal(b200pm_handle c, float* normal) { return pm_export(c, nullptr, normal, nullptr, nullptr); }
 int b200pm_get_sel_prob(b200pm_handle c, float* sel) { return pm_export(c, nullptr, nullptr, sel, nullptr); }

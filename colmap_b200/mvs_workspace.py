@@ -564,3 +564,54 @@ class PatchMatchController:
         done += run_phase(self.options, mine)
         barrier()
         return done
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# b200pm_run_workspace: the controller in C++ (include/b200_patch_match.h), image decoding through a callback
+# ---------------------------------------------------------------------------------------------------------------------
+_LOAD_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+                            ctypes.POINTER(ctypes.POINTER(ctypes.c_uint8)))
+
+
+class _CWorkspace(ctypes.Structure):
+    _fields_ = [("workspace_path", ctypes.c_char_p), ("stereo_folder", ctypes.c_char_p), ("config_path", ctypes.c_char_p),
+                ("gpu_indices", ctypes.POINTER(ctypes.c_int)), ("num_gpu_indices", ctypes.c_int),
+                ("write_consistency_graph", ctypes.c_int), ("load_gray", _LOAD_FN), ("load_gray_user", ctypes.c_void_p),
+                ("rank", ctypes.c_int), ("world_size", ctypes.c_int), ("phase", ctypes.c_int)]
+
+
+def run_workspace(options: PatchMatchOptions, workspace_path: str, config_path: str = "", stereo_folder: str = "stereo",
+                  gpu_indices: Optional[Sequence[int]] = None, rank: int = 0, world: int = 1, phase: int = 0) -> int:
+    """PatchMatchController::Run in C++ (b200pm_run_workspace): reads the workspace, runs every problem on the GPU(s),
+    writes the map files, skips outputs that exist.  Images are decoded by PIL through the entry's callback - the place
+    where COLMAP's adapter calls Bitmap::Read.  Returns the number of problems processed."""
+    from ._lib import load_library
+    from .patch_match import _COptions
+    lib = load_library()
+    lib.b200pm_run_workspace.argtypes = [ctypes.POINTER(_COptions), ctypes.POINTER(_CWorkspace), ctypes.POINTER(ctypes.c_int)]
+    lib.b200pm_last_error.restype = ctypes.c_char_p
+    libc = ctypes.CDLL(None)
+    libc.malloc.restype = ctypes.c_void_p
+    libc.malloc.argtypes = [ctypes.c_size_t]
+
+    def load(_user, path, pw, ph, pdata):
+        try:
+            bm = _read_gray(path.decode(), options.max_image_size)
+        except Exception:
+            return -1
+        buf = libc.malloc(bm.size)                       # released by the library with free()
+        ctypes.memmove(buf, bm.ctypes.data, bm.size)
+        pw[0], ph[0] = int(bm.shape[1]), int(bm.shape[0])
+        pdata[0] = ctypes.cast(buf, ctypes.POINTER(ctypes.c_uint8))
+        return 0
+    cb = _LOAD_FN(load)
+    gi = list(gpu_indices) if gpu_indices is not None else []
+    arr = (ctypes.c_int * max(len(gi), 1))(*gi)
+    w = _CWorkspace(workspace_path.encode(), stereo_folder.encode(), config_path.encode() if config_path else None,
+                    arr if gi else None, len(gi), int(options.write_consistency_graph), cb, None, rank, world, phase)
+    co = options.to_c()
+    n = ctypes.c_int(0)
+    rc = lib.b200pm_run_workspace(ctypes.byref(co), ctypes.byref(w), ctypes.byref(n))
+    if rc != 0:
+        raise WorkspaceError(f"b200pm_run_workspace failed ({rc}): {lib.b200pm_last_error().decode()}")
+    return n.value

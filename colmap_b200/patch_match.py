@@ -56,6 +56,7 @@ class _CProblem(ctypes.Structure):
         ("src_depth", ctypes.POINTER(_f32p)),
         ("ref_depth_init", _f32p), ("ref_normal_init", _f32p),
         ("src_image_idxs", _i32p),
+        ("maps_on_device", ctypes.c_int),
     ]
 
 
@@ -137,8 +138,8 @@ class Problem:
     ref_image_idx: int = -1
     src_image_idxs: List[int] = field(default_factory=list)
     images: Optional[List[Image]] = None
-    depth_maps: Optional[List[np.ndarray]] = None    # (H, W) float32 each
-    normal_maps: Optional[List[np.ndarray]] = None   # (3, H, W) float32 each
+    depth_maps: Optional[List[np.ndarray]] = None    # (H, W) float32 each - numpy arrays, or CUDA torch tensors
+    normal_maps: Optional[List[np.ndarray]] = None   # (3, H, W) float32 each   (device-resident maps, see workspace.py)
 
 
 def marshal(options: PatchMatchOptions, problem: Problem):
@@ -172,13 +173,22 @@ def marshal(options: PatchMatchOptions, problem: Problem):
     cp.src_R = c_arr(np.stack([np.asarray(s.R, np.float32).reshape(9) for s in srcs]) if n else np.zeros(0), np.float32).ctypes.data_as(_f32p)
     cp.src_T = c_arr(np.stack([np.asarray(s.T, np.float32).reshape(3) for s in srcs]) if n else np.zeros(0), np.float32).ctypes.data_as(_f32p)
     if options.geom_consistency and problem.depth_maps is not None and problem.normal_maps is not None:
+        on_device = hasattr(problem.depth_maps[problem.ref_image_idx], "data_ptr")   # CUDA torch tensors: stay in HBM
+
+        def map_ptr(a):
+            if on_device:
+                assert a.is_cuda and a.is_contiguous() and str(a.dtype) == "torch.float32"
+                keep.append(a)
+                return ctypes.cast(ctypes.c_void_p(a.data_ptr()), _f32p)
+            return c_arr(a, np.float32).ctypes.data_as(_f32p)
         dptrs = (_f32p * max(n, 1))()
         for k, i in enumerate(problem.src_image_idxs):
-            dptrs[k] = c_arr(problem.depth_maps[i], np.float32).ctypes.data_as(_f32p)
+            dptrs[k] = map_ptr(problem.depth_maps[i])
         keep.append(dptrs)
         cp.src_depth = ctypes.cast(dptrs, ctypes.POINTER(_f32p))
-        cp.ref_depth_init = c_arr(problem.depth_maps[problem.ref_image_idx], np.float32).ctypes.data_as(_f32p)
-        cp.ref_normal_init = c_arr(problem.normal_maps[problem.ref_image_idx], np.float32).ctypes.data_as(_f32p)
+        cp.ref_depth_init = map_ptr(problem.depth_maps[problem.ref_image_idx])
+        cp.ref_normal_init = map_ptr(problem.normal_maps[problem.ref_image_idx])
+        cp.maps_on_device = 1 if on_device else 0
     cp.src_image_idxs = c_arr(problem.src_image_idxs, np.int32).ctypes.data_as(_i32p)
     co = options.to_c()
     if co.sigma_spatial <= 0:
@@ -205,6 +215,8 @@ def _bind(lib):
     lib.b200pm_get_depth.argtypes = [H, _f32p]
     lib.b200pm_get_normal.argtypes = [H, _f32p]
     lib.b200pm_get_sel_prob.argtypes = [H, _f32p]
+    lib.b200pm_get_depth_device.argtypes = [H, ctypes.c_void_p]
+    lib.b200pm_get_normal_device.argtypes = [H, ctypes.c_void_p]
     lib.b200pm_get_consistency.argtypes = [H, ctypes.POINTER(_i32p), ctypes.POINTER(ctypes.c_size_t)]
     lib.b200pm_get_consistency_mask.argtypes = [H, _u8p]
     lib.b200pm_free.argtypes = [ctypes.c_void_p]
@@ -295,6 +307,23 @@ class PatchMatch:
         rc = self._lib.b200pm_get_normal(self._h, out.ctypes.data_as(_f32p))
         if rc != 0:
             self._err("b200pm_get_normal", rc)
+        return out
+
+    def GetDepthMapDevice(self, out):
+        """Depth map into a CUDA torch tensor (H, W) float32 on the handle's GPU: no host copy."""
+        h, w, _ = self._dims
+        assert out.is_cuda and out.is_contiguous() and tuple(out.shape) == (h, w)
+        rc = self._lib.b200pm_get_depth_device(self._h, ctypes.c_void_p(out.data_ptr()))
+        if rc != 0:
+            self._err("b200pm_get_depth_device", rc)
+        return out
+
+    def GetNormalMapDevice(self, out):
+        h, w, _ = self._dims
+        assert out.is_cuda and out.is_contiguous() and tuple(out.shape) == (3, h, w)
+        rc = self._lib.b200pm_get_normal_device(self._h, ctypes.c_void_p(out.data_ptr()))
+        if rc != 0:
+            self._err("b200pm_get_normal_device", rc)
         return out
 
     def GetSelProbMap(self) -> np.ndarray:

@@ -128,6 +128,63 @@ def make_patch_match_scene(width=1920, height=1080, num_src=8, seed=0, with_gt_m
     return out
 
 
+def make_workspace_scene(width, height, num_images, seed=0, device=None):
+    """A workspace-shaped scene (BASELINE config C4): `num_images` views of one textured height field, cameras on a ring
+    (mutual triangulation angles of a few degrees), every view a reference image.  Rendered with torch on `device` when
+    given (4K frames take seconds per view in numpy).  Returns dict(images=[Image], depth_gt=[...], depth_min, depth_max,
+    centers)."""
+    rng = np.random.default_rng(seed)
+    hf = _HeightField(rng)
+    f = 0.9 * width
+    K = np.array([[f, 0, (width - 1) / 2.0], [0, f, (height - 1) / 2.0], [0, 0, 1]], np.float64)
+    tex = _Texture(rng, min_wavelength=5.0 * hf.z0 / f)
+    target = np.array([0.0, 0.0, hf.z0])
+    centers = []
+    for k in range(num_images):
+        ang = 2 * np.pi * k / num_images
+        rad = hf.z0 * np.tan(np.deg2rad(rng.uniform(4.0, 9.0)))
+        centers.append(np.array([rad * np.cos(ang), rad * np.sin(ang), rng.uniform(-0.15, 0.15)]))
+    images, depths = [], []
+    for c in centers:
+        R = _look_at_R(c, target + rng.uniform(-0.1, 0.1, 3) * np.array([1, 1, 0]))
+        T = -R @ c
+        if device is None:
+            img, d, _ = _render(hf, tex, K, R, T, width, height)
+        else:
+            img, d = _render_torch(hf, tex, K, R, T, width, height, device)
+        images.append(Image(bitmap=img, K=K.astype(np.float32), R=R.astype(np.float32), T=T.astype(np.float32)))
+        depths.append(d)
+    dmin, dmax = min(float(d.min()) for d in depths), max(float(d.max()) for d in depths)
+    return dict(images=images, depth_gt=depths, depth_min=0.75 * dmin, depth_max=1.25 * dmax, centers=np.stack(centers))
+
+
+def _render_torch(hf, tex, K, R, T, width, height, device, contrast=45.0):
+    """_render on a torch device (same ray / height-field intersection and texture; bench inputs, not bit-pinned)."""
+    import torch
+    C = -R.T @ T
+    dd = torch.float64
+    u = torch.arange(width, dtype=dd, device=device)[None, :].expand(height, width)
+    v = torch.arange(height, dtype=dd, device=device)[:, None].expand(height, width)
+    dcx = (u - K[0, 2]) / K[0, 0]
+    dcy = (v - K[1, 2]) / K[1, 1]
+    dx = R[0, 0] * dcx + R[1, 0] * dcy + R[2, 0]
+    dy = R[0, 1] * dcx + R[1, 1] * dcy + R[2, 1]
+    dz = R[0, 2] * dcx + R[1, 2] * dcy + R[2, 2]
+
+    def h(x, y):
+        return hf.z0 + hf.sx * x + hf.sy * y + hf.amp * torch.sin(hf.kx * x + hf.px) * torch.cos(hf.ky * y + hf.py)
+    t = (hf.z0 - C[2]) / dz
+    for _ in range(12):
+        t = (h(C[0] + t * dx, C[1] + t * dy) - C[2]) / dz
+    x = (C[0] + t * dx).to(torch.float32)
+    y = (C[1] + t * dy).to(torch.float32)
+    acc = torch.zeros_like(x)
+    for fx, fy, ph, a in zip(tex.fx, tex.fy, tex.ph, tex.amp):
+        acc += float(a) * torch.sin(float(fx) * x + float(fy) * y + float(ph))
+    img = torch.clamp(torch.round(128.0 + contrast * acc), 0, 255).to(torch.uint8)
+    return img.cpu().numpy(), t.to(torch.float32).cpu().numpy()
+
+
 # --------------------------------------------------------------------------------------------------
 # Bundle adjustment scenes (colmap::SynthesizeDataset / SynthesizeNoise semantics, tracks sampled directly)
 # --------------------------------------------------------------------------------------------------

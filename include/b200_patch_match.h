@@ -72,6 +72,11 @@ typedef struct b200pm_problem {
   const float* ref_depth_init;    /* H*W or NULL */
   const float* ref_normal_init;   /* 3*H*W slice-major or NULL */
   const int* src_image_idxs;      /* [num_src] global image ids reported by get_consistency; NULL -> 0..num_src-1 */
+  int maps_on_device;             /* 0: src_depth / ref_depth_init / ref_normal_init are host pointers (the reference's
+                                   * contract); 1: they are DEVICE pointers on the handle's GPU - the photometric maps
+                                   * stay in HBM between the two phases of a workspace run (b200pm_get_*_device on the
+                                   * producing handle, an NCCL all-gather between ranks) instead of the reference's
+                                   * round trip through `.photometric.bin` files (patch_match.cc:182-197) */
 } b200pm_problem;
 
 typedef struct b200pm_context* b200pm_handle;
@@ -108,6 +113,9 @@ float b200pm_last_pass_ms(b200pm_handle h, int which);
 int b200pm_get_depth(b200pm_handle h, float* depth);
 int b200pm_get_normal(b200pm_handle h, float* normal);
 int b200pm_get_sel_prob(b200pm_handle h, float* sel_prob);
+/* The same depth / normal maps written into DEVICE buffers of the caller (same layouts, the handle's GPU); no host copy. */
+int b200pm_get_depth_device(b200pm_handle h, float* d_depth);
+int b200pm_get_normal_device(b200pm_handle h, float* d_normal);
 
 /* PatchMatchCuda::GetConsistentImageIdxs (patch_match_cuda.cu:1367-1391): flat
  * int list [col,row,n,idx_1..idx_n]... ; *data is malloc'ed, release with
@@ -122,6 +130,32 @@ void b200pm_destroy(b200pm_handle h);
  * problem (a workspace run creates hundreds of them); this returns the cached blocks to the driver. */
 void b200_release_cached_memory(void);
 const char* b200pm_last_error(void);
+
+/* ---- workspace-level entry: PatchMatchController::Run (src/colmap/mvs/patch_match.cc:170-207,385-535) ------------------
+ * Reads <workspace>/sparse/{cameras,images,points3D}.bin (mvs::Model::ReadFromCOLMAP, model.cc:56-100), the problem list
+ * <workspace>/<stereo>/patch-match.cfg (ReadProblems :240-372), resolves depth ranges from the sparse points (:419-431),
+ * and for every problem writes <stereo>/{depth_maps,normal_maps,consistency_graphs}/<image>.<photometric|geometric>.bin.
+ * Outputs that already exist are skipped (:410-414).  With options.geom_consistency the photometric pass (no filter) runs
+ * for every problem first, then the geometric pass reads those maps back (:176-204).  One worker thread per entry of
+ * gpu_indices (list a device twice to keep two problems in flight on it, :375-384).
+ * Image decoding is the caller's (COLMAP's Bitmap::Read): load_gray returns a malloc'ed 8-bit grey bitmap; NULL selects
+ * the built-in binary PGM (P5) reader.  A bitmap whose size differs from the camera's rescales K (Image::Rescale,
+ * mvs/image.cc:66-95).  Multi-process runs (one process per GPU) pass rank / world_size - problems are dealt largest
+ * first - and run phase 1, a barrier of their own, then phase 2. */
+typedef int (*b200pm_load_gray_fn)(void* user, const char* path, int* width, int* height, uint8_t** data);
+typedef struct b200pm_workspace {
+  const char* workspace_path;
+  const char* stereo_folder;      /* NULL -> "stereo" */
+  const char* config_path;        /* NULL -> <workspace>/<stereo>/patch-match.cfg */
+  const int* gpu_indices;         /* NULL -> {options.gpu_index} */
+  int num_gpu_indices;
+  int write_consistency_graph;
+  b200pm_load_gray_fn load_gray;
+  void* load_gray_user;
+  int rank, world_size;           /* 0, 1 for a single process */
+  int phase;                      /* 0: everything; 1: photometric pass of a geometric run only; 2: final pass only */
+} b200pm_workspace;
+int b200pm_run_workspace(const b200pm_options* options, const b200pm_workspace* w, int* num_processed);
 
 #ifdef __cplusplus
 }

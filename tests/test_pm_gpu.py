@@ -282,3 +282,20 @@ def test_c2_full_size_statistical_parity_with_the_real_reference_cuda():
     assert (dd < 1e-4).mean() > 0.55          # north_star: within 1e-4 m where both converge
     assert (dd < 1e-3).mean() > 0.97
     assert np.median((ref["normal"] * got["normal"]).sum(0)[both]) > 0.9999
+
+
+def test_two_phase_with_device_resident_maps_equals_the_host_round_trip():
+    """SURVEY 8(e) geometric exchange: the photometric maps exported device-to-device (b200pm_get_*_device) and handed to
+    the geometric problems as device pointers (b200pm_problem::maps_on_device) give bit-identical results to the
+    reference's contract (host maps in, host maps out)."""
+    import torch
+    from colmap_b200.workspace import run_two_phase
+    sc = make_patch_match_scene(96, 72, 3, seed=6)
+    images = sc["images"]
+    srcs = [[j for j in range(4) if j != i] for i in range(4)]
+    o = PatchMatchOptions(depth_min=sc["depth_min"], depth_max=sc["depth_max"], num_iterations=1, gpu_index="0")
+    host = run_two_phase(images, srcs, o, 0, 1)
+    dev = run_two_phase(images, srcs, o, 0, 1, device=torch.device("cuda", 0))
+    for i in range(4):
+        assert np.array_equal(_bits(host[i][0]), _bits(dev[i][0])) and np.array_equal(_bits(host[i][1]), _bits(dev[i][1]))
+        assert (dev[i][0] > 0).mean() > 0.5
