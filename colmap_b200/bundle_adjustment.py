@@ -20,9 +20,11 @@ import numpy as np
 
 from ._lib import load_library
 
-SIMPLE_PINHOLE, PINHOLE, SIMPLE_RADIAL, RADIAL = 0, 1, 2, 3
-SIMPLE_RADIAL_FISHEYE, RADIAL_FISHEYE = 8, 9      # CameraModelId (sensor/models.h:90-109)
-MODEL_NUM_PARAMS = {0: 3, 1: 4, 2: 4, 3: 5, 8: 4, 9: 5}
+# CameraModelId (sensor/models.h:90-109)
+SIMPLE_PINHOLE, PINHOLE, SIMPLE_RADIAL, RADIAL, OPENCV, OPENCV_FISHEYE, FULL_OPENCV, FOV = 0, 1, 2, 3, 4, 5, 6, 7
+SIMPLE_RADIAL_FISHEYE, RADIAL_FISHEYE, THIN_PRISM_FISHEYE, RAD_TAN_THIN_PRISM_FISHEYE = 8, 9, 10, 11
+SIMPLE_DIVISION, DIVISION, SIMPLE_FISHEYE, FISHEYE, EUCM, EQUIRECTANGULAR = 12, 13, 14, 15, 16, 17
+MODEL_NUM_PARAMS = {0: 3, 1: 4, 2: 4, 3: 5, 4: 8, 5: 8, 6: 12, 7: 5, 8: 4, 9: 5, 10: 12, 11: 16, 12: 4, 13: 5, 14: 3, 15: 4, 16: 6, 17: 2}
 AUTO, DENSE_SCHUR, SPARSE_SCHUR, ITERATIVE_SCHUR = 0, 1, 2, 3
 TRIVIAL, SOFT_L1, CAUCHY, HUBER = 0, 1, 2, 3
 CONVERGENCE, NO_CONVERGENCE, FAILURE = 0, 1, 2
@@ -40,7 +42,7 @@ class _COptions(ctypes.Structure):
                 ("initial_trust_region_radius", ctypes.c_double), ("max_trust_region_radius", ctypes.c_double),
                 ("min_trust_region_radius", ctypes.c_double), ("min_relative_decrease", ctypes.c_double),
                 ("min_lm_diagonal", ctypes.c_double), ("max_lm_diagonal", ctypes.c_double), ("eta", ctypes.c_double),
-                ("jacobi_scaling", ctypes.c_int), ("gpu_index", ctypes.c_int)]
+                ("jacobi_scaling", ctypes.c_int), ("gpu_index", ctypes.c_int), ("refine_sensor_from_rig", ctypes.c_int)]
 
 
 _f64p = ctypes.POINTER(ctypes.c_double)
@@ -55,7 +57,9 @@ class _CProblem(ctypes.Structure):
                 ("camera_param_offset", _i32p), ("camera_params", _f64p), ("camera_constant", _u8p),
                 ("num_points", ctypes.c_int64), ("points", _f64p), ("point_constant", _u8p),
                 ("num_observations", ctypes.c_int64), ("obs_pose_idx", _i32p), ("obs_camera_idx", _i32p),
-                ("obs_point_idx", _i32p), ("obs_xy", _f64p), ("num_config_images", ctypes.c_int32)]
+                ("obs_point_idx", _i32p), ("obs_xy", _f64p), ("num_config_images", ctypes.c_int32),
+                ("num_sensors", ctypes.c_int32), ("sensor_from_rig", _f64p), ("sensor_constant", _u8p),
+                ("camera_sensor_idx", _i32p)]
 
 
 class _CSummary(ctypes.Structure):
@@ -99,7 +103,7 @@ class BundleAdjustmentOptions:
                          int(self.constant_rig_from_world_rotation), self.loss_function_type, self.loss_function_scale,
                          self.linear_solver_type, self.max_num_iterations, self.max_linear_solver_iterations,
                          self.function_tolerance, self.gradient_tolerance, self.parameter_tolerance,
-                         1e4, 1e16, 1e-32, 1e-3, 1e-6, 1e32, 0.1, 1, self.gpu_index)
+                         1e4, 1e16, 1e-32, 1e-3, 1e-6, 1e32, 0.1, 1, self.gpu_index, int(self.refine_sensor_from_rig))
 
 
 @dataclass
@@ -216,10 +220,22 @@ class FlatProblem:
         self.obs_point = c(obs_point, np.int32)
         self.obs_xy = c(obs_xy, np.float64).reshape(-1, 2)
         self.num_config_images = 0      # config.NumImages(); 0 = poses that appear in observations
+        # rigs: non-reference sensors (cam_from_world = sensor_from_rig * rig_from_world); empty for trivial frames
+        self.sensors = np.zeros((0, 7), np.float64)
+        self.sensor_constant = np.zeros(0, np.uint8)
+        self.cam_sensor = -np.ones(len(self.cam_model), np.int32)
+
+    def set_sensors(self, sensors, sensor_constant, cam_sensor):
+        c = np.ascontiguousarray
+        self.sensors = c(sensors, np.float64).reshape(-1, 7)
+        self.sensor_constant = c(sensor_constant, np.uint8)
+        self.cam_sensor = c(cam_sensor, np.int32)
+        return self
 
     def copy(self):
         f = self._copy()
         f.num_config_images = self.num_config_images
+        f.sensors, f.sensor_constant, f.cam_sensor = self.sensors.copy(), self.sensor_constant, self.cam_sensor
         return f
 
     def _copy(self):
@@ -242,6 +258,11 @@ class FlatProblem:
         p.obs_pose_idx = self.obs_pose.ctypes.data_as(_i32p); p.obs_camera_idx = self.obs_cam.ctypes.data_as(_i32p)
         p.obs_point_idx = self.obs_point.ctypes.data_as(_i32p); p.obs_xy = self.obs_xy.ctypes.data_as(_f64p)
         p.num_config_images = int(self.num_config_images)
+        p.num_sensors = len(self.sensors)
+        if len(self.sensors):
+            p.sensor_from_rig = self.sensors.ctypes.data_as(_f64p)
+            p.sensor_constant = self.sensor_constant.ctypes.data_as(_u8p)
+        p.camera_sensor_idx = self.cam_sensor.ctypes.data_as(_i32p)
         return p
 
 
@@ -295,6 +316,7 @@ def shard_flat_problem(flat: FlatProblem, rank: int, world: int) -> "FlatProblem
                         flat.obs_pose[sel], flat.obs_cam[sel], flat.obs_point[sel] - lo, flat.obs_xy[sel])
     local.point_ids = np.arange(lo, hi)
     local.num_config_images = flat.num_config_images or int(len(np.unique(flat.obs_pose)))
+    local.sensors, local.sensor_constant, local.cam_sensor = flat.sensors.copy(), flat.sensor_constant, flat.cam_sensor
     return local
 
 

@@ -34,7 +34,9 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
-#define BA_MAXDK 5
+#define BA_MAXDK 5      // variable intrinsics of the narrow (<= 5-parameter) models: hand-written Jacobians, DC <= 11 kernels
+#define BA_MAXP 16      // parameters of one camera (RAD_TAN_THIN_PRISM_FISHEYE)
+#define BA_MAXCB 22     // width of a camera-side "camera block": [sensor_from_rig tangent (6, rigs only) | variable intrinsics (<= 16)]
 #define BA_BLOCK 256
 #define BA_CHUNK 512
 #define BA_HD __host__ __device__ __forceinline__
@@ -47,13 +49,17 @@
 // ------------------------------------------------------------------------------------------------
 // camera models + reprojection (host/device so the CPU test tier can check them without a GPU)
 // ------------------------------------------------------------------------------------------------
-BA_HD int ba_model_num_params(int id) { return id == 0 ? 3 : (id == 1 ? 4 : (id == 2 ? 4 : (id == 3 ? 5 : (id == 8 ? 4 : (id == 9 ? 5 : -1))))); }
-BA_HD int ba_param_group(int id, int k) {  // 0 focal, 1 principal point, 2 extra (models.h:462-520)
-  switch (id) {
-    case 0: return k == 0 ? 0 : 1;
-    case 1: return k < 2 ? 0 : 1;
-    default: return k == 0 ? 0 : (k < 3 ? 1 : 2);
-  }
+BA_HD bool ba_model_is_narrow(int id) { return id == 0 || id == 1 || id == 2 || id == 3 || id == 8 || id == 9; }
+BA_HD int ba_model_num_params(int id) {
+  return id == 0 ? 3 : (id == 1 ? 4 : (id == 2 ? 4 : (id == 3 ? 5 : (id == 8 ? 4 : (id == 9 ? 5 : ba_wide_model_num_params(id))))));
+}
+// 0 focal, 1 principal point, 2 extra, 3 metadata (never refined) - the Initialize*Idxs of sensor/models.h:1206-2740: every
+// model is (f, cx, cy, extra...) or (fx, fy, cx, cy, extra...); EQUIRECTANGULAR's (width, height) are sensor metadata
+BA_HD int ba_param_group(int id, int k) {
+  if (id == 17) return 3;
+  const bool single = id == 0 || id == 2 || id == 3 || id == 8 || id == 9 || id == 12 || id == 14;
+  if (single) return k == 0 ? 0 : (k < 3 ? 1 : 2);
+  return k < 2 ? 0 : (k < 4 ? 1 : 2);
 }
 
 // ImgFromCamWithJac (sensor/models_jacobian.h:139-398); depth guard models.h:281-285.  Jp = d(x,y)/d(params) as two
@@ -226,9 +232,18 @@ struct BaDev {
   int loss_type; double loss_scale;
   // parameters (current / candidate)
   double *poses, *cams, *pts, *nposes_, *ncams_, *npts_;
+  // rigs + wide models: cam_from_world = sensor_from_rig * rig_from_world; a camera-side "camera block" is
+  // [sensor_from_rig tangent (cam_ns = 6 when variable) | variable intrinsics (cam_nvar)], one block per camera
+  int wide;                     // any camera model beyond the <= 5-parameter family, or any rig sensor: wide kernels + s_pack layout
+  int nsensors;
+  double *sensors, *nsensors_;  // [7*nsensors] current / candidate sensor_from_rig
+  const int *cam_sensor, *cam_ns, *sens_cam;   // [ncams] sensor index or -1; [ncams] 0 | 6; [nsensors] camera of the sensor
+  const int* cam_width;         // [ncams] cam_ns + cam_nvar: width of the camera block
+  const int* blk_split;         // [nblk] 6 where a camera block holds both a sensor and an intrinsics part (block-Jacobi keeps them apart)
+  const int4* chunks_off; int nchunks_off;   // sub-block pairs of camera blocks wider than 6 (see ba_build_cam_offdiag_kernel)
   // static per-block-variable maps
   const int *pose_off; const unsigned char* pose_mask;                 // [nposes]
-  const int *cam_model, *cam_poff, *cam_off, *cam_nvar; const signed char* cam_var;  // [ncams], cam_var [ncams*5]
+  const int *cam_model, *cam_poff, *cam_off, *cam_nvar; const signed char* cam_var;  // [ncams], cam_var [ncams*BA_MAXP]
   const int* pt_var;                                                    // [npts] -> variable index or -1
   const int* vpt_point;                                                 // [nvpt] -> global point index
   // slots (block-packed observations)
@@ -287,64 +302,93 @@ __device__ __forceinline__ double ba_block_sum(double v, double* sm) {
   return t;  // valid in thread 0
 }
 
-// Residual, robustified + Jacobi-scaled Jacobian rows of ONE observation, in registers.  Shared by the slot-ordered and
-// the camera-ordered linearisation passes: both evaluate the same expression tree on the same inputs, so the two fp32
-// copies of the camera-side Jacobian hold identical values (the PCG operator stays symmetric) without any scattered
-// store.  Returns 1/2 rho(|r|^2).
+// ImgFromCamWithJac of ANY of the eighteen models: the hand-written Jacobians of the <= 5-parameter family, forward-mode
+// dual numbers (ba_models.cuh) for the twelve others.  Jp: two rows of stride BA_MAXP.
+// (not inlined: the dual-number evaluation of eight parameter counts is compiled once, not once per kernel instantiation)
+__host__ __device__ __noinline__ bool ba_img_from_cam_any(int id, const double* q, double u, double v, double w, double* x, double* y, double* Jp,
+                               double* Juvw) {
+  if (ba_model_is_narrow(id)) {
+    double J5[10];
+    if (!ba_img_from_cam(id, q, u, v, w, x, y, J5, Juvw)) return false;
+    const int P = ba_model_num_params(id);
+    for (int k = 0; k < 5; ++k) if (k < P) { Jp[k] = J5[k]; Jp[BA_MAXP + k] = J5[5 + k]; }
+    return true;
+  }
+  double xy[2], Jw[2 * BA_MAXP];
+  bool ok = false;
+  int P = 0;
+  switch (ba_wide_model_num_params(id)) {
+    case 2: P = 2; ok = ba_project_wide_with_jac<2>(id, q, u, v, w, xy, Juvw, Jw); break;
+    case 3: P = 3; ok = ba_project_wide_with_jac<3>(id, q, u, v, w, xy, Juvw, Jw); break;
+    case 4: P = 4; ok = ba_project_wide_with_jac<4>(id, q, u, v, w, xy, Juvw, Jw); break;
+    case 5: P = 5; ok = ba_project_wide_with_jac<5>(id, q, u, v, w, xy, Juvw, Jw); break;
+    case 6: P = 6; ok = ba_project_wide_with_jac<6>(id, q, u, v, w, xy, Juvw, Jw); break;
+    case 8: P = 8; ok = ba_project_wide_with_jac<8>(id, q, u, v, w, xy, Juvw, Jw); break;
+    case 12: P = 12; ok = ba_project_wide_with_jac<12>(id, q, u, v, w, xy, Juvw, Jw); break;
+    case 16: P = 16; ok = ba_project_wide_with_jac<16>(id, q, u, v, w, xy, Juvw, Jw); break;
+    default: return false;
+  }
+  if (!ok) return false;
+  *x = xy[0]; *y = xy[1];
+  for (int k = 0; k < P; ++k) { Jp[k] = Jw[k]; Jp[BA_MAXP + k] = Jw[P + k]; }
+  return true;
+}
+// residual only, any model, trivial frame or rig sensor (sensor == nullptr: identity): the candidate-cost evaluation
+__host__ __device__ __noinline__ bool ba_residual_any(int id, const double* point, const double* rig, const double* sensor, const double* params,
+                           double ox, double oy, double* res) {
+  double pr[3], pc[3];
+  ba_quat_rotate_jac(rig, point, pr, nullptr);
+  pr[0] += rig[4]; pr[1] += rig[5]; pr[2] += rig[6];
+  if (sensor) { ba_quat_rotate_jac(sensor, pr, pc, nullptr); pc[0] += sensor[4]; pc[1] += sensor[5]; pc[2] += sensor[6]; }
+  else { pc[0] = pr[0]; pc[1] = pr[1]; pc[2] = pr[2]; }
+  double x = 0, y = 0;
+  bool ok;
+  if (ba_model_is_narrow(id)) { double J5[10], Juvw[6]; ok = ba_img_from_cam(id, params, pc[0], pc[1], pc[2], &x, &y, J5, Juvw); }
+  else { ok = ba_project_wide<double>(id, params, pc[0], pc[1], pc[2], &x, &y); }
+  if (!ok) { res[0] = res[1] = 0.0; return false; }
+  res[0] = x - ox; res[1] = y - oy;
+  return true;
+}
+// RigReprojErrorCostFunctor / ReprojErrorCostFunctor (reprojection_error.h:217-420) with analytic derivatives:
+// p_cam = R(q_s) (R(q_r) X + t_r) + t_s.  J_rig / J_sensor: 2x7 ambient; J_params: two rows of stride BA_MAXP.
+__host__ __device__ __noinline__ bool ba_reproj_rig(int id, const double* point, const double* rig, const double* sensor, const double* params, double ox,
+                         double oy, double* res, double* J_point, double* J_rig, double* J_sensor, double* J_params) {
+  double pr[3], Jqr[12], pc[3], Jqs[12], Rs[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Rr[9];
+  ba_quat_rotate_jac(rig, point, pr, Jqr);
+  pr[0] += rig[4]; pr[1] += rig[5]; pr[2] += rig[6];
+  if (sensor) {
+    ba_quat_rotate_jac(sensor, pr, pc, Jqs);
+    pc[0] += sensor[4]; pc[1] += sensor[5]; pc[2] += sensor[6];
+    ba_quat_to_R(sensor, Rs);
+  } else { pc[0] = pr[0]; pc[1] = pr[1]; pc[2] = pr[2]; }
+  double x, y, Juvw[6];
+  for (int k = 0; k < 2 * BA_MAXP; ++k) J_params[k] = 0.0;
+  if (!ba_img_from_cam_any(id, params, pc[0], pc[1], pc[2], &x, &y, J_params, Juvw)) {
+    res[0] = res[1] = 0.0;
+    for (int k = 0; k < 6; ++k) J_point[k] = 0.0;
+    for (int k = 0; k < 14; ++k) { J_rig[k] = 0.0; J_sensor[k] = 0.0; }
+    for (int k = 0; k < 2 * BA_MAXP; ++k) J_params[k] = 0.0;
+    return false;
+  }
+  res[0] = x - ox; res[1] = y - oy;
+  double A[6];   // d(x, y) / d(p_rig) = J_uvw R_s
+  for (int r = 0; r < 2; ++r) for (int c = 0; c < 3; ++c) A[3 * r + c] = Juvw[3 * r] * Rs[c] + Juvw[3 * r + 1] * Rs[3 + c] + Juvw[3 * r + 2] * Rs[6 + c];
+  ba_quat_to_R(rig, Rr);
+  for (int r = 0; r < 2; ++r) {
+    for (int c = 0; c < 3; ++c) J_point[3 * r + c] = A[3 * r] * Rr[c] + A[3 * r + 1] * Rr[3 + c] + A[3 * r + 2] * Rr[6 + c];
+    for (int c = 0; c < 4; ++c) J_rig[7 * r + c] = A[3 * r] * Jqr[c] + A[3 * r + 1] * Jqr[4 + c] + A[3 * r + 2] * Jqr[8 + c];
+    for (int c = 0; c < 3; ++c) J_rig[7 * r + 4 + c] = A[3 * r + c];
+    for (int c = 0; c < 4; ++c) J_sensor[7 * r + c] = sensor ? Juvw[3 * r] * Jqs[c] + Juvw[3 * r + 1] * Jqs[4 + c] + Juvw[3 * r + 2] * Jqs[8 + c] : 0.0;
+    for (int c = 0; c < 3; ++c) J_sensor[7 * r + 4 + c] = sensor ? Juvw[3 * r + c] : 0.0;
+  }
+  return true;
+}
+
+// Robust-loss corrector (ceres Corrector), Jacobi scaling and the scaled residual of ONE observation whose raw rows are
+// in registers: the common tail of the narrow and the wide linearisation.  co / nvc: offset and width of the camera block.
 template <int DC>
-__device__ __forceinline__ double ba_obs_linearize(const BaDev& D, const double* __restrict__ poses,
-                                                   const double* __restrict__ cams, const double* __restrict__ pts,
-                                                   int pi, int ci, int ti, int lp, double ox, double oy, int apply_scale,
-                                                   double* Jc, double* Jpt, double* rr) {
-  const int id = D.cam_model[ci];
-  double pose[7], pt[3], prm[5];
-#pragma unroll
-  for (int k = 0; k < 7; ++k) pose[k] = poses[7 * (long long)pi + k];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) pt[k] = pts[3 * (long long)ti + k];
-  const int P = ba_model_num_params(id);
-  const int poff = D.cam_poff[ci];
-#pragma unroll
-  for (int k = 0; k < 5; ++k) prm[k] = (k < P) ? cams[poff + k] : 0.0;
-  double res[2], Jps[14], Jpr[10];
-#pragma unroll
-  for (int k = 0; k < 10; ++k) Jpr[k] = 0.0;
-  ba_reproj(id, pt, pose, prm, ox, oy, res, Jpt, Jps, Jpr, 5);
-  const double sq = res[0] * res[0] + res[1] * res[1];
-  double rho[3];
-  ba_loss(D.loss_type, D.loss_scale, sq, rho);
-#pragma unroll
-  for (int k = 0; k < 2 * DC; ++k) Jc[k] = 0.0;
-  const int po = D.pose_off[pi], co = D.cam_off[ci], nv = D.cam_nvar[ci];
-  if (po >= 0) {
-    const unsigned m = D.pose_mask[pi];
-    const double PJ[12] = {pose[3], pose[2], -pose[1], -pose[2], pose[3], pose[0], pose[1], -pose[0], pose[3], -pose[0], -pose[1], -pose[2]};
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        double v = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v += Jps[7 * r + k] * PJ[3 * k + c];
-        Jc[DC * r + c] = ((m >> c) & 1u) ? v : 0.0;
-      }
-#pragma unroll
-      for (int c = 0; c < 3; ++c) Jc[DC * r + 3 + c] = ((m >> (3 + c)) & 1u) ? Jps[7 * r + 4 + c] : 0.0;
-    }
-  }
-  if (co >= 0) {
-#pragma unroll
-    for (int k = 0; k < DC - 6; ++k) {
-      if (k < nv) {
-        const int var = D.cam_var[5 * ci + k];
-        // pick the entry with selects so that the array stays in registers
-        double v0 = 0.0, v1 = 0.0;
-#pragma unroll
-        for (int j = 0; j < 5; ++j) if (j == var) { v0 = Jpr[j]; v1 = Jpr[5 + j]; }
-        Jc[6 + k] = v0; Jc[DC + 6 + k] = v1;
-      }
-    }
-  }
+__device__ __forceinline__ void ba_obs_finish(const BaDev& D, const double* res, const double* rho, double sq, int po, int co,
+                                              int nvc, int lp, int apply_scale, double* Jc, double* Jpt, double* rr) {
   if (lp < 0) {
 #pragma unroll
     for (int k = 0; k < 6; ++k) Jpt[k] = 0.0;
@@ -380,7 +424,7 @@ __device__ __forceinline__ double ba_obs_linearize(const BaDev& D, const double*
     }
     if (co >= 0) {
 #pragma unroll
-      for (int c = 0; c < DC - 6; ++c) if (c < nv) { const double sc = D.scale_c[co + c]; Jc[6 + c] *= sc; Jc[DC + 6 + c] *= sc; }
+      for (int c = 0; c < DC - 6; ++c) if (c < nvc) { const double sc = D.scale_c[co + c]; Jc[6 + c] *= sc; Jc[DC + 6 + c] *= sc; }
     }
     if (lp >= 0) {
 #pragma unroll
@@ -388,20 +432,117 @@ __device__ __forceinline__ double ba_obs_linearize(const BaDev& D, const double*
     }
   }
   rr[0] = rs * res[0]; rr[1] = rs * res[1];
+}
+
+// Residual, robustified + Jacobi-scaled Jacobian rows of ONE observation, in registers.  Shared by the slot-ordered and
+// the camera-ordered linearisation passes: both evaluate the same expression tree on the same inputs, so the two fp32
+// copies of the camera-side Jacobian hold identical values (the PCG operator stays symmetric) without any scattered
+// store.  Returns 1/2 rho(|r|^2).  WIDE = false: trivial frames and the <= 5-parameter models (the tuned path);
+// WIDE = true: any of the eighteen models, rig sensors.
+template <int DC, bool WIDE>
+__device__ __forceinline__ double ba_obs_linearize(const BaDev& D, const double* __restrict__ poses,
+                                                   const double* __restrict__ cams, const double* __restrict__ pts,
+                                                   int pi, int ci, int ti, int lp, double ox, double oy, int apply_scale,
+                                                   double* Jc, double* Jpt, double* rr) {
+  const int id = D.cam_model[ci];
+  double pose[7], pt[3];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) pose[k] = poses[7 * (long long)pi + k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) pt[k] = pts[3 * (long long)ti + k];
+  const int P = ba_model_num_params(id);
+  const int poff = D.cam_poff[ci];
+  const int po = D.pose_off[pi], co = D.cam_off[ci], nv = D.cam_nvar[ci];
+  double res[2], rho[3], sq;
+#pragma unroll
+  for (int k = 0; k < 2 * DC; ++k) Jc[k] = 0.0;
+  if (!WIDE) {
+    double prm[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) prm[k] = (k < P) ? cams[poff + k] : 0.0;
+    double Jps[14], Jpr[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) Jpr[k] = 0.0;
+    ba_reproj(id, pt, pose, prm, ox, oy, res, Jpt, Jps, Jpr, 5);
+    sq = res[0] * res[0] + res[1] * res[1];
+    ba_loss(D.loss_type, D.loss_scale, sq, rho);
+    if (po >= 0) {
+      const unsigned m = D.pose_mask[pi];
+      const double PJ[12] = {pose[3], pose[2], -pose[1], -pose[2], pose[3], pose[0], pose[1], -pose[0], pose[3], -pose[0], -pose[1], -pose[2]};
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          double v = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v += Jps[7 * r + k] * PJ[3 * k + c];
+          Jc[DC * r + c] = ((m >> c) & 1u) ? v : 0.0;
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Jc[DC * r + 3 + c] = ((m >> (3 + c)) & 1u) ? Jps[7 * r + 4 + c] : 0.0;
+      }
+    }
+    if (co >= 0) {
+#pragma unroll
+      for (int k = 0; k < DC - 6; ++k) {
+        if (k < nv) {
+          const int var = D.cam_var[BA_MAXP * ci + k];
+          // pick the entry with selects so that the array stays in registers
+          double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+          for (int j = 0; j < 5; ++j) if (j == var) { v0 = Jpr[j]; v1 = Jpr[5 + j]; }
+          Jc[6 + k] = v0; Jc[DC + 6 + k] = v1;
+        }
+      }
+    }
+    ba_obs_finish<DC>(D, res, rho, sq, po, co, nv, lp, apply_scale, Jc, Jpt, rr);
+  } else {
+    double prm[BA_MAXP], sens[7];
+    for (int k = 0; k < BA_MAXP; ++k) prm[k] = (k < P) ? cams[poff + k] : 0.0;
+    const int si = D.cam_sensor[ci], ns = D.cam_ns[ci];
+    if (si >= 0) for (int k = 0; k < 7; ++k) sens[k] = D.sensors[7 * (long long)si + k];
+    double Jrig[14], Jsen[14], Jprm[2 * BA_MAXP];
+    ba_reproj_rig(id, pt, pose, si >= 0 ? sens : nullptr, prm, ox, oy, res, Jpt, Jrig, Jsen, Jprm);
+    sq = res[0] * res[0] + res[1] * res[1];
+    ba_loss(D.loss_type, D.loss_scale, sq, rho);
+    for (int blk = 0; blk < 2; ++blk) {   // rig_from_world, then sensor_from_rig: quaternion (x) R^3 tangent
+      const bool on = blk == 0 ? (po >= 0) : (co >= 0 && ns == 6);
+      if (!on) continue;
+      const double* q = blk == 0 ? pose : sens;
+      const double* Ja = blk == 0 ? Jrig : Jsen;
+      const unsigned m = blk == 0 ? D.pose_mask[pi] : 0x3fu;
+      const int jo = blk == 0 ? 0 : 6;
+      const double PJ[12] = {q[3], q[2], -q[1], -q[2], q[3], q[0], q[1], -q[0], q[3], -q[0], -q[1], -q[2]};
+      for (int r = 0; r < 2; ++r) {
+        for (int c = 0; c < 3; ++c) {
+          double v = 0;
+          for (int k = 0; k < 4; ++k) v += Ja[7 * r + k] * PJ[3 * k + c];
+          Jc[DC * r + jo + c] = ((m >> c) & 1u) ? v : 0.0;
+        }
+        for (int c = 0; c < 3; ++c) Jc[DC * r + jo + 3 + c] = ((m >> (3 + c)) & 1u) ? Ja[7 * r + 4 + c] : 0.0;
+      }
+    }
+    if (co >= 0)
+      for (int k = 0; k < nv; ++k) {
+        const int var = D.cam_var[BA_MAXP * ci + k];
+        if (6 + ns + k < DC) { Jc[6 + ns + k] = Jprm[var]; Jc[DC + 6 + ns + k] = Jprm[BA_MAXP + var]; }
+      }
+    ba_obs_finish<DC>(D, res, rho, sq, po, co, ns + nv, lp, apply_scale, Jc, Jpt, rr);
+  }
   return 0.5 * rho[0];
 }
 
 // Linearisation, pass 1 (slot order = track order): scaled Jacobians Jc / Jp (fp32), residual, per-slot cost.
 // (two CTAs per SM: the register cap of 128 matters - at 130 the occupancy halves)
-template <int DC>
-__global__ void __launch_bounds__(BA_BLOCK, 2) ba_linearize_slot_kernel(const BaDev D, int apply_scale, double* cost_out) {
+template <int DC, bool WIDE>
+__global__ void __launch_bounds__(BA_BLOCK, WIDE ? 1 : 2) ba_linearize_slot_kernel(const BaDev D, int apply_scale, double* cost_out) {
   __shared__ double sm[8];
   const long long s = (long long)blockIdx.x * BA_BLOCK + threadIdx.x;
   double cost = 0.0;
   const int pi = D.s_pose[s];
   double Jc[2 * DC], Jpt[6], rr[2] = {0.0, 0.0};
   if (pi >= 0) {
-    cost = ba_obs_linearize<DC>(D, D.poses, D.cams, D.pts, pi, D.s_cam[s], D.s_pt[s], D.s_lpt[s], D.s_xy[s],
+    cost = ba_obs_linearize<DC, WIDE>(D, D.poses, D.cams, D.pts, pi, D.s_cam[s], D.s_pt[s], D.s_lpt[s], D.s_xy[s],
                                 D.s_xy[D.nslots + s], apply_scale, Jc, Jpt, rr);
   } else {
 #pragma unroll
@@ -421,15 +562,15 @@ __global__ void __launch_bounds__(BA_BLOCK, 2) ba_linearize_slot_kernel(const Ba
 }
 // Linearisation, pass 2 (camera order): the same rows again, written as JcC / JpC / rC for the passes that reduce per
 // camera-side block.  Recomputing (one 24-byte point gather per observation) replaces 2*DC + 2 scattered stores.
-template <int DC>
-__global__ void __launch_bounds__(BA_BLOCK, 2) ba_linearize_cam_kernel(const BaDev D, int apply_scale) {
+template <int DC, bool WIDE>
+__global__ void __launch_bounds__(BA_BLOCK, WIDE ? 1 : 2) ba_linearize_cam_kernel(const BaDev D, int apply_scale) {
   const long long k = (long long)blockIdx.x * BA_BLOCK + threadIdx.x;
   const int run = D.c_run[k];
   if (run < 0) return;
   const int2 pc = D.runs_pc[run];
   const int2 tl = D.c_pack[k];
   double Jc[2 * DC], Jpt[6], rr[2];
-  ba_obs_linearize<DC>(D, D.poses, D.cams, D.pts, pc.x, pc.y, tl.x, tl.y, D.xyC[BA_U(0, k)], D.xyC[BA_U(1, k)], apply_scale,
+  ba_obs_linearize<DC, WIDE>(D, D.poses, D.cams, D.pts, pc.x, pc.y, tl.x, tl.y, D.xyC[BA_U(0, k)], D.xyC[BA_U(1, k)], apply_scale,
                        Jc, Jpt, rr);
 #pragma unroll
   for (int c = 0; c < 2 * DC; ++c) D.JcC[BA_JC(c, k)] = (float)Jc[c];
@@ -441,7 +582,8 @@ __global__ void __launch_bounds__(BA_BLOCK, 2) ba_linearize_cam_kernel(const BaD
 // cost of the candidate parameters + per-residual cost change (accurate near convergence)
 __global__ void __launch_bounds__(BA_BLOCK) ba_cost_kernel(const BaDev D, const double* __restrict__ poses,
                                                            const double* __restrict__ cams,
-                                                           const double* __restrict__ pts, double* cost_out) {
+                                                           const double* __restrict__ pts, const double* __restrict__ sensors,
+                                                           double* cost_out) {
   __shared__ double sm[8];
   const long long s = (long long)blockIdx.x * BA_BLOCK + threadIdx.x;
   double cost = 0.0, delta = 0.0;
@@ -449,13 +591,21 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_cost_kernel(const BaDev D, const 
   if (pi >= 0) {
     const int ci = D.s_cam[s], ti = D.s_pt[s];
     const int id = D.cam_model[ci];
-    double pose[7], pt[3], prm[5];
+    double pose[7], pt[3], res[2];
     for (int k = 0; k < 7; ++k) pose[k] = poses[7 * (long long)pi + k];
     for (int k = 0; k < 3; ++k) pt[k] = pts[3 * (long long)ti + k];
     const int P = ba_model_num_params(id);
-    for (int k = 0; k < P; ++k) prm[k] = cams[D.cam_poff[ci] + k];
-    double res[2];
-    ba_reproj(id, pt, pose, prm, D.s_xy[s], D.s_xy[D.nslots + s], res, nullptr, nullptr, nullptr);
+    if (!D.wide) {
+      double prm[5];
+      for (int k = 0; k < P; ++k) prm[k] = cams[D.cam_poff[ci] + k];
+      ba_reproj(id, pt, pose, prm, D.s_xy[s], D.s_xy[D.nslots + s], res, nullptr, nullptr, nullptr);
+    } else {
+      double prm[BA_MAXP], sens[7];
+      for (int k = 0; k < P; ++k) prm[k] = cams[D.cam_poff[ci] + k];
+      const int si = D.cam_sensor[ci];
+      if (si >= 0) for (int k = 0; k < 7; ++k) sens[k] = sensors[7 * (long long)si + k];
+      ba_residual_any(id, pt, pose, si >= 0 ? sens : nullptr, prm, D.s_xy[s], D.s_xy[D.nslots + s], res);
+    }
     double rho[3];
     ba_loss(D.loss_type, D.loss_scale, res[0] * res[0] + res[1] * res[1], rho);
     cost = 0.5 * rho[0];
@@ -473,7 +623,7 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_colnorm_kernel(const BaDev D) {
   const int pi = D.s_pose[s];
   if (pi < 0) return;
   const int ci = D.s_cam[s], DC = D.DC;
-  const int po = D.pose_off[pi], co = D.cam_off[ci], nv = D.cam_nvar[ci], lp = D.s_lpt[s];
+  const int po = D.pose_off[pi], co = D.cam_off[ci], nv = D.cam_width[ci], lp = D.s_lpt[s];
   if (po >= 0) for (int c = 0; c < 6; ++c) { const double a = D.Jc[BA_JC(c, s)], b = D.Jc[BA_JC((DC + c), s)]; atomicAdd(&D.scale_c[po + c], a * a + b * b); }
   if (co >= 0) for (int c = 0; c < nv; ++c) { const double a = D.Jc[BA_JC((6 + c), s)], b = D.Jc[BA_JC((DC + 6 + c), s)]; atomicAdd(&D.scale_c[co + c], a * a + b * b); }
   if (lp >= 0) for (int c = 0; c < 3; ++c) { const double a = D.Jp[BA_JP(c, s)], b = D.Jp[BA_JP((3 + c), s)]; atomicAdd(&D.scale_p[3 * (long long)lp + c], a * a + b * b); }
@@ -507,23 +657,41 @@ __global__ void ba_build_pt_kernel(const BaDev D) {
 }
 // || x - Plus(x, -g) ||_inf with the unscaled gradient g = g_scaled / scale
 __global__ void ba_gradmax_kernel(const BaDev D) {
+  // The three kinds of blocks (poses, cameras, points) occupy thread ranges padded to whole warps: every warp runs ONE of
+  // the branches.  (With the three branches inside one warp, ptxas 12.9 for sm_100a shares uniform registers between the
+  // divergent paths and the point lanes compute their address from a clobbered value: illegal address, seen on rigs.)
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long np32 = ((long long)D.nposes + 31) & ~31LL, nc32 = ((long long)D.ncams + 31) & ~31LL;
   double m = 0.0;
-  if (i < D.nposes) {
-    const int off = D.pose_off[i];
-    if (off >= 0) {
-      double d[3], qn[4];
-      for (int k = 0; k < 3; ++k) d[k] = -D.gc[off + k] / D.scale_c[off + k];
-      ba_quat_plus(D.poses + 7 * i, d, qn);
-      for (int k = 0; k < 4; ++k) m = fmax(m, fabs(qn[k] - D.poses[7 * i + k]));
-      for (int k = 3; k < 6; ++k) m = fmax(m, fabs(D.gc[off + k] / D.scale_c[off + k]));
+  if (i < np32) {
+    if (i < D.nposes) {
+      const int off = D.pose_off[i];
+      if (off >= 0) {
+        double d[3], qn[4];
+        for (int k = 0; k < 3; ++k) d[k] = -D.gc[off + k] / D.scale_c[off + k];
+        ba_quat_plus(D.poses + 7 * i, d, qn);
+        for (int k = 0; k < 4; ++k) m = fmax(m, fabs(qn[k] - D.poses[7 * i + k]));
+        for (int k = 3; k < 6; ++k) m = fmax(m, fabs(D.gc[off + k] / D.scale_c[off + k]));
+      }
     }
-  } else if (i < D.nposes + D.ncams) {
-    const int c = (int)(i - D.nposes), off = D.cam_off[c];
-    if (off >= 0) for (int k = 0; k < D.cam_nvar[c]; ++k) m = fmax(m, fabs(D.gc[off + k] / D.scale_c[off + k]));
-  } else if (i < (long long)D.nposes + D.ncams + 3LL * D.nvpt) {
-    const long long k = i - D.nposes - D.ncams;
-    m = fabs(D.gp[k] / D.scale_p[k]);
+  } else if (i < np32 + nc32) {
+    const int c = (int)(i - np32);
+    const int off = c < D.ncams ? D.cam_off[c] : -1;
+    if (off >= 0) {
+      int k0 = 0;
+      if (D.wide && D.cam_ns[c] == 6) {   // sensor_from_rig tangent: the quaternion part through Plus, like a pose
+        double d[3], qn[4];
+        const double* q = D.sensors + 7 * (long long)D.cam_sensor[c];
+        for (int k = 0; k < 3; ++k) d[k] = -D.gc[off + k] / D.scale_c[off + k];
+        ba_quat_plus(q, d, qn);
+        for (int k = 0; k < 4; ++k) m = fmax(m, fabs(qn[k] - q[k]));
+        k0 = 3;
+      }
+      for (int k = k0; k < D.cam_width[c]; ++k) m = fmax(m, fabs(D.gc[off + k] / D.scale_c[off + k]));
+    }
+  } else {
+    const long long k = i - np32 - nc32;
+    if (k < 3LL * D.nvpt) m = fabs(D.gp[k] / D.scale_p[k]);
   }
   for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0 && m > 0.0) {
@@ -539,8 +707,8 @@ __global__ void __launch_bounds__(BA_SC_BLOCK) ba_build_cam_sorted_kernel(const 
   const int chunk = blockIdx.x * (BA_SC_BLOCK / 32) + (threadIdx.x >> 5);
   if (chunk >= D.nchunks) return;
   const int lane = threadIdx.x & 31;
-  const int4 ch = D.chunks[chunk];
-  const int comp0 = ch.w & 0xff, n = ch.w >> 8;
+  const int4 ch = D.chunks[chunk];   // w = first column | width << 8 | first row inside the block << 16 | block width << 24
+  const int comp0 = ch.w & 0xff, n = (ch.w >> 8) & 0xff, lr0 = (ch.w >> 16) & 0xff, bw = (ch.w >> 24) & 0xff;
   double g[6] = {0, 0, 0, 0, 0, 0}, H[21];
 #pragma unroll
   for (int i = 0; i < 21; ++i) H[i] = 0.0;
@@ -591,7 +759,67 @@ __global__ void __launch_bounds__(BA_SC_BLOCK) ba_build_cam_sorted_kernel(const 
     for (int c = r; c < 6; ++c) {
       double t = H[idx++];
       for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if (lane == 0 && r < n && c < n) { atomicAdd(&Hb[r * n + c], t); if (c != r) atomicAdd(&Hb[c * n + r], t); }
+      if (lane == 0 && r < n && c < n) { atomicAdd(&Hb[(lr0 + r) * bw + lr0 + c], t); if (c != r) atomicAdd(&Hb[(lr0 + c) * bw + lr0 + r], t); }
+    }
+}
+
+// Camera blocks wider than six columns (wide intrinsics, sensor + intrinsics): the diagonal 6-ranges go through the
+// chunk kernels above / below, the pairs (A, B) of different 6-ranges through this one.  SCHUR = false: H_cc block
+// += J_A^T J_B; SCHUR = true: SCHUR_JACOBI block -= V_A^T Hinv V_B with V = J_p^T J_c.  One warp per pair chunk.
+template <bool SCHUR>
+__global__ void __launch_bounds__(BA_SC_BLOCK) ba_cam_offdiag_kernel(const BaDev D) {
+  const int chunk = blockIdx.x * (BA_SC_BLOCK / 32) + (threadIdx.x >> 5);
+  if (chunk >= D.nchunks_off) return;
+  const int lane = threadIdx.x & 31;
+  const int4 ch = D.chunks_off[chunk];   // {first obs, end obs, block offset, compA | nA << 8 | compB << 16 | nB << 24}
+  const int cA = ch.w & 0xff, nA = (ch.w >> 8) & 0xff, cB = (ch.w >> 16) & 0xff, nB = (ch.w >> 24) & 0xff;
+  const int blk = D.off2blk[ch.z], bw = D.blk_start[blk + 1] - D.blk_start[blk];
+  double G[36];
+#pragma unroll
+  for (int i = 0; i < 36; ++i) G[i] = 0.0;
+  for (int k = ch.x + lane; k < ch.y; k += 32) {
+    double a0[6], a1[6], b0[6], b1[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      a0[c] = (c < nA) ? (double)D.JcC[BA_JC(cA + c, k)] : 0.0; a1[c] = (c < nA) ? (double)D.JcC[BA_JC(D.DC + cA + c, k)] : 0.0;
+      b0[c] = (c < nB) ? (double)D.JcC[BA_JC(cB + c, k)] : 0.0; b1[c] = (c < nB) ? (double)D.JcC[BA_JC(D.DC + cB + c, k)] : 0.0;
+    }
+    if (!SCHUR) {
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) G[6 * r + c] += a0[r] * b0[c] + a1[r] * b1[c];
+    } else {
+      const int lp = D.c_pack[k].y;
+      if (lp < 0) continue;
+      const double* I = D.Hpp_inv + 6 * (long long)lp;
+      const double Hi[9] = {I[0], I[1], I[2], I[1], I[3], I[4], I[2], I[4], I[5]};
+      double p0[3], p1[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { p0[c] = D.JpC[BA_JP(c, k)]; p1[c] = D.JpC[BA_JP(3 + c, k)]; }
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        // row r of V_A^T Hinv (V_A(t, r) = p0[t] a0[r] + p1[t] a1[r])
+        const double v0 = p0[0] * a0[r] + p1[0] * a1[r], v1 = p0[1] * a0[r] + p1[1] * a1[r], v2 = p0[2] * a0[r] + p1[2] * a1[r];
+        const double g0 = v0 * Hi[0] + v1 * Hi[3] + v2 * Hi[6], g1 = v0 * Hi[1] + v1 * Hi[4] + v2 * Hi[7], g2 = v0 * Hi[2] + v1 * Hi[5] + v2 * Hi[8];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) G[6 * r + c] += g0 * (p0[0] * b0[c] + p1[0] * b1[c]) + g1 * (p0[1] * b0[c] + p1[1] * b1[c]) + g2 * (p0[2] * b0[c] + p1[2] * b1[c]);
+      }
+    }
+  }
+  double* Mb = (SCHUR ? D.Mbb : D.Hbb) + D.blk_pack[blk];
+  const int lrA = cA - 6, lrB = cB - 6;
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      double t = G[6 * r + c];
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0 && r < nA && c < nB) {
+        const double v = SCHUR ? -t : t;
+        atomicAdd(&Mb[(lrA + r) * bw + lrB + c], v);
+        atomicAdd(&Mb[(lrB + c) * bw + lrA + r], v);
+      }
     }
 }
 
@@ -608,7 +836,7 @@ __global__ void __launch_bounds__(BA_SC_BLOCK) ba_schur_cam_kernel(const BaDev D
   if (chunk >= D.nchunks) return;
   const int lane = threadIdx.x & 31;
   const int4 ch = D.chunks[chunk];
-  const int comp0 = ch.w & 0xff, n = ch.w >> 8;
+  const int comp0 = ch.w & 0xff, n = (ch.w >> 8) & 0xff, lr0 = (ch.w >> 16) & 0xff, bw = (ch.w >> 24) & 0xff;
   const bool want_T = (comp0 == 0) || !D.intr_by_pt;
   double g[6] = {0, 0, 0, 0, 0, 0}, T[21];
 #pragma unroll
@@ -690,7 +918,7 @@ __global__ void __launch_bounds__(BA_SC_BLOCK) ba_schur_cam_kernel(const BaDev D
       for (int c = r; c < 6; ++c) {
         double t = T[idx++];
         for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (lane == 0 && r < n && c < n) { atomicAdd(&M[r * n + c], -t); if (c != r) atomicAdd(&M[c * n + r], -t); }
+        if (lane == 0 && r < n && c < n) { atomicAdd(&M[(lr0 + r) * bw + lr0 + c], -t); if (c != r) atomicAdd(&M[(lr0 + c) * bw + lr0 + r], -t); }
       }
   }
 }
@@ -730,12 +958,12 @@ __global__ void ba_schur_pt_kernel(const BaDev D) {
   const int s0 = D.vpt_s0[k], s1 = D.vpt_s1[k];
   for (int s = s0; s < s1; ++s) {
     const int ci = D.s_cam[s];
-    const int co = D.cam_off[ci], nv = D.cam_nvar[ci];
+    const int co = D.cam_off[ci], nv = D.cam_width[ci];
     if (co < 0) continue;
     bool first = true;
     for (int s2 = s0; s2 < s && first; ++s2) if (D.s_cam[s2] == ci) first = false;
     if (!first) continue;
-    double V[15];
+    double V[3 * BA_MAXCB];
     for (int t = 0; t < 3 * nv; ++t) V[t] = 0.0;
     for (int s2 = s; s2 < s1; ++s2) {
       if (D.s_cam[s2] != ci) continue;
@@ -755,34 +983,44 @@ __global__ void ba_schur_pt_kernel(const BaDev D) {
     }
   }
 }
-// invert the preconditioner blocks (Cholesky, n <= 6); one thread per block
+// invert the preconditioner blocks (Cholesky); one thread per block.  MAXN = 6: the narrow layout (pose blocks and <= 5
+// intrinsics); MAXN = BA_MAXCB: wide camera blocks.  A camera block that holds a sensor_from_rig part AND an intrinsics
+// part is two parameter blocks for ceres' SCHUR_JACOBI: blk_split keeps their diagonal sub-blocks and drops the cross terms.
+template <int MAXN>
 __global__ void ba_invert_blocks_kernel(const BaDev D) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= D.nblk) return;
   const int n = D.blk_start[b + 1] - D.blk_start[b];
   const double* M = D.Mbb + D.blk_pack[b];
-  double L[36];
-  bool ok = true;
-  for (int j = 0; j < n && ok; ++j) {
-    double d = M[j * n + j];
-    for (int k = 0; k < j; ++k) d -= L[j * n + k] * L[j * n + k];
-    if (!(d > 0)) { ok = false; break; }
-    d = sqrt(d); L[j * n + j] = d;
-    for (int i = j + 1; i < n; ++i) {
-      double s = M[i * n + j];
-      for (int k = 0; k < j; ++k) s -= L[i * n + k] * L[j * n + k];
-      L[i * n + j] = s / d;
-    }
-  }
   double* O = D.Minv + D.blk_pack[b];
-  for (int c = 0; c < n; ++c) {
-    double col[6];
-    for (int r = 0; r < n; ++r) col[r] = r == c ? 1.0 : 0.0;
-    if (ok) {
-      for (int i = 0; i < n; ++i) { double s = col[i]; for (int k = 0; k < i; ++k) s -= L[i * n + k] * col[k]; col[i] = s / L[i * n + i]; }
-      for (int i = n - 1; i >= 0; --i) { double s = col[i]; for (int k = i + 1; k < n; ++k) s -= L[k * n + i] * col[k]; col[i] = s / L[i * n + i]; }
+  const int split = (MAXN > 6 && D.blk_split) ? D.blk_split[b] : 0;
+  double L[MAXN * MAXN];
+  for (int r = 0; r < n; ++r) for (int c = 0; c < n; ++c) O[r * n + c] = 0.0;
+  for (int seg = 0; seg < 2; ++seg) {
+    const int s0 = seg == 0 ? 0 : split, s1 = seg == 0 ? (split ? split : n) : n;
+    if (seg == 1 && split == 0) break;
+    const int m = s1 - s0;
+    bool ok = true;
+    for (int j = 0; j < m && ok; ++j) {
+      double d = M[(s0 + j) * n + s0 + j];
+      for (int k = 0; k < j; ++k) d -= L[j * m + k] * L[j * m + k];
+      if (!(d > 0)) { ok = false; break; }
+      d = sqrt(d); L[j * m + j] = d;
+      for (int i = j + 1; i < m; ++i) {
+        double s = M[(s0 + i) * n + s0 + j];
+        for (int k = 0; k < j; ++k) s -= L[i * m + k] * L[j * m + k];
+        L[i * m + j] = s / d;
+      }
     }
-    for (int r = 0; r < n; ++r) O[r * n + c] = col[r];
+    for (int c = 0; c < m; ++c) {
+      double col[MAXN];
+      for (int r = 0; r < m; ++r) col[r] = r == c ? 1.0 : 0.0;
+      if (ok) {
+        for (int i = 0; i < m; ++i) { double s = col[i]; for (int k = 0; k < i; ++k) s -= L[i * m + k] * col[k]; col[i] = s / L[i * m + i]; }
+        for (int i = m - 1; i >= 0; --i) { double s = col[i]; for (int k = i + 1; k < m; ++k) s -= L[k * m + i] * col[k]; col[i] = s / L[i * m + i]; }
+      }
+      for (int r = 0; r < m; ++r) O[(s0 + r) * n + s0 + c] = col[r];
+    }
   }
 }
 
@@ -831,11 +1069,19 @@ __global__ void ba_pcg_direction_kernel(const BaDev D) {
 __device__ __forceinline__ double ba_shfl_down_f64(double v, int off) { return __shfl_down_sync(0xffffffffu, v, off); }
 __device__ __forceinline__ double ba_shfl_f64(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
+// s_pack.y = (camera-block offset + 1) | width << (19 | 17) | head lane << 22 | last lane << 27: 19 + 3 bits for the narrow
+// layout (width <= 5), 17 + 5 bits when the problem has wide camera blocks
+__device__ __forceinline__ void ba_unpack_cam(unsigned pky, int wide, int& co, int& nv) {
+  if (wide) { co = (int)(pky & 0x1ffffu) - 1; nv = (int)((pky >> 17) & 31u); }
+  else { co = (int)(pky & 0x7ffffu) - 1; nv = (int)((pky >> 19) & 7u); }
+}
 template <int DC>
 __device__ __forceinline__ void ba_spmv_slot(const BaDev& D, const long long s, const int lane, const double* __restrict__ pvec) {
   const int4 pk = __ldg(D.s_pack + s);          // all per-slot indices in one coalesced 16-byte load
   const unsigned pky = (unsigned)pk.y;
-  const int po = pk.x, co = (int)(pky & 0x7ffffu) - 1, nv = (int)((pky >> 19) & 7u);
+  const int po = pk.x;
+  int co, nv;
+  ba_unpack_cam(pky, DC > 11 ? D.wide : 0, co, nv);
   const int lp = pk.z;
   const long long cp = pk.w;                     // -1 on padding slots
   int head = lane, last = lane;
@@ -922,7 +1168,7 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_schur_spmv_kernel(const BaDev D, 
   double J0[DC], J1[DC], y0 = 0.0, y1 = 0.0;
   if (pi >= 0) {
     const int ci = D.s_cam[s];
-    po = D.pose_off[pi]; co = D.cam_off[ci]; nv = D.cam_nvar[ci];
+    po = D.pose_off[pi]; co = D.cam_off[ci]; nv = D.cam_width[ci];
 #pragma unroll
     for (int c = 0; c < DC; ++c) { J0[c] = D.Jc[BA_JC(c, s)]; J1[c] = D.Jc[BA_JC((DC + c), s)]; }
     if (po >= 0) {
@@ -1279,7 +1525,7 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_giant_accumulate_kernel(const BaD
   const int pi = D.s_pose[s];
   if (pi < 0) return;
   const int ci = D.s_cam[s], DC = D.DC;
-  const int po = D.pose_off[pi], co = D.cam_off[ci], nv = D.cam_nvar[ci], lp = D.s_lpt[s];
+  const int po = D.pose_off[pi], co = D.cam_off[ci], nv = D.cam_width[ci], lp = D.s_lpt[s];
   double y0 = 0.0, y1 = 0.0;
   if (po >= 0) for (int c = 0; c < 6; ++c) { const double v = vec[po + c]; y0 += D.Jc[BA_JC(c, s)] * v; y1 += D.Jc[BA_JC((DC + c), s)] * v; }
   if (co >= 0) for (int c = 0; c < nv; ++c) { const double v = vec[co + c]; y0 += D.Jc[BA_JC((6 + c), s)] * v; y1 += D.Jc[BA_JC((DC + 6 + c), s)] * v; }
@@ -1294,7 +1540,7 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_giant_finish_kernel(const BaDev D
   double m = 0.0;
   if (pi >= 0) {
     const int ci = D.s_cam[s], DC = D.DC;
-    const int po = D.pose_off[pi], co = D.cam_off[ci], nv = D.cam_nvar[ci], lp = D.s_lpt[s];
+    const int po = D.pose_off[pi], co = D.cam_off[ci], nv = D.cam_width[ci], lp = D.s_lpt[s];
     double y0 = 0.0, y1 = 0.0;
     if (po >= 0) for (int c = 0; c < 6; ++c) { const double v = vec[po + c]; y0 += D.Jc[BA_JC(c, s)] * v; y1 += D.Jc[BA_JC((DC + c), s)] * v; }
     if (co >= 0) for (int c = 0; c < nv; ++c) { const double v = vec[co + c]; y0 += D.Jc[BA_JC((6 + c), s)] * v; y1 += D.Jc[BA_JC((DC + 6 + c), s)] * v; }
@@ -1329,7 +1575,9 @@ template <int DC>
 __device__ __forceinline__ void ba_slot_rows(const BaDev& D, long long s, float* J0, float* J1, int* idx) {
   const int4 pk = __ldg(D.s_pack + s);
   const unsigned pky = (unsigned)pk.y;
-  const int po = pk.x, co = (int)(pky & 0x7ffffu) - 1, nv = (int)((pky >> 19) & 7u);
+  const int po = pk.x;
+  int co, nv;
+  ba_unpack_cam(pky, DC > 11 ? D.wide : 0, co, nv);
 #pragma unroll
   for (int c = 0; c < DC; ++c) { J0[c] = D.Jc[BA_JC(c, s)]; J1[c] = D.Jc[BA_JC(DC + c, s)]; }
 #pragma unroll
@@ -1457,7 +1705,7 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_backsub_model_kernel(const BaDev 
   double y0 = 0.0, y1 = 0.0;
   if (pi >= 0) {
     const int ci = D.s_cam[s];
-    const int po = D.pose_off[pi], co = D.cam_off[ci], nv = D.cam_nvar[ci];
+    const int po = D.pose_off[pi], co = D.cam_off[ci], nv = D.cam_width[ci];
     if (po >= 0) for (int c = 0; c < 6; ++c) { const double v = D.x[po + c]; y0 += D.Jc[BA_JC(c, s)] * v; y1 += D.Jc[BA_JC((DC + c), s)] * v; }
     if (co >= 0) for (int c = 0; c < nv; ++c) { const double v = D.x[co + c]; y0 += D.Jc[BA_JC((6 + c), s)] * v; y1 += D.Jc[BA_JC((DC + 6 + c), s)] * v; }
   }
@@ -1503,7 +1751,9 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_backsub_warp_kernel(const BaDev D
   const int lane = threadIdx.x & 31;
   const int4 pk = __ldg(D.s_pack + s);
   const unsigned pky = (unsigned)pk.y;
-  const int po = pk.x, co = (int)(pky & 0x7ffffu) - 1, nv = (int)((pky >> 19) & 7u);
+  const int po = pk.x;
+  int co, nv;
+  ba_unpack_cam(pky, DC > 11 ? D.wide : 0, co, nv);
   const int lp = pk.z;
   const long long cp = pk.w;
   float J0[DC], J1[DC], jp[6];
@@ -1553,8 +1803,11 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_backsub_warp_kernel(const BaDev D
 
 // candidate parameters = Plus(current, scale * step)
 __global__ void ba_update_kernel(const BaDev D) {
+  // thread ranges padded to whole warps, one kind of block per warp (see ba_gradmax_kernel)
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < D.nposes) {
+  const long long np32 = ((long long)D.nposes + 31) & ~31LL, nc32 = ((long long)D.ncams + 31) & ~31LL;
+  if (i < np32) {
+    if (i >= D.nposes) return;
     const int off = D.pose_off[i];
     for (int k = 0; k < 7; ++k) D.nposes_[7 * i + k] = D.poses[7 * i + k];
     if (off >= 0) {
@@ -1564,14 +1817,27 @@ __global__ void ba_update_kernel(const BaDev D) {
       ba_quat_plus(D.poses + 7 * i, d, D.nposes_ + 7 * i);
       for (int k = 0; k < 3; ++k) D.nposes_[7 * i + 4 + k] = D.poses[7 * i + 4 + k] + d[3 + k];
     }
-  } else if (i < D.nposes + D.ncams) {
-    const int c = (int)(i - D.nposes);
+  } else if (i < np32 + nc32) {
+    const int c = (int)(i - np32);
+    if (c >= D.ncams) return;
     const int P = ba_model_num_params(D.cam_model[c]);
     for (int k = 0; k < P; ++k) D.ncams_[D.cam_poff[c] + k] = D.cams[D.cam_poff[c] + k];
     const int off = D.cam_off[c];
-    if (off >= 0) for (int k = 0; k < D.cam_nvar[c]; ++k) D.ncams_[D.cam_poff[c] + D.cam_var[5 * c + k]] += D.x[off + k] * D.scale_c[off + k];
-  } else if (i < (long long)D.nposes + D.ncams + D.npts) {
-    const long long p = i - D.nposes - D.ncams;
+    const int ns = D.wide ? D.cam_ns[c] : 0;
+    if (off >= 0) for (int k = 0; k < D.cam_nvar[c]; ++k) D.ncams_[D.cam_poff[c] + D.cam_var[BA_MAXP * c + k]] += D.x[off + ns + k] * D.scale_c[off + ns + k];
+    if (D.wide && D.cam_sensor[c] >= 0) {   // the camera's sensor_from_rig: Plus(current, scaled step) or a copy
+      const long long si = D.cam_sensor[c];
+      for (int k = 0; k < 7; ++k) D.nsensors_[7 * si + k] = D.sensors[7 * si + k];
+      if (off >= 0 && ns == 6) {
+        double d[6];
+        for (int k = 0; k < 6; ++k) d[k] = D.x[off + k] * D.scale_c[off + k];
+        ba_quat_plus(D.sensors + 7 * si, d, D.nsensors_ + 7 * si);
+        for (int k = 0; k < 3; ++k) D.nsensors_[7 * si + 4 + k] = D.sensors[7 * si + 4 + k] + d[3 + k];
+      }
+    }
+  } else {
+    const long long p = i - np32 - nc32;
+    if (p >= D.npts) return;
     const int v = D.pt_var[p];
     for (int k = 0; k < 3; ++k) D.npts_[3 * p + k] = D.pts[3 * p + k] + (v >= 0 ? D.dp[3 * (long long)v + k] * D.scale_p[3 * (long long)v + k] : 0.0);
   }
@@ -1627,14 +1893,14 @@ __global__ void ba_setup_run_kernel(long long nobs_c, const int* __restrict__ ru
 __global__ void ba_setup_pack_kernel(long long nslots, const int* __restrict__ s_pose, const int* __restrict__ s_cam,
                                      const int* __restrict__ s_lpt, const int* __restrict__ s_seg, const int* __restrict__ s2c,
                                      const int* __restrict__ pose_off, const int* __restrict__ cam_off,
-                                     const int* __restrict__ cam_nvar, int4* __restrict__ s_pack) {
+                                     const int* __restrict__ cam_width, int wide, int4* __restrict__ s_pack) {
   const long long sl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (sl >= nslots) return;
   const int pose = s_pose[sl];
   if (pose < 0) { s_pack[sl] = make_int4(-1, 0, -1, -1); return; }
   const int cam = s_cam[sl];
   const unsigned seg = (unsigned)s_seg[sl];
-  const unsigned y = (unsigned)(cam_off[cam] + 1) | ((unsigned)cam_nvar[cam] << 19) | ((seg & 0xffu) << 22) | ((seg >> 8) << 27);
+  const unsigned y = (unsigned)(cam_off[cam] + 1) | ((unsigned)cam_width[cam] << (wide ? 17 : 19)) | ((seg & 0xffu) << 22) | ((seg >> 8) << 27);
   s_pack[sl] = make_int4(pose_off[pose], (int)y, s_lpt[sl], s2c[sl]);
 }
 
@@ -1735,19 +2001,25 @@ static void ba_launch_backsub(const BaDev& D, cudaStream_t s) {
     ba_giant_finish_kernel<1><<<D.nblocks_giant1 - D.nblocks_giant0, BA_BLOCK, 0, s>>>(D, D.x);
   }
 }
-template <int DC>
+template <int DC, bool WIDE>
 static void ba_launch_linearize_dc(const BaDev& D, int apply_scale, cudaStream_t s) {
-  ba_linearize_slot_kernel<DC><<<D.nblocks, BA_BLOCK, 0, s>>>(D, apply_scale, &D.ctl->cost);
-  if (D.nobs_c) ba_linearize_cam_kernel<DC><<<(unsigned)((D.nobs_c + BA_BLOCK - 1) / BA_BLOCK), BA_BLOCK, 0, s>>>(D, apply_scale);
+  ba_linearize_slot_kernel<DC, WIDE><<<D.nblocks, BA_BLOCK, 0, s>>>(D, apply_scale, &D.ctl->cost);
+  if (D.nobs_c) ba_linearize_cam_kernel<DC, WIDE><<<(unsigned)((D.nobs_c + BA_BLOCK - 1) / BA_BLOCK), BA_BLOCK, 0, s>>>(D, apply_scale);
 }
+// DC = 6 + widest camera block.  6..11: the narrow layout (trivial frames, <= 5-parameter models); 14 / 18 / 22 / 28: the wide
+// instantiations (any model, rig sensors), DC rounded up to the next of them.
 static void ba_launch_linearize(const BaDev& D, int apply_scale, cudaStream_t s) {
   switch (D.DC) {
-    case 6: ba_launch_linearize_dc<6>(D, apply_scale, s); break;
-    case 7: ba_launch_linearize_dc<7>(D, apply_scale, s); break;
-    case 8: ba_launch_linearize_dc<8>(D, apply_scale, s); break;
-    case 9: ba_launch_linearize_dc<9>(D, apply_scale, s); break;
-    case 10: ba_launch_linearize_dc<10>(D, apply_scale, s); break;
-    default: ba_launch_linearize_dc<11>(D, apply_scale, s); break;
+    case 6: ba_launch_linearize_dc<6, false>(D, apply_scale, s); break;
+    case 7: ba_launch_linearize_dc<7, false>(D, apply_scale, s); break;
+    case 8: ba_launch_linearize_dc<8, false>(D, apply_scale, s); break;
+    case 9: ba_launch_linearize_dc<9, false>(D, apply_scale, s); break;
+    case 10: ba_launch_linearize_dc<10, false>(D, apply_scale, s); break;
+    case 11: ba_launch_linearize_dc<11, false>(D, apply_scale, s); break;
+    case 14: ba_launch_linearize_dc<14, true>(D, apply_scale, s); break;
+    case 18: ba_launch_linearize_dc<18, true>(D, apply_scale, s); break;
+    case 22: ba_launch_linearize_dc<22, true>(D, apply_scale, s); break;
+    default: ba_launch_linearize_dc<28, true>(D, apply_scale, s); break;
   }
 }
 #define BA_DISPATCH_DC(FN, D, s)                 \
@@ -1757,7 +2029,11 @@ static void ba_launch_linearize(const BaDev& D, int apply_scale, cudaStream_t s)
     case 8: FN<8>(D, s); break;                  \
     case 9: FN<9>(D, s); break;                  \
     case 10: FN<10>(D, s); break;                \
-    default: FN<11>(D, s); break;                \
+    case 11: FN<11>(D, s); break;                \
+    case 14: FN<14>(D, s); break;                \
+    case 18: FN<18>(D, s); break;                \
+    case 22: FN<22>(D, s); break;                \
+    default: FN<28>(D, s); break;                \
   }
 
 
@@ -1811,7 +2087,7 @@ void b200ba_options_init(b200ba_options* o) {
   o->max_linear_solver_iterations = 200; o->function_tolerance = 0.0; o->gradient_tolerance = 1e-4;
   o->parameter_tolerance = 0.0; o->initial_trust_region_radius = 1e4; o->max_trust_region_radius = 1e16;
   o->min_trust_region_radius = 1e-32; o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6;
-  o->max_lm_diagonal = 1e32; o->eta = 0.1; o->jacobi_scaling = 1; o->gpu_index = -1;
+  o->max_lm_diagonal = 1e32; o->eta = 0.1; o->jacobi_scaling = 1; o->gpu_index = -1; o->refine_sensor_from_rig = 1;
 }
 
 // FixGaugeWithTwoCamsFromWorld (bundle_adjustment_ceres.cc:308-417), trivial frames, poses in ascending image id.
@@ -2052,7 +2328,14 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   // ---------------------------------------------------------------- flatten (host)
   const int NP = p->num_poses, NCAM = p->num_cameras;
   const long long NPT = p->num_points, NOBS = p->num_observations;
-  for (int c = 0; c < NCAM; ++c) if (ba_model_num_params(p->camera_model_id[c]) < 0) return ba_fail(-2, "unsupported camera model (supported: SIMPLE_PINHOLE, PINHOLE, SIMPLE_RADIAL, RADIAL, SIMPLE_RADIAL_FISHEYE, RADIAL_FISHEYE)");
+  for (int c = 0; c < NCAM; ++c) if (ba_model_num_params(p->camera_model_id[c]) < 0) return ba_fail(-2, "unknown camera model id");
+  const int NS = p->num_sensors;
+  bool wide = NS > 0;
+  for (int c = 0; c < NCAM; ++c) {
+    if (!ba_model_is_narrow(p->camera_model_id[c])) wide = true;
+    if (p->camera_sensor_idx && p->camera_sensor_idx[c] >= NS) return ba_fail(-2, "camera_sensor_idx out of range");
+  }
+  if (NS > 0 && (!p->sensor_from_rig || !p->camera_sensor_idx)) return ba_fail(-2, "rig sensors need sensor_from_rig and camera_sensor_idx");
   std::vector<unsigned char> pose_used(NP, 0), cam_used(NCAM, 0), pt_used(NPT, 0);
   for (long long i = 0; i < NOBS; ++i) {   // range check and "block appears in an observation" in one pass
     const int a = p->obs_pose_idx[i], b = p->obs_camera_idx[i], c = p->obs_point_idx[i];
@@ -2084,7 +2367,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   tick("validate + used flags");
   std::vector<int> pose_off(NP, -1), cam_off(NCAM, -1), cam_nvar(NCAM, 0), cam_poff(NCAM), cam_model(NCAM), pt_var(NPT, -1);
   std::vector<unsigned char> pose_mask(NP, 0);
-  std::vector<signed char> cam_var(5 * (size_t)NCAM, 0);
+  std::vector<signed char> cam_var(BA_MAXP * (size_t)NCAM, 0);
   int off = 0, neff = 0, dkmax = 0;
   std::vector<int> blk_start, blk_pack;
   int pack = 0;
@@ -2098,6 +2381,8 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
     neff += __builtin_popcount(m);
   }
   long long ncamparams = 0;
+  std::vector<int> cam_sensor(NCAM, -1), cam_ns(NCAM, 0), cam_width(NCAM, 0), sens_cam(NS, -1), blk_split;
+  blk_split.assign(blk_start.size(), 0);
   for (int c = 0; c < NCAM; ++c) {
     const int id = p->camera_model_id[c], P = ba_model_num_params(id);
     cam_model[c] = id; cam_poff[c] = p->camera_param_offset[c];
@@ -2106,11 +2391,25 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
     if (!(p->camera_constant && p->camera_constant[c]) && cam_used[c])
       for (int k = 0; k < P; ++k) {
         const int g = ba_param_group(id, k);
-        const int refine = g == 0 ? o->refine_focal_length : (g == 1 ? o->refine_principal_point : o->refine_extra_params);
-        if (refine) cam_var[5 * (size_t)c + nv++] = (signed char)k;
+        const int refine = g == 0 ? o->refine_focal_length : (g == 1 ? o->refine_principal_point : (g == 2 ? o->refine_extra_params : 0));
+        if (refine) cam_var[BA_MAXP * (size_t)c + nv++] = (signed char)k;
       }
     cam_nvar[c] = nv;
-    if (nv) { cam_off[c] = off; blk_start.push_back(off); blk_pack.push_back(pack); off += nv; pack += nv * nv; neff += nv; dkmax = std::max(dkmax, nv); }
+    // the camera's sensor_from_rig (non-reference rig sensor): variable iff refined, not constant and observed
+    // (ParameterizeRigsAndFrames, bundle_adjustment_ceres.cc:478-539)
+    const int si = (NS > 0) ? p->camera_sensor_idx[c] : -1;
+    cam_sensor[c] = si;
+    if (si >= 0) {
+      if (sens_cam[si] >= 0) return ba_fail(-2, "a sensor_from_rig pose must belong to exactly one camera");
+      sens_cam[si] = c;
+      if (o->refine_sensor_from_rig && !(p->sensor_constant && p->sensor_constant[si]) && cam_used[c]) cam_ns[c] = 6;
+    }
+    const int w = cam_ns[c] + nv;
+    cam_width[c] = w;
+    if (w) {
+      cam_off[c] = off; blk_start.push_back(off); blk_pack.push_back(pack); blk_split.push_back((cam_ns[c] && nv) ? 6 : 0);
+      off += w; pack += w * w; neff += w; dkmax = std::max(dkmax, w);
+    }
   }
   const int nc = off, nblk = (int)blk_start.size();
   blk_start.push_back(nc); blk_pack.push_back(pack);
@@ -2266,7 +2565,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   const int nblocks = (int)(nslots / BA_BLOCK);
   blk_pt0.resize(nblocks, nvpt); blk_npt.resize(nblocks, 0);
   if (nslots >= (1LL << 31)) return ba_fail(-3, "problem too large for 32-bit slot indices");
-  if (nc >= (1 << 19) - 1) return ba_fail(-3, "camera-side dimension above 2^19 is not supported");
+  if (nc >= (1 << (wide ? 17 : 19)) - 1) return ba_fail(-3, wide ? "camera-side dimension above 2^17 is not supported with wide camera blocks" : "camera-side dimension above 2^19 is not supported");
   tick("slot arrays");
   if (host_only) {
     if (g_ba_layout_out) {
@@ -2281,7 +2580,11 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   }
   // ---------------------------------------------------------------- device setup
   BaDev D; memset(&D, 0, sizeof(D));
-  D.nposes = NP; D.ncams = NCAM; D.npts = (int)NPT; D.nvpt = nvpt; D.nc = nc; D.DC = 6 + dkmax; D.nblocks = nblocks;
+  int DCsel = 6 + dkmax;
+  if (wide) DCsel = dkmax <= 8 ? 14 : (dkmax <= 12 ? 18 : (dkmax <= 16 ? 22 : 28));
+  else if (dkmax > BA_MAXDK) return ba_fail(-3, "internal: narrow layout with a camera block wider than five");
+  D.nposes = NP; D.ncams = NCAM; D.npts = (int)NPT; D.nvpt = nvpt; D.nc = nc; D.DC = DCsel; D.nblocks = nblocks;
+  D.wide = wide ? 1 : 0; D.nsensors = NS;
   D.nblocks_var = nblocks_var; D.nslots = nslots; D.loss_type = o->loss_function_type; D.loss_scale = o->loss_function_scale;
   D.nblk = nblk;
   std::vector<double> h_poses(p->poses, p->poses + 7 * (size_t)NP), h_cams(p->camera_params, p->camera_params + ncamparams),
@@ -2297,6 +2600,16 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   { int* t; BA_CUDA(pool.upload(&t, cam_off, st)); D.cam_off = t; }
   { int* t; BA_CUDA(pool.upload(&t, cam_nvar, st)); D.cam_nvar = t; }
   { signed char* t; BA_CUDA(pool.upload(&t, cam_var, st)); D.cam_var = t; }
+  { int* t; BA_CUDA(pool.upload(&t, cam_width, st)); D.cam_width = t; }
+  { int* t; BA_CUDA(pool.upload(&t, cam_sensor, st)); D.cam_sensor = t; }
+  { int* t; BA_CUDA(pool.upload(&t, cam_ns, st)); D.cam_ns = t; }
+  { int* t; BA_CUDA(pool.upload(&t, sens_cam, st)); D.sens_cam = t; }
+  { int* t; BA_CUDA(pool.upload(&t, blk_split, st)); D.blk_split = t; }
+  std::vector<double> h_sens(p->sensor_from_rig ? p->sensor_from_rig : nullptr, p->sensor_from_rig ? p->sensor_from_rig + 7 * (size_t)NS : nullptr);
+  h_sens.resize(7 * (size_t)NS, 0.0);
+  for (int k = 0; k < NS; ++k) if (sens_cam[k] >= 0 && cam_ns[sens_cam[k]]) { double* q = h_sens.data() + 7 * (size_t)k; const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]); for (int c = 0; c < 4; ++c) q[c] /= n; }
+  BA_CUDA(pool.upload(&D.sensors, h_sens, st)); BA_CUDA(pool.alloc(&D.nsensors_, h_sens.size()));
+  if (NS) BA_CUDA(cudaMemcpyAsync(D.nsensors_, D.sensors, sizeof(double) * h_sens.size(), cudaMemcpyDeviceToDevice, st));
   { int* t; BA_CUDA(pool.upload(&t, pt_var, st)); D.pt_var = t; }
   { int* t; BA_CUDA(pool.upload(&t, vpt_point, st)); D.vpt_point = t; }
   { int* t; BA_CUDA(pool.upload(&t, s_lpt, st)); D.s_lpt = t; }
@@ -2304,7 +2617,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   // per-slot arrays, (camera, pose) order, runs: built on the device from the caller's arrays
   const long long nobs_c = nobs_eff;   // every non-padding slot is an observation connected to a variable block
   const long long nobs_c_pad = (nobs_c + BA_BLOCK - 1) / BA_BLOCK * BA_BLOCK;
-  std::vector<int4> runs, chunks;
+  std::vector<int4> runs, chunks, chunks_off;
   std::vector<int2> runs_pc;
   int intr_by_pt = 0;
   {
@@ -2346,7 +2659,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
     }
     BA_CUDA(pool.alloc(&d_run_start, (size_t)nruns + 1)); BA_CUDA(pool.alloc(&d_run_key, (size_t)nruns + 1));
     if (nobs_c) ba_setup_run_kernel<<<cb, 256, 0, st>>>(nobs_c, d_incl, t_crun, d_head, d_key_sorted, d_run_start, d_run_key);
-    ba_setup_pack_kernel<<<sb, 256, 0, st>>>(nslots, t_pose, t_cam, D.s_lpt, D.s_seg, t_s2c, D.pose_off, D.cam_off, D.cam_nvar, t_spack);
+    ba_setup_pack_kernel<<<sb, 256, 0, st>>>(nslots, t_pose, t_cam, D.s_lpt, D.s_seg, t_s2c, D.pose_off, D.cam_off, D.cam_width, D.wide, t_spack);
     std::vector<int> run_start((size_t)nruns + 1);
     std::vector<unsigned long long> run_key((size_t)nruns + 1);
     if (nruns) {
@@ -2356,22 +2669,32 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
     }
     run_start[nruns] = (int)nobs_c;
     // runs of equal (camera, pose); chunks (<= BA_CHUNK observations of one pose block / one intrinsics block)
-    auto add_chunks = [&](long long k0, long long k1, int out, int comp0, int ncomp) {
-      for (long long c0 = k0; c0 < k1; c0 += BA_CHUNK) chunks.push_back(make_int4((int)c0, (int)std::min<long long>(c0 + BA_CHUNK, k1), out, comp0 | (ncomp << 8)));
+    // chunk word: first column | width << 8 | first row inside the block << 16 | block width << 24
+    auto add_chunks = [&](long long k0, long long k1, int out, int comp0, int ncomp, int lr0, int bw) {
+      for (long long c0 = k0; c0 < k1; c0 += BA_CHUNK) chunks.push_back(make_int4((int)c0, (int)std::min<long long>(c0 + BA_CHUNK, k1), out, comp0 | (ncomp << 8) | (lr0 << 16) | (bw << 24)));
+    };
+    auto add_pair_chunks = [&](long long k0, long long k1, int blk_off, int cA, int nA, int cB, int nB) {
+      for (long long c0 = k0; c0 < k1; c0 += BA_CHUNK) chunks_off.push_back(make_int4((int)c0, (int)std::min<long long>(c0 + BA_CHUNK, k1), blk_off, cA | (nA << 8) | (cB << 16) | (nB << 24)));
     };
     long long cam_start = 0;
     for (int r = 0; r < nruns; ++r) {
       const int pose = (int)(run_key[r] & 0xffffffffu), cam = (int)(run_key[r] >> 32);
       const long long k = run_start[r], e = run_start[r + 1];
-      runs.push_back(make_int4(pose_off[pose], cam_off[cam], cam_nvar[cam], 0));
+      runs.push_back(make_int4(pose_off[pose], cam_off[cam], cam_width[cam], 0));
       runs_pc.push_back(make_int2(pose, cam));
-      if (pose_off[pose] >= 0) add_chunks(k, e, pose_off[pose], 0, 6);
+      if (pose_off[pose] >= 0) add_chunks(k, e, pose_off[pose], 0, 6, 0, 6);
       const bool cam_ends = (r + 1 == nruns) || (int)(run_key[r + 1] >> 32) != cam;
-      // a variable-intrinsics camera seen from several poses: some track may see it twice -> the intrinsics blocks of
+      // a variable camera block seen from several poses: some track may see it twice -> the camera blocks of
       // the preconditioner need the cross terms between observations of one point (ba_schur_pt_kernel)
       if (!cam_ends && cam_off[cam] >= 0) intr_by_pt = 1;
       if (cam_ends) {
-        if (cam_off[cam] >= 0) add_chunks(cam_start, e, cam_off[cam], 6, cam_nvar[cam]);
+        if (cam_off[cam] >= 0) {
+          const int w = cam_width[cam];
+          for (int a = 0; a < w; a += 6) {   // 6-column ranges of the block: diagonal ranges here, pairs of ranges separately
+            add_chunks(cam_start, e, cam_off[cam] + a, 6 + a, std::min(6, w - a), a, w);
+            for (int b = a + 6; b < w; b += 6) add_pair_chunks(cam_start, e, cam_off[cam], 6 + a, std::min(6, w - a), 6 + b, std::min(6, w - b));
+          }
+        }
         cam_start = e;
       }
     }
@@ -2400,6 +2723,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   D.nblocks_warp = nblocks_warp; D.nblocks_giant0 = nblocks_giant0; D.nblocks_giant1 = nblocks_giant1;
   BA_CUDA(pool.alloc(&D.zg, (size_t)3 * nvpt));
   { int4* t; BA_CUDA(pool.upload(&t, chunks, st)); D.chunks = t; }
+  { int4* t; BA_CUDA(pool.upload(&t, chunks_off, st)); D.chunks_off = t; D.nchunks_off = (int)chunks_off.size(); }
   { int4* t; BA_CUDA(pool.upload(&t, runs, st)); D.runs = t; }
   D.nchunks = (int)chunks.size(); D.nobs_c = nobs_c; BA_CUDA(pool.alloc(&D.r, (size_t)2 * nslots)); BA_CUDA(pool.alloc(&D.cost_slot, (size_t)nslots));
   BA_CUDA(pool.alloc(&D.scale_c, (size_t)nc)); BA_CUDA(pool.alloc(&D.scale_p, (size_t)3 * nvpt));
@@ -2437,9 +2761,14 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
     launches += 2;
   };
 
+  const bool dbg = getenv("B200BA_CHECK") != nullptr;   // diagnostic: synchronise and test for asynchronous errors after every group of launches
+#define BA_CHECKPOINT(label)                                                                                   \
+  do { if (dbg) { cudaError_t e__ = cudaStreamSynchronize(st); if (e__ == cudaSuccess) e__ = cudaGetLastError(); \
+       if (e__ != cudaSuccess) return ba_fail(-100, std::string("checkpoint ") + label + ": " + cudaGetErrorString(e__)); } } while (0)
   BA_CUDA(cudaEventRecord(ev0, st));
   // iteration 0: Jacobian, jacobi scaling
   linearize_current(0);
+  BA_CHECKPOINT("linearize(0)");
   BA_CUDA(cudaMemsetAsync(D.scale_c, 0, sizeof(double) * (nc ? nc : 1), st));
   BA_CUDA(cudaMemsetAsync(D.scale_p, 0, sizeof(double) * (nvpt ? 3 * (size_t)nvpt : 1), st));
   ba_colnorm_kernel<<<nblocks, BA_BLOCK, 0, st>>>(D);
@@ -2447,7 +2776,9 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   if (nc) ba_make_scale_kernel<<<gc_blocks, 256, 0, st>>>(D.scale_c, nc, o->jacobi_scaling);
   if (nvpt) ba_make_scale_kernel<<<(3 * nvpt + 255) / 256, 256, 0, st>>>(D.scale_p, 3LL * nvpt, o->jacobi_scaling);
   launches += 3;
+  BA_CHECKPOINT("colnorm");
   linearize_current(1);  // store the scaled Jacobian (fp32) in both orders
+  BA_CHECKPOINT("linearize(1)");
   BA_CUDA(read_ctl());
   double cost = h.cost;
   sum->initial_cost = cost;
@@ -2471,11 +2802,16 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
     BA_CUDA(cudaMemsetAsync(D.Hbb, 0, sizeof(double) * (pack ? pack : 1), st));
     BA_CUDA(zero_field(&D.ctl->gmax));
     if (D.nchunks) ba_build_cam_sorted_kernel<<<(D.nchunks + BA_SC_BLOCK / 32 - 1) / (BA_SC_BLOCK / 32), BA_SC_BLOCK, 0, st>>>(D);
+    BA_CHECKPOINT("build_cam_sorted");
+    if (D.nchunks_off) ba_cam_offdiag_kernel<false><<<(D.nchunks_off + BA_SC_BLOCK / 32 - 1) / (BA_SC_BLOCK / 32), BA_SC_BLOCK, 0, st>>>(D);
+    BA_CHECKPOINT("cam_offdiag<false>");
     BA_CUDA(allreduce(D.gc, nc, ncclDouble, ncclSum));
     BA_CUDA(allreduce(D.Hbb, pack, ncclDouble, ncclSum));
     if (nc) ba_diag_from_blocks_kernel<<<gc_blocks, 256, 0, st>>>(D);
     if (nvpt) ba_build_pt_kernel<<<gp_blocks, 256, 0, st>>>(D);
-    { const long long n = (long long)NP + NCAM + 3LL * nvpt; ba_gradmax_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(D); }
+    BA_CHECKPOINT("diag + build_pt");
+      { const long long n = (((long long)NP + 31) & ~31LL) + (((long long)NCAM + 31) & ~31LL) + 3LL * nvpt; ba_gradmax_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(D); }
+    BA_CHECKPOINT("gradmax");
     launches += 4;
     BA_CUDA(allreduce(&D.ctl->gmax, 1, ncclDouble, ncclMax));
     // The gradient-norm test of this iteration is read back together with the first linear-solve batch (one host
@@ -2497,14 +2833,17 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
       }
       if (nvpt && nc) {
         if (D.nchunks) ba_schur_cam_kernel<<<(D.nchunks + BA_SC_BLOCK / 32 - 1) / (BA_SC_BLOCK / 32), BA_SC_BLOCK, 0, st>>>(D);
+        if (D.nchunks_off && !intr_by_pt) ba_cam_offdiag_kernel<true><<<(D.nchunks_off + BA_SC_BLOCK / 32 - 1) / (BA_SC_BLOCK / 32), BA_SC_BLOCK, 0, st>>>(D);
         if (dkmax > 0 && intr_by_pt) ba_schur_pt_kernel<<<gp_blocks, 256, 0, st>>>(D);
         launches += 1 + (dkmax > 0 && intr_by_pt ? 1 : 0);
       }
       BA_CUDA(allreduce(D.rhs, nc, ncclDouble, ncclSum));
       BA_CUDA(allreduce(D.Mbb, pack, ncclDouble, ncclSum));
       BA_CUDA(allreduce(d_fail, 1, ncclInt32, ncclMax));
-      if (nblk) ba_invert_blocks_kernel<<<(nblk + 127) / 128, 128, 0, st>>>(D);
+      BA_CHECKPOINT("damp + schur_cam / schur_pt");
+      if (nblk) { if (D.wide) ba_invert_blocks_kernel<BA_MAXCB><<<(nblk + 127) / 128, 128, 0, st>>>(D); else ba_invert_blocks_kernel<6><<<(nblk + 127) / 128, 128, 0, st>>>(D); }
       launches += 4;
+      BA_CHECKPOINT("invert_blocks");
       // PCG
       BA_CUDA(cudaMemsetAsync(D.ctl, 0, offsetof(BaCtl, iters_total), st));  // keeps iters_total
       BA_CUDA(cudaMemcpyAsync(&D.ctl->cost, &cost, sizeof(double), cudaMemcpyHostToDevice, st));
@@ -2555,12 +2894,15 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
           sum->termination_type = B200BA_CONVERGENCE; finished = true; break;
         }
       }
+      BA_CHECKPOINT("linear solve");
       BA_CUDA(zero_field(&D.ctl->model));
       BA_DISPATCH_DC(ba_launch_backsub, D, st);
-      { const long long n = (long long)NP + NCAM + NPT; ba_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(D); }
+      BA_CHECKPOINT("backsub");
+      { const long long n = (((long long)NP + 31) & ~31LL) + (((long long)NCAM + 31) & ~31LL) + NPT; ba_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(D); }
       BA_CUDA(zero_field(&D.ctl->new_cost));
       BA_CUDA(zero_field(&D.ctl->cost_delta));
-      ba_cost_kernel<<<nblocks, BA_BLOCK, 0, st>>>(D, D.nposes_, D.ncams_, D.npts_, &D.ctl->new_cost);
+      ba_cost_kernel<<<nblocks, BA_BLOCK, 0, st>>>(D, D.nposes_, D.ncams_, D.npts_, D.nsensors_, &D.ctl->new_cost);
+      BA_CHECKPOINT("update + cost");
       BA_CUDA(allreduce(&D.ctl->model, 1, ncclDouble, ncclSum));
       BA_CUDA(allreduce(&D.ctl->new_cost, 1, ncclDouble, ncclSum));
       BA_CUDA(allreduce(&D.ctl->cost_delta, 1, ncclDouble, ncclSum));
@@ -2576,7 +2918,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
       if (!failed && model > 0 && rho_q > o->min_relative_decrease) {
         accepted = true;
         sum->num_successful_steps++;
-        std::swap(D.poses, D.nposes_); std::swap(D.cams, D.ncams_); std::swap(D.pts, D.npts_);
+        std::swap(D.poses, D.nposes_); std::swap(D.cams, D.ncams_); std::swap(D.pts, D.npts_); std::swap(D.sensors, D.nsensors_);
         const double cost_change = cost_change_acc;
         linearize_current(1);
         BA_CUDA(read_ctl());
@@ -2609,7 +2951,11 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   BA_CUDA(cudaMemcpy(h_cams.data(), D.cams, sizeof(double) * h_cams.size(), cudaMemcpyDeviceToHost));
   BA_CUDA(cudaMemcpy(h_pts.data(), D.pts, sizeof(double) * h_pts.size(), cudaMemcpyDeviceToHost));
   for (int i = 0; i < NP; ++i) if (pose_off[i] >= 0) memcpy(p->poses + 7 * (size_t)i, h_poses.data() + 7 * (size_t)i, 56);
-  for (int c = 0; c < NCAM; ++c) for (int k = 0; k < cam_nvar[c]; ++k) { const int idx = cam_poff[c] + cam_var[5 * (size_t)c + k]; p->camera_params[idx] = h_cams[idx]; }
+  for (int c = 0; c < NCAM; ++c) for (int k = 0; k < cam_nvar[c]; ++k) { const int idx = cam_poff[c] + cam_var[BA_MAXP * (size_t)c + k]; p->camera_params[idx] = h_cams[idx]; }
+  if (NS) {
+    BA_CUDA(cudaMemcpy(h_sens.data(), D.sensors, sizeof(double) * h_sens.size(), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < NS; ++k) if (sens_cam[k] >= 0 && cam_ns[sens_cam[k]]) memcpy(p->sensor_from_rig + 7 * (size_t)k, h_sens.data() + 7 * (size_t)k, 56);
+  }
   for (long long i = 0; i < NPT; ++i) if (pt_var[i] >= 0) memcpy(p->points + 3 * i, h_pts.data() + 3 * i, 24);
   return 0;   // pool, stream and events are released by their guards
 }
@@ -2622,6 +2968,17 @@ int b200ba_test_reproj(int model_id, const double* point, const double* pose, co
   return ba_reproj(model_id, point, pose, params, xy[0], xy[1], res, J_point, J_pose, J_params) ? 1 : 0;
 }
 void b200ba_test_quat_plus(const double* q, const double* d, double* out) { ba_quat_plus(q, d, out); }
+// RigReprojErrorCostFunctor with analytic derivatives, any of the eighteen models (host evaluation of the device code):
+// sensor == NULL -> trivial frame.  J_params is [2 x P] row-major.  Returns 1 / 0 (behind the camera) / -1 (unknown model).
+int b200ba_test_reproj_rig(int model_id, const double* point, const double* rig, const double* sensor, const double* params,
+                           const double* xy, double* res, double* J_point, double* J_rig, double* J_sensor, double* J_params) {
+  const int P = ba_model_num_params(model_id);
+  if (P < 0) return -1;
+  double Jp[2 * BA_MAXP];
+  const bool ok = ba_reproj_rig(model_id, point, rig, sensor, params, xy[0], xy[1], res, J_point, J_rig, J_sensor, Jp);
+  for (int k = 0; k < P; ++k) { J_params[k] = Jp[k]; J_params[P + k] = Jp[BA_MAXP + k]; }
+  return ok ? 1 : 0;
+}
 
 // The twelve camera models outside the radial pinhole family (ba_models.cuh: formulas + dual numbers), host evaluation for the CPU
 // test tier: xy[2], J_uvw[2x3], J_params[2xP].  Returns 1 / 0 (depth guard) / -1 (unknown model).

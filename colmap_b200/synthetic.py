@@ -214,10 +214,37 @@ def _quat_rotate(q, p):
 
 
 _MODEL_DEFAULTS = {0: [1280.0, 512.0, 384.0], 1: [1280.0, 1280.0, 512.0, 384.0], 2: [1280.0, 512.0, 384.0, 0.05],
-                   3: [1280.0, 512.0, 384.0, 0.05, 0.01], 8: [1280.0, 512.0, 384.0, 0.05], 9: [1280.0, 512.0, 384.0, 0.05, 0.01]}
+                   3: [1280.0, 512.0, 384.0, 0.05, 0.01], 8: [1280.0, 512.0, 384.0, 0.05], 9: [1280.0, 512.0, 384.0, 0.05, 0.01],
+                   # the twelve models beyond the radial pinhole family (sensor/models.h:533-800): mild distortion
+                   4: [1280.0, 1270.0, 512.0, 384.0, 0.04, -0.01, 1e-3, -8e-4],                               # OPENCV
+                   5: [1280.0, 1270.0, 512.0, 384.0, 0.03, -0.01, 2e-3, -1e-3],                               # OPENCV_FISHEYE
+                   6: [1280.0, 1270.0, 512.0, 384.0, 0.04, -0.01, 1e-3, -8e-4, 2e-3, 0.01, -3e-3, 1e-3],      # FULL_OPENCV
+                   7: [1280.0, 1270.0, 512.0, 384.0, 0.3],                                                    # FOV
+                   10: [1280.0, 1270.0, 512.0, 384.0, 0.03, -0.01, 1e-3, -8e-4, 2e-3, -1e-3, 5e-4, -4e-4],    # THIN_PRISM_FISHEYE
+                   11: [1280.0, 1270.0, 512.0, 384.0, 0.03, -0.01, 2e-3, -1e-3, 5e-4, -2e-4, 1e-3, -8e-4, 5e-4, -4e-4, 3e-4, -2e-4],
+                   12: [1280.0, 512.0, 384.0, -0.02], 13: [1280.0, 1270.0, 512.0, 384.0, -0.02],              # (SIMPLE_)DIVISION
+                   14: [1280.0, 512.0, 384.0], 15: [1280.0, 1270.0, 512.0, 384.0],                            # (SIMPLE_)FISHEYE
+                   16: [1280.0, 1270.0, 512.0, 384.0, 0.5, 1.1],                                              # EUCM
+                   17: [2048.0, 1024.0]}                                                                      # EQUIRECTANGULAR
 
 
 def _project(model, params, pc):
+    if model not in (0, 1, 2, 3, 8, 9):   # wide models: the product's own host formulas (b200ba_test_project_wide), point by point
+        import ctypes
+        from ._lib import load_library
+        lib = load_library()
+        f64p = ctypes.POINTER(ctypes.c_double)
+        lib.b200ba_test_project_wide.argtypes = [ctypes.c_int, f64p, f64p, f64p, f64p, f64p]
+        out = np.empty((len(pc), 2))
+        P = params.shape[-1]
+        xy = np.zeros(2); Ju = np.zeros(6); Jp = np.zeros(2 * P)
+        pcc = np.ascontiguousarray(pc, np.float64); prm = np.ascontiguousarray(params, np.float64)
+        for k in range(len(pc)):
+            ok = lib.b200ba_test_project_wide(int(model), prm[k].ctypes.data_as(f64p), pcc[k].ctypes.data_as(f64p), xy.ctypes.data_as(f64p),
+                                              Ju.ctypes.data_as(f64p), Jp.ctypes.data_as(f64p))
+            assert ok == 1, (model, pcc[k])
+            out[k] = xy
+        return out
     uu = pc[..., 0] / pc[..., 2]
     vv = pc[..., 1] / pc[..., 2]
     if model == 0:
@@ -335,3 +362,69 @@ def flat_to_reconstruction(flat):
         im.points2D.append(Point2D(flat.obs_xy[o].copy(), pid))
         rec.points3D[pid].track.append((im.image_id, len(im.points2D) - 1))
     return rec
+
+
+def synthesize_rig_problem(num_frames, num_sensors, num_points, track_length, models=(2,), seed=42, point2D_stddev=1.0,
+                           point3D_stddev=0.05, translation_stddev=0.01, rotation_stddev_deg=1.0, sensor_translation_stddev=0.005,
+                           sensor_rotation_stddev_deg=0.3):
+    """Rig scene (SynthesizeDataset with num_cameras_per_rig > 1, scene/synthetic.cc:341-672): ONE rig of `num_sensors`
+    cameras (sensor 0 = reference sensor, the others carry a sensor_from_rig pose), `num_frames` frames (one
+    rig_from_world pose each), every point seen from `track_length` random (frame, sensor) pairs.  In the flat problem
+    obs_pose_idx is the FRAME and obs_camera_idx the sensor's camera.  Returns (ground truth, noisy) FlatProblems."""
+    from .bundle_adjustment import MODEL_NUM_PARAMS, FlatProblem
+    rng = np.random.default_rng(seed)
+    pts = rng.uniform(-1, 1, (num_points, 3))
+    pts /= np.linalg.norm(pts, axis=1, keepdims=True)
+    view = -rng.uniform(-1, 1, (num_frames, 3))
+    view /= np.linalg.norm(view, axis=1, keepdims=True)
+    q = _quat_from_two_vectors(view, np.array([0.0, 0.0, 1.0]))
+    poses = np.concatenate([q, _quat_rotate(q, 5.0 * view)], axis=1)                 # rig_from_world per frame
+    # sensor_from_rig of the non-reference sensors: a few degrees of rotation, a 0.1-0.3 baseline
+    ns = num_sensors - 1
+    ax = rng.normal(size=(ns, 3)); ax /= np.linalg.norm(ax, axis=1, keepdims=True)
+    ang = np.deg2rad(rng.uniform(2.0, 6.0, ns))
+    sq = np.concatenate([ax * np.sin(ang / 2)[:, None], np.cos(ang / 2)[:, None]], axis=1)
+    st = rng.uniform(-0.3, 0.3, (ns, 3))
+    sensors = np.concatenate([sq, st], axis=1)
+    cam_model = [models[i % len(models)] for i in range(num_sensors)]
+    cam_off, off = [], 0
+    for m in cam_model:
+        cam_off.append(off); off += MODEL_NUM_PARAMS[m]
+    cam_params = np.concatenate([np.asarray(_MODEL_DEFAULTS[m]) for m in cam_model])
+    cam_sensor = np.array([-1] + list(range(ns)), np.int32)
+    # tracks over (frame, sensor) slots
+    slots = num_frames * num_sensors
+    obs_point = np.repeat(np.arange(num_points, dtype=np.int32), track_length)
+    keys = rng.random((num_points, slots))
+    sel = np.argsort(keys, axis=1)[:, :track_length].reshape(-1)
+    obs_pose = (sel // num_sensors).astype(np.int32)
+    obs_cam = (sel % num_sensors).astype(np.int32)
+    pr = _quat_rotate(poses[obs_pose, :4], pts[obs_point]) + poses[obs_pose, 4:]
+    pc = pr.copy()
+    nr = obs_cam > 0
+    pc[nr] = _quat_rotate(sensors[obs_cam[nr] - 1, :4], pr[nr]) + sensors[obs_cam[nr] - 1, 4:]
+    xy = np.empty((len(obs_pose), 2))
+    for c in range(num_sensors):
+        msk = obs_cam == c
+        m = cam_model[c]
+        prm = np.broadcast_to(cam_params[cam_off[c]:cam_off[c] + MODEL_NUM_PARAMS[m]], (int(msk.sum()), MODEL_NUM_PARAMS[m]))
+        xy[msk] = _project(m, prm, pc[msk])
+    gt = FlatProblem(poses, np.zeros(num_frames, np.uint8), -np.ones(num_frames, np.int8), cam_model, cam_off, cam_params,
+                     np.zeros(num_sensors, np.uint8), pts, np.zeros(num_points, np.uint8), obs_pose, obs_cam, obs_point, xy)
+    gt.set_sensors(sensors, np.zeros(ns, np.uint8), cam_sensor)
+    noisy = gt.copy()
+    if rotation_stddev_deg > 0:
+        a = np.deg2rad(rng.normal(0, rotation_stddev_deg, num_frames))
+        noisy.poses[:, :4] = _quat_mul(noisy.poses[:, :4], np.stack([0 * a, 0 * a, np.sin(a / 2), np.cos(a / 2)], 1))
+    if translation_stddev > 0:
+        noisy.poses[:, 4:] += rng.normal(0, translation_stddev, (num_frames, 3))
+    if ns and sensor_rotation_stddev_deg > 0:
+        a = np.deg2rad(rng.normal(0, sensor_rotation_stddev_deg, ns))
+        noisy.sensors[:, :4] = _quat_mul(noisy.sensors[:, :4], np.stack([0 * a, 0 * a, np.sin(a / 2), np.cos(a / 2)], 1))
+    if ns and sensor_translation_stddev > 0:
+        noisy.sensors[:, 4:] += rng.normal(0, sensor_translation_stddev, (ns, 3))
+    if point2D_stddev > 0:
+        noisy.obs_xy = noisy.obs_xy + rng.normal(0, point2D_stddev, noisy.obs_xy.shape)
+    if point3D_stddev > 0:
+        noisy.points += rng.normal(0, point3D_stddev, noisy.points.shape)
+    return gt, noisy

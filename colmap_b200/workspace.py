@@ -62,17 +62,16 @@ def all_gather_maps(local: Dict[int, "np.ndarray"], num_images: int, shape, devi
         idx[k] = i
         v = local[i]
         buf[k].copy_(v if hasattr(v, "data_ptr") else torch.from_numpy(np.ascontiguousarray(v, np.float32)))   # D2D when resident
-    idx_all = torch.empty((world,) + tuple(idx.shape), dtype=idx.dtype, device=dev)
-    buf_all = torch.empty((world,) + tuple(buf.shape), dtype=buf.dtype, device=dev)
+    idx_all = torch.empty((world * cap,), dtype=idx.dtype, device=dev)                    # rank-major concatenation
+    buf_all = torch.empty((world * cap,) + tuple(shape), dtype=buf.dtype, device=dev)
     dist.all_gather_into_tensor(idx_all, idx)
     dist.all_gather_into_tensor(buf_all, buf)       # the depth-map exchange
     out: List = [None] * num_images
     ids = idx_all.cpu().numpy()
-    for r in range(world):
-        for k in range(cap):
-            i = int(ids[r, k])
-            if i >= 0:
-                out[i] = buf_all[r, k] if on_device else buf_all[r, k].cpu().numpy()
+    for k in range(world * cap):
+        i = int(ids[k])
+        if i >= 0:
+            out[i] = buf_all[k] if on_device else buf_all[k].cpu().numpy()
     return out
 
 

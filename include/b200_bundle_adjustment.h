@@ -28,10 +28,15 @@
 extern "C" {
 #endif
 
-/* CameraModelId values (src/colmap/sensor/models.h:90-109).  Supported here: the radial pinhole family and its two
- * equidistant-fisheye counterparts (models with <= 5 parameters). */
-enum { B200BA_SIMPLE_PINHOLE = 0, B200BA_PINHOLE = 1, B200BA_SIMPLE_RADIAL = 2, B200BA_RADIAL = 3,
-       B200BA_SIMPLE_RADIAL_FISHEYE = 8, B200BA_RADIAL_FISHEYE = 9 };
+/* CameraModelId values (src/colmap/sensor/models.h:90-109): all eighteen models are on the solve path.  The radial
+ * pinhole family and its two equidistant-fisheye counterparts (<= 5 parameters) go through hand-written Jacobians and
+ * the narrow kernels; the other twelve through forward-mode dual numbers (colmap_b200/csrc/ba_models.cuh) and the
+ * wide kernel instantiations. */
+enum { B200BA_SIMPLE_PINHOLE = 0, B200BA_PINHOLE = 1, B200BA_SIMPLE_RADIAL = 2, B200BA_RADIAL = 3, B200BA_OPENCV = 4,
+       B200BA_OPENCV_FISHEYE = 5, B200BA_FULL_OPENCV = 6, B200BA_FOV = 7, B200BA_SIMPLE_RADIAL_FISHEYE = 8,
+       B200BA_RADIAL_FISHEYE = 9, B200BA_THIN_PRISM_FISHEYE = 10, B200BA_RAD_TAN_THIN_PRISM_FISHEYE = 11,
+       B200BA_SIMPLE_DIVISION = 12, B200BA_DIVISION = 13, B200BA_SIMPLE_FISHEYE = 14, B200BA_FISHEYE = 15, B200BA_EUCM = 16,
+       B200BA_EQUIRECTANGULAR = 17 };
 
 /* ceres::LinearSolverType subset COLMAP selects (bundle_adjustment_ceres.cc:202-212). */
 enum { B200BA_AUTO = 0, B200BA_DENSE_SCHUR = 1, B200BA_SPARSE_SCHUR = 2, B200BA_ITERATIVE_SCHUR = 3 };
@@ -68,9 +73,13 @@ typedef struct b200ba_options {
   double eta;                           /* 0.1: CG forcing term (q-tolerance) for ITERATIVE_SCHUR */
   int jacobi_scaling;                   /* 1 */
   int gpu_index;                        /* -1 = current device */
+  int refine_sensor_from_rig;           /* 1 (BundleAdjustmentOptions::refine_sensor_from_rig, bundle_adjustment.h:187) */
 } b200ba_options;
 
-/* Flat problem with trivial frames (sensor_from_rig = identity, one image per frame). */
+/* Flat problem.  Trivial frames: one pose per image.  Rigs (non-trivial frames, reprojection_error.h:344-420,
+ * bundle_adjustment_ceres.cc:753-827): obs_pose_idx indexes the rig_from_world pose of the FRAME (shared by the frame's
+ * images) and a camera that is a non-reference sensor carries a sensor_from_rig pose;
+ * cam_from_world = sensor_from_rig * rig_from_world. */
 typedef struct b200ba_problem {
   int num_poses;
   double* poses;                           /* [7*num_poses] qx qy qz qw tx ty tz (geometry/rigid3.h:46-49), in/out */
@@ -91,6 +100,10 @@ typedef struct b200ba_problem {
   const double* obs_xy;                    /* [2*num_observations] */
   int32_t num_config_images;               /* config.NumImages(): drives the AUTO linear-solver choice (bundle_adjustment_ceres.cc:131,
                                             * 204-210); 0 = the number of poses that appear in observations */
+  int32_t num_sensors;                     /* non-reference rig sensors (0 for trivial frames) */
+  double* sensor_from_rig;                 /* [7*num_sensors] qx qy qz qw tx ty tz, in/out */
+  const uint8_t* sensor_constant;          /* [num_sensors] HasConstantSensorFromRigPose / reference sensor absent (:526-539), or NULL */
+  const int32_t* camera_sensor_idx;        /* [num_cameras] index into sensor_from_rig, -1 = reference sensor; NULL = all -1 */
 } b200ba_problem;
 
 /* BundleAdjustmentSummary (bundle_adjustment.h:63-74) + the ceres::Solver::Summary fields

@@ -39,12 +39,15 @@
 
 #include "../include/b200_bundle_adjustment.h"
 
-#define MAXDK 5
-#define JC (6 + MAXDK)
+#define MAXDK 16             /* variable intrinsics of one camera (RAD_TAN_THIN_PRISM_FISHEYE has 16 parameters) */
+#define JS 6                  /* column of the sensor_from_rig tangent block in a Jacobian row */
+#define JI 12                 /* column of the intrinsics block */
+#define JC (12 + MAXDK)       /* [pose 6 | sensor 6 | intrinsics] */
 
 /* ------------------------------------------------------------------------- camera models */
+static int wide_num_params(int id);
 static int model_num_params(int id) {
-  switch (id) { case 0: return 3; case 1: case 2: case 8: return 4; case 3: case 9: return 5; default: return -1; }
+  switch (id) { case 0: return 3; case 1: case 2: case 8: return 4; case 3: case 9: return 5; default: return wide_num_params(id); }
 }
 /* FisheyeProjectionWithJac (models_jacobian.h:44-83): (a, b) -> (atan r / r)(a, b); J = d(out) / d(a, b), row-major */
 static void fisheye_with_jac(double a, double b, double* fa, double* fb, double J[4]) {
@@ -55,13 +58,11 @@ static void fisheye_with_jac(double a, double b, double* fa, double* fb, double 
   J[0] = s + a * a * g; J[1] = a * b * g; J[2] = J[1]; J[3] = s + b * b * g;
 }
 /* parameter groups (focal, principal point, extra): models.h:462-520 */
-static int param_group(int id, int k) { /* 0 focal, 1 pp, 2 extra */
-  switch (id) {
-    case 0: return k == 0 ? 0 : 1;
-    case 1: return k < 2 ? 0 : 1;
-    case 2: return k == 0 ? 0 : (k < 3 ? 1 : 2);
-    default: return k == 0 ? 0 : (k < 3 ? 1 : 2);
-  }
+static int param_group(int id, int k) { /* 0 focal, 1 pp, 2 extra, 3 metadata (never refined) */
+  if (id == 17) return 3;   /* EQUIRECTANGULAR {width, height}: sensor metadata (bundle_adjustment_ceres.cc:435-441) */
+  const int single = (id == 0 || id == 2 || id == 3 || id == 8 || id == 9 || id == 12 || id == 14);   /* f, cx, cy, ... */
+  if (single) return k == 0 ? 0 : (k < 3 ? 1 : 2);
+  return k < 2 ? 0 : (k < 4 ? 1 : 2);                                                                /* fx, fy, cx, cy, ... */
 }
 
 /* ImgFromCamWithJac (models_jacobian.h:139-398).  Returns 0 if the depth guard fails. */
@@ -316,6 +317,57 @@ int ba_oracle_reproj(int model_id, const double* point, const double* pose, cons
 }
 void ba_oracle_quat_plus(const double* q, const double* d, double* out) { quat_plus(q, d, out); }
 
+
+/* ImgFromCamWithJac of ANY model: hand-written Jacobians for the <= 5-parameter family, complex step for the others */
+static int img_from_cam_any(int id, const double* q, double u, double v, double w, double* x, double* y, double* Jp /*2xP*/,
+                            double* Juvw /*2x3*/) {
+  if (wide_num_params(id) < 0) return img_from_cam(id, q, u, v, w, x, y, Jp, Juvw);
+  const double uvw[3] = {u, v, w};
+  double xy[2];
+  if (ba_oracle_project_wide(id, q, uvw, xy, Juvw, Jp) != 1) return 0;
+  *x = xy[0]; *y = xy[1];
+  return 1;
+}
+/* RigReprojErrorCostFunctor / ReprojErrorCostFunctor with analytic derivatives (reprojection_error.h:62-135,344-420):
+ * p_cam = R(q_s) (R(q_r) X + t_r) + t_s with sensor == NULL meaning the identity (trivial frame / reference sensor).
+ * J_rig, J_sensor: 2x7 ambient (qx qy qz qw tx ty tz), J_params 2xP, J_point 2x3.  Returns 0 behind the camera. */
+int ba_oracle_reproj_rig(int model_id, const double* point, const double* rig, const double* sensor, const double* params,
+                         const double* xy, double* res, double* J_point, double* J_rig, double* J_sensor, double* J_params) {
+  const int P = model_num_params(model_id);
+  double pr[3], Jqr[12], pc[3], Jqs[12], Rs[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Rr[9];
+  quat_rotate_jac(rig, point, pr, Jqr);
+  pr[0] += rig[4]; pr[1] += rig[5]; pr[2] += rig[6];
+  if (sensor) {
+    quat_rotate_jac(sensor, pr, pc, Jqs);
+    pc[0] += sensor[4]; pc[1] += sensor[5]; pc[2] += sensor[6];
+    quat_to_R(sensor, Rs);
+  } else { pc[0] = pr[0]; pc[1] = pr[1]; pc[2] = pr[2]; memset(Jqs, 0, sizeof(Jqs)); }
+  double x, y, Juvw[6], Jp[2 * MAXDK];
+  if (!img_from_cam_any(model_id, params, pc[0], pc[1], pc[2], &x, &y, Jp, Juvw)) {
+    res[0] = res[1] = 0;
+    if (J_point) memset(J_point, 0, 48);
+    if (J_rig) memset(J_rig, 0, 112);
+    if (J_sensor) memset(J_sensor, 0, 112);
+    if (J_params) memset(J_params, 0, 16 * P);
+    return 0;
+  }
+  res[0] = x - xy[0]; res[1] = y - xy[1];
+  double A[6];   /* d(x, y) / d(p_rig) = Juvw * R_s */
+  for (int r = 0; r < 2; ++r) for (int c = 0; c < 3; ++c) A[3 * r + c] = Juvw[3 * r] * Rs[c] + Juvw[3 * r + 1] * Rs[3 + c] + Juvw[3 * r + 2] * Rs[6 + c];
+  quat_to_R(rig, Rr);
+  if (J_point) for (int r = 0; r < 2; ++r) for (int c = 0; c < 3; ++c) J_point[3 * r + c] = A[3 * r] * Rr[c] + A[3 * r + 1] * Rr[3 + c] + A[3 * r + 2] * Rr[6 + c];
+  if (J_rig) for (int r = 0; r < 2; ++r) {
+    for (int c = 0; c < 4; ++c) J_rig[7 * r + c] = A[3 * r] * Jqr[c] + A[3 * r + 1] * Jqr[4 + c] + A[3 * r + 2] * Jqr[8 + c];
+    for (int c = 0; c < 3; ++c) J_rig[7 * r + 4 + c] = A[3 * r + c];
+  }
+  if (J_sensor) for (int r = 0; r < 2; ++r) {
+    for (int c = 0; c < 4; ++c) J_sensor[7 * r + c] = sensor ? Juvw[3 * r] * Jqs[c] + Juvw[3 * r + 1] * Jqs[4 + c] + Juvw[3 * r + 2] * Jqs[8 + c] : 0.0;
+    for (int c = 0; c < 3; ++c) J_sensor[7 * r + 4 + c] = sensor ? Juvw[3 * r + c] : 0.0;
+  }
+  if (J_params) memcpy(J_params, Jp, 16 * P);
+  return 1;
+}
+
 /* ------------------------------------------------------------------------- loss (Ceres LossFunction + Corrector) */
 static void loss_eval(int type, double a, double s, double rho[3]) {
   const double b = a * a, c = 1.0 / b;
@@ -339,6 +391,7 @@ typedef struct {
   int* pose_off;      /* [num_poses] camera-side offset or -1 */
   uint8_t* pose_mask; /* [num_poses] 6-bit active tangent dims */
   int* cam_off;       /* [num_cameras] or -1 */
+  int* sens_off;      /* [num_sensors] camera-side offset of the sensor_from_rig block or -1 */
   int* cam_nvar;
   int (*cam_var)[MAXDK];
   int* pt_var;        /* [num_points] index among variable points or -1 */
@@ -371,6 +424,7 @@ static int flatten(ba_flat* F) {
   F->pose_off = (int*)malloc(sizeof(int) * p->num_poses);
   F->pose_mask = (uint8_t*)malloc(p->num_poses);
   F->cam_off = (int*)malloc(sizeof(int) * p->num_cameras);
+  F->sens_off = (int*)malloc(sizeof(int) * (p->num_sensors + 1));
   F->cam_nvar = (int*)calloc(p->num_cameras, sizeof(int));
   F->cam_var = (int(*)[MAXDK])calloc(p->num_cameras, sizeof(int[MAXDK]));
   F->pt_var = (int*)malloc(sizeof(int) * p->num_points);
@@ -391,6 +445,17 @@ static int flatten(ba_flat* F) {
     if (p->pose_fixed_translation_dim && p->pose_fixed_translation_dim[i] >= 0) m &= ~(1u << (3 + p->pose_fixed_translation_dim[i]));
     F->pose_off[i] = off; F->pose_mask[i] = m; off += 6; F->nvp++;
   }
+  {  /* sensor_from_rig blocks (ParameterizeRigsAndFrames, bundle_adjustment_ceres.cc:478-539): variable iff refined,
+        not constant, and its camera is observed */
+    uint8_t* sens_used = (uint8_t*)calloc(p->num_sensors + 1, 1);
+    for (int c = 0; c < p->num_cameras; ++c) if (cam_used[c] && p->camera_sensor_idx && p->camera_sensor_idx[c] >= 0) sens_used[p->camera_sensor_idx[c]] = 1;
+    for (int k = 0; k < p->num_sensors; ++k) {
+      const int cst = !o->refine_sensor_from_rig || (p->sensor_constant && p->sensor_constant[k]) || !sens_used[k];
+      F->sens_off[k] = cst ? -1 : off;
+      if (!cst) off += 6;
+    }
+    free(sens_used);
+  }
   for (int c = 0; c < p->num_cameras; ++c) {
     const int id = p->camera_model_id[c], P = model_num_params(id);
     if (P < 0) return -2;
@@ -398,7 +463,7 @@ static int flatten(ba_flat* F) {
     if (!(p->camera_constant && p->camera_constant[c]) && cam_used[c])
       for (int k = 0; k < P; ++k) {
         const int g = param_group(id, k);
-        const int refine = g == 0 ? o->refine_focal_length : (g == 1 ? o->refine_principal_point : o->refine_extra_params);
+        const int refine = g == 0 ? o->refine_focal_length : (g == 1 ? o->refine_principal_point : (g == 2 ? o->refine_extra_params : 0));
         if (refine) F->cam_var[c][nv++] = k;
       }
     F->cam_nvar[c] = nv;
@@ -415,7 +480,8 @@ static int flatten(ba_flat* F) {
   F->obs = (int64_t*)malloc(sizeof(int64_t) * (p->num_observations ? p->num_observations : 1));
   F->nobs = 0;
   for (int64_t i = 0; i < p->num_observations; ++i)
-    if (F->pose_off[p->obs_pose_idx[i]] >= 0 || F->cam_off[p->obs_camera_idx[i]] >= 0 || F->pt_var[p->obs_point_idx[i]] >= 0)
+    if (F->pose_off[p->obs_pose_idx[i]] >= 0 || F->cam_off[p->obs_camera_idx[i]] >= 0 || F->pt_var[p->obs_point_idx[i]] >= 0 ||
+        (p->camera_sensor_idx && p->camera_sensor_idx[p->obs_camera_idx[i]] >= 0 && F->sens_off[p->camera_sensor_idx[p->obs_camera_idx[i]]] >= 0))
       F->obs[F->nobs++] = i;
   qsort_r(F->obs, F->nobs, sizeof(int64_t), cmp_obs, F);
   F->pt_start = (int64_t*)calloc(F->nvpt + 1, sizeof(int64_t));
@@ -436,7 +502,7 @@ static int flatten(ba_flat* F) {
 }
 
 /* residuals (+ Jacobians in tangent space, loss-corrected) at parameters (poses, cams, points); returns cost */
-static double linearize(ba_flat* F, const double* poses, const double* cams, const double* pts, int want_jac) {
+static double linearize(ba_flat* F, const double* poses, const double* sens, const double* cams, const double* pts, int want_jac) {
   const b200ba_problem* p = F->p;
   const b200ba_options* o = F->o;
   double cost = 0.0, delta = 0.0;
@@ -445,8 +511,10 @@ static double linearize(ba_flat* F, const double* poses, const double* cams, con
     const int64_t i = F->obs[j];
     const int pi = p->obs_pose_idx[i], ci = p->obs_camera_idx[i], ti = p->obs_point_idx[i];
     const int id = p->camera_model_id[ci];
-    double res[2], Jpt[6], Jps[14], Jpr[10];
-    ba_oracle_reproj(id, pts + 3 * ti, poses + 7 * pi, cams + p->camera_param_offset[ci], p->obs_xy + 2 * i, res, Jpt, Jps, Jpr);
+    const int si = p->camera_sensor_idx ? p->camera_sensor_idx[ci] : -1;
+    double res[2], Jpt[6], Jps[14], Jss[14], Jpr[2 * MAXDK];
+    ba_oracle_reproj_rig(id, pts + 3 * ti, poses + 7 * pi, si >= 0 ? sens + 7 * si : NULL, cams + p->camera_param_offset[ci],
+                         p->obs_xy + 2 * i, res, Jpt, Jps, Jss, Jpr);
     const double s = res[0] * res[0] + res[1] * res[1];
     double rho[3];
     loss_eval(o->loss_function_type, o->loss_function_scale, s, rho);
@@ -456,24 +524,28 @@ static double linearize(ba_flat* F, const double* poses, const double* cams, con
     double* Jp = F->Jp + 6 * j;
     if (want_jac) {
       memset(Jc, 0, sizeof(double) * 2 * JC);
-      if (F->pose_off[pi] >= 0) {
-        const double* q = poses + 7 * pi;
-        const uint8_t m = F->pose_mask[pi];
+      for (int blk = 0; blk < 2; ++blk) {   /* rig_from_world pose, then sensor_from_rig: quaternion (x) R^3 tangent */
+        const int boff = blk == 0 ? F->pose_off[pi] : (si >= 0 ? F->sens_off[si] : -1);
+        if (boff < 0) continue;
+        const double* q = blk == 0 ? poses + 7 * pi : sens + 7 * si;
+        const double* Ja = blk == 0 ? Jps : Jss;
+        const uint8_t m = blk == 0 ? F->pose_mask[pi] : 0x3f;
+        const int jo = blk == 0 ? 0 : JS;
         /* J_quat (2x4) * PlusJacobian (4x3) of EigenQuaternionManifold at delta = 0 */
         const double PJ[12] = {q[3], q[2], -q[1], -q[2], q[3], q[0], q[1], -q[0], q[3], -q[0], -q[1], -q[2]};
         for (int r = 0; r < 2; ++r) {
           for (int c = 0; c < 3; ++c) {
             double v = 0;
-            for (int k = 0; k < 4; ++k) v += Jps[7 * r + k] * PJ[3 * k + c];
-            Jc[JC * r + c] = ((m >> c) & 1) ? v : 0.0;
+            for (int k = 0; k < 4; ++k) v += Ja[7 * r + k] * PJ[3 * k + c];
+            Jc[JC * r + jo + c] = ((m >> c) & 1) ? v : 0.0;
           }
-          for (int c = 0; c < 3; ++c) Jc[JC * r + 3 + c] = ((m >> (3 + c)) & 1) ? Jps[7 * r + 4 + c] : 0.0;
+          for (int c = 0; c < 3; ++c) Jc[JC * r + jo + 3 + c] = ((m >> (3 + c)) & 1) ? Ja[7 * r + 4 + c] : 0.0;
         }
       }
       if (F->cam_off[ci] >= 0) {
         const int P = model_num_params(id);
         for (int r = 0; r < 2; ++r)
-          for (int k = 0; k < F->cam_nvar[ci]; ++k) Jc[JC * r + 6 + k] = Jpr[P * r + F->cam_var[ci][k]];
+          for (int k = 0; k < F->cam_nvar[ci]; ++k) Jc[JC * r + JI + k] = Jpr[P * r + F->cam_var[ci][k]];
       }
       if (F->pt_var[ti] >= 0) memcpy(Jp, Jpt, 48); else memset(Jp, 0, 48);
     }
@@ -536,27 +608,31 @@ static int chol_solve(int n, double* A, double* b) { /* in place LL^T, dense */
   return 1;
 }
 
-/* camera-side offsets of observation j: pose block (6) and intrinsics block (nv) */
-static inline void obs_blocks(const ba_flat* F, int64_t j, int* po, int* co, int* nv) {
+/* camera-side blocks of observation j: rig_from_world pose (6), sensor_from_rig (6), intrinsics (nv); off < 0 = constant.
+ * jo = first column of the block inside a Jacobian row */
+typedef struct { int off[3], n[3], jo[3]; } obs_blk;
+static inline void obs_blocks(const ba_flat* F, int64_t j, obs_blk* B) {
   const int64_t i = F->obs[j];
-  *po = F->pose_off[F->p->obs_pose_idx[i]];
   const int ci = F->p->obs_camera_idx[i];
-  *co = F->cam_off[ci]; *nv = F->cam_nvar[ci];
+  const int si = F->p->camera_sensor_idx ? F->p->camera_sensor_idx[ci] : -1;
+  B->off[0] = F->pose_off[F->p->obs_pose_idx[i]]; B->n[0] = 6; B->jo[0] = 0;
+  B->off[1] = si >= 0 ? F->sens_off[si] : -1; B->n[1] = 6; B->jo[1] = JS;
+  B->off[2] = F->cam_off[ci]; B->n[2] = F->cam_nvar[ci]; B->jo[2] = JI;
 }
 /* y (2) = Jc_scaled(j) * x */
 static inline void jc_times(const ba_flat* F, int64_t j, const double* x, double y[2]) {
-  int po, co, nv; obs_blocks(F, j, &po, &co, &nv);
+  obs_blk B; obs_blocks(F, j, &B);
   const double* Jc = F->Jc + 2 * JC * j;
   y[0] = y[1] = 0;
-  if (po >= 0) for (int c = 0; c < 6; ++c) { const double v = F->scale_c[po + c] * x[po + c]; y[0] += Jc[c] * v; y[1] += Jc[JC + c] * v; }
-  if (co >= 0) for (int c = 0; c < nv; ++c) { const double v = F->scale_c[co + c] * x[co + c]; y[0] += Jc[6 + c] * v; y[1] += Jc[JC + 6 + c] * v; }
+  for (int w = 0; w < 3; ++w)
+    if (B.off[w] >= 0) for (int c = 0; c < B.n[w]; ++c) { const double v = F->scale_c[B.off[w] + c] * x[B.off[w] + c]; y[0] += Jc[B.jo[w] + c] * v; y[1] += Jc[JC + B.jo[w] + c] * v; }
 }
 /* out += Jc_scaled(j)^T u */
 static inline void jct_times_add(const ba_flat* F, int64_t j, const double u[2], double* out) {
-  int po, co, nv; obs_blocks(F, j, &po, &co, &nv);
+  obs_blk B; obs_blocks(F, j, &B);
   const double* Jc = F->Jc + 2 * JC * j;
-  if (po >= 0) for (int c = 0; c < 6; ++c) out[po + c] += F->scale_c[po + c] * (Jc[c] * u[0] + Jc[JC + c] * u[1]);
-  if (co >= 0) for (int c = 0; c < nv; ++c) out[co + c] += F->scale_c[co + c] * (Jc[6 + c] * u[0] + Jc[JC + 6 + c] * u[1]);
+  for (int w = 0; w < 3; ++w)
+    if (B.off[w] >= 0) for (int c = 0; c < B.n[w]; ++c) out[B.off[w] + c] += F->scale_c[B.off[w] + c] * (Jc[B.jo[w] + c] * u[0] + Jc[JC + B.jo[w] + c] * u[1]);
 }
 
 typedef struct {
@@ -613,10 +689,10 @@ static void schur_jacobi(const ba_flat* F, const ba_lin* L, const int* blk_start
   double* Mloc = (double*)calloc(msize, sizeof(double));   /* per-thread partial blocks, joined below */
 #pragma omp for schedule(static) nowait
   for (int64_t j = 0; j < F->nobs; ++j) {
-    int po, co, nv; obs_blocks(F, j, &po, &co, &nv);
+    obs_blk B; obs_blocks(F, j, &B);
     const double* Jc = F->Jc + 2 * JC * j;
-    for (int which = 0; which < 2; ++which) {
-      const int off = which == 0 ? po : co, n = which == 0 ? 6 : nv, jo = which == 0 ? 0 : 6;
+    for (int which = 0; which < 3; ++which) {
+      const int off = B.off[which], n = B.n[which], jo = B.jo[which];
       if (off < 0) continue;
       int b = 0; /* block index by binary search */
       { int lo = 0, hi = nblk - 1; while (lo < hi) { const int mid = (lo + hi + 1) / 2; if (blk_start[mid] <= off) lo = mid; else hi = mid - 1; } b = lo; }
@@ -633,20 +709,20 @@ static void schur_jacobi(const ba_flat* F, const ba_lin* L, const int* blk_start
     const double* Hi = L->Hpp_inv + 9 * k;
     /* distinct blocks among this point's observations */
     for (int64_t j = s; j < e2; ++j) {
-      for (int which = 0; which < 2; ++which) {
-        int po, co, nv; obs_blocks(F, j, &po, &co, &nv);
-        const int off = which == 0 ? po : co, n = which == 0 ? 6 : nv;
+      for (int which = 0; which < 3; ++which) {
+        obs_blk B; obs_blocks(F, j, &B);
+        const int off = B.off[which], n = B.n[which];
         if (off < 0) continue;
         /* only handle the block at its first occurrence within the point */
         int first = 1;
-        for (int64_t j2 = s; j2 < j && first; ++j2) { int po2, co2, nv2; obs_blocks(F, j2, &po2, &co2, &nv2); if ((which == 0 ? po2 : co2) == off) first = 0; }
+        for (int64_t j2 = s; j2 < j && first; ++j2) { obs_blk B2; obs_blocks(F, j2, &B2); if (B2.off[which] == off) first = 0; }
         if (!first) continue;
-        double V[3 * MAXDK > 18 ? 3 * MAXDK : 18];
+        double V[3 * MAXDK];
         memset(V, 0, sizeof(V));
         for (int64_t j2 = j; j2 < e2; ++j2) {
-          int po2, co2, nv2; obs_blocks(F, j2, &po2, &co2, &nv2);
-          if ((which == 0 ? po2 : co2) != off) continue;
-          const double* Jc = F->Jc + 2 * JC * j2; const double* Jp = F->Jp + 6 * j2; const int jo = which == 0 ? 0 : 6;
+          obs_blk B2; obs_blocks(F, j2, &B2);
+          if (B2.off[which] != off) continue;
+          const double* Jc = F->Jc + 2 * JC * j2; const double* Jp = F->Jp + 6 * j2; const int jo = B2.jo[which];
           for (int a = 0; a < 3; ++a)
             for (int c = 0; c < n; ++c)
               V[a * n + c] += F->scale_p[3 * k + a] * F->scale_c[off + c] * (Jp[a] * Jc[jo + c] + Jp[3 + a] * Jc[JC + jo + c]);
@@ -671,7 +747,7 @@ static void schur_jacobi(const ba_flat* F, const ba_lin* L, const int* blk_start
 #pragma omp parallel for schedule(static)
   for (int b = 0; b < nblk; ++b) {
     const int n = blk_start[b + 1] - blk_start[b];
-    double A[36], col[6];
+    double A[MAXDK * MAXDK], col[MAXDK];
     for (int c = 0; c < n; ++c) {
       memcpy(A, M + blk_pack[b], sizeof(double) * n * n);
       for (int r = 0; r < n; ++r) col[r] = r == c ? 1.0 : 0.0;
@@ -683,8 +759,16 @@ static void schur_jacobi(const ba_flat* F, const ba_lin* L, const int* blk_start
 }
 
 /* gradient max norm through the manifold: || x - Plus(x, -g) ||_inf */
-static double gradient_max_norm(const ba_flat* F, const double* poses, const double* gc, const double* gp) {
+static double gradient_max_norm(const ba_flat* F, const double* poses, const double* sens, const double* gc, const double* gp) {
   double m = 0;
+  for (int i = 0; i < F->p->num_sensors; ++i) {
+    const int off = F->sens_off[i];
+    if (off < 0) continue;
+    double d[3] = {-gc[off], -gc[off + 1], -gc[off + 2]}, qn[4];
+    quat_plus(sens + 7 * i, d, qn);
+    for (int k = 0; k < 4; ++k) m = fmax(m, fabs(qn[k] - sens[7 * i + k]));
+    for (int k = 3; k < 6; ++k) m = fmax(m, fabs(gc[off + k]));
+  }
   for (int i = 0; i < F->p->num_poses; ++i) {
     const int off = F->pose_off[i];
     if (off < 0) continue;
@@ -698,9 +782,16 @@ static double gradient_max_norm(const ba_flat* F, const double* poses, const dou
   return m;
 }
 
-static void apply_step(const ba_flat* F, const double* poses, const double* cams, const double* pts, const double* dc, const double* dp,
-                       double* nposes, double* ncams, double* npts, int64_t ncamparams) {
+static void apply_step(const ba_flat* F, const double* poses, const double* sens, const double* cams, const double* pts, const double* dc, const double* dp,
+                       double* nposes, double* nsens, double* ncams, double* npts, int64_t ncamparams) {
   const b200ba_problem* p = F->p;
+  memcpy(nsens, sens, sizeof(double) * 7 * p->num_sensors);
+  for (int i = 0; i < p->num_sensors; ++i) {
+    const int off = F->sens_off[i];
+    if (off < 0) continue;
+    quat_plus(sens + 7 * i, dc + off, nsens + 7 * i);
+    for (int k = 0; k < 3; ++k) nsens[7 * i + 4 + k] = sens[7 * i + 4 + k] + dc[off + 3 + k];
+  }
   memcpy(nposes, poses, sizeof(double) * 7 * p->num_poses);
   memcpy(ncams, cams, sizeof(double) * ncamparams);
   memcpy(npts, pts, sizeof(double) * 3 * p->num_points);
@@ -730,6 +821,7 @@ int ba_oracle_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* 
   int neff = 0;
   for (int i = 0; i < p->num_poses; ++i) if (F.pose_off[i] >= 0) neff += __builtin_popcount(F.pose_mask[i]);
   for (int c = 0; c < p->num_cameras; ++c) neff += F.cam_nvar[c];
+  for (int k = 0; k < p->num_sensors; ++k) if (F.sens_off[k] >= 0) neff += 6;
   neff += (int)(3 * F.nvpt);
   sum->num_effective_parameters = neff;
   int lst = o->linear_solver_type;
@@ -752,6 +844,9 @@ int ba_oracle_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* 
   double* pts = (double*)malloc(sizeof(double) * 3 * p->num_points); memcpy(pts, p->points, sizeof(double) * 3 * p->num_points);
   /* ParameterizeRigsAndFrames normalises quaternions (bundle_adjustment_ceres.cc:514) */
   for (int i = 0; i < p->num_poses; ++i) if (F.pose_off[i] >= 0) { double* q = poses + 7 * i; const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]); for (int k = 0; k < 4; ++k) q[k] /= n; }
+  double* sens = (double*)malloc(sizeof(double) * (7 * p->num_sensors + 1)); double* nsens = (double*)malloc(sizeof(double) * (7 * p->num_sensors + 1));
+  if (p->num_sensors) memcpy(sens, p->sensor_from_rig, sizeof(double) * 7 * p->num_sensors);
+  for (int i = 0; i < p->num_sensors; ++i) if (F.sens_off[i] >= 0) { double* q = sens + 7 * i; const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]); for (int k = 0; k < 4; ++k) q[k] /= n; }
   double* nposes = (double*)malloc(sizeof(double) * 7 * p->num_poses);
   double* ncams = (double*)malloc(sizeof(double) * (ncamparams + 1));
   double* npts = (double*)malloc(sizeof(double) * 3 * p->num_points);
@@ -761,13 +856,14 @@ int ba_oracle_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* 
   ba_lin L; L.Hpp_inv = (double*)malloc(sizeof(double) * (9 * F.nvpt + 1)); L.Dc2 = (double*)malloc(sizeof(double) * (nc + 1)); L.Dp2 = (double*)malloc(sizeof(double) * (np3 + 1));
   double* diag_c = (double*)malloc(sizeof(double) * (nc + 1)); double* diag_p = (double*)malloc(sizeof(double) * (np3 + 1));
   /* camera-side parameter blocks */
-  int nblk = 0; int* blk_start = (int*)malloc(sizeof(int) * (p->num_poses + p->num_cameras + 2)); int* blk_pack = (int*)malloc(sizeof(int) * (p->num_poses + p->num_cameras + 2));
+  int nblk = 0; int* blk_start = (int*)malloc(sizeof(int) * (p->num_poses + p->num_sensors + p->num_cameras + 2)); int* blk_pack = (int*)malloc(sizeof(int) * (p->num_poses + p->num_sensors + p->num_cameras + 2));
   { int pk = 0;
     for (int i = 0; i < p->num_poses; ++i) if (F.pose_off[i] >= 0) { blk_start[nblk] = F.pose_off[i]; blk_pack[nblk] = pk; pk += 36; nblk++; }
+    for (int i = 0; i < p->num_sensors; ++i) if (F.sens_off[i] >= 0) { blk_start[nblk] = F.sens_off[i]; blk_pack[nblk] = pk; pk += 36; nblk++; }
     for (int c = 0; c < p->num_cameras; ++c) if (F.cam_off[c] >= 0) { blk_start[nblk] = F.cam_off[c]; blk_pack[nblk] = pk; pk += F.cam_nvar[c] * F.cam_nvar[c]; nblk++; }
     blk_start[nblk] = nc; blk_pack[nblk] = pk; }
 
-  double cost = linearize(&F, poses, cams, pts, 1);
+  double cost = linearize(&F, poses, sens, cams, pts, 1);
   sum->initial_cost = cost;
   double radius = o->initial_trust_region_radius, decrease_factor = 2.0;
   int iter = 0, have_scale = 0;
@@ -783,9 +879,9 @@ int ba_oracle_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* 
         double* loc = (double*)calloc(nc + 1, sizeof(double));
 #pragma omp for schedule(static) nowait
         for (int64_t j = 0; j < F.nobs; ++j) {
-          int po, co, nv; obs_blocks(&F, j, &po, &co, &nv); const double* Jc = F.Jc + 2 * JC * j;
-          if (po >= 0) for (int c = 0; c < 6; ++c) loc[po + c] += Jc[c] * Jc[c] + Jc[JC + c] * Jc[JC + c];
-          if (co >= 0) for (int c = 0; c < nv; ++c) loc[co + c] += Jc[6 + c] * Jc[6 + c] + Jc[JC + 6 + c] * Jc[JC + 6 + c];
+          obs_blk B; obs_blocks(&F, j, &B); const double* Jc = F.Jc + 2 * JC * j;
+          for (int w = 0; w < 3; ++w)
+            if (B.off[w] >= 0) for (int c = 0; c < B.n[w]; ++c) loc[B.off[w] + c] += Jc[B.jo[w] + c] * Jc[B.jo[w] + c] + Jc[JC + B.jo[w] + c] * Jc[JC + B.jo[w] + c];
         }
 #pragma omp critical
         for (int i = 0; i < nc; ++i) F.scale_c[i] += loc[i];
@@ -810,9 +906,9 @@ int ba_oracle_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* 
 #pragma omp for schedule(static) nowait
       for (int64_t j = 0; j < F.nobs; ++j) {
         jct_times_add(&F, j, F.r + 2 * j, lg);
-        int po, co, nv; obs_blocks(&F, j, &po, &co, &nv); const double* Jc = F.Jc + 2 * JC * j;
-        if (po >= 0) for (int c = 0; c < 6; ++c) ld[po + c] += F.scale_c[po + c] * F.scale_c[po + c] * (Jc[c] * Jc[c] + Jc[JC + c] * Jc[JC + c]);
-        if (co >= 0) for (int c = 0; c < nv; ++c) ld[co + c] += F.scale_c[co + c] * F.scale_c[co + c] * (Jc[6 + c] * Jc[6 + c] + Jc[JC + 6 + c] * Jc[JC + 6 + c]);
+        obs_blk B; obs_blocks(&F, j, &B); const double* Jc = F.Jc + 2 * JC * j;
+        for (int w = 0; w < 3; ++w)
+          if (B.off[w] >= 0) for (int c = 0; c < B.n[w]; ++c) { const double sc = F.scale_c[B.off[w] + c]; ld[B.off[w] + c] += sc * sc * (Jc[B.jo[w] + c] * Jc[B.jo[w] + c] + Jc[JC + B.jo[w] + c] * Jc[JC + B.jo[w] + c]); }
       }
 #pragma omp critical
       for (int i = 0; i < nc; ++i) { gc[i] += lg[i]; diag_c[i] += ld[i]; }
@@ -833,7 +929,7 @@ int ba_oracle_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* 
       double* ugc = dc; double* ugp = dp;
       for (int i = 0; i < nc; ++i) ugc[i] = gc[i] / F.scale_c[i];
       for (int64_t i = 0; i < np3; ++i) ugp[i] = gp[i] / F.scale_p[i];
-      if (gradient_max_norm(&F, poses, ugc, ugp) <= o->gradient_tolerance) { sum->termination_type = B200BA_CONVERGENCE; break; }
+      if (gradient_max_norm(&F, poses, sens, ugc, ugp) <= o->gradient_tolerance) { sum->termination_type = B200BA_CONVERGENCE; break; }
     }
     /* inner loop: retry with smaller radius until a step is accepted (Jacobian unchanged) */
     int accepted = 0;
@@ -937,9 +1033,9 @@ int ba_oracle_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* 
         double* udc = (double*)malloc(sizeof(double) * (nc + 1)); double* udp = (double*)malloc(sizeof(double) * (np3 + 1));
         for (int i = 0; i < nc; ++i) udc[i] = dc[i] * F.scale_c[i];
         for (int64_t i = 0; i < np3; ++i) udp[i] = dp[i] * F.scale_p[i];
-        apply_step(&F, poses, cams, pts, udc, udp, nposes, ncams, npts, ncamparams);
+        apply_step(&F, poses, sens, cams, pts, udc, udp, nposes, nsens, ncams, npts, ncamparams);
         free(udc); free(udp);
-        new_cost = linearize(&F, nposes, ncams, npts, 0);
+        new_cost = linearize(&F, nposes, nsens, ncams, npts, 0);
         /* cost change summed residual by residual: same quantity as cost - new_cost without the cancellation */
         rho_q = (-F.cost_delta) / model;
       }
@@ -948,8 +1044,9 @@ int ba_oracle_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* 
         accepted = 1;
         sum->num_successful_steps++;
         memcpy(poses, nposes, sizeof(double) * 7 * p->num_poses); memcpy(cams, ncams, sizeof(double) * ncamparams); memcpy(pts, npts, sizeof(double) * 3 * p->num_points);
+        memcpy(sens, nsens, sizeof(double) * 7 * p->num_sensors);
         const double cost_change = -F.cost_delta;
-        cost = linearize(&F, poses, cams, pts, 1);
+        cost = linearize(&F, poses, sens, cams, pts, 1);
         const double t = 2.0 * rho_q - 1.0;
         radius = radius / fmax(1.0 / 3.0, 1.0 - t * t * t);
         radius = fmin(o->max_trust_region_radius, radius);
@@ -967,6 +1064,8 @@ done:
   sum->final_cost = cost;
   /* write back only variable blocks; constants stay bit-identical */
   for (int i = 0; i < p->num_poses; ++i) if (F.pose_off[i] >= 0) memcpy(p->poses + 7 * i, poses + 7 * i, 56);
+  for (int i = 0; i < p->num_sensors; ++i) if (F.sens_off[i] >= 0) memcpy(p->sensor_from_rig + 7 * i, sens + 7 * i, 56);
+  free(sens); free(nsens); free(F.sens_off);
   for (int c = 0; c < p->num_cameras; ++c) if (F.cam_off[c] >= 0) for (int k = 0; k < F.cam_nvar[c]; ++k) { const int idx = p->camera_param_offset[c] + F.cam_var[c][k]; p->camera_params[idx] = cams[idx]; }
   for (int64_t i = 0; i < p->num_points; ++i) if (F.pt_var[i] >= 0) memcpy(p->points + 3 * i, pts + 3 * i, 24);
   free(poses); free(cams); free(pts); free(nposes); free(ncams); free(npts); free(gc); free(gp); free(dc); free(dp); free(rhs);

@@ -21,6 +21,7 @@ def lib():
         L.ba_oracle_solve.argtypes = [ctypes.POINTER(_COptions), ctypes.POINTER(_CProblem), ctypes.POINTER(_CSummary)]
         L.ba_oracle_reproj.argtypes = [ctypes.c_int, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p]
         L.ba_oracle_quat_plus.argtypes = [_f64p, _f64p, _f64p]
+        L.ba_oracle_reproj_rig.argtypes = [ctypes.c_int, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p]
         _LIB = L
     return _LIB
 
@@ -42,3 +43,15 @@ def reproj(model_id, point, pose, params, xy):
                                 params.ctypes.data_as(_f64p), xy.ctypes.data_as(_f64p), res.ctypes.data_as(_f64p),
                                 Jpt.ctypes.data_as(_f64p), Jps.ctypes.data_as(_f64p), Jpr.ctypes.data_as(_f64p))
     return ok, res, Jpt, Jps, Jpr
+
+
+def reproj_rig(model_id, point, rig, sensor, params, xy):
+    """ba_oracle_reproj_rig: residual + Jacobians of cam_from_world = sensor_from_rig * rig_from_world (sensor None = identity)."""
+    d = lambda a: np.ascontiguousarray(a, np.float64)
+    point, rig, params, xy = d(point), d(rig), d(params), d(xy)
+    sp = d(sensor).ctypes.data_as(_f64p) if sensor is not None else None
+    res = np.zeros(2); Jpt = np.zeros((2, 3)); Jr = np.zeros((2, 7)); Js = np.zeros((2, 7)); Jpr = np.zeros((2, len(params)))
+    ok = lib().ba_oracle_reproj_rig(model_id, point.ctypes.data_as(_f64p), rig.ctypes.data_as(_f64p), sp, params.ctypes.data_as(_f64p),
+                                    xy.ctypes.data_as(_f64p), res.ctypes.data_as(_f64p), Jpt.ctypes.data_as(_f64p),
+                                    Jr.ctypes.data_as(_f64p), Js.ctypes.data_as(_f64p), Jpr.ctypes.data_as(_f64p))
+    return ok, res, Jpt, Jr, Js, Jpr

@@ -259,3 +259,75 @@ def test_cross_backend_with_the_reference_caspar_solver():
     pa, pb = a.cam_params.reshape(-1, 4), b.cam_params.reshape(-1, 4)
     assert np.abs(pa[:, 0] - pb[:, 0]).max() < 20.0 and np.abs(pa[:, 1:3] - pb[:, 1:3]).max() < 10.0, msg
     assert np.abs(pa[:, 3] - pb[:, 3]).max() < 1.5e-2, msg
+
+
+# ---------------------------------------------------------------- the twelve wide camera models + rigs on the solve path
+from colmap_b200.bundle_adjustment import (DIVISION, EQUIRECTANGULAR, EUCM, FISHEYE, FOV, FULL_OPENCV, OPENCV, OPENCV_FISHEYE,
+                                           RAD_TAN_THIN_PRISM_FISHEYE, SIMPLE_DIVISION, SIMPLE_FISHEYE, THIN_PRISM_FISHEYE)
+
+
+@pytest.mark.parametrize("models,shared,kw", [
+    ((OPENCV,), False, {}),
+    ((OPENCV,), True, dict(refine_principal_point=True)),                       # 8-wide intrinsics block, shared: cross terms
+    ((OPENCV_FISHEYE, FISHEYE, SIMPLE_RADIAL), False, {}),                      # wide + narrow mixed
+    ((FULL_OPENCV,), True, dict(refine_principal_point=True)),                  # 12-wide block: two 6-ranges + their pair
+    ((RAD_TAN_THIN_PRISM_FISHEYE,), True, dict(refine_principal_point=True)),   # 16-wide block
+    ((FOV, EUCM, DIVISION, SIMPLE_DIVISION), False, {}),
+    ((SIMPLE_FISHEYE, THIN_PRISM_FISHEYE), True, dict(linear_solver_type=ITERATIVE_SCHUR)),
+    ((EQUIRECTANGULAR, PINHOLE), False, {}),                                    # metadata parameters are never refined
+    ((OPENCV_FISHEYE, FULL_OPENCV), False, dict(linear_solver_type=ITERATIVE_SCHUR)),   # own wide cameras, PCG: SCHUR_JACOBI blocks
+                                                                                        # of 6 and 10 columns from the 6-range pairs
+])
+def test_wide_model_grid_parity(models, shared, kw):
+    """models_jacobian.h:322-1565 on the solve path: every model beyond the <= 5-parameter family through the wide kernel
+    instantiations, against the oracle (whose wide Jacobians come from the complex-step method).  High-order distortion
+    models converge slowly along nearly flat directions (k5, k6, s-terms): when a run stops at the iteration limit instead
+    of the gradient tolerance the two trajectories (fp32-stored vs fp64 Jacobians) are compared at 1e-4 in the cost."""
+    n_img = 12 if shared else 16
+    gt, noisy = synthesize_ba_problem(n_img, 1200, 8, models=models, shared_camera=shared, seed=19, point2D_stddev=0.3,
+                                      point3D_stddev=0.02, rotation_stddev_deg=0.3)
+    _gauge(noisy)
+    # (1) the arithmetic: three LM iterations from the same start must agree tightly (same gradient, damping, reduced system)
+    a, sg, b, sr = _both(BundleAdjustmentOptions(max_num_iterations=3, **kw), noisy)
+    assert sg.num_residuals == sr.num_residuals and sg.num_effective_parameters == sr.num_effective_parameters
+    assert abs(sg.initial_cost - sr.initial_cost) <= 1e-9 * sr.initial_cost
+    assert abs(sg.final_cost - sr.final_cost) <= 1e-6 * sr.final_cost
+    for u, v in ((a.poses, b.poses), (a.points, b.points), (a.cam_params, b.cam_params)):
+        assert np.allclose(u, v, rtol=1e-5, atol=1e-5 * max(1.0, np.abs(v).max()))
+    # (2) the full run: back at the noise floor; the cost agrees to 1e-5 where both runs reach the gradient tolerance and
+    # to 1e-3 where they stop at the iteration limit inside the flat valley of a high-order model
+    a, sg, b, sr = _both(BundleAdjustmentOptions(**kw), noisy)
+    converged = sg.termination_type == 0 and sr.termination_type == 0
+    assert abs(sg.final_cost - sr.final_cost) <= (REL if converged else 1e-3) * sr.final_cost
+    rmse = np.sqrt(2 * sg.final_cost / (sg.num_residuals / 2))
+    assert rmse < 0.3 * np.sqrt(2) * 1.1
+    if converged and not kw.get("refine_principal_point"):
+        for u, v in ((a.poses, b.poses), (a.points, b.points)):
+            assert np.allclose(u, v, rtol=1e-4, atol=1e-4 * max(1.0, np.abs(v).max()))
+
+
+@pytest.mark.parametrize("kw,sensor_const,models", [
+    ({}, None, (SIMPLE_RADIAL,)),                                               # everything variable
+    (dict(refine_sensor_from_rig=False), None, (SIMPLE_RADIAL, PINHOLE)),       # RigReprojErrorConstantRigCostFunctor
+    ({}, [1, 0], (OPENCV, SIMPLE_RADIAL, FISHEYE)),                             # one sensor constant, wide models in the rig
+    (dict(refine_rig_from_world=False), None, (SIMPLE_RADIAL,)),                # frames fixed, sensors + intrinsics + points move
+    (dict(linear_solver_type=ITERATIVE_SCHUR, refine_principal_point=True), None, (PINHOLE, SIMPLE_RADIAL, RADIAL)),
+])
+def test_rig_parity(kw, sensor_const, models):
+    """Non-trivial frames (reprojection_error.h:344-420, bundle_adjustment_ceres.cc:753-827): cam_from_world =
+    sensor_from_rig * rig_from_world, the sensor_from_rig poses as camera-side blocks of their own."""
+    from colmap_b200.synthetic import synthesize_rig_problem
+    gt, noisy = synthesize_rig_problem(10, 3, 800, 8, models=models, seed=23, point2D_stddev=0.5)
+    _gauge(noisy)
+    if sensor_const is not None:
+        noisy.sensor_constant = np.array(sensor_const, np.uint8)
+    before = noisy.copy()
+    a, sg, b, sr = _both(BundleAdjustmentOptions(**kw), noisy)
+    _assert_parity(a, sg, b, sr, param_rel=1e-4)
+    assert np.allclose(a.sensors, b.sensors, rtol=1e-4, atol=1e-4)
+    if kw.get("refine_sensor_from_rig") is False:
+        assert np.array_equal(a.sensors, before.sensors)                        # constant blocks bit-identical
+    if sensor_const is not None:
+        assert np.array_equal(a.sensors[0], before.sensors[0]) and not np.array_equal(a.sensors[1], before.sensors[1])
+    if kw.get("refine_rig_from_world") is False:
+        assert np.array_equal(a.poses, before.poses)
