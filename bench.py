@@ -470,7 +470,7 @@ def main():
     ap.add_argument("--c4-images", type=int, default=-1,
                     help="images of the C4-shaped workspace leg: -1 = 3 per GPU when 8 GPUs run (the configuration's GPU count), "
                          "else skipped; 0 = skip; 200 = the full configuration")
-    ap.add_argument("--b5", type=int, default=-1, help="BA config B5 leg: -1 = only when 8 GPUs run, 0 = skip, 1 = run")
+    ap.add_argument("--b5", type=int, default=1, help="BA config B5 leg (2000 cameras, 2M points, 12M observations; strong scaling over the ranks): 1 = run, 0 = skip")
     args = ap.parse_args()
 
     rank = _env_int("RANK", 0)
@@ -567,7 +567,7 @@ def main():
     wall_per_step = max_over_ranks(wall_ms / args.steps, "cuda")
 
     ba_sharded = None
-    want_b5 = args.b5 == 1 or (args.b5 == -1 and world == 8)
+    want_b5 = args.b5 == 1
     if distributed and not args.no_ba:
         try:
             ba_sharded = bench_ba_sharded(args.steps, args.warmup, rank, world, local_rank, with_b5=want_b5)

@@ -2048,6 +2048,8 @@ struct BaNccl {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool ok = false;
 };
@@ -2063,8 +2065,10 @@ static BaNccl& ba_nccl() {
       n.CommInitRank = (decltype(n.CommInitRank))dlsym(h, "ncclCommInitRank");
       n.AllReduce = (decltype(n.AllReduce))dlsym(h, "ncclAllReduce");
       n.CommDestroy = (decltype(n.CommDestroy))dlsym(h, "ncclCommDestroy");
+      n.GroupStart = (decltype(n.GroupStart))dlsym(h, "ncclGroupStart");
+      n.GroupEnd = (decltype(n.GroupEnd))dlsym(h, "ncclGroupEnd");
       n.GetErrorString = (decltype(n.GetErrorString))dlsym(h, "ncclGetErrorString");
-      n.ok = n.GetUniqueId && n.CommInitRank && n.AllReduce && n.CommDestroy;
+      n.ok = n.GetUniqueId && n.CommInitRank && n.AllReduce && n.CommDestroy && n.GroupStart && n.GroupEnd;
     }
   }
   return n;
@@ -2352,6 +2356,9 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
     const ncclResult_t r = ba_nccl().AllReduce(buf, buf, count, dt, op, comm->comm, st);
     return r == ncclSuccess ? cudaSuccess : cudaErrorUnknown;
   };
+  // consecutive small all-reduces of one LM iteration travel as ONE NCCL group (one launch, one latency)
+  auto group_begin = [&]() { if (sharded) ba_nccl().GroupStart(); };
+  auto group_end = [&]() { if (sharded) ba_nccl().GroupEnd(); };
   if (sharded) {  // a block is "used" if any rank observes it: keeps the camera-side layout identical on every rank
     std::vector<int> flags(NP + NCAM);
     for (int i = 0; i < NP; ++i) flags[i] = pose_used[i];
@@ -2805,8 +2812,10 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
     BA_CHECKPOINT("build_cam_sorted");
     if (D.nchunks_off) ba_cam_offdiag_kernel<false><<<(D.nchunks_off + BA_SC_BLOCK / 32 - 1) / (BA_SC_BLOCK / 32), BA_SC_BLOCK, 0, st>>>(D);
     BA_CHECKPOINT("cam_offdiag<false>");
+    group_begin();
     BA_CUDA(allreduce(D.gc, nc, ncclDouble, ncclSum));
     BA_CUDA(allreduce(D.Hbb, pack, ncclDouble, ncclSum));
+    group_end();
     if (nc) ba_diag_from_blocks_kernel<<<gc_blocks, 256, 0, st>>>(D);
     if (nvpt) ba_build_pt_kernel<<<gp_blocks, 256, 0, st>>>(D);
     BA_CHECKPOINT("diag + build_pt");
@@ -2837,9 +2846,11 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
         if (dkmax > 0 && intr_by_pt) ba_schur_pt_kernel<<<gp_blocks, 256, 0, st>>>(D);
         launches += 1 + (dkmax > 0 && intr_by_pt ? 1 : 0);
       }
+      group_begin();
       BA_CUDA(allreduce(D.rhs, nc, ncclDouble, ncclSum));
       BA_CUDA(allreduce(D.Mbb, pack, ncclDouble, ncclSum));
       BA_CUDA(allreduce(d_fail, 1, ncclInt32, ncclMax));
+      group_end();
       BA_CHECKPOINT("damp + schur_cam / schur_pt");
       if (nblk) { if (D.wide) ba_invert_blocks_kernel<BA_MAXCB><<<(nblk + 127) / 128, 128, 0, st>>>(D); else ba_invert_blocks_kernel<6><<<(nblk + 127) / 128, 128, 0, st>>>(D); }
       launches += 4;
@@ -2903,9 +2914,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
       BA_CUDA(zero_field(&D.ctl->cost_delta));
       ba_cost_kernel<<<nblocks, BA_BLOCK, 0, st>>>(D, D.nposes_, D.ncams_, D.npts_, D.nsensors_, &D.ctl->new_cost);
       BA_CHECKPOINT("update + cost");
-      BA_CUDA(allreduce(&D.ctl->model, 1, ncclDouble, ncclSum));
-      BA_CUDA(allreduce(&D.ctl->new_cost, 1, ncclDouble, ncclSum));
-      BA_CUDA(allreduce(&D.ctl->cost_delta, 1, ncclDouble, ncclSum));
+      BA_CUDA(allreduce(&D.ctl->new_cost, 3, ncclDouble, ncclSum));   // new_cost, model, cost_delta are adjacent in BaCtl
       launches += 3;
       BA_CUDA(read_ctl());
       const int failed = h.fail;
@@ -2921,8 +2930,9 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
         std::swap(D.poses, D.nposes_); std::swap(D.cams, D.ncams_); std::swap(D.pts, D.npts_); std::swap(D.sensors, D.nsensors_);
         const double cost_change = cost_change_acc;
         linearize_current(1);
-        BA_CUDA(read_ctl());
-        cost = h.cost;
+        // the cost at the accepted point is the candidate cost just evaluated: no third host round trip per LM iteration
+        // (the re-linearisation sums the same per-observation values; it only differs in the order of the block sums)
+        cost = new_cost;
         const double t = 2.0 * rho_q - 1.0;
         radius = radius / std::max(1.0 / 3.0, 1.0 - t * t * t);
         radius = std::min(o->max_trust_region_radius, radius);
