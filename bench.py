@@ -292,8 +292,9 @@ def bench_b5(steps, warmup, rank, world, local_rank, comm):
 
 
 def bench_ba_sharded(steps, warmup, rank, world, local_rank, with_b5=False):
-    """BA leg at N > 1: the same B3 problem, points sharded over the ranks (strong scaling), one NCCL all-reduce of the
-    camera-side vector per PCG iteration inside b200ba_solve_sharded."""
+    """BA leg at N > 1: the same B3 problem, points sharded over the ranks (strong scaling), one all-reduce of the
+    camera-side vector per PCG iteration inside b200ba_solve_sharded (the library's peer-memory kernel; NCCL only for
+    the set-up exchanges and as the fallback when peers cannot map each other)."""
     import torch
     import torch.distributed as dist
     from colmap_b200.bundle_adjustment import (ITERATIVE_SCHUR, BAComm, BundleAdjustmentOptions, shard_flat_problem,
@@ -322,14 +323,17 @@ def bench_ba_sharded(steps, warmup, rank, world, local_rank, with_b5=False):
             b5 = bench_b5(min(steps, 2), 1, rank, world, local_rank, comm)
         except Exception as e:
             b5 = {"error": repr(e)}
+    collective = ("one-shot all-reduce kernel over NVLink peer memory (cudaIpc symmetric buffers), one launch per collective"
+                  if comm.peer_memory() else "ncclAllReduce")
     comm.close()
     from colmap_b200.sharding import max_over_ranks
     dev_ms = max_over_ranks(dev_ms, "cuda"); wall_ms = max_over_ranks(wall_ms, "cuda")
     out = {"metric": "ba_lm_iterations_per_s", "value": lm / (dev_ms * 1e-3), "unit": "LM iterations/s", "dtype": "f64",
            "n_gpus": world, "scaling": "strong", "ms_per_step": dev_ms / steps, "lm_iterations_per_solve": lm / steps,
-           "config": {"workload": B3_WORKLOAD + "; points sharded over the ranks"},
+           "config": {"workload": B3_WORKLOAD + "; points sharded over the ranks", "collective": collective},
            "e2e": {"value": lm / (wall_ms * 1e-3), "unit": "LM iterations/s", "ms_per_step": wall_ms / steps},
-           "final_cost": s.final_cost, "termination_type": s.termination_type}
+           "final_cost": s.final_cost, "termination_type": s.termination_type,
+           "pcg_iterations_per_solve": s.num_linear_solver_iterations}
     if b5 is not None:
         out["b5"] = b5
     return out

@@ -273,6 +273,8 @@ def _bind(lib):
     lib.b200ba_comm_init.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
     lib.b200ba_comm_destroy.argtypes = [ctypes.c_void_p]
     lib.b200ba_comm_destroy.restype = None
+    lib.b200ba_comm_peer_memory.argtypes = [ctypes.c_void_p]
+    lib.b200ba_comm_peer_memory.restype = ctypes.c_int
     lib.b200ba_solve_sharded.argtypes = [ctypes.POINTER(_COptions), ctypes.POINTER(_CProblem), ctypes.c_void_p,
                                          ctypes.POINTER(_CSummary)]
     lib.b200ba_options_init.argtypes = [ctypes.POINTER(_COptions)]
@@ -341,6 +343,10 @@ class BAComm:
         if rc != 0:
             raise BundleAdjustmentError(f"b200ba_comm_unique_id failed ({rc}): {lib.b200ba_last_error().decode()}")
         return buf.raw
+
+    def peer_memory(self) -> bool:
+        """True once the small collectives run as the library's own one-shot all-reduce over NVLink peer memory."""
+        return bool(self._h) and bool(self._lib.b200ba_comm_peer_memory(self._h))
 
     def close(self):
         if self._h:

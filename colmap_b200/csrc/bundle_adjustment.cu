@@ -986,42 +986,39 @@ __global__ void ba_schur_pt_kernel(const BaDev D) {
 // invert the preconditioner blocks (Cholesky); one thread per block.  MAXN = 6: the narrow layout (pose blocks and <= 5
 // intrinsics); MAXN = BA_MAXCB: wide camera blocks.  A camera block that holds a sensor_from_rig part AND an intrinsics
 // part is two parameter blocks for ceres' SCHUR_JACOBI: blk_split keeps their diagonal sub-blocks and drops the cross terms.
+// One thread per COLUMN of a diagonal block (nc threads, not nblk): the thread factorises the (sub-)block its column
+// belongs to - a few dozen flops, done redundantly by the block's columns - and back-substitutes its own unit vector.
+// Same operations in the same order as a block-serial inversion, a sixth of its latency.
 template <int MAXN>
 __global__ void ba_invert_blocks_kernel(const BaDev D) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= D.nblk) return;
-  const int n = D.blk_start[b + 1] - D.blk_start[b];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D.nc) return;
+  const int b = D.off2blk[i], r0 = D.blk_start[b], n = D.blk_start[b + 1] - r0, cc = i - r0;
   const double* M = D.Mbb + D.blk_pack[b];
   double* O = D.Minv + D.blk_pack[b];
-  const int split = (MAXN > 6 && D.blk_split) ? D.blk_split[b] : 0;
+  const int split = (MAXN > 6 && D.blk_split) ? D.blk_split[b] : 0;   // [pose | intrinsics] blocks are inverted separately
+  const int s0 = (split && cc >= split) ? split : 0, s1 = split ? (cc >= split ? n : split) : n;
+  const int m = s1 - s0, c = cc - s0;
   double L[MAXN * MAXN];
-  for (int r = 0; r < n; ++r) for (int c = 0; c < n; ++c) O[r * n + c] = 0.0;
-  for (int seg = 0; seg < 2; ++seg) {
-    const int s0 = seg == 0 ? 0 : split, s1 = seg == 0 ? (split ? split : n) : n;
-    if (seg == 1 && split == 0) break;
-    const int m = s1 - s0;
-    bool ok = true;
-    for (int j = 0; j < m && ok; ++j) {
-      double d = M[(s0 + j) * n + s0 + j];
-      for (int k = 0; k < j; ++k) d -= L[j * m + k] * L[j * m + k];
-      if (!(d > 0)) { ok = false; break; }
-      d = sqrt(d); L[j * m + j] = d;
-      for (int i = j + 1; i < m; ++i) {
-        double s = M[(s0 + i) * n + s0 + j];
-        for (int k = 0; k < j; ++k) s -= L[i * m + k] * L[j * m + k];
-        L[i * m + j] = s / d;
-      }
-    }
-    for (int c = 0; c < m; ++c) {
-      double col[MAXN];
-      for (int r = 0; r < m; ++r) col[r] = r == c ? 1.0 : 0.0;
-      if (ok) {
-        for (int i = 0; i < m; ++i) { double s = col[i]; for (int k = 0; k < i; ++k) s -= L[i * m + k] * col[k]; col[i] = s / L[i * m + i]; }
-        for (int i = m - 1; i >= 0; --i) { double s = col[i]; for (int k = i + 1; k < m; ++k) s -= L[k * m + i] * col[k]; col[i] = s / L[i * m + i]; }
-      }
-      for (int r = 0; r < m; ++r) O[(s0 + r) * n + s0 + c] = col[r];
+  bool ok = true;
+  for (int j = 0; j < m && ok; ++j) {
+    double d = M[(s0 + j) * n + s0 + j];
+    for (int k = 0; k < j; ++k) d -= L[j * m + k] * L[j * m + k];
+    if (!(d > 0)) { ok = false; break; }
+    d = sqrt(d); L[j * m + j] = d;
+    for (int r = j + 1; r < m; ++r) {
+      double t = M[(s0 + r) * n + s0 + j];
+      for (int k = 0; k < j; ++k) t -= L[r * m + k] * L[j * m + k];
+      L[r * m + j] = t / d;
     }
   }
+  double col[MAXN];
+  for (int r = 0; r < m; ++r) col[r] = r == c ? 1.0 : 0.0;
+  if (ok) {
+    for (int r = 0; r < m; ++r) { double t = col[r]; for (int k = 0; k < r; ++k) t -= L[r * m + k] * col[k]; col[r] = t / L[r * m + r]; }
+    for (int r = m - 1; r >= 0; --r) { double t = col[r]; for (int k = r + 1; k < m; ++k) t -= L[k * m + r] * col[k]; col[r] = t / L[r * m + r]; }
+  }
+  for (int r = 0; r < n; ++r) O[r * n + cc] = (r >= s0 && r < s1) ? col[r - s0] : 0.0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1377,7 +1374,8 @@ __device__ __forceinline__ double ba_cta_allsum(double v, double* sm /* [33] */)
 // p = z + beta p ; q = D_c^2 p — the SpMV adds the rest).  do_post = 0 for the very first call of a solve.
 #define BA_PCG_EPT 4   // elements per thread handled from registers (nc <= BA_PCG_T * BA_PCG_EPT takes the fast path)
 __global__ void __launch_bounds__(BA_PCG_T) ba_pcg_mid_kernel(const BaDev D, double q_tolerance, double r_tolerance,
-                                                              int max_iters, int zero_q, int do_post) {
+                                                              int max_iters, int zero_q, int do_post, int r_in_smem) {
+  extern __shared__ double s_r[];   // [nc] when r_in_smem
   __shared__ double sm[33];
   __shared__ int s_done;
   BaCtl* c = D.ctl;
@@ -1411,13 +1409,14 @@ __global__ void __launch_bounds__(BA_PCG_T) ba_pcg_mid_kernel(const BaDev D, dou
       for (int e = 0; e < BA_PCG_EPT; ++e) {
         const int i = threadIdx.x + e * BA_PCG_T;
         const double x = xv[e] + alpha * pv[e], r = rv[e] - alpha * qv[e];
-        if (i < nc) { X[i] = x; R[i] = r; a += -x * (bv[e] + r); w += r * r; }
+        if (i < nc) { X[i] = x; R[i] = r; if (r_in_smem) s_r[i] = r; a += -x * (bv[e] + r); w += r * r; }
       }
     } else {
       for (int i = threadIdx.x; i < nc; i += BA_PCG_T) {
         const double x = X[i] + alpha * P[i];
         const double r = R[i] - alpha * Q[i];
         X[i] = x; R[i] = r;
+        if (r_in_smem) s_r[i] = r;
         a += -x * (RHS[i] + r);
         w += r * r;
       }
@@ -1452,14 +1451,28 @@ __global__ void __launch_bounds__(BA_PCG_T) ba_pcg_mid_kernel(const BaDev D, dou
     it += 1;
     last_rho = rho_in;
   }
+  // z = M^-1 r, block row by block row.  The residual of the whole camera side sits in shared memory when it fits (the
+  // rows of a block belong to different threads), and the row of M^-1 is fetched with one batch of predicated loads
+  // instead of a dependent load per column: this kernel is a chain of latencies, not of bytes.
+  if (r_in_smem && !do_post) {
+    for (int i = threadIdx.x; i < nc; i += BA_PCG_T) s_r[i] = R[i];
+    __syncthreads();
+  }
+  const double* __restrict__ RV = r_in_smem ? s_r : R;
   double v = 0.0;
   for (int i = threadIdx.x; i < nc; i += BA_PCG_T) {
     const int4 ri = D.row_info[i];   // {first row of the block, offset of this row of Minv, block size}
     const double* __restrict__ M = MI + ri.y;
+    const double* __restrict__ rb = RV + ri.x;
+    double m[11];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) m[k] = k < ri.z ? M[k] : 0.0;
     double t = 0;
-    for (int k = 0; k < ri.z; ++k) t += M[k] * R[ri.x + k];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) if (k < ri.z) t += m[k] * rb[k];
+    for (int k = 11; k < ri.z; ++k) t += M[k] * rb[k];
     Z[i] = t;
-    v += t * R[i];
+    v += t * RV[i];
   }
   const double rho = ba_cta_allsum(v, sm);
   const bool first = (it == 0);   // first iteration: p = z (never reads the uninitialised / recycled p buffer)
@@ -1468,6 +1481,136 @@ __global__ void __launch_bounds__(BA_PCG_T) ba_pcg_mid_kernel(const BaDev D, dou
     const double p = first ? Z[i] : Z[i] + beta * P[i];
     P[i] = p;
     Q[i] = zero_q ? 0.0 : DC2[i] * p;
+  }
+  if (threadIdx.x == 0) c->rho = rho;
+}
+
+// Latency-tuned form of ba_pcg_mid_kernel for camera sides of up to BA_PCG_T * BA_MID_EPT unknowns (B3: 4993).  The
+// single CTA is a chain of dependent memory round trips, so everything a thread will need is requested up front:
+// r, x, b and the block-row descriptors stream into shared memory with cp.async while p, q arrive in registers and the
+// first reduction runs; the rows of M^-1 are fetched with batched predicated loads.  Same arithmetic, in the same
+// order, as ba_pcg_mid_kernel (bit-identical results).
+#define BA_MID_EPT 5
+#define BA_MID_STAGE_BYTES_PER_ROW 40   // r, x, b (doubles) + row_info (int4)
+__global__ void __launch_bounds__(BA_PCG_T) ba_pcg_mid_staged_kernel(const BaDev D, double q_tolerance, double r_tolerance,
+                                                                     int max_iters, int zero_q, int do_post) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  __shared__ double sm[33];
+  __shared__ double sm2[2][33];
+  __shared__ int s_done;
+  BaCtl* c = D.ctl;
+  if (c->done) return;
+  const int nc = D.nc;
+  int4* s_ri = (int4*)s_raw;                      // [nc]
+  double* s_r = (double*)(s_ri + nc);             // [nc]
+  double* s_x = s_r + nc;                         // [nc]
+  double* s_b = s_x + nc;                         // [nc]
+  double* __restrict__ X = D.x; double* __restrict__ R = D.rr; double* __restrict__ P = D.p; double* __restrict__ Q = D.q;
+  double* __restrict__ Z = D.z;
+  const double* __restrict__ RHS = D.rhs; const double* __restrict__ DC2 = D.Dc2; const double* __restrict__ MI = D.Minv;
+#pragma unroll
+  for (int e = 0; e < BA_MID_EPT; ++e) {
+    const int i = threadIdx.x + e * BA_PCG_T;
+    if (i < nc) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(s_ri + i)), "l"(D.row_info + i) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(s_r + i)), "l"(R + i) : "memory");
+      if (do_post) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(s_x + i)), "l"(X + i) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(s_b + i)), "l"(RHS + i) : "memory");
+      }
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  int it = c->it;
+  double last_rho = c->last_rho;
+  const double rho_in = c->rho, norm_b = c->norm_b, Q0 = c->Q0;
+  double pv[BA_MID_EPT];
+#pragma unroll
+  for (int e = 0; e < BA_MID_EPT; ++e) pv[e] = 0.0;
+  if (do_post) {
+    double qv[BA_MID_EPT], v = 0.0;
+#pragma unroll
+    for (int e = 0; e < BA_MID_EPT; ++e) { const int i = threadIdx.x + e * BA_PCG_T; pv[e] = i < nc ? P[i] : 0.0; qv[e] = i < nc ? Q[i] : 0.0; }
+#pragma unroll
+    for (int e = 0; e < BA_MID_EPT; ++e) { const int i = threadIdx.x + e * BA_PCG_T; if (i < nc) v += pv[e] * qv[e]; }
+    const double pq = ba_cta_allsum(v, sm);
+    if (!(pq > 0.0)) { if (threadIdx.x == 0) c->done = 1; asm volatile("cp.async.wait_all;" ::: "memory"); return; }
+    const double alpha = rho_in / pq;
+    asm volatile("cp.async.wait_all;" ::: "memory");   // own elements only: no barrier needed yet
+    double a = 0.0, w = 0.0;
+#pragma unroll
+    for (int e = 0; e < BA_MID_EPT; ++e) {
+      const int i = threadIdx.x + e * BA_PCG_T;
+      if (i < nc) {
+        const double x = s_x[i] + alpha * pv[e], r = s_r[i] - alpha * qv[e];
+        X[i] = x; R[i] = r; s_r[i] = r;
+        a += -x * (s_b[i] + r); w += r * r;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); w += __shfl_xor_sync(0xffffffffu, w, o); }
+    const int wid = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sm2[0][wid] = a; sm2[1][wid] = w; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      double ta = sm2[0][threadIdx.x], tw = sm2[1][threadIdx.x];   // BA_PCG_T / 32 == 32 warps
+      for (int o = 16; o > 0; o >>= 1) { ta += __shfl_xor_sync(0xffffffffu, ta, o); tw += __shfl_xor_sync(0xffffffffu, tw, o); }
+      if (threadIdx.x == 0) {
+        const double Q1 = ta, rnorm2 = tw;
+        int done = 0;
+        c->it = it + 1; c->iters_total += 1;
+        if (r_tolerance > 0.0) {
+          if (rnorm2 <= r_tolerance * r_tolerance * norm_b || it + 1 >= max_iters) done = 1;
+        } else {
+          const double zeta = (it + 1) * (Q1 - Q0) / Q1;
+          if (zeta < q_tolerance || it + 1 >= max_iters) done = 1;
+        }
+        c->Q0 = Q1; c->Q1 = 0.0; c->rnorm2 = 0.0;
+        c->last_rho = rho_in; c->rho = 0.0; c->pq = 0.0;
+        c->done = done;
+        s_done = done;
+      }
+    }
+    __syncthreads();   // publishes s_r (the rows of a block belong to different threads)
+    if (s_done) return;
+    it += 1;
+    last_rho = rho_in;
+  } else {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+  }
+  double dv[BA_MID_EPT], zv[BA_MID_EPT], v = 0.0;
+#pragma unroll
+  for (int e = 0; e < BA_MID_EPT; ++e) { const int i = threadIdx.x + e * BA_PCG_T; dv[e] = (i < nc && !zero_q) ? DC2[i] : 0.0; }
+#pragma unroll
+  for (int e = 0; e < BA_MID_EPT; ++e) {
+    const int i = threadIdx.x + e * BA_PCG_T;
+    zv[e] = 0.0;
+    if (i < nc) {
+      const int4 ri = s_ri[i];   // {first row of the block, offset of this row of Minv, block size}
+      const double* __restrict__ M = MI + ri.y;
+      const double* rb = s_r + ri.x;
+      double m[11];
+#pragma unroll
+      for (int k = 0; k < 11; ++k) m[k] = k < ri.z ? M[k] : 0.0;
+      double t = 0;
+#pragma unroll
+      for (int k = 0; k < 11; ++k) if (k < ri.z) t += m[k] * rb[k];
+      for (int k = 11; k < ri.z; ++k) t += M[k] * rb[k];
+      Z[i] = t; zv[e] = t;
+      v += t * s_r[i];
+    }
+  }
+  const double rho = ba_cta_allsum(v, sm);
+  const bool first = (it == 0);   // first iteration: p = z (never reads the uninitialised / recycled p buffer)
+  const double beta = first ? 0.0 : rho / last_rho;
+#pragma unroll
+  for (int e = 0; e < BA_MID_EPT; ++e) {
+    const int i = threadIdx.x + e * BA_PCG_T;
+    if (i < nc) {
+      const double p = first ? zv[e] : zv[e] + beta * pv[e];
+      P[i] = p;
+      Q[i] = zero_q ? 0.0 : dv[e] * p;
+    }
   }
   if (threadIdx.x == 0) c->rho = rho;
 }
@@ -2073,10 +2216,140 @@ static BaNccl& ba_nccl() {
   }
   return n;
 }
+// ---- one-shot all-reduce over NVLink peer memory -------------------------------------------------------------------------
+// The collectives of a sharded solve are tiny (the camera-side vector of a PCG iteration is a few thousand doubles) and
+// latency-bound.  Every rank owns a symmetric buffer (cudaMalloc + cudaIpc*MemHandle, mapped by every peer once per
+// communicator) of 16-byte cells  cell[2 parities][world][cap] = {lo32, seq, hi32, seq}:  a double travels as two 8-byte
+// words that each carry the sequence number of the collective, so the data is its own arrival flag (the "LL" idea: no
+// fence, no separate flag, one NVLink one-way latency).  One kernel launch per collective: every thread PUSHES its
+// elements of the local partial into cell[parity][rank][i] of every peer (posted 16-byte stores; 8-byte halves are
+// delivered whole), then spins on the world cells of the same elements in its own buffer and combines them in rank order
+// - all ranks produce bit-identical results, like ncclAllReduce.  The sequence number lives in device memory and only
+// advances when the kernel really ran (the PCG launches behind a converged solve return early on every rank alike).
+// Two parities suffice: a rank can be at most one collective ahead of a peer, because finishing collective s+1 needs
+// that peer's cells of s+1, which it only sends after it has consumed collective s.
+#define BA_P2P_MAX_WORLD 8
+#define BA_P2P_MAX_BYTES (2u << 20)     // larger payloads (bandwidth-bound) go through NCCL
+enum { BA_RED_F64_SUM = 0, BA_RED_F64_MAX = 1, BA_RED_I32_MAX = 2 };
+struct BaP2PSeg { void* ptr; int count; int kind; };
+struct BaP2PArgs {
+  BaP2PSeg seg[3];
+  int nseg, total, rank, world;
+  unsigned long long cap;                 // cells per (parity, rank)
+  char* peer[BA_P2P_MAX_WORLD];           // base of every rank's symmetric buffer as mapped here (peer[rank] = own)
+  unsigned long long* state;              // local: [0] sequence, [1] finished-CTA counter, [2] time-out flag
+  const int* done;                        // optional: skip when *done (identical on all ranks)
+};
+__device__ __forceinline__ uint4* ba_p2p_cell(char* base, int world, unsigned long long cap, int parity, int r) {
+  return (uint4*)base + ((size_t)parity * world + r) * cap;
+}
+__global__ void __launch_bounds__(256) ba_p2p_allreduce_kernel(const BaP2PArgs A) {
+  if (A.done && *A.done) return;
+  const unsigned long long seq64 = *(volatile unsigned long long*)&A.state[0] + 1;
+  const unsigned seq = (unsigned)seq64;
+  const int parity = (int)(seq64 & 1);
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.total; i += stride) {
+    int s = 0, j = i;
+    while (s + 1 < A.nseg && j >= A.seg[s].count) { j -= A.seg[s].count; ++s; }
+    const int kind = A.seg[s].kind;
+    const double v = kind == BA_RED_I32_MAX ? (double)((const int*)A.seg[s].ptr)[j] : ((const double*)A.seg[s].ptr)[j];
+    const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+    for (int r = 0; r < A.world; ++r) {
+      uint4* c = ba_p2p_cell(A.peer[r], A.world, A.cap, parity, A.rank) + i;
+      asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(c), "r"(lo), "r"(seq), "r"(hi), "r"(seq) : "memory");
+    }
+    double acc = 0.0;
+    const long long t0 = clock64();
+    for (int r = 0; r < A.world; ++r) {
+      const uint4* c = ba_p2p_cell(A.peer[A.rank], A.world, A.cap, parity, r) + i;
+      unsigned a, fa, b, fb;
+      for (;;) {
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(fa), "=r"(b), "=r"(fb) : "l"(c) : "memory");
+        if (fa == seq && fb == seq) break;
+        if (clock64() - t0 > 20000000000LL) { A.state[2] = 1; break; }   // ~10 s: a peer died; the host reports it
+      }
+      const double w = __hiloint2double((int)b, (int)a);
+      acc = r == 0 ? w : (kind == BA_RED_F64_SUM ? acc + w : fmax(acc, w));
+    }
+    if (kind == BA_RED_I32_MAX) ((int*)A.seg[s].ptr)[j] = (int)acc; else ((double*)A.seg[s].ptr)[j] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&A.state[1], 1ULL) == gridDim.x - 1) { A.state[1] = 0; __threadfence(); *(volatile unsigned long long*)&A.state[0] = seq64; }
+  }
+}
+
+struct BaP2P {
+  bool tried = false, ok = false;
+  size_t cap = 0, bytes = 0;
+  char* local = nullptr;
+  char* peer[BA_P2P_MAX_WORLD] = {};
+  unsigned long long* state = nullptr;
+};
 struct b200ba_comm {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
+  BaP2P p2p;
 };
+static void ba_p2p_teardown(b200ba_comm* c) {
+  BaP2P& P = c->p2p;
+  for (int r = 0; r < BA_P2P_MAX_WORLD; ++r) if (P.peer[r] && r != c->rank) cudaIpcCloseMemHandle(P.peer[r]);
+  if (P.local) cudaFree(P.local);
+  if (P.state) cudaFree(P.state);
+  P = BaP2P();
+}
+// Collective (every rank calls it with the same `need`): maps the symmetric buffers.  Any failure leaves ok = false and
+// the solve keeps using NCCL for its collectives.
+static void ba_p2p_ensure(b200ba_comm* c, size_t need_doubles, cudaStream_t st) {
+  BaP2P& P = c->p2p;
+  if (P.tried && (!P.ok || need_doubles <= P.cap)) return;
+  if (P.tried) { cudaStreamSynchronize(st); ba_p2p_teardown(c); }
+  P.tried = true;
+  if (c->world > BA_P2P_MAX_WORLD || getenv("B200BA_NO_P2P")) return;
+  const size_t cap = std::max<size_t>((need_doubles + 1023) & ~(size_t)1023, 64 * 1024);
+  const size_t bytes = sizeof(uint4) * 2 * c->world * cap;
+  int good = 1;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (cudaMalloc(&P.local, bytes) != cudaSuccess) { P.local = nullptr; good = 0; }
+  if (good && cudaMalloc(&P.state, 4 * sizeof(unsigned long long)) != cudaSuccess) { P.state = nullptr; good = 0; }
+  if (good && (cudaMemsetAsync(P.local, 0, bytes, st) != cudaSuccess || cudaMemsetAsync(P.state, 0, 4 * sizeof(unsigned long long), st) != cudaSuccess)) good = 0;
+  if (good && cudaIpcGetMemHandle(&mine, P.local) != cudaSuccess) good = 0;
+  cudaGetLastError();
+  // handles (and the "good so far" votes) travel as an all-reduce(sum) of a buffer in which every rank fills its own row
+  const int row = (int)(sizeof(cudaIpcMemHandle_t) / sizeof(int)) + 1;
+  std::vector<int> h((size_t)row * c->world, 0);
+  memcpy(&h[(size_t)row * c->rank], &mine, sizeof(mine));
+  h[(size_t)row * c->rank + row - 1] = good;
+  int* d = nullptr;
+  if (cudaMalloc(&d, sizeof(int) * h.size()) != cudaSuccess) { cudaGetLastError(); return; }   // cannot even vote: peers time out in NCCL, as they would anyway
+  cudaMemcpyAsync(d, h.data(), sizeof(int) * h.size(), cudaMemcpyHostToDevice, st);
+  ba_nccl().AllReduce(d, d, h.size(), ncclInt32, ncclSum, c->comm, st);
+  cudaMemcpyAsync(h.data(), d, sizeof(int) * h.size(), cudaMemcpyDeviceToHost, st);
+  cudaStreamSynchronize(st);
+  for (int r = 0; r < c->world; ++r) good &= h[(size_t)row * r + row - 1];
+  int opened = good;
+  if (good) {
+    for (int r = 0; r < c->world && opened; ++r) {
+      if (r == c->rank) { P.peer[r] = P.local; continue; }
+      cudaIpcMemHandle_t hd;
+      memcpy(&hd, &h[(size_t)row * r], sizeof(hd));
+      void* q = nullptr;
+      if (cudaIpcOpenMemHandle(&q, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); opened = 0; }
+      else P.peer[r] = (char*)q;
+    }
+  }
+  // second vote: everybody mapped everybody (also the barrier that orders the memsets before the first push)
+  cudaMemcpyAsync(d, &opened, sizeof(int), cudaMemcpyHostToDevice, st);
+  ba_nccl().AllReduce(d, d, 1, ncclInt32, ncclMin, c->comm, st);
+  cudaMemcpyAsync(&opened, d, sizeof(int), cudaMemcpyDeviceToHost, st);
+  cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (!opened) { ba_p2p_teardown(c); P.tried = true; return; }
+  P.cap = cap; P.bytes = bytes; P.ok = true;
+}
 
 static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summary* sum, b200ba_comm* comm);
 
@@ -2299,8 +2572,10 @@ int b200ba_comm_init(const void* id128, int rank, int world, b200ba_comm_t* out)
   *out = c;
   return 0;
 }
+int b200ba_comm_peer_memory(b200ba_comm_t c) { return c && c->p2p.ok ? 1 : 0; }
 void b200ba_comm_destroy(b200ba_comm_t c) {
   if (!c) return;
+  ba_p2p_teardown(c);
   if (c->comm) ba_nccl().CommDestroy(c->comm);
   delete c;
 }
@@ -2350,15 +2625,56 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   BaStreamGuard guard;
   if (!host_only) BA_CUDA(cudaStreamCreateWithFlags(&guard.st, cudaStreamNonBlocking));
   const cudaStream_t st = guard.st;
-  // all-reduce of a device buffer over the ranks of a sharded solve (no-op otherwise)
-  auto allreduce = [&](void* buf, size_t count, ncclDataType_t dt, ncclRedOp_t op) -> cudaError_t {
-    if (!sharded || count == 0) return cudaSuccess;
-    const ncclResult_t r = ba_nccl().AllReduce(buf, buf, count, dt, op, comm->comm, st);
-    return r == ncclSuccess ? cudaSuccess : cudaErrorUnknown;
+  // all-reduce of device buffers over the ranks of a sharded solve (no-op otherwise).  Calls between group_begin() and
+  // group_end() travel together: as ONE launch of the peer-memory kernel when the communicator has its symmetric
+  // buffers mapped (ba_p2p_ensure) and the payload is latency-sized, else as one NCCL group.
+  struct PendingRed { void* buf; size_t count; ncclDataType_t dt; ncclRedOp_t op; const int* done; };
+  std::vector<PendingRed> pending;
+  bool in_group = false;
+  int p2p_launches = 0, p2p_sms = 148;
+  if (sharded && !host_only) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&p2p_sms, cudaDevAttrMultiProcessorCount, dev); }
+  auto flush_reds = [&]() -> cudaError_t {
+    if (pending.empty()) return cudaSuccess;
+    size_t total = 0;
+    bool p2p = comm->p2p.ok && pending.size() <= 3;
+    for (const PendingRed& r : pending) {
+      total += r.count;
+      const bool f64 = r.dt == ncclDouble && (r.op == ncclSum || r.op == ncclMax), i32 = r.dt == ncclInt32 && r.op == ncclMax;
+      if (!f64 && !i32) p2p = false;
+    }
+    if (p2p && (total > comm->p2p.cap || total * sizeof(double) > BA_P2P_MAX_BYTES)) p2p = false;
+    if (p2p) {
+      BaP2PArgs A;
+      memset(&A, 0, sizeof(A));
+      for (size_t i = 0; i < pending.size(); ++i) {
+        const PendingRed& r = pending[i];
+        A.seg[i].ptr = r.buf; A.seg[i].count = (int)r.count;
+        A.seg[i].kind = r.dt == ncclInt32 ? BA_RED_I32_MAX : (r.op == ncclSum ? BA_RED_F64_SUM : BA_RED_F64_MAX);
+      }
+      A.nseg = (int)pending.size(); A.total = (int)total; A.rank = comm->rank; A.world = comm->world; A.cap = comm->p2p.cap;
+      for (int r = 0; r < comm->world; ++r) A.peer[r] = comm->p2p.peer[r];
+      A.state = comm->p2p.state; A.done = pending[0].done;
+      const int ctas = (int)std::min<size_t>(2 * (size_t)p2p_sms, std::max<size_t>(1, (total + 255) / 256));   // all CTAs resident: they wait for each other's peers
+      ba_p2p_allreduce_kernel<<<ctas, 256, 0, st>>>(A);
+      ++p2p_launches;
+      pending.clear();
+      return cudaGetLastError();
+    }
+    ncclResult_t res = ncclSuccess;
+    if (pending.size() > 1) ba_nccl().GroupStart();
+    for (const PendingRed& r : pending) { const ncclResult_t q = ba_nccl().AllReduce(r.buf, r.buf, r.count, r.dt, r.op, comm->comm, st); if (q != ncclSuccess) res = q; }
+    if (pending.size() > 1) ba_nccl().GroupEnd();
+    pending.clear();
+    return res == ncclSuccess ? cudaSuccess : cudaErrorUnknown;
   };
-  // consecutive small all-reduces of one LM iteration travel as ONE NCCL group (one launch, one latency)
-  auto group_begin = [&]() { if (sharded) ba_nccl().GroupStart(); };
-  auto group_end = [&]() { if (sharded) ba_nccl().GroupEnd(); };
+  auto allreduce_if = [&](void* buf, size_t count, ncclDataType_t dt, ncclRedOp_t op, const int* done) -> cudaError_t {
+    if (!sharded || count == 0) return cudaSuccess;
+    pending.push_back({buf, count, dt, op, done});
+    return in_group ? cudaSuccess : flush_reds();
+  };
+  auto allreduce = [&](void* buf, size_t count, ncclDataType_t dt, ncclRedOp_t op) -> cudaError_t { return allreduce_if(buf, count, dt, op, nullptr); };
+  auto group_begin = [&]() { in_group = true; };
+  auto group_end = [&]() -> cudaError_t { in_group = false; return sharded ? flush_reds() : cudaSuccess; };
   if (sharded) {  // a block is "used" if any rank observes it: keeps the camera-side layout identical on every rank
     std::vector<int> flags(NP + NCAM);
     for (int i = 0; i < NP; ++i) flags[i] = pose_used[i];
@@ -2737,6 +3053,11 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   BA_CUDA(pool.alloc(&D.Hpp, (size_t)6 * nvpt)); BA_CUDA(pool.alloc(&D.Hpp_inv, (size_t)6 * nvpt)); BA_CUDA(pool.alloc(&D.gp, (size_t)3 * nvpt));
   BA_CUDA(pool.alloc(&D.diag_p, (size_t)3 * nvpt)); BA_CUDA(pool.alloc(&D.Dp2, (size_t)3 * nvpt)); BA_CUDA(pool.alloc(&D.dp, (size_t)3 * nvpt));
   BA_CUDA(pool.alloc(&D.gc, (size_t)nc)); BA_CUDA(pool.alloc(&D.diag_c, (size_t)nc)); BA_CUDA(pool.alloc(&D.Dc2, (size_t)nc)); BA_CUDA(pool.alloc(&D.rhs, (size_t)nc));
+  if (sharded) {   // symmetric peer buffers for the latency-bound collectives of the LM / PCG loops (kept by the communicator)
+    const size_t grouped = (size_t)nc + (size_t)pack + 1;
+    ba_p2p_ensure(comm, grouped * sizeof(double) <= BA_P2P_MAX_BYTES ? grouped : ((size_t)nc * sizeof(double) <= BA_P2P_MAX_BYTES ? (size_t)nc : 4), st);
+    if (getenv("B200BA_VERBOSE") && comm->rank == 0) fprintf(stderr, "[b200ba] peer-memory all-reduce: %s (cap %zu doubles)\n", comm->p2p.ok ? "on" : "off (NCCL)", comm->p2p.cap);
+  }
   BA_CUDA(pool.alloc(&D.Hbb, (size_t)pack)); BA_CUDA(pool.alloc(&D.Mbb, (size_t)pack)); BA_CUDA(pool.alloc(&D.Minv, (size_t)pack));
   BA_CUDA(pool.alloc(&D.x, (size_t)nc)); BA_CUDA(pool.alloc(&D.rr, (size_t)nc)); BA_CUDA(pool.alloc(&D.z, (size_t)nc)); BA_CUDA(pool.alloc(&D.p, (size_t)nc)); BA_CUDA(pool.alloc(&D.q, (size_t)nc));
   const bool want_exact = (lst != B200BA_ITERATIVE_SCHUR);
@@ -2761,10 +3082,22 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   BaCtl h;
   auto read_ctl = [&]() -> cudaError_t { cudaError_t e = cudaMemcpyAsync(&h, D.ctl, sizeof(BaCtl), cudaMemcpyDeviceToHost, st); if (e != cudaSuccess) return e; return cudaStreamSynchronize(st); };
   auto zero_field = [&](double* field) { return cudaMemsetAsync(field, 0, sizeof(double), st); };
+  // B200BA_PROFILE=1: device-timeline breakdown of the solve by phase (events between the launches; the interval that
+  // ends at a "host" mark is GPU idle time spent waiting for the host round trip).  Diagnostic only.
+  enum { PF_LIN, PF_BUILD, PF_AR_BUILD, PF_DIAG, PF_DAMP_SCHUR, PF_AR_SCHUR, PF_INVERT, PF_PCG_INIT, PF_SPMV, PF_AR_Q, PF_MID,
+         PF_HOST, PF_BACKSUB, PF_UPDATE_COST, PF_AR_COST, PF_N };
+  static const char* const pf_names[PF_N] = {"linearize", "build (cam blocks, gradient)", "all-reduce gc+Hbb", "diag/build_pt/gradmax(+AR)",
+      "damp + schur_cam", "all-reduce rhs+Mbb", "invert blocks", "pcg init", "spmv (both passes)", "all-reduce q", "pcg mid",
+      "host round trip (GPU idle)", "backsub", "update + cost", "all-reduce cost"};
+  const bool prof_on = getenv("B200BA_PROFILE") != nullptr;
+  std::vector<cudaEvent_t> pf_ev; std::vector<int> pf_tag;
+  auto mark = [&](int tag) { if (!prof_on) return; cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return; cudaEventRecord(e, st); pf_ev.push_back(e); pf_tag.push_back(tag); };
   auto linearize_current = [&](int apply_scale) {
     zero_field(&D.ctl->cost);
     ba_launch_linearize(D, apply_scale, st);
+    mark(PF_LIN);
     allreduce(&D.ctl->cost, 1, ncclDouble, ncclSum);
+    mark(PF_AR_COST);
     launches += 2;
   };
 
@@ -2799,6 +3132,10 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   bool finished = false;
   const bool verbose = getenv("B200BA_VERBOSE") != nullptr;
   const bool fused_pcg = nc <= BA_PCG_FUSED_MAX && getenv("B200BA_PCG_MULTI") == nullptr;
+  const size_t mid_smem = (fused_pcg && (size_t)nc * sizeof(double) <= 160 * 1024 && getenv("B200BA_MID_GLOBAL") == nullptr) ? (size_t)nc * sizeof(double) : 0;
+  if (mid_smem) BA_CUDA(cudaFuncSetAttribute(ba_pcg_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  const size_t mid_staged = (fused_pcg && nc <= BA_PCG_T * BA_MID_EPT && getenv("B200BA_MID_PLAIN") == nullptr) ? (size_t)nc * BA_MID_STAGE_BYTES_PER_ROW : 0;
+  if (mid_staged) BA_CUDA(cudaFuncSetAttribute(ba_pcg_mid_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BA_PCG_T * BA_MID_EPT * BA_MID_STAGE_BYTES_PER_ROW));
   if (const char* e = getenv("B200BA_CS_TILES")) { const int t = atoi(e); g_ba_cs_tiles = (t == 4 || t == 2 || t == 1) ? t : 0; }
   if (const char* e = getenv("B200BA_SPMV_SMEM")) g_ba_spmv_smem = atoi(e) != 0;
   double last_gmax = 0.0;
@@ -2812,10 +3149,12 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
     BA_CHECKPOINT("build_cam_sorted");
     if (D.nchunks_off) ba_cam_offdiag_kernel<false><<<(D.nchunks_off + BA_SC_BLOCK / 32 - 1) / (BA_SC_BLOCK / 32), BA_SC_BLOCK, 0, st>>>(D);
     BA_CHECKPOINT("cam_offdiag<false>");
+    mark(PF_BUILD);
     group_begin();
     BA_CUDA(allreduce(D.gc, nc, ncclDouble, ncclSum));
     BA_CUDA(allreduce(D.Hbb, pack, ncclDouble, ncclSum));
-    group_end();
+    BA_CUDA(group_end());
+    mark(PF_AR_BUILD);
     if (nc) ba_diag_from_blocks_kernel<<<gc_blocks, 256, 0, st>>>(D);
     if (nvpt) ba_build_pt_kernel<<<gp_blocks, 256, 0, st>>>(D);
     BA_CHECKPOINT("diag + build_pt");
@@ -2823,6 +3162,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
     BA_CHECKPOINT("gradmax");
     launches += 4;
     BA_CUDA(allreduce(&D.ctl->gmax, 1, ncclDouble, ncclMax));
+    mark(PF_DIAG);
     // The gradient-norm test of this iteration is read back together with the first linear-solve batch (one host
     // round trip less per LM iteration); if it says "converged" the enqueued solve is discarded.
     bool check_gmax = true;
@@ -2846,14 +3186,17 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
         if (dkmax > 0 && intr_by_pt) ba_schur_pt_kernel<<<gp_blocks, 256, 0, st>>>(D);
         launches += 1 + (dkmax > 0 && intr_by_pt ? 1 : 0);
       }
+      mark(PF_DAMP_SCHUR);
       group_begin();
       BA_CUDA(allreduce(D.rhs, nc, ncclDouble, ncclSum));
       BA_CUDA(allreduce(D.Mbb, pack, ncclDouble, ncclSum));
       BA_CUDA(allreduce(d_fail, 1, ncclInt32, ncclMax));
-      group_end();
+      BA_CUDA(group_end());
+      mark(PF_AR_SCHUR);
       BA_CHECKPOINT("damp + schur_cam / schur_pt");
-      if (nblk) { if (D.wide) ba_invert_blocks_kernel<BA_MAXCB><<<(nblk + 127) / 128, 128, 0, st>>>(D); else ba_invert_blocks_kernel<6><<<(nblk + 127) / 128, 128, 0, st>>>(D); }
+      if (nblk && nc) { if (D.wide) ba_invert_blocks_kernel<BA_MAXCB><<<(nc + 127) / 128, 128, 0, st>>>(D); else ba_invert_blocks_kernel<6><<<(nc + 127) / 128, 128, 0, st>>>(D); }
       launches += 4;
+      mark(PF_INVERT);
       BA_CHECKPOINT("invert_blocks");
       // PCG
       BA_CUDA(cudaMemsetAsync(D.ctl, 0, offsetof(BaCtl, iters_total), st));  // keeps iters_total
@@ -2865,9 +3208,10 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
       } else if (nc) {
         ba_pcg_init_kernel<<<gc_blocks, 256, 0, st>>>(D);
         ++launches;
+        mark(PF_PCG_INIT);
         int issued = 0;
         const bool zero_q = sharded && comm->rank != 0;   // D_c^2 p is contributed by rank 0 only
-        if (fused_pcg) { ba_pcg_mid_kernel<<<1, BA_PCG_T, 0, st>>>(D, q_tol, r_tol, max_cg, zero_q ? 1 : 0, 0); ++launches; }
+        if (fused_pcg) { if (mid_staged) ba_pcg_mid_staged_kernel<<<1, BA_PCG_T, mid_staged, st>>>(D, q_tol, r_tol, max_cg, zero_q ? 1 : 0, 0); else ba_pcg_mid_kernel<<<1, BA_PCG_T, mid_smem, st>>>(D, q_tol, r_tol, max_cg, zero_q ? 1 : 0, 0, mid_smem ? 1 : 0); ++launches; }
         for (;;) {
           const int batch = std::min(8, max_cg - issued);
           for (int b = 0; b < batch; ++b) {
@@ -2879,10 +3223,14 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
             if (b == 0) BA_CUDA(cudaEventRecord(evs0, st));  // first SpMV of a batch always does real work
             BA_DISPATCH_DC(ba_launch_spmv, D, st);
             if (b == 0) BA_CUDA(cudaEventRecord(evs1, st));
-            BA_CUDA(allreduce(D.q, nc, ncclDouble, ncclSum));  // the one data-path collective of a PCG iteration
+            mark(PF_SPMV);
+            BA_CUDA(allreduce_if(D.q, nc, ncclDouble, ncclSum, &D.ctl->done));  // the one data-path collective of a PCG iteration
+            mark(PF_AR_Q);
             if (fused_pcg) {
-              ba_pcg_mid_kernel<<<1, BA_PCG_T, 0, st>>>(D, q_tol, r_tol, max_cg, zero_q ? 1 : 0, 1);
+              if (mid_staged) ba_pcg_mid_staged_kernel<<<1, BA_PCG_T, mid_staged, st>>>(D, q_tol, r_tol, max_cg, zero_q ? 1 : 0, 1);
+              else ba_pcg_mid_kernel<<<1, BA_PCG_T, mid_smem, st>>>(D, q_tol, r_tol, max_cg, zero_q ? 1 : 0, 1, mid_smem ? 1 : 0);
               launches += 3;
+              mark(PF_MID);
             } else {
               ba_pcg_dot_pq_kernel<<<gc_blocks, 256, 0, st>>>(D);
               ba_pcg_update_kernel<<<gc_blocks, 256, 0, st>>>(D);
@@ -2892,6 +3240,7 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
           }
           issued += batch;
           BA_CUDA(read_ctl());
+          mark(PF_HOST);
           if (batch > 0) { float ms = 0; cudaEventElapsedTime(&ms, evs0, evs1); spmv_ms += ms; spmv_launches += 1; }
           if (h.done || issued >= max_cg) break;
         }
@@ -2908,15 +3257,19 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
       BA_CHECKPOINT("linear solve");
       BA_CUDA(zero_field(&D.ctl->model));
       BA_DISPATCH_DC(ba_launch_backsub, D, st);
+      mark(PF_BACKSUB);
       BA_CHECKPOINT("backsub");
       { const long long n = (((long long)NP + 31) & ~31LL) + (((long long)NCAM + 31) & ~31LL) + NPT; ba_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(D); }
       BA_CUDA(zero_field(&D.ctl->new_cost));
       BA_CUDA(zero_field(&D.ctl->cost_delta));
       ba_cost_kernel<<<nblocks, BA_BLOCK, 0, st>>>(D, D.nposes_, D.ncams_, D.npts_, D.nsensors_, &D.ctl->new_cost);
       BA_CHECKPOINT("update + cost");
+      mark(PF_UPDATE_COST);
       BA_CUDA(allreduce(&D.ctl->new_cost, 3, ncclDouble, ncclSum));   // new_cost, model, cost_delta are adjacent in BaCtl
+      mark(PF_AR_COST);
       launches += 3;
       BA_CUDA(read_ctl());
+      mark(PF_HOST);
       const int failed = h.fail;
       const double model = h.model, new_cost = h.new_cost;
       // cost change summed residual by residual (same quantity as cost - new_cost, without the cancellation)
@@ -2951,9 +3304,24 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   float solve_ms = 0;
   BA_CUDA(cudaEventElapsedTime(&solve_ms, ev0, ev1));
   sum->solve_ms = solve_ms;
+  if (prof_on) {
+    double acc[PF_N] = {0}; int cnt[PF_N] = {0};
+    for (size_t k = 1; k < pf_ev.size(); ++k) { float ms = 0; if (cudaEventElapsedTime(&ms, pf_ev[k - 1], pf_ev[k]) == cudaSuccess) { acc[pf_tag[k]] += ms; cnt[pf_tag[k]]++; } }
+    for (cudaEvent_t e : pf_ev) cudaEventDestroy(e);
+    if (!sharded || comm->rank == 0) {
+      const int lm = sum->num_successful_steps + sum->num_unsuccessful_steps;
+      fprintf(stderr, "[b200ba profile] world %d, %d LM iterations, %.1f ms on the device\n", sharded ? comm->world : 1, lm, solve_ms);
+      for (int t = 0; t < PF_N; ++t) if (cnt[t]) fprintf(stderr, "[b200ba profile] %-30s %8.2f ms %5.1f %%  n=%6d  %7.1f us each  %7.1f us / LM it\n", pf_names[t], acc[t], 100.0 * acc[t] / solve_ms, cnt[t], 1e3 * acc[t] / cnt[t], 1e3 * acc[t] / std::max(lm, 1));
+    }
+  }
+  if (sharded && comm->p2p.ok) {
+    unsigned long long timed_out = 0;
+    BA_CUDA(cudaMemcpy(&timed_out, comm->p2p.state + 2, sizeof(timed_out), cudaMemcpyDeviceToHost));
+    if (timed_out) return ba_fail(-111, "peer-memory all-reduce timed out waiting for a rank");
+  }
   sum->final_cost = cost;
   sum->num_linear_solver_iterations = h.iters_total - discarded_pcg;
-  sum->kernel_launches = launches;
+  sum->kernel_launches = launches + p2p_launches;
   sum->spmv_launches = spmv_launches;
   sum->spmv_ms_total = spmv_ms;
   // write back variable blocks only (constants stay bit-identical)

@@ -143,6 +143,10 @@ int b200ba_solve(const b200ba_options* o, b200ba_problem* p, b200ba_summary* out
 typedef struct b200ba_comm* b200ba_comm_t;
 int b200ba_comm_unique_id(void* id128);
 int b200ba_comm_init(const void* id128, int rank, int world_size, b200ba_comm_t* out);
+/* 1 once the communicator's ranks have mapped each other's symmetric buffers (cudaIpc over NVLink) and the small
+ * collectives of a sharded solve run as the library's own one-shot peer-memory all-reduce kernel; 0 = NCCL only (before
+ * the first sharded solve, world > 8, no peer access, or B200BA_NO_P2P set). */
+int b200ba_comm_peer_memory(b200ba_comm_t comm);
 void b200ba_comm_destroy(b200ba_comm_t comm);
 int b200ba_solve_sharded(const b200ba_options* o, b200ba_problem* local_shard, b200ba_comm_t comm, b200ba_summary* out);
 

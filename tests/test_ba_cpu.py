@@ -166,7 +166,7 @@ def test_library_exports_every_declared_ba_symbol():
     hdr = open(os.path.join(ROOT, "include", "b200_bundle_adjustment.h")).read()
     names = set(re.findall(r"\b(b200ba_[a-z_0-9]+)\s*\(", hdr))
     assert names == {"b200ba_options_init", "b200ba_fix_gauge_two_cams_from_world", "b200ba_solve", "b200ba_last_error",
-                     "b200ba_comm_unique_id", "b200ba_comm_init", "b200ba_comm_destroy", "b200ba_solve_sharded",
+                     "b200ba_comm_unique_id", "b200ba_comm_init", "b200ba_comm_destroy", "b200ba_comm_peer_memory", "b200ba_solve_sharded",
                      "b200ba_assemble", "b200ba_assembly_problem", "b200ba_assembly_free"}
     for n in names:
         assert hasattr(lib, n), n

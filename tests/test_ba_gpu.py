@@ -298,7 +298,9 @@ def test_wide_model_grid_parity(models, shared, kw):
     # to 1e-3 where they stop at the iteration limit inside the flat valley of a high-order model
     a, sg, b, sr = _both(BundleAdjustmentOptions(**kw), noisy)
     converged = sg.termination_type == 0 and sr.termination_type == 0
-    assert abs(sg.final_cost - sr.final_cost) <= (REL if converged else 1e-3) * sr.final_cost
+    msg = (f"ours {sg.final_cost!r} (type {sg.termination_type}, {sg.num_successful_steps}+{sg.num_unsuccessful_steps} steps) "
+           f"oracle {sr.final_cost!r} (type {sr.termination_type}, {sr.num_successful_steps}+{sr.num_unsuccessful_steps} steps)")
+    assert abs(sg.final_cost - sr.final_cost) <= (REL if converged else 1e-3) * sr.final_cost, msg
     rmse = np.sqrt(2 * sg.final_cost / (sg.num_residuals / 2))
     assert rmse < 0.3 * np.sqrt(2) * 1.1
     if converged and not kw.get("refine_principal_point"):

@@ -1,5 +1,5 @@
-"""Two-GPU test of the point-sharded BA solve (NCCL all-reduce inside the LM / PCG loops): must reproduce the
-single-GPU solution.  Needs >= 2 CUDA devices (gpurun --gpus 2); skipped otherwise."""
+"""Two-GPU test of the point-sharded BA solve (all-reduces inside the LM / PCG loops, through the library's peer-memory
+kernel and through NCCL): both must reproduce the single-GPU solution and each other.  Needs >= 2 CUDA devices (gpurun --gpus 2); skipped otherwise."""
 import os
 import sys
 
@@ -11,6 +11,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _worker(rank, world, id_q, out_q):
+    try:
+        _worker_body(rank, world, id_q, out_q)
+    except BaseException as e:   # the parent must hear about it instead of waiting for its time-out
+        import traceback
+        out_q.put([(rank, "error", traceback.format_exc())])
+        raise
+
+
+def _worker_body(rank, world, id_q, out_q):
     sys.path.insert(0, ROOT)
     import torch
     torch.cuda.set_device(rank)
@@ -21,18 +30,32 @@ def _worker(rank, world, id_q, out_q):
     noisy.pose_constant = noisy.pose_constant.copy(); noisy.pose_fixed_dim = noisy.pose_fixed_dim.copy()
     noisy.pose_constant[0] = 1
     noisy.pose_fixed_dim[1] = int(np.argmax(np.abs(noisy.poses[1, 4:] - noisy.poses[0, 4:])))
-    if rank == 0:
-        idb = BAComm.unique_id()
-        for _ in range(world - 1):
-            id_q.put(idb)
-    else:
-        idb = id_q.get(timeout=120)
-    comm = BAComm(idb, rank, world)
-    local = shard_flat_problem(noisy, rank, world)
-    s = solve_flat_sharded(BundleAdjustmentOptions(linear_solver_type=ITERATIVE_SCHUR, max_num_iterations=25, gpu_index=rank), local, comm)
-    comm.close()
-    out_q.put((rank, local.poses, local.cam_params, local.point_ids, local.points, s.final_cost, s.num_residuals,
-               s.num_successful_steps + s.num_unsuccessful_steps))
+    out = []
+    for mode in ("peer", "nccl"):   # the library's one-shot peer-memory all-reduce, then plain NCCL (B200BA_NO_P2P)
+        if mode == "nccl":
+            os.environ["B200BA_NO_P2P"] = "1"
+        else:
+            os.environ.pop("B200BA_NO_P2P", None)
+        if rank == 0:
+            idb = BAComm.unique_id()
+            for _ in range(world - 1):
+                id_q.put(idb)
+        else:
+            idb = id_q.get(timeout=120)
+        comm = BAComm(idb, rank, world)
+        local = shard_flat_problem(noisy, rank, world)
+        o = BundleAdjustmentOptions(linear_solver_type=ITERATIVE_SCHUR, max_num_iterations=25, gpu_index=rank)
+        s = solve_flat_sharded(o, local, comm)
+        peer = comm.peer_memory()
+        if mode == "peer":   # a second solve on the same communicator reuses the mapped buffers (sequence numbers carry on)
+            local2 = shard_flat_problem(noisy, rank, world)
+            s2 = solve_flat_sharded(o, local2, comm)
+            # (not bitwise: the partial runs of the camera-ordered pass are combined with fp64 atomics)
+            assert abs(s2.final_cost - s.final_cost) <= 1e-7 * s.final_cost and np.allclose(local2.poses, local.poses, rtol=0, atol=1e-5), (s2.final_cost, s.final_cost)
+        comm.close()
+        out.append((rank, local.poses, local.cam_params, local.point_ids, local.points, s.final_cost, s.num_residuals,
+                    s.num_successful_steps + s.num_unsuccessful_steps, peer))
+    out_q.put(out)
 
 
 def test_sharded_solve_matches_single_gpu():
@@ -48,10 +71,29 @@ def test_sharded_solve_matches_single_gpu():
     procs = [ctx.Process(target=_worker, args=(r, 2, id_q, out_q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted([out_q.get(timeout=600) for _ in range(2)], key=lambda x: x[0])
+    both = []
+    try:
+        for _ in range(2):
+            b = out_q.get(timeout=300)
+            assert not (isinstance(b[0][1], str) and b[0][1] == "error"), b[0][2]
+            both.append(b)
+    finally:
+        for p in procs:
+            p.join(timeout=30 if len(both) < 2 else 120)
+            if p.is_alive():
+                p.kill()
     for p in procs:
-        p.join(timeout=120)
         assert p.exitcode == 0
+    both.sort(key=lambda x: x[0][0])
+    res = [both[0][0], both[1][0]]          # peer-memory collectives
+    res_nccl = [both[0][1], both[1][1]]     # NCCL collectives
+    assert res[0][8] and res[1][8], "the ranks could not map each other's buffers: the peer-memory all-reduce did not run"
+    assert not res_nccl[0][8] and not res_nccl[1][8]
+    # the two transports sum the same partials (two ranks: a + b either way); what differs between any two runs is the
+    # order of the fp64 atomics inside a rank, i.e. rounding
+    for a, b in zip(res, res_nccl):
+        assert abs(a[5] - b[5]) <= 1e-7 * b[5], (a[5], b[5])
+        assert np.allclose(a[1], b[1], rtol=0, atol=1e-5) and np.allclose(a[2], b[2], rtol=1e-5, atol=1e-5) and np.allclose(a[4], b[4], rtol=0, atol=1e-5)
     gt, noisy = synthesize_ba_problem(40, 8000, 6, models=(SIMPLE_RADIAL,), seed=13)
     noisy.pose_constant = noisy.pose_constant.copy(); noisy.pose_fixed_dim = noisy.pose_fixed_dim.copy()
     noisy.pose_constant[0] = 1
