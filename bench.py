@@ -586,15 +586,15 @@ def main():
             c4 = {"error": repr(e)}
     if rank == 0:
         n_sweeps = 4 * C2["num_iterations"]
-        # one sweep = rand + pixel + serial pass; the dominant kernel is pm_pixel_kernel (NCC of 3 of the 4 alternative
-        # hypotheses against every source image, one warp per pixel)
+        # one sweep = rand (+ msg on a second stream) + pixel + serial pass; pm_pixel_kernel (NCC of 3 of the 4 alternative
+        # hypotheses, one warp per pixel, exact early-out) and pm_serial_kernel (column-serial) take about half each
         pixel_launch_ms = pass_ms[1] / args.steps / n_sweeps
         sweep_launch_ms = sweep_ms / args.steps / n_sweeps
         alg_bytes = (41 + 17 * N) * W * H            # per pixel per sweep, photometric (whole sweep)
         peak, peak_src = _peaks()
         achieved = alg_bytes / (sweep_launch_ms * 1e-3) / 1e9
         taps_per_sweep = W * H * 4 * N * 121          # 4 hypotheses x N images x 121 bilinear taps per pixel
-        roofline = {"bound": "hbm", "kernel": "pm_pixel_kernel (+ pm_rand_kernel, pm_serial_kernel = one sweep)",
+        roofline = {"bound": "hbm", "kernel": "pm_pixel_kernel (+ pm_rand_kernel | pm_msg_kernel, pm_serial_kernel = one sweep)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": _ncu_traffic("pm_sweep"), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": sweep_launch_ms,
@@ -602,8 +602,9 @@ def main():
                                           "serial": pass_ms[2] / args.steps / n_sweeps},
                     "taps_per_s": taps_per_sweep / (sweep_launch_ms * 1e-3),
                     "note": "the faithful sweep is instruction-issue bound, not HBM bound (DESIGN.md §2): 177 algorithmic "
-                            "bytes but 3872 bilinear taps (~45 instructions each) per pixel per sweep; ncu: 70% issue-slot "
-                            "utilisation in the dominant kernel"}
+                            "bytes per pixel per sweep against up to 3872 bilinear taps (~45 instructions each; the exact "
+                            "early-out of the pixel pass skips about half of them, taps_per_s counts all 3872); ncu: 67% "
+                            "issue-slot utilisation in pm_pixel_kernel, 51-53% in the column-serial pm_serial_kernel"}
         line = {"metric": "patchmatch_mpixels_per_s", "value": world * mpix / (ms_per_step * 1e-3), "unit": "Mpixels/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

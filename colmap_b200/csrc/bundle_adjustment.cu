@@ -580,6 +580,7 @@ __global__ void __launch_bounds__(BA_BLOCK, WIDE ? 1 : 2) ba_linearize_cam_kerne
   D.rC[BA_U(1, k)] = rr[1];
 }
 // cost of the candidate parameters + per-residual cost change (accurate near convergence)
+template <bool WIDE>
 __global__ void __launch_bounds__(BA_BLOCK) ba_cost_kernel(const BaDev D, const double* __restrict__ poses,
                                                            const double* __restrict__ cams,
                                                            const double* __restrict__ pts, const double* __restrict__ sensors,
@@ -595,7 +596,7 @@ __global__ void __launch_bounds__(BA_BLOCK) ba_cost_kernel(const BaDev D, const 
     for (int k = 0; k < 7; ++k) pose[k] = poses[7 * (long long)pi + k];
     for (int k = 0; k < 3; ++k) pt[k] = pts[3 * (long long)ti + k];
     const int P = ba_model_num_params(id);
-    if (!D.wide) {
+    if (!WIDE) {   // (separate instantiations: the wide path's local arrays and calls would otherwise size the narrow one)
       double prm[5];
       for (int k = 0; k < P; ++k) prm[k] = cams[D.cam_poff[ci] + k];
       ba_reproj(id, pt, pose, prm, D.s_xy[s], D.s_xy[D.nslots + s], res, nullptr, nullptr, nullptr);
@@ -693,10 +694,15 @@ __global__ void ba_gradmax_kernel(const BaDev D) {
     const long long k = i - np32 - nc32;
     if (k < 3LL * D.nvpt) m = fabs(D.gp[k] / D.scale_p[k]);
   }
+  __shared__ double s_m[32];
   for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0 && m > 0.0) {
+  if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {   // one atomic per CTA (tens of thousands of per-warp atomics on one address took 20 us)
+    m = threadIdx.x < ((blockDim.x + 31) >> 5) ? s_m[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     // atomic max on non-negative doubles through their integer representation
-    atomicMax(reinterpret_cast<unsigned long long*>(&D.ctl->gmax), (unsigned long long)__double_as_longlong(m));
+    if (threadIdx.x == 0 && m > 0.0) atomicMax(reinterpret_cast<unsigned long long*>(&D.ctl->gmax), (unsigned long long)__double_as_longlong(m));
   }
 }
 
@@ -3079,7 +3085,11 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
   int launches = 0, spmv_launches = 0;
   double spmv_ms = 0.0;
   const int gc_blocks = (nc + 255) / 256, gp_blocks = (nvpt + 255) / 256;
-  BaCtl h;
+  // the control block is read back into pinned memory (a pageable destination makes the copy a staged, slower one)
+  static thread_local BaCtl* h_pinned = nullptr;
+  if (!h_pinned && cudaHostAlloc((void**)&h_pinned, sizeof(BaCtl), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); h_pinned = nullptr; }
+  BaCtl h_pageable;
+  BaCtl& h = h_pinned ? *h_pinned : h_pageable;
   auto read_ctl = [&]() -> cudaError_t { cudaError_t e = cudaMemcpyAsync(&h, D.ctl, sizeof(BaCtl), cudaMemcpyDeviceToHost, st); if (e != cudaSuccess) return e; return cudaStreamSynchronize(st); };
   auto zero_field = [&](double* field) { return cudaMemsetAsync(field, 0, sizeof(double), st); };
   // B200BA_PROFILE=1: device-timeline breakdown of the solve by phase (events between the launches; the interval that
@@ -3262,7 +3272,8 @@ static int ba_solve_impl(const b200ba_options* o, b200ba_problem* p, b200ba_summ
       { const long long n = (((long long)NP + 31) & ~31LL) + (((long long)NCAM + 31) & ~31LL) + NPT; ba_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(D); }
       BA_CUDA(zero_field(&D.ctl->new_cost));
       BA_CUDA(zero_field(&D.ctl->cost_delta));
-      ba_cost_kernel<<<nblocks, BA_BLOCK, 0, st>>>(D, D.nposes_, D.ncams_, D.npts_, D.nsensors_, &D.ctl->new_cost);
+      if (D.wide) ba_cost_kernel<true><<<nblocks, BA_BLOCK, 0, st>>>(D, D.nposes_, D.ncams_, D.npts_, D.nsensors_, &D.ctl->new_cost);
+      else ba_cost_kernel<false><<<nblocks, BA_BLOCK, 0, st>>>(D, D.nposes_, D.ncams_, D.npts_, D.nsensors_, &D.ctl->new_cost);
       BA_CHECKPOINT("update + cost");
       mark(PF_UPDATE_COST);
       BA_CUDA(allreduce(&D.ctl->new_cost, 3, ncclDouble, ncclSum));   // new_cost, model, cost_delta are adjacent in BaCtl
