@@ -149,8 +149,25 @@ class Point2D:
 class Image:
     image_id: int
     camera_id: int
-    cam_from_world: np.ndarray   # 7: qx qy qz qw tx ty tz (Rigid3d::params)
+    cam_from_world: np.ndarray   # 7: qx qy qz qw tx ty tz (Rigid3d::params); with rigs: derived, the frame holds the pose
     points2D: List[Point2D] = field(default_factory=list)
+    frame_id: Optional[int] = None   # None = trivial frame (frame id == image id, the image is its rig's reference sensor)
+
+
+@dataclass
+class Rig:
+    """scene/rig.h: the reference sensor defines the rig frame, the other sensors carry sensor_from_rig.  A sensor is a
+    camera (sensor_t{CAMERA, camera_id}); a camera belongs to exactly one rig."""
+    rig_id: int
+    ref_sensor: int                                          # camera id of the reference sensor
+    sensors: Dict[int, np.ndarray] = field(default_factory=dict)   # non-reference sensors: camera id -> sensor_from_rig (7)
+
+
+@dataclass
+class Frame:
+    frame_id: int
+    rig_id: int
+    rig_from_world: np.ndarray   # 7
 
 
 @dataclass
@@ -164,16 +181,24 @@ class Reconstruction:
     cameras: Dict[int, Camera] = field(default_factory=dict)
     images: Dict[int, Image] = field(default_factory=dict)
     points3D: Dict[int, Point3D] = field(default_factory=dict)
+    rigs: Dict[int, Rig] = field(default_factory=dict)       # empty = trivial frames throughout
+    frames: Dict[int, Frame] = field(default_factory=dict)
+
+    def IsRefInFrame(self, image_id) -> bool:
+        """Image::IsRefInFrame: the image's camera is the reference sensor of its frame's rig."""
+        im = self.images[image_id]
+        return im.frame_id is None or self.rigs[self.frames[im.frame_id].rig_id].ref_sensor == im.camera_id
 
 
 class BundleAdjustmentConfig:
-    """BundleAdjustmentConfig (bundle_adjustment.h:77-151), trivial frames (frame id == image id)."""
+    """BundleAdjustmentConfig (bundle_adjustment.h:77-151); with trivial frames the frame id is the image id."""
 
     def __init__(self):
         self.fixed_gauge_ = UNSPECIFIED_GAUGE
         self.image_ids_ = set()
         self.constant_cam_intrinsics_ = set()
         self.constant_rig_from_world_poses_ = set()
+        self.constant_sensor_from_rig_poses_ = set()
         self.variable_point3D_ids_ = set()
         self.constant_point3D_ids_ = set()
         self.ignored_point3D_ids_ = set()
@@ -190,6 +215,9 @@ class BundleAdjustmentConfig:
     def SetConstantRigFromWorldPose(self, frame_id): self.constant_rig_from_world_poses_.add(frame_id)
     def SetVariableRigFromWorldPose(self, frame_id): self.constant_rig_from_world_poses_.discard(frame_id)
     def HasConstantRigFromWorldPose(self, frame_id): return frame_id in self.constant_rig_from_world_poses_
+    def SetConstantSensorFromRigPose(self, sensor_id): self.constant_sensor_from_rig_poses_.add(sensor_id)       # sensor id = camera id
+    def SetVariableSensorFromRigPose(self, sensor_id): self.constant_sensor_from_rig_poses_.discard(sensor_id)
+    def HasConstantSensorFromRigPose(self, sensor_id): return sensor_id in self.constant_sensor_from_rig_poses_
     def AddVariablePoint(self, pid): self.variable_point3D_ids_.add(pid)
     def AddConstantPoint(self, pid): self.constant_point3D_ids_.add(pid)
     def IgnorePoint(self, pid): self.ignored_point3D_ids_.add(pid)
@@ -367,6 +395,8 @@ def solve_flat_sharded(options: "BundleAdjustmentOptions", local: FlatProblem, c
 def flatten_reconstruction(options: BundleAdjustmentOptions, config: BundleAdjustmentConfig, rec: Reconstruction):
     """DefaultBundleAdjuster's problem assembly (bundle_adjustment_ceres.cc:606-664,688-888) -> FlatProblem.
     Returns (flat, image_ids, camera_ids, point_ids) with the id lists giving the flat order."""
+    if rec.frames:
+        return _flatten_reconstruction_rigs(options, config, rec)
     image_ids = sorted(rec.images.keys())            # poses of images outside the config are constant
     camera_ids = sorted(rec.cameras.keys())
     point_ids = sorted(rec.points3D.keys())
@@ -435,17 +465,171 @@ def flatten_reconstruction(options: BundleAdjustmentOptions, config: BundleAdjus
     return flat, image_ids, camera_ids, point_ids
 
 
+def _rigid_compose(a, b):
+    """(a * b): x -> a(b(x)) for 7-vectors qx qy qz qw tx ty tz."""
+    from .synthetic import _quat_mul, _quat_rotate
+    q = _quat_mul(a[None, :4], b[None, :4])[0]
+    t = _quat_rotate(a[None, :4], b[None, 4:])[0] + a[4:]
+    return np.concatenate([q, t])
+
+
+def _rigid_inverse(a):
+    from .synthetic import _quat_rotate
+    qi = np.array([-a[0], -a[1], -a[2], a[3]])
+    return np.concatenate([qi, -_quat_rotate(qi[None], a[None, 4:])[0]])
+
+
+def _flatten_reconstruction_rigs(options, config, rec):
+    """flatten_reconstruction for reconstructions with rigs and frames (AddImageWithNonTrivialFrame, ParameterizeRigsAndFrames,
+    the rig-aware FixGaugeWithTwoCamsFromWorld: bundle_adjustment_ceres.cc:308-417,470-538,752-827).  Flat layout: pose k =
+    frame k (ascending frame id) holding rig_from_world, followed by one CONSTANT pose per image outside the config that
+    a config point brings in (a copy of its frame's rig_from_world: the reference bakes those observations with a constant
+    pose, :846-878); sensor s = the s-th non-reference camera in ascending camera id.  The gauge is applied here.
+    Returns (flat, frame_ids, camera_ids, point_ids); flat.sensor_camera_ids lists the sensors' camera ids.
+    One deliberate difference: for an outside image on a NON-reference sensor whose sensor_from_rig is being refined the
+    reference freezes the product sensor_from_rig * rig_from_world; here the frozen rig_from_world is composed with the
+    current sensor_from_rig (the flat problem ties the sensor to the camera, not to the observation)."""
+    frame_ids, camera_ids, point_ids = sorted(rec.frames), sorted(rec.cameras), sorted(rec.points3D)
+    frame_idx = {f: k for k, f in enumerate(frame_ids)}
+    cam_idx = {c: k for k, c in enumerate(camera_ids)}
+    pt_idx = {p: k for k, p in enumerate(point_ids)}
+    cam_rig = {}
+    for r in rec.rigs.values():
+        cam_rig[r.ref_sensor] = r.rig_id
+        for c in r.sensors:
+            cam_rig[c] = r.rig_id
+    sensor_cams = [c for c in camera_ids if c in cam_rig and rec.rigs[cam_rig[c]].ref_sensor != c]
+    sensor_idx = {c: k for k, c in enumerate(sensor_cams)}
+    cfg_images = sorted(config.Images())
+    obs_pose, obs_cam, obs_point, obs_xy = [], [], [], []
+    point_num_obs, parameterized_images = {}, []
+    for image_id in cfg_images:                       # AddImageToProblem (:688-827)
+        im = rec.images[image_id]
+        n0 = len(obs_pose)
+        for p2 in im.points2D:
+            pid = p2.point3D_id
+            if pid < 0 or pid not in rec.points3D or config.IsIgnoredPoint(pid):
+                continue
+            if len(rec.points3D[pid].track) < options.min_track_length:
+                continue
+            point_num_obs[pid] = point_num_obs.get(pid, 0) + 1
+            obs_pose.append(frame_idx[im.frame_id]); obs_cam.append(cam_idx[im.camera_id]); obs_point.append(pt_idx[pid])
+            obs_xy.append(p2.xy)
+        if len(obs_pose) > n0:
+            parameterized_images.append(image_id)
+    poses = [rec.frames[f].rig_from_world for f in frame_ids]
+    extra_pose_of_image = {}
+    for pid in sorted(config.VariablePoints() | config.ConstantPoints()):        # AddPointToProblem (:829-888)
+        pt = rec.points3D[pid]
+        if options.min_track_length > 0 and len(pt.track) < options.min_track_length:
+            continue
+        if point_num_obs.get(pid, 0) == len(pt.track):
+            continue
+        for image_id, p2_idx in pt.track:
+            if config.HasImage(image_id):
+                continue
+            im = rec.images[image_id]
+            if image_id not in extra_pose_of_image:
+                extra_pose_of_image[image_id] = len(poses)
+                poses.append(rec.frames[im.frame_id].rig_from_world.copy())
+            point_num_obs[pid] = point_num_obs.get(pid, 0) + 1
+            obs_pose.append(extra_pose_of_image[image_id]); obs_cam.append(cam_idx[im.camera_id]); obs_point.append(pt_idx[pid])
+            obs_xy.append(im.points2D[p2_idx].xy)
+    num_poses = len(poses)
+    pose_constant = np.ones(num_poses, np.uint8)
+    for image_id in cfg_images:
+        f = rec.images[image_id].frame_id
+        if not config.HasConstantRigFromWorldPose(f):
+            pose_constant[frame_idx[f]] = 0
+    cam_in_cfg = {rec.images[i].camera_id for i in parameterized_images}
+    cam_constant = np.array([1 if (c not in cam_in_cfg or config.HasConstantCamIntrinsics(c)) else 0 for c in camera_ids], np.uint8)
+    point_constant = np.ones(len(point_ids), np.uint8)
+    for pid, n in point_num_obs.items():
+        if options.refine_points3D and len(rec.points3D[pid].track) <= n:
+            point_constant[pt_idx[pid]] = 0
+    for pid in config.ConstantPoints():
+        point_constant[pt_idx[pid]] = 1
+    # ParameterizeRigsAndFrames (:470-538): sensor_from_rig constant when not refined, constant in the config, or when the
+    # rig's reference sensor is not part of the problem
+    # (a sensor_from_rig is a parameter block only through a parameterized image of the config on that camera, :752-827;
+    # images outside the config contribute constant-pose observations)
+    sensor_constant = np.array([1 if (not options.refine_sensor_from_rig or config.HasConstantSensorFromRigPose(c)
+                                      or c not in cam_in_cfg) else 0 for c in sensor_cams], np.uint8)
+    param_rigs = {rec.frames[rec.images[i].frame_id].rig_id for i in parameterized_images}
+    for rig_id in param_rigs:
+        rig = rec.rigs[rig_id]
+        if rig.ref_sensor not in cam_in_cfg:
+            for c in rig.sensors:
+                sensor_constant[sensor_idx[c]] = 1
+    cam_sensor = np.array([sensor_idx.get(c, -1) for c in camera_ids], np.int32)
+    cam_off, off = [], 0
+    for c in camera_ids:
+        cam_off.append(off); off += MODEL_NUM_PARAMS[rec.cameras[c].model_id]
+    flat = FlatProblem(np.stack(poses) if poses else np.zeros((0, 7)), pose_constant, -np.ones(num_poses, np.int8),
+                       [rec.cameras[c].model_id for c in camera_ids], cam_off,
+                       np.concatenate([rec.cameras[c].params for c in camera_ids]) if camera_ids else np.zeros(0), cam_constant,
+                       np.stack([rec.points3D[p].xyz for p in point_ids]) if point_ids else np.zeros((0, 3)), point_constant,
+                       obs_pose, obs_cam, obs_point, np.asarray(obs_xy, np.float64).reshape(-1, 2))
+    flat.set_sensors(np.stack([rec.rigs[cam_rig[c]].sensors[c] for c in sensor_cams]) if sensor_cams else np.zeros((0, 7)),
+                     sensor_constant, cam_sensor)
+    flat.num_config_images = config.NumImages()
+    flat.parameterized_image_ids = set(parameterized_images)
+    flat.sensor_camera_ids = sensor_cams
+    flat.num_frames = len(frame_ids)
+    # ---- gauge
+    three_points = config.FixedGauge() == THREE_POINTS
+    if config.FixedGauge() == TWO_CAMS_FROM_WORLD and options.refine_rig_from_world:
+        def const_sensor(image_id):       # IsParameterizedConstSensor (:324-343)
+            s = sensor_idx.get(rec.images[image_id].camera_id, -1)
+            return s < 0 or bool(flat.sensor_constant[s])
+        image1 = image2 = None
+        dim2, done = 0, False
+        for i in parameterized_images:
+            if config.HasConstantRigFromWorldPose(rec.images[i].frame_id) and const_sensor(i):
+                if image1 is None:
+                    image1 = i
+                elif rec.images[image1].frame_id != rec.images[i].frame_id:
+                    done = True             # two frames are already fixed
+                    break
+        if not done:
+            for i in parameterized_images:
+                f = rec.images[i].frame_id
+                if image1 is None and const_sensor(i):
+                    image1 = i
+                elif (image1 is not None and rec.images[image1].frame_id != f and const_sensor(i)
+                      and not config.HasConstantRigFromWorldPose(f)):       # its rig_from_world is a parameter block
+                    base = _rigid_compose(rec.frames[rec.images[image1].frame_id].rig_from_world,
+                                          _rigid_inverse(rec.frames[f].rig_from_world))[4:]
+                    mi = int(np.argmax(np.abs(base)))
+                    if abs(base[mi]) > 1e-9:
+                        image2, dim2 = i, mi
+                        break
+            if image1 is None or image2 is None:
+                three_points = True         # "Falling back to fixing Gauge with three points" (:390-394)
+            else:
+                f1, f2 = rec.images[image1].frame_id, rec.images[image2].frame_id
+                flat.pose_constant[frame_idx[f1]] = 1
+                if not config.HasConstantRigFromWorldPose(f2):
+                    flat.pose_fixed_dim[frame_idx[f2]] = dim2
+    if three_points:
+        fix_gauge_three_points(flat)
+    return flat, frame_ids, camera_ids, point_ids
+
+
 class _CScene(ctypes.Structure):
     _fields_ = [("num_images", ctypes.c_int), ("image_id", ctypes.POINTER(ctypes.c_uint32)), ("image_camera", _i32p),
                 ("cam_from_world", _f64p), ("point2D_offset", ctypes.POINTER(ctypes.c_int64)), ("point2D_xy", _f64p),
                 ("point2D_point3D", ctypes.POINTER(ctypes.c_int64)), ("num_cameras", ctypes.c_int), ("camera_model_id", _i32p),
                 ("camera_param_offset", _i32p), ("camera_params", _f64p), ("num_points3D", ctypes.c_int64), ("xyz", _f64p),
-                ("track_offset", ctypes.POINTER(ctypes.c_int64)), ("track_image", _i32p), ("track_point2D", _i32p)]
+                ("track_offset", ctypes.POINTER(ctypes.c_int64)), ("track_image", _i32p), ("track_point2D", _i32p),
+                ("num_frames", ctypes.c_int), ("image_frame", _i32p), ("rig_from_world", _f64p), ("frame_rig", _i32p),
+                ("num_rigs", ctypes.c_int), ("rig_ref_camera", _i32p), ("camera_rig", _i32p), ("camera_sensor_from_rig", _f64p)]
 
 
 class _CConfig(ctypes.Structure):
     _fields_ = [("image_in_config", _u8p), ("image_constant_pose", _u8p), ("camera_constant", _u8p), ("point_variable", _u8p),
-                ("point_constant", _u8p), ("point_ignored", _u8p), ("fixed_gauge", ctypes.c_int), ("min_track_length", ctypes.c_int)]
+                ("point_constant", _u8p), ("point_ignored", _u8p), ("fixed_gauge", ctypes.c_int), ("min_track_length", ctypes.c_int),
+                ("frame_constant_pose", _u8p), ("camera_constant_sensor_from_rig", _u8p)]
 
 
 def assemble_reconstruction(options: BundleAdjustmentOptions, config: BundleAdjustmentConfig, rec: Reconstruction):
@@ -486,6 +670,27 @@ def assemble_reconstruction(options: BundleAdjustmentOptions, config: BundleAdju
                  P(timg, _i32p), P(tp2, _i32p))
     cf = _CConfig(P(f_in, _u8p), P(f_cp, _u8p), P(f_cc, _u8p), P(f_pv, _u8p), P(f_pc, _u8p), P(f_pi, _u8p), int(config.FixedGauge()),
                   int(options.min_track_length))
+    frame_ids = sorted(rec.frames)
+    if frame_ids:       # rigs and frames
+        rig_ids = sorted(rec.rigs)
+        fr_idx = {f: k for k, f in enumerate(frame_ids)}; rig_idx = {r: k for k, r in enumerate(rig_ids)}
+        cam_rig_id = {}
+        for r in rec.rigs.values():
+            cam_rig_id[r.ref_sensor] = r.rig_id
+            for cc in r.sensors:
+                cam_rig_id[cc] = r.rig_id
+        img_frame = c([fr_idx[rec.images[i].frame_id] for i in image_ids], np.int32)
+        rfw = c(np.stack([rec.frames[f].rig_from_world for f in frame_ids]), np.float64)
+        frame_rig = c([rig_idx[rec.frames[f].rig_id] for f in frame_ids], np.int32)
+        rig_ref = c([cam_idx[rec.rigs[r].ref_sensor] for r in rig_ids], np.int32)
+        cam_rig = c([rig_idx[cam_rig_id[k]] for k in camera_ids], np.int32)
+        ident = np.array([0, 0, 0, 1, 0, 0, 0], np.float64)
+        cam_sfr = c(np.stack([rec.rigs[cam_rig_id[k]].sensors.get(k, ident) for k in camera_ids]), np.float64)
+        f_fc = flags(frame_ids, config.HasConstantRigFromWorldPose); f_sc = flags(camera_ids, config.HasConstantSensorFromRigPose)
+        sc.num_frames = len(frame_ids); sc.image_frame = P(img_frame, _i32p); sc.rig_from_world = P(rfw, _f64p)
+        sc.frame_rig = P(frame_rig, _i32p); sc.num_rigs = len(rig_ids); sc.rig_ref_camera = P(rig_ref, _i32p)
+        sc.camera_rig = P(cam_rig, _i32p); sc.camera_sensor_from_rig = P(cam_sfr, _f64p)
+        cf.frame_constant_pose = P(f_fc, _u8p); cf.camera_constant_sensor_from_rig = P(f_sc, _u8p)
     co, h = options.to_c(), ctypes.c_void_p()
     rc = lib.b200ba_assemble(ctypes.byref(co), ctypes.byref(sc), ctypes.byref(cf), ctypes.byref(h))
     if rc != 0:
@@ -502,9 +707,15 @@ def assemble_reconstruction(options: BundleAdjustmentOptions, config: BundleAdju
                            arr(pr.obs_camera_idx, n_obs, np.int32), arr(pr.obs_point_idx, n_obs, np.int32),
                            arr(pr.obs_xy, 2 * n_obs, np.float64))
         flat.num_config_images = int(pr.num_config_images)
+        if pr.num_sensors > 0 or frame_ids:
+            ns = int(pr.num_sensors)
+            flat.set_sensors(arr(pr.sensor_from_rig, 7 * ns, np.float64), arr(pr.sensor_constant, ns, np.uint8),
+                             arr(pr.camera_sensor_idx, n_cam, np.int32))
+            flat.sensor_camera_ids = [camera_ids[k] for k in range(n_cam) if flat.cam_sensor[k] >= 0]
+            flat.num_frames = len(frame_ids)
     finally:
         lib.b200ba_assembly_free(h)
-    return flat, image_ids, camera_ids, point_ids
+    return flat, (frame_ids if frame_ids else image_ids), camera_ids, point_ids
 
 
 def fix_gauge_three_points(flat: FlatProblem) -> int:
@@ -553,6 +764,20 @@ class BundleAdjuster:
         rec = self.reconstruction_
         flat, image_ids, camera_ids, point_ids = flatten_reconstruction(self.options_, self.config_, rec)
         lib = _bind(load_library())
+        if rec.frames:      # rigs: the flattening applied the gauge; poses are frames, sensors the non-reference cameras
+            summary = solve_flat(self.options_, flat)
+            for k, f in enumerate(image_ids):
+                rec.frames[f].rig_from_world[:] = flat.poses[k]
+            for k, c in enumerate(flat.sensor_camera_ids):
+                for rig in rec.rigs.values():
+                    if c in rig.sensors:
+                        rig.sensors[c][:] = flat.sensors[k]
+            for k, c in enumerate(camera_ids):
+                n = MODEL_NUM_PARAMS[rec.cameras[c].model_id]
+                rec.cameras[c].params[:] = flat.cam_params[flat.cam_off[k]:flat.cam_off[k] + n]
+            for k, p in enumerate(point_ids):
+                rec.points3D[p].xyz[:] = flat.points[k]
+            return summary
         if self.config_.FixedGauge() == TWO_CAMS_FROM_WORLD and self.options_.refine_rig_from_world:
             # gauge search runs over the images of the config in ascending id (std::set<image_t>), :346-385
             co, cp = self.options_.to_c(), flat.to_c()

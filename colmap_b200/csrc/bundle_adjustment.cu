@@ -2251,6 +2251,7 @@ __device__ __forceinline__ uint4* ba_p2p_cell(char* base, int world, unsigned lo
 }
 __global__ void __launch_bounds__(256) ba_p2p_allreduce_kernel(const BaP2PArgs A) {
   if (A.done && *A.done) return;
+  if (*(volatile unsigned long long*)&A.state[2]) return;   // an earlier collective timed out: the solve is lost, do not wait again
   const unsigned long long seq64 = *(volatile unsigned long long*)&A.state[0] + 1;
   const unsigned seq = (unsigned)seq64;
   const int parity = (int)(seq64 & 1);
@@ -2273,7 +2274,7 @@ __global__ void __launch_bounds__(256) ba_p2p_allreduce_kernel(const BaP2PArgs A
       for (;;) {
         asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(fa), "=r"(b), "=r"(fb) : "l"(c) : "memory");
         if (fa == seq && fb == seq) break;
-        if (clock64() - t0 > 20000000000LL) { A.state[2] = 1; break; }   // ~10 s: a peer died; the host reports it
+        if (clock64() - t0 > 120000000000LL) { A.state[2] = 1; break; }   // ~60 s: a peer died; the host reports it
       }
       const double w = __hiloint2double((int)b, (int)a);
       acc = r == 0 ? w : (kind == BA_RED_F64_SUM ? acc + w : fmax(acc, w));
@@ -2416,6 +2417,9 @@ struct b200ba_assembly {
   std::vector<uint8_t> pose_constant, cam_constant, point_constant;
   std::vector<int8_t> pose_fixed_dim;
   std::vector<int32_t> cam_model, cam_off, obs_pose, obs_cam, obs_point;
+  std::vector<double> sensors;              // rigs: sensor_from_rig of the non-reference cameras
+  std::vector<uint8_t> sensor_constant;
+  std::vector<int32_t> cam_sensor;
   b200ba_problem problem;
 };
 extern "C" {
@@ -2427,11 +2431,35 @@ int b200ba_assemble(const b200ba_options* o, const b200ba_scene* sc, const b200b
   auto flag = [](const uint8_t* f, int64_t i) { return f && f[i]; };
   for (int i = 0; i < NI; ++i) if (sc->image_camera[i] < 0 || sc->image_camera[i] >= NC) return ba_fail(-2, "image references a camera outside the scene");
   for (int c = 0; c < NC; ++c) if (ba_model_num_params(sc->camera_model_id[c]) < 0) return ba_fail(-2, "unsupported camera model");
+  const int NF = sc->num_frames;
+  const bool rigs = NF > 0;
+  if (rigs) {
+    if (!sc->image_frame || !sc->rig_from_world || !sc->frame_rig || !sc->rig_ref_camera || !sc->camera_rig || !sc->camera_sensor_from_rig)
+      return ba_fail(-2, "frames need image_frame, rig_from_world, frame_rig, rig_ref_camera, camera_rig and camera_sensor_from_rig");
+    for (int i = 0; i < NI; ++i) if (sc->image_frame[i] < 0 || sc->image_frame[i] >= NF) return ba_fail(-2, "image references a frame outside the scene");
+    for (int f = 0; f < NF; ++f) if (sc->frame_rig[f] < 0 || sc->frame_rig[f] >= sc->num_rigs) return ba_fail(-2, "frame references a rig outside the scene");
+    for (int c = 0; c < NC; ++c) if (sc->camera_rig[c] < 0 || sc->camera_rig[c] >= sc->num_rigs) return ba_fail(-2, "camera references a rig outside the scene");
+    for (int r = 0; r < sc->num_rigs; ++r) if (sc->rig_ref_camera[r] < 0 || sc->rig_ref_camera[r] >= NC) return ba_fail(-2, "rig references a camera outside the scene");
+  }
   b200ba_assembly* A = new b200ba_assembly();
   std::vector<int64_t> point_num_obs((size_t)NPT, 0);
   auto track_len = [&](int64_t pid) { return sc->track_offset[pid + 1] - sc->track_offset[pid]; };
+  std::vector<int> extra_pose_of_image;     // rigs: constant pose entry of an image outside the config (-1 = none yet)
+  if (rigs) { extra_pose_of_image.assign(NI, -1); A->poses.assign(sc->rig_from_world, sc->rig_from_world + 7 * (size_t)NF); }
   auto push = [&](int img, int64_t pid, const double* xy) {
-    A->obs_pose.push_back(img); A->obs_cam.push_back(sc->image_camera[img]); A->obs_point.push_back((int32_t)pid);
+    int pose = img;
+    if (rigs) {
+      if (flag(cfg->image_in_config, img)) pose = sc->image_frame[img];
+      else {
+        if (extra_pose_of_image[img] < 0) {
+          extra_pose_of_image[img] = (int)(A->poses.size() / 7);
+          const double* f = sc->rig_from_world + 7 * (size_t)sc->image_frame[img];
+          A->poses.insert(A->poses.end(), f, f + 7);
+        }
+        pose = extra_pose_of_image[img];
+      }
+    }
+    A->obs_pose.push_back(pose); A->obs_cam.push_back(sc->image_camera[img]); A->obs_point.push_back((int32_t)pid);
     A->obs_xy.push_back(xy[0]); A->obs_xy.push_back(xy[1]);
     point_num_obs[pid] += 1;
   };
@@ -2465,14 +2493,16 @@ int b200ba_assemble(const b200ba_options* o, const b200ba_scene* sc, const b200b
       push(img, pid, sc->point2D_xy + 2 * k);
     }
   }
-  A->poses.assign(sc->cam_from_world, sc->cam_from_world + 7 * (size_t)NI);
-  A->pose_constant.assign(NI, 1);
-  A->pose_fixed_dim.assign(NI, -1);
+  if (!rigs) A->poses.assign(sc->cam_from_world, sc->cam_from_world + 7 * (size_t)NI);
+  const int NPOSE = (int)(A->poses.size() / 7);
+  A->pose_constant.assign(NPOSE, 1);
+  A->pose_fixed_dim.assign(NPOSE, -1);
   std::vector<uint8_t> cam_in_cfg(NC, 0);
   for (int i = 0; i < NI; ++i)
     if (flag(cfg->image_in_config, i)) {
       if (image_parameterized[i]) cam_in_cfg[sc->image_camera[i]] = 1;
-      if (!flag(cfg->image_constant_pose, i)) A->pose_constant[i] = 0;
+      if (rigs) { if (!flag(cfg->frame_constant_pose, sc->image_frame[i])) A->pose_constant[sc->image_frame[i]] = 0; }
+      else if (!flag(cfg->image_constant_pose, i)) A->pose_constant[i] = 0;
     }
   // cameras seen only through constant-pose factors of outside images stay constant (:863-878)
   A->cam_constant.resize(NC);
@@ -2491,7 +2521,7 @@ int b200ba_assemble(const b200ba_options* o, const b200ba_scene* sc, const b200b
   }
   b200ba_problem& P = A->problem;
   memset(&P, 0, sizeof(P));
-  P.num_poses = NI; P.poses = A->poses.data(); P.pose_constant = A->pose_constant.data(); P.pose_fixed_translation_dim = A->pose_fixed_dim.data();
+  P.num_poses = NPOSE; P.poses = A->poses.data(); P.pose_constant = A->pose_constant.data(); P.pose_fixed_translation_dim = A->pose_fixed_dim.data();
   P.num_cameras = NC; P.camera_model_id = A->cam_model.data(); P.camera_param_offset = A->cam_off.data(); P.camera_params = A->cam_params.data();
   P.camera_constant = A->cam_constant.data();
   P.num_points = NPT; P.points = A->points.data(); P.point_constant = A->point_constant.data();
@@ -2499,9 +2529,66 @@ int b200ba_assemble(const b200ba_options* o, const b200ba_scene* sc, const b200b
   P.obs_pose_idx = A->obs_pose.data(); P.obs_camera_idx = A->obs_cam.data(); P.obs_point_idx = A->obs_point.data(); P.obs_xy = A->obs_xy.data();
   P.num_config_images = 0;
   for (int i = 0; i < NI; ++i) if (flag(cfg->image_in_config, i)) P.num_config_images += 1;   // config.NumImages() (:131)
-  // FixGauge (:270-417), TWO_CAMS_FROM_WORLD: the search runs over the config's images in ascending image id
   bool three_points = cfg->fixed_gauge == 2;
-  if (cfg->fixed_gauge == 1 && o->refine_rig_from_world) {
+  if (rigs) {
+    // ParameterizeRigsAndFrames (:470-538): sensor_from_rig is constant when not refined, constant in the config, or when
+    // the reference sensor of its rig is not part of the problem.  Sensors = non-reference cameras, ascending camera index.
+    A->cam_sensor.assign(NC, -1);
+    for (int c = 0; c < NC; ++c)
+      if (sc->rig_ref_camera[sc->camera_rig[c]] != c) {
+        A->cam_sensor[c] = (int32_t)A->sensor_constant.size();
+        A->sensors.insert(A->sensors.end(), sc->camera_sensor_from_rig + 7 * (size_t)c, sc->camera_sensor_from_rig + 7 * (size_t)c + 7);
+        // (a parameter block only through a parameterized image of the config on that camera; outside images are baked)
+        A->sensor_constant.push_back((!o->refine_sensor_from_rig || flag(cfg->camera_constant_sensor_from_rig, c) || !cam_in_cfg[c]) ? 1 : 0);
+      }
+    std::vector<uint8_t> rig_param(sc->num_rigs, 0);
+    for (int i = 0; i < NI; ++i) if (flag(cfg->image_in_config, i) && image_parameterized[i]) rig_param[sc->frame_rig[sc->image_frame[i]]] = 1;
+    for (int c = 0; c < NC; ++c) {
+      const int r = sc->camera_rig[c];
+      if (A->cam_sensor[c] >= 0 && rig_param[r] && !cam_in_cfg[sc->rig_ref_camera[r]]) A->sensor_constant[A->cam_sensor[c]] = 1;
+    }
+    P.num_sensors = (int)A->sensor_constant.size();
+    P.sensor_from_rig = A->sensors.data(); P.sensor_constant = A->sensor_constant.data(); P.camera_sensor_idx = A->cam_sensor.data();
+    // FixGaugeWithTwoCamsFromWorld with rigs (:308-417), over the parameterized images in ascending image id
+    if (cfg->fixed_gauge == 1 && o->refine_rig_from_world) {
+      auto const_sensor = [&](int img) { const int sidx = A->cam_sensor[sc->image_camera[img]]; return sidx < 0 || A->sensor_constant[sidx]; };   // IsParameterizedConstSensor
+      int image1 = -1, image2 = -1, dim2 = 0;
+      bool done = false;
+      for (int i = 0; i < NI && !done; ++i) {
+        if (!flag(cfg->image_in_config, i) || !image_parameterized[i]) continue;
+        if (flag(cfg->frame_constant_pose, sc->image_frame[i]) && const_sensor(i)) {
+          if (image1 < 0) image1 = i;
+          else if (sc->image_frame[image1] != sc->image_frame[i]) done = true;   // two frames are already fixed
+        }
+      }
+      if (!done) {
+        for (int i = 0; i < NI; ++i) {
+          if (!flag(cfg->image_in_config, i) || !image_parameterized[i]) continue;
+          const int f = sc->image_frame[i];
+          if (image1 < 0 && const_sensor(i)) { image1 = i; continue; }
+          if (image1 >= 0 && sc->image_frame[image1] != f && const_sensor(i) && !flag(cfg->frame_constant_pose, f)) {
+            // baseline = (frame1_from_world * inverse(frame_from_world)).translation = t1 - R1 R^T t
+            const double* a = sc->rig_from_world + 7 * (size_t)sc->image_frame[image1];
+            const double* b = sc->rig_from_world + 7 * (size_t)f;
+            double Ra[9], Rb[9], ci[3], base[3];
+            ba_quat_to_R(a, Ra); ba_quat_to_R(b, Rb);
+            for (int r = 0; r < 3; ++r) ci[r] = -(Rb[r] * b[4] + Rb[3 + r] * b[5] + Rb[6 + r] * b[6]);
+            for (int r = 0; r < 3; ++r) base[r] = Ra[3 * r] * ci[0] + Ra[3 * r + 1] * ci[1] + Ra[3 * r + 2] * ci[2] + a[4 + r];
+            int mi = 0;
+            for (int r = 1; r < 3; ++r) if (fabs(base[r]) > fabs(base[mi])) mi = r;
+            if (fabs(base[mi]) > 1e-9) { image2 = i; dim2 = mi; break; }
+          }
+        }
+        if (image1 < 0 || image2 < 0) three_points = true;   // "Falling back to fixing Gauge with three points" (:390-394)
+        else {
+          A->pose_constant[sc->image_frame[image1]] = 1;
+          if (!flag(cfg->frame_constant_pose, sc->image_frame[image2])) A->pose_fixed_dim[sc->image_frame[image2]] = (int8_t)dim2;
+        }
+      }
+    }
+  }
+  // FixGauge (:270-417), TWO_CAMS_FROM_WORLD, trivial frames: the search runs over the config's images in ascending image id
+  if (!rigs && cfg->fixed_gauge == 1 && o->refine_rig_from_world) {
     std::vector<int> idx;
     for (int i = 0; i < NI; ++i) if (flag(cfg->image_in_config, i) && image_parameterized[i]) idx.push_back(i);   // parameterized_image_ids_
     std::vector<double> sp(7 * idx.size());

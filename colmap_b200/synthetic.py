@@ -428,3 +428,52 @@ def synthesize_rig_problem(num_frames, num_sensors, num_points, track_length, mo
     if point3D_stddev > 0:
         noisy.points += rng.normal(0, point3D_stddev, noisy.points.shape)
     return gt, noisy
+
+
+def synthesize_rig_reconstruction(num_rigs, num_cameras_per_rig, num_frames_per_rig, num_points3D, model=2, seed=0,
+                                  point2D_stddev=0.0):
+    """SynthesizeDataset with rigs (scene/synthetic.cc:341-672) as a Reconstruction of the Python mirror: `num_rigs` rigs of
+    `num_cameras_per_rig` cameras each (own intrinsics; the first camera of a rig is its reference sensor), every rig
+    with `num_frames_per_rig` frames, one image per (frame, sensor), image / camera / frame / rig ids ascending from 1 in
+    that order, every point observed by every image (as in the reference's small test scenes)."""
+    from .bundle_adjustment import Camera, Frame, Image, MODEL_NUM_PARAMS, Point2D, Point3D, Reconstruction, Rig, _rigid_compose
+    rng = np.random.default_rng(seed)
+    rec = Reconstruction()
+    pts = rng.uniform(-1, 1, (num_points3D, 3))
+    pts /= np.linalg.norm(pts, axis=1, keepdims=True)
+    for k in range(num_points3D):
+        rec.points3D[k + 1] = Point3D(xyz=pts[k].copy())
+    cam_id = img_id = frame_id = 0
+    for r in range(1, num_rigs + 1):
+        cams = []
+        for _ in range(num_cameras_per_rig):
+            cam_id += 1
+            rec.cameras[cam_id] = Camera(cam_id, model, np.asarray(_MODEL_DEFAULTS[model], np.float64).copy())
+            cams.append(cam_id)
+        rig = Rig(r, cams[0])
+        for c in cams[1:]:
+            ax = rng.normal(size=3); ax /= np.linalg.norm(ax)
+            ang = np.deg2rad(rng.uniform(2.0, 6.0))
+            rig.sensors[c] = np.concatenate([ax * np.sin(ang / 2), [np.cos(ang / 2)], rng.uniform(-0.3, 0.3, 3)])
+        rec.rigs[r] = rig
+        for _ in range(num_frames_per_rig):
+            frame_id += 1
+            view = -rng.uniform(-1, 1, 3); view /= np.linalg.norm(view)
+            q = _quat_from_two_vectors(view[None], np.array([0.0, 0.0, 1.0]))[0]
+            rfw = np.concatenate([q, _quat_rotate(q[None], 5.0 * view[None])[0]])
+            rec.frames[frame_id] = Frame(frame_id, r, rfw)
+            for c in cams:
+                img_id += 1
+                cfw = rfw if c == rig.ref_sensor else _rigid_compose(rig.sensors[c], rfw)
+                pc = _quat_rotate(np.broadcast_to(cfw[:4], (num_points3D, 4)), pts) + cfw[4:]
+                prm = rec.cameras[c].params
+                xy = _project(model, np.broadcast_to(prm, (num_points3D, MODEL_NUM_PARAMS[model])), pc)
+                if point2D_stddev > 0:
+                    xy = xy + rng.normal(0, point2D_stddev, xy.shape)
+                im = Image(img_id, c, cfw.copy(), frame_id=frame_id)
+                for k in range(num_points3D):
+                    im.points2D.append(Point2D(xy[k].copy(), k + 1))
+                    rec.points3D[k + 1].track.append((img_id, k))
+                rec.images[img_id] = im
+    return rec
+

@@ -152,7 +152,7 @@ int b200ba_solve_sharded(const b200ba_options* o, b200ba_problem* local_shard, b
 
 /* ---- problem assembly from a Reconstruction + BundleAdjustmentConfig ----
  * DefaultBundleAdjuster's constructor (bundle_adjustment_ceres.cc:606-664: AddImageToProblem :688-751, AddPointToProblem
- * :829-888, ParameterizeCameras / ParameterizePoints :478-565, FixGauge :270-417) for trivial frames, on flat views of the
+ * :829-888, ParameterizeCameras / ParameterizeRigsAndFrames / ParameterizePoints :419-565, FixGauge :270-417), on flat views of the
  * reference's containers.  The adapter fills the views with plain loops over Reconstruction (no hash-map walks remain on
  * the solve path), calls b200ba_assemble, b200ba_solve on the assembled problem, and copies the three in/out arrays back. */
 typedef struct b200ba_scene {
@@ -172,6 +172,16 @@ typedef struct b200ba_scene {
   const int64_t* track_offset;      /* [num_points3D+1] */
   const int32_t* track_image;       /* image INDEX of every track element */
   const int32_t* track_point2D;     /* index of the element inside that image's point2D list */
+  /* ---- rigs and frames (scene/rig.h, scene/frame.h); num_frames == 0: trivial frames, cam_from_world above is the pose.
+   * With frames the pose of an image is sensor_from_rig(camera) * rig_from_world(frame) and cam_from_world is ignored. */
+  int num_frames;                   /* ascending frame id */
+  const int32_t* image_frame;       /* [num_images] frame index */
+  const double* rig_from_world;     /* [7*num_frames] */
+  const int32_t* frame_rig;         /* [num_frames] rig index */
+  int num_rigs;
+  const int32_t* rig_ref_camera;    /* [num_rigs] camera index of the rig's reference sensor */
+  const int32_t* camera_rig;        /* [num_cameras] rig the camera is a sensor of */
+  const double* camera_sensor_from_rig;   /* [7*num_cameras]; ignored for reference sensors */
 } b200ba_scene;
 
 typedef struct b200ba_config {      /* BundleAdjustmentConfig (bundle_adjustment.h:77-151) as flags over the scene arrays */
@@ -184,12 +194,19 @@ typedef struct b200ba_config {      /* BundleAdjustmentConfig (bundle_adjustment
   int fixed_gauge;                      /* 0 UNSPECIFIED, 1 TWO_CAMS_FROM_WORLD (:308-417), 2 THREE_POINTS (:270-306; points in
                                          * ascending id, the reference walks a hash map) - enum at bundle_adjustment.h:44-48 */
   int min_track_length;                 /* BundleAdjustmentOptions::min_track_length */
+  /* with frames (scene.num_frames > 0): image_constant_pose is ignored, these two are read instead */
+  const uint8_t* frame_constant_pose;                /* [num_frames] HasConstantRigFromWorldPose */
+  const uint8_t* camera_constant_sensor_from_rig;    /* [num_cameras] HasConstantSensorFromRigPose */
 } b200ba_config;
 
 typedef struct b200ba_assembly* b200ba_assembly_t;
 int b200ba_assemble(const b200ba_options* o, const b200ba_scene* scene, const b200ba_config* config, b200ba_assembly_t* out);
 /* the assembled problem; flat pose / camera / point indices equal the scene's image / camera / point indices.  The
- * arrays belong to the assembly; poses, camera_params and points are copies that b200ba_solve updates in place. */
+ * arrays belong to the assembly; poses, camera_params and points are copies that b200ba_solve updates in place.
+ * With frames: pose k = frame k (rig_from_world) for k < num_frames, followed by one constant pose per image outside the
+ * config that a config point brought in (a copy of its frame's pose; the reference bakes those observations with a
+ * constant pose, bundle_adjustment_ceres.cc:846-878); sensor s = the s-th non-reference camera in ascending camera
+ * index (problem->sensor_from_rig, updated in place by the solve). */
 b200ba_problem* b200ba_assembly_problem(b200ba_assembly_t a);
 void b200ba_assembly_free(b200ba_assembly_t a);
 

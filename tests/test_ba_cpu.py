@@ -592,3 +592,65 @@ def test_oracle_recovers_ground_truth_with_rig_and_wide_models():
     assert np.abs(noisy.sensors[:, 4:] - gt.sensors[:, 4:]).max() < 5e-3
     dq = np.abs(np.sum(noisy.sensors[:, :4] * gt.sensors[:, :4], axis=1))
     assert np.all(dq > 1 - 1e-5)
+
+
+def _noisy_rig_reconstruction(seed=4):
+    """NominalMultiCameraRig's scene (bundle_adjustment_ceres_test.cc:183-220): 2 rigs x 3 cameras x 5 frames, 200 points, noise
+    0.5 px / 0.1 (points) / 0.5 deg + 0.1 (rig_from_world).  Returns (ground truth, noisy) reconstructions."""
+    import copy
+    from colmap_b200.synthetic import _quat_mul, synthesize_rig_reconstruction
+    gt = synthesize_rig_reconstruction(2, 3, 5, 200, model=SIMPLE_RADIAL, seed=seed, point2D_stddev=0.5)
+    noisy = copy.deepcopy(gt)
+    rng = np.random.default_rng(seed + 100)
+    for p in noisy.points3D.values():
+        p.xyz += rng.normal(0, 0.1, 3)
+    for f in noisy.frames.values():
+        a = np.deg2rad(rng.normal(0, 0.5))
+        f.rig_from_world[:4] = _quat_mul(f.rig_from_world[None, :4], np.array([[0, 0, np.sin(a / 2), np.cos(a / 2)]]))[0]
+        f.rig_from_world[4:] += rng.normal(0, 0.1, 3)
+    return gt, noisy
+
+
+def test_rig_assembly_with_images_outside_the_config_and_oracle_solve():
+    """A local-BA-shaped rig problem: only the images of two frames are in the config, two config points bring in their
+    observations from images outside it.  Those observations sit on CONSTANT copies of their frames' poses appended after
+    the frame poses (the reference bakes them with a constant pose, bundle_adjustment_ceres.cc:846-878), their cameras
+    become constant (:880-884); the C++ assembly equals the Python mirror; the oracle's solve leaves every constant
+    block bit-identical and moves the variable ones."""
+    import oracle_ba
+    from colmap_b200.bundle_adjustment import (BundleAdjustmentConfig, TWO_CAMS_FROM_WORLD, assemble_reconstruction,
+                                               flatten_reconstruction)
+    gt, rec = _noisy_rig_reconstruction()
+    cfg = BundleAdjustmentConfig()
+    in_cfg = [i for i, im in rec.images.items() if im.frame_id in (1, 2)]      # rig 1, frames 1 and 2: images 1..6
+    for i in in_cfg:
+        cfg.AddImage(i)
+    cfg.AddVariablePoint(7); cfg.AddConstantPoint(9)
+    cfg.FixGauge(TWO_CAMS_FROM_WORLD)
+    o = BundleAdjustmentOptions(max_num_iterations=10)
+    flat_py, frame_ids, camera_ids, point_ids = flatten_reconstruction(o, cfg, rec)
+    flat = assemble_reconstruction(o, cfg, rec)[0]
+    for name in ("poses", "pose_constant", "pose_fixed_dim", "cam_constant", "point_constant", "obs_pose", "obs_cam", "obs_point",
+                 "obs_xy", "sensors", "sensor_constant", "cam_sensor"):
+        assert np.array_equal(getattr(flat, name), getattr(flat_py, name)), name
+    n_out = len(rec.images) - len(in_cfg)
+    assert len(flat.poses) == len(frame_ids) + n_out                      # one constant pose per outside image
+    assert np.all(flat.pose_constant[len(frame_ids):] == 1)
+    assert len(flat.obs_pose) == 200 * len(in_cfg) + 2 * n_out            # every point from the six images + 2 points from the others
+    # points other than 7 have part of their track outside the problem: constant; 7 is fully inside now: variable; 9 constant
+    assert flat.point_constant[point_ids.index(7)] == 0 and flat.point_constant[point_ids.index(9)] == 1
+    assert int((flat.point_constant == 0).sum()) == 1
+    assert np.all(flat.cam_constant[3:] == 1) and np.all(flat.cam_constant[:3] == 0)     # rig 2's cameras: outside images only
+    before = flat.copy()
+    s = oracle_ba.solve(o, flat)
+    # point 9 is constant: its 15 observations from rig 2 (constant cameras, baked poses, sensors that are no parameter blocks)
+    # touch nothing variable and do not count (bundle_adjustment.h:66-68)
+    assert s.termination_type in (0, 1) and s.num_residuals == 2 * (len(flat.obs_pose) - 15)
+    assert s.num_effective_parameters == (12 - 7) + 2 * 6 + 3 * 2 + 3          # frames 1, 2 minus the gauge, rig 1's sensors, cameras 1-3, point 7
+    assert np.array_equal(flat.poses[2:], before.poses[2:])               # frames 3.. and the outside copies untouched
+    assert np.array_equal(flat.poses[0], before.poses[0])                 # gauge: frame 1 fixed
+    assert not np.array_equal(flat.poses[1], before.poses[1])
+    assert not np.array_equal(flat.sensors[:2], before.sensors[:2]) and np.array_equal(flat.sensors[2:], before.sensors[2:])
+    moved = np.nonzero(np.any(flat.points != before.points, axis=1))[0]
+    assert [point_ids[k] for k in moved] == [7]
+    assert s.final_cost < s.initial_cost

@@ -333,3 +333,41 @@ def test_rig_parity(kw, sensor_const, models):
         assert np.array_equal(a.sensors[0], before.sensors[0]) and not np.array_equal(a.sensors[1], before.sensors[1])
     if kw.get("refine_rig_from_world") is False:
         assert np.array_equal(a.poses, before.poses)
+
+
+def test_reconstruction_level_api_with_rigs_recovers_ground_truth():
+    """NominalMultiCameraRig (bundle_adjustment_ceres_test.cc:183-220) through the BundleAdjuster mirror on the GPU: 2 rigs x
+    3 cameras x 5 frames, 200 points, noisy points and rig poses, two-cams gauge; every frame, sensor_from_rig, camera and
+    point variable.  The solve returns to the noise floor, recovers the sensor_from_rig poses and the relative geometry
+    (the reference asks 0.1 deg / 0.1 units after alignment), and agrees with the oracle on the same flat problem."""
+    import copy
+    from test_ba_cpu import _noisy_rig_reconstruction
+    from colmap_b200.bundle_adjustment import flatten_reconstruction
+    gt, rec = _noisy_rig_reconstruction()
+    cfg = BundleAdjustmentConfig()
+    for i in rec.images:
+        cfg.AddImage(i)
+    cfg.FixGauge(TWO_CAMS_FROM_WORLD)
+    o = BundleAdjustmentOptions()
+    rec_o = copy.deepcopy(rec)
+    summary = CreateDefaultBundleAdjuster(o, cfg, rec).Solve()
+    n_obs = 200 * len(rec.images)
+    assert summary.termination_type in (0, 1) and summary.num_residuals == 2 * n_obs
+    # 200 x 3 points + 10 x 6 frames - 7 (gauge) + 4 x 6 sensors + 6 x 2 intrinsics
+    assert summary.num_effective_parameters == 600 + 60 - 7 + 24 + 12
+    rmse = np.sqrt(2 * summary.final_cost / n_obs)
+    assert rmse < 0.5 * np.sqrt(2) * 1.05
+    for r in rec.rigs:
+        for c, sfr in rec.rigs[r].sensors.items():
+            g = gt.rigs[r].sensors[c]
+            assert abs(np.dot(sfr[:4], g[:4])) > np.cos(np.deg2rad(0.1) / 2), (r, c)
+            assert np.abs(sfr[4:] - g[4:]).max() < 0.02, (r, c, sfr[4:] - g[4:])
+    P = np.stack([rec.points3D[k].xyz for k in sorted(rec.points3D)][:60]); G = np.stack([gt.points3D[k].xyz for k in sorted(gt.points3D)][:60])
+    dp = np.linalg.norm(P[:, None] - P[None], axis=-1); dg = np.linalg.norm(G[:, None] - G[None], axis=-1)
+    assert np.abs(dp / (dp.sum() / dg.sum()) - dg).max() < 0.1
+    # the oracle on the same problem
+    flat = flatten_reconstruction(o, cfg, rec_o)[0]
+    so = oracle_ba.solve(o, flat)
+    assert so.num_effective_parameters == summary.num_effective_parameters
+    assert abs(so.final_cost - summary.final_cost) <= REL * so.final_cost
+    assert np.allclose(np.stack([rec.frames[f].rig_from_world for f in sorted(rec.frames)]), flat.poses, rtol=REL, atol=REL)

@@ -203,3 +203,44 @@ def test_known_answers_bundle_adjustment_scenarios():
         from test_ba_cpu import _pack
         L = _pack(flat, o)
         assert (L["num_residuals"], L["num_effective_parameters"]) == (c["num_residuals"], c["num_effective_parameters"]), c["name"]
+
+
+def _rig_scenario(c):
+    from colmap_b200.bundle_adjustment import BundleAdjustmentConfig, SIMPLE_RADIAL, THREE_POINTS, TWO_CAMS_FROM_WORLD
+    from colmap_b200.synthetic import synthesize_rig_reconstruction
+    gauges = {"TWO_CAMS_FROM_WORLD": TWO_CAMS_FROM_WORLD, "THREE_POINTS": THREE_POINTS}
+    rec = synthesize_rig_reconstruction(*c["dataset"], model=SIMPLE_RADIAL, seed=11, point2D_stddev=1.0)
+    for i in c.get("delete_observations_of_images", []):        # Reconstruction::DeleteObservation for every point of the image
+        for k, p2 in enumerate(rec.images[i].points2D):
+            if p2.point3D_id >= 0:
+                rec.points3D[p2.point3D_id].track = [t for t in rec.points3D[p2.point3D_id].track if t != (i, k)]
+                p2.point3D_id = -1
+    cfg = BundleAdjustmentConfig()
+    for i in (sorted(rec.images) if c["images"] == "all" else c["images"]):
+        cfg.AddImage(i)
+    for f in c.get("constant_frames", []): cfg.SetConstantRigFromWorldPose(f)
+    for s in c.get("constant_sensors", []): cfg.SetConstantSensorFromRigPose(s)
+    if "gauge" in c:
+        cfg.FixGauge(gauges[c["gauge"]])
+    return rec, cfg, BundleAdjustmentOptions(max_num_iterations=2, **c.get("options", {}))
+
+
+def test_known_answers_bundle_adjustment_rig_scenarios():
+    """The rig scenarios of bundle_adjustment_ceres_test.cc (TwoViewRig, ManyViewRig*, the three FixGaugeWithTwoCamsFromWorld*
+    sequences with rigs, the three-points fallback): residual / effective-parameter counts of the problem the C++ assembly
+    builds, counted by the oracle and by the product's own host flattening; the C++ assembly equals the Python mirror."""
+    from colmap_b200.bundle_adjustment import assemble_reconstruction, flatten_reconstruction
+    from test_ba_cpu import _pack
+    for c in KA["bundle_adjustment_rig_scenarios"]["cases"]:
+        rec, cfg, o = _rig_scenario(c)
+        flat_py = flatten_reconstruction(o, cfg, rec)[0]
+        flat = assemble_reconstruction(o, cfg, rec)[0]
+        for name in ("poses", "pose_constant", "pose_fixed_dim", "cam_constant", "point_constant", "obs_pose", "obs_cam", "obs_point",
+                     "obs_xy", "sensors", "sensor_constant", "cam_sensor"):
+            assert np.array_equal(getattr(flat, name), getattr(flat_py, name)), (c["name"], name)
+        s = oracle_ba.solve(o, flat)
+        assert s.num_effective_parameters == c["num_effective_parameters"], (c["name"], s.num_effective_parameters)
+        if "num_residuals" in c:
+            assert s.num_residuals == c["num_residuals"], c["name"]
+        L = _pack(flat, o)
+        assert L["num_effective_parameters"] == c["num_effective_parameters"], (c["name"], L["num_effective_parameters"])
