@@ -598,7 +598,7 @@ def main():
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": _ncu_traffic("pm_sweep"), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": sweep_launch_ms,
-                    "pass_ms_per_sweep": {"rand": pass_ms[0] / args.steps / n_sweeps, "pixel": pixel_launch_ms,
+                    "pass_ms_per_sweep": {"rand_and_msg": pass_ms[0] / args.steps / n_sweeps, "pixel": pixel_launch_ms,
                                           "serial": pass_ms[2] / args.steps / n_sweeps},
                     "taps_per_s": taps_per_sweep / (sweep_launch_ms * 1e-3),
                     "note": "the faithful sweep is instruction-issue bound, not HBM bound (DESIGN.md §2): 177 algorithmic "

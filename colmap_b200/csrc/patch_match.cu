@@ -1615,6 +1615,7 @@ int b200pm_run(b200pm_handle c) {
           if (P.geom) { if (!pr) PM_LAUNCH_PIXEL(true, false, 8); else if (c->pix_minb == 8) PM_LAUNCH_PIXEL(true, true, 8); else if (c->pix_minb == 7) PM_LAUNCH_PIXEL(true, true, 7); else PM_LAUNCH_PIXEL(true, true, 6); }
           else { if (!pr) PM_LAUNCH_PIXEL(false, false, 8); else if (c->pix_minb == 8) PM_LAUNCH_PIXEL(false, true, 8); else if (c->pix_minb == 7) PM_LAUNCH_PIXEL(false, true, 7); else PM_LAUNCH_PIXEL(false, true, 6); }
 #undef PM_LAUNCH_PIXEL
+          if (nchunks == 1) mark(2);   // pixel | serial boundary of the per-pass times (one chunk: both passes on the main stream)
           cudaStream_t ss = nchunks > 1 ? c->chunk_stream[k] : s;
           if (nchunks > 1) {
             cudaEventRecord(c->chunk_ev[k], s);
@@ -1627,7 +1628,7 @@ int b200pm_run(b200pm_handle c) {
           if (nchunks > 1) cudaEventRecord(c->chunk_ev[PM_MAX_CHUNKS + k], ss);
           launches += 2;
         }
-        mark(2);
+        if (nchunks > 1) mark(2);
         if (nchunks > 1) for (int k = 0; k < nchunks; ++k) cudaStreamWaitEvent(s, c->chunk_ev[PM_MAX_CHUNKS + k], 0);
         launches += 2;
         mark(3);
