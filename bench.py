@@ -105,6 +105,18 @@ def _ncu_traffic(name):
     return None
 
 
+def _use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU legs (rank 0 only) are meant to use every host core.  The
+    oracles are OpenMP code on the process' libgomp, so the team size is raised there.  Returns the thread count in use."""
+    import ctypes
+    n = os.cpu_count() or 1
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n)
+    except OSError:
+        n = int(os.environ.get("OMP_NUM_THREADS", n))
+    return n
+
+
 def _oracle_pm_sample(threads=None):
     """Bounded CPU sample of the same workload with the oracle: a 240x136 crop-scale scene (1/63.5 of the
     pixels of C2), 8 sources, the full 5 iterations; Mpixels/s is per reference pixel so it is comparable."""
@@ -116,6 +128,7 @@ def _oracle_pm_sample(threads=None):
     sc = make_patch_match_scene(w, h, C2["num_src"], seed=0)
     o = PatchMatchOptions(depth_min=sc["depth_min"], depth_max=sc["depth_max"], geom_consistency=False,
                           window_radius=C2["window_radius"], num_iterations=C2["num_iterations"])
+    _use_all_host_threads()
     t = time.time()
     oracle_pm.run(o, sc["problem"])
     dt = time.time() - t
@@ -150,6 +163,7 @@ def _oracle_ba_sample(noisy, max_iters=100):
     import oracle_ba
     from colmap_b200.bundle_adjustment import ITERATIVE_SCHUR, BundleAdjustmentOptions
     o = BundleAdjustmentOptions(linear_solver_type=ITERATIVE_SCHUR, max_num_iterations=max_iters)
+    _use_all_host_threads()
     t = time.time()
     s = oracle_ba.solve(o, _fresh(noisy))
     dt = time.time() - t

@@ -8,7 +8,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_json_contract():
-    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")        # force the CPU legs even where a GPU exists
+    # force the CPU legs even where a GPU exists; OMP_NUM_THREADS=1 is what torchrun exports to every rank - the CPU legs
+    # must raise their OpenMP team to all host cores themselves (with one thread the B3 leg alone would take many minutes)
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
@@ -25,4 +27,4 @@ def test_reference_arm_json_contract():
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     ba = d["ba"]
     assert ba["impl"] == "reference" and ba["metric"] == "ba_lm_iterations_per_s" and ba["value"] > 0
-    assert ba["cpu_baseline"]["kind"] == "port" and ba["cpu_baseline"]["cores"] >= 1
+    assert ba["cpu_baseline"]["kind"] == "port" and ba["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
