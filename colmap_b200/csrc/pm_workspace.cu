@@ -81,7 +81,8 @@ int read_colmap_model(const std::string& ws, WsModel* M) {
       uint32_t id; Img im;
       if (!rd(f, &id) || !rd(f, im.q, 4) || !rd(f, im.t, 3) || !rd(f, &im.cam)) { fclose(f); return fail(-20, "images.bin: truncated"); }
       for (int ch; (ch = fgetc(f)) > 0;) im.name.push_back((char)ch);
-      uint64_t m = 0; rd(f, &m);
+      uint64_t m = 0;
+      if (!rd(f, &m) || m > (1ULL << 32)) { fclose(f); return fail(-20, "images.bin: truncated"); }   // (a corrupt count must not wrap the seek)
       if (fseek(f, (long)(24 * m), SEEK_CUR) != 0) { fclose(f); return fail(-20, "images.bin: truncated"); }
       imgs[id] = im;
     }
@@ -145,7 +146,9 @@ int load_pgm(void*, const char* path, int* w, int* h, uint8_t** data) {
   skip(); if (fscanf(f, "%d", h) != 1) { fclose(f); return -1; }
   skip(); if (fscanf(f, "%d", &maxv) != 1 || maxv != 255) { fclose(f); return -1; }
   fgetc(f);
+  if (*w <= 0 || *h <= 0 || *w > (1 << 16) || *h > (1 << 16)) { fclose(f); return -1; }   // a corrupt header must not size the allocation
   *data = (uint8_t*)malloc((size_t)*w * *h);
+  if (!*data) { fclose(f); return -1; }
   const bool ok = fread(*data, 1, (size_t)*w * *h, f) == (size_t)*w * *h;
   fclose(f);
   if (!ok) { free(*data); *data = nullptr; return -1; }
