@@ -315,3 +315,41 @@ def test_controller_thread_pool_follows_gpu_index_list(tmp_path):
     assert len({t for _, _, t in state["log"][:6]}) == 2
     c2 = PatchMatchController(PatchMatchOptions(gpu_index="-1"), tmp)
     assert c2.ReadGpuIndices(num_devices=4) == [0, 1, 2, 3] and PatchMatchController(PatchMatchOptions(gpu_index="1, 3"), tmp).ReadGpuIndices() == [1, 3]
+
+
+def test_run_workspace_fails_loudly_without_a_workspace_or_a_gpu(tmp_path):
+    """b200pm_run_workspace (the controller in C++) has no CPU path: a missing sparse model, a corrupt one and - with a valid
+    workspace - the absence of a CUDA device are all reported as errors, nothing is written."""
+    from colmap_b200.mvs_workspace import WorkspaceError, run_workspace
+    from colmap_b200.patch_match import PatchMatchOptions
+    o = PatchMatchOptions()
+    with pytest.raises(WorkspaceError, match="cannot open"):
+        run_workspace(o, str(tmp_path / "nowhere"))
+    ws = tmp_path / "ws"
+    (ws / "sparse").mkdir(parents=True)
+    (ws / "sparse" / "cameras.bin").write_bytes(np.array([1], np.uint64).tobytes() + b"\x01\x00")          # count 1, then truncated
+    with pytest.raises(WorkspaceError, match="truncated"):
+        run_workspace(o, str(ws))
+    # a structurally valid (tiny) workspace: without a device the call must refuse, not fall back
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    import struct
+    cam = struct.pack("<Q", 1) + struct.pack("<IiQQ", 1, 1, 64, 48) + struct.pack("<4d", 50.0, 50.0, 32.0, 24.0)
+    (ws / "sparse" / "cameras.bin").write_bytes(cam)
+    imgs = struct.pack("<Q", 2)
+    for i in (1, 2):
+        imgs += struct.pack("<I", i) + struct.pack("<4d", 1.0, 0.0, 0.0, 0.0) + struct.pack("<3d", 0.1 * i, 0.0, 0.0) + struct.pack("<I", 1)
+        imgs += f"im{i}.pgm".encode() + b"\x00" + struct.pack("<Q", 0)
+    (ws / "sparse" / "images.bin").write_bytes(imgs)
+    pts = struct.pack("<Q", 1) + struct.pack("<Q", 1) + struct.pack("<3d", 0.0, 0.0, 3.0) + bytes([1, 2, 3]) + struct.pack("<d", 0.5)
+    pts += struct.pack("<Q", 2) + struct.pack("<II", 1, 0) + struct.pack("<II", 2, 0)
+    (ws / "sparse" / "points3D.bin").write_bytes(pts)
+    (ws / "stereo").mkdir()
+    (ws / "stereo" / "patch-match.cfg").write_text("im1.pgm\n__all__\nim2.pgm\n__all__\n")
+    (ws / "images").mkdir()
+    for i in (1, 2):
+        (ws / "images" / f"im{i}.pgm").write_bytes(b"P5\n64 48\n255\n" + bytes(64 * 48))
+    with pytest.raises(WorkspaceError, match="CUDA|device|GPU"):
+        run_workspace(o, str(ws), gpu_indices=[0])
+    assert not (ws / "stereo" / "depth_maps").exists() or not any((ws / "stereo" / "depth_maps").iterdir())
