@@ -490,6 +490,9 @@ def _flatten_reconstruction_rigs(options, config, rec):
     reference freezes the product sensor_from_rig * rig_from_world; here the frozen rig_from_world is composed with the
     current sensor_from_rig (the flat problem ties the sensor to the camera, not to the observation)."""
     frame_ids, camera_ids, point_ids = sorted(rec.frames), sorted(rec.cameras), sorted(rec.points3D)
+    for im in rec.images.values():
+        if im.frame_id not in rec.frames:
+            raise BundleAdjustmentError(f"image {im.image_id}: a reconstruction with frames needs a frame for every image")
     frame_idx = {f: k for k, f in enumerate(frame_ids)}
     cam_idx = {c: k for k, c in enumerate(camera_ids)}
     pt_idx = {p: k for k, p in enumerate(point_ids)}
